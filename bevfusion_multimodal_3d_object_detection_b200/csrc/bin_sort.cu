@@ -1,0 +1,227 @@
+// S1a — fused bin-and-sort of points by BEV cell: one launch, one thread-block cluster per frame.
+//
+// There is no binning code in the reference; the cell convention is the one its target generator
+// uses for box centres (src/centernet_target.py:222-224,250-257,285): voxel=(max-min)/W,
+// px=(x-x_min)/voxel, reject px<0 or px>=W, ix=int(px), flat=iy*W+ix.  Here it is evaluated in fp32
+// with IEEE subtract/divide (no reciprocal, no FMA) so that a numpy float32 restatement is bit-exact.
+//
+//   grid (CL, B), cluster (CL,1,1), 256 threads.  CTA `rank` of frame b owns the contiguous slice
+//   [rank*slice, (rank+1)*slice) of the frame's points.
+//     phase 1  stream the slice (x,y only), write cell[], count into a per-CTA shared-memory
+//              histogram over the H*W cells (+1 overflow bin for out-of-grid points);
+//     phase 2  cluster-wide exclusive scan over (cell, rank) through distributed shared memory:
+//              the cells are dealt out to the CTAs, each CTA reads the CL counts of its cells from
+//              its peers' histograms, scans, writes offsets[] and overwrites the peers' histogram
+//              entries with the start position of (cell, rank);
+//     phase 3  one warp per CTA walks its slice in point order, 32 points a step: match.any groups
+//              the lanes that hit the same cell, the group takes `count` consecutive slots from the
+//              cell's cursor in shared memory — a stable counting sort, no global atomics, no
+//              second pass over the points, deterministic output.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace b200bev {
+namespace {
+
+constexpr int kBinThreads = 256;
+constexpr int kMaxCluster = 8;
+
+struct BinArgs {
+  const float* pts;
+  int B, N, C;
+  float x_min, y_min, vx, vy;
+  int W, H;
+  int32_t* cell;
+  int32_t* perm;
+  int32_t* offsets;
+  int slice;        // points per CTA, multiple of 32
+  int cache_cells;  // keep the slice's cell ids in shared memory between phase 1 and 3
+};
+
+__device__ __forceinline__ int cell_of(float x, float y, const BinArgs& a) {
+  const float px = __fdiv_rn(__fsub_rn(x, a.x_min), a.vx);
+  const float py = __fdiv_rn(__fsub_rn(y, a.y_min), a.vy);
+  // written so that NaN is rejected too
+  if (!(px >= 0.0f) || !(px < (float)a.W) || !(py >= 0.0f) || !(py < (float)a.H)) return -1;
+  return (int)py * a.W + (int)px;  // truncation == floor for non-negative values
+}
+
+__global__ void __launch_bounds__(kBinThreads) bin_sort_kernel(BinArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = kBinThreads / 32;
+  const int HW = a.W * a.H;
+  const int nb = HW + 1;
+
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* hist = smem;          // nb: count, then cursor, of (cell, this rank)
+  uint32_t* cta_tot = hist + nb;  // kMaxCluster: number of points in each rank's share of the cells
+  uint32_t* wsum = cta_tot + kMaxCluster;  // nwarps
+  int32_t* cells_s = reinterpret_cast<int32_t*>(wsum + nwarps);
+
+  for (int i = tid; i < nb; i += kBinThreads) hist[i] = 0;
+  __syncthreads();
+
+  const int start = rank * a.slice;
+  const int end = min(a.N, start + a.slice);
+  const float* pts = a.pts + (size_t)b * a.N * a.C;
+  int32_t* cell_out = a.cell + (size_t)b * a.N;
+
+  // ---- phase 1: cell ids + per-CTA histogram ----
+  const bool vec2 = ((a.C & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.pts) & 7) == 0);
+  for (int i = start + tid; i < end; i += kBinThreads) {
+    float x, y;
+    if (vec2) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(pts + (size_t)i * a.C));
+      x = xy.x;
+      y = xy.y;
+    } else {
+      x = __ldg(pts + (size_t)i * a.C);
+      y = __ldg(pts + (size_t)i * a.C + 1);
+    }
+    const int c = cell_of(x, y, a);
+    cell_out[i] = c;
+    if (a.cache_cells) cells_s[i - start] = c;
+    atomicAdd(&hist[c < 0 ? HW : c], 1u);
+  }
+  cluster.sync();
+
+  // ---- phase 2: exclusive scan over (cell, rank), cells dealt out to the CTAs ----
+  const int share = ceil_div(nb, CL);
+  const int lo = rank * share, hi = min(nb, lo + share);
+  {
+    uint32_t mine = 0;
+    for (int bin = lo + tid; bin < hi; bin += kBinThreads)
+      for (int q = 0; q < CL; ++q) mine += cluster.map_shared_rank(hist, q)[bin];
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, d);
+    if (lane == 0) wsum[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < nwarps; ++w) t += wsum[w];
+      for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cta_tot, q)[rank] = t;
+    }
+  }
+  cluster.sync();
+  uint32_t carry = 0;
+  for (int q = 0; q < rank; ++q) carry += cta_tot[q];
+  int32_t* offsets = a.offsets + (size_t)b * nb;
+  for (int base = lo; base < hi; base += kBinThreads) {
+    const int bin = base + tid;
+    const bool ok = bin < hi;
+    uint32_t cnt[kMaxCluster];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int q = 0; q < kMaxCluster; ++q) {
+      cnt[q] = (ok && q < CL) ? cluster.map_shared_rank(hist, q)[bin] : 0u;
+      tot += cnt[q];
+    }
+    const uint32_t incl = (uint32_t)warp_incl_scan((int)tot, lane);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < nwarps; ++w) {
+      const uint32_t v = wsum[w];
+      if (w < warp) before += v;
+      total += v;
+    }
+    if (ok) {
+      uint32_t run = carry + before + incl - tot;
+      offsets[bin] = (int32_t)run;
+#pragma unroll
+      for (int q = 0; q < kMaxCluster; ++q) {
+        if (q < CL) {
+          cluster.map_shared_rank(hist, q)[bin] = run;
+          run += cnt[q];
+        }
+      }
+    }
+    carry += total;
+    __syncthreads();
+  }
+  cluster.sync();
+
+  // ---- phase 3: stable placement, one warp, slice walked in point order ----
+  if (warp == 0) {
+    int32_t* perm = a.perm + (size_t)b * a.N;
+    const int32_t* src = a.cache_cells ? (cells_s - start) : cell_out;
+    constexpr int U = 4;
+    for (int i0 = start; i0 < end; i0 += 32 * U) {
+      int c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 32 + lane;
+        c[u] = (i < end) ? src[i] : -2;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 32 + lane;
+        const bool valid = i < end;
+        const int bin = c[u] < 0 ? HW : c[u];
+        const unsigned peers = __match_any_sync(FULL_MASK, valid ? bin : (0x40000000 | lane));
+        const int rk = __popc(peers & lanemask_lt());
+        const uint32_t cur = valid ? hist[bin] : 0u;
+        __syncwarp();
+        if (valid && rk == 0) hist[bin] = cur + (uint32_t)__popc(peers);
+        __syncwarp();
+        if (valid) perm[cur + rk] = i;
+      }
+    }
+  }
+  // peers may still be reading this CTA's shared memory in phase 2 only; phase 3 is local, but a
+  // CTA must not exit while a peer could still address its shared memory.
+  cluster.sync();
+}
+
+}  // namespace
+}  // namespace b200bev
+
+using namespace b200bev;
+
+extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, int C, float x_min, float y_min, float voxel_x,
+                                float voxel_y, int W, int H, int32_t* cell, int32_t* perm, int32_t* offsets,
+                                void* stream) {
+  if (!points || !cell || !perm || !offsets || B <= 0 || N <= 0 || C < 2 || W <= 0 || H <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (!(voxel_x > 0.0f) || !(voxel_y > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((long long)W * H > 48000 || B > 65535) return B200BEV_ERR_UNSUPPORTED;
+
+  BinArgs a{};
+  a.pts = points; a.B = B; a.N = N; a.C = C;
+  a.x_min = x_min; a.y_min = y_min; a.vx = voxel_x; a.vy = voxel_y; a.W = W; a.H = H;
+  a.cell = cell; a.perm = perm; a.offsets = offsets;
+
+  int CL = 1;
+  while (CL < kMaxCluster && N / (CL * 2) >= 1024) CL *= 2;
+  a.slice = ceil_div(ceil_div(N, CL), 32) * 32;
+  const size_t fixed = ((size_t)W * H + 1 + kMaxCluster + kBinThreads / 32) * sizeof(uint32_t);
+  size_t smem = fixed + (size_t)a.slice * sizeof(int32_t);
+  a.cache_cells = 1;
+  if (smem > 200 * 1024) {
+    a.cache_cells = 0;
+    smem = fixed;
+  }
+  if (smem > 48 * 1024)
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CL, B, 1);
+  cfg.blockDim = dim3(kBinThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, bin_sort_kernel, a));
+  return launch_status();
+}

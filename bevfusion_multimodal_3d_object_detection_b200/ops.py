@@ -1,0 +1,299 @@
+"""torch-tensor front end of the C-ABI: checks arguments, allocates outputs, passes raw device
+pointers and the current CUDA stream to libb200bev.so.  PyTorch is plumbing here (memory, streams);
+every op below runs a hand-written kernel or raises — nothing falls back to torch or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+DEFAULT_PC_RANGE = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)  # configs/base.yaml:48, src/centernet_target.py:390
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(dev: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name}: tensor is on {t.device}; the b200bev hot path runs on CUDA only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i32(values: Sequence[int]):
+    return (C.c_int32 * len(values))(*[int(v) for v in values])
+
+
+def voxel_size(pc_range: Sequence[float], W: int, H: int) -> Tuple[float, float]:
+    """voxel = (max - min) / cells in float64, rounded once to fp32 (src/centernet_target.py:222-224)."""
+    x_min, y_min, _, x_max, y_max, _ = pc_range
+    return (float(x_max) - float(x_min)) / W, (float(y_max) - float(y_min)) / H
+
+
+# ------------------------------------------------------------------------------------------------
+# S1a
+# ------------------------------------------------------------------------------------------------
+def bin_sort(points: torch.Tensor, W: int, H: int,
+             pc_range: Sequence[float] = DEFAULT_PC_RANGE) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """points (B,N,C) -> cell (B,N) i32, perm (B,N) i32, offsets (B,H*W+1) i32."""
+    points = _need_cuda(points, "points")
+    if points.dim() != 3:
+        raise ValueError("points must be (B, N, C)")
+    B, N, Cc = points.shape
+    dev = points.device
+    cell = torch.empty((B, N), dtype=torch.int32, device=dev)
+    perm = torch.empty((B, N), dtype=torch.int32, device=dev)
+    offsets = torch.empty((B, H * W + 1), dtype=torch.int32, device=dev)
+    vx, vy = voxel_size(pc_range, W, H)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_bin_sort(_ptr(points), B, N, Cc, pc_range[0], pc_range[1], vx, vy, W, H,
+                                               _ptr(cell), _ptr(perm), _ptr(offsets), _stream(dev)))
+    return cell, perm, offsets
+
+
+# ------------------------------------------------------------------------------------------------
+# S1b / S1c
+# ------------------------------------------------------------------------------------------------
+def fold_batchnorm(weight: torch.Tensor, bias: Optional[torch.Tensor], bn) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Folds an eval-mode BatchNorm1d (or Identity) into a k=1 Conv1d: returns (W', b') in float64.
+
+    y = g*(Wx + b - mean)/sqrt(var + eps) + beta  ==  (W*s) x + ((b - mean)*s + beta),  s = g/sqrt(var+eps)
+    (src/encoders.py:289-295 with bn in eval mode).
+    """
+    w = weight.detach().double().reshape(weight.shape[0], -1)
+    b = torch.zeros(w.shape[0], dtype=torch.float64, device=w.device) if bias is None else bias.detach().double()
+    if isinstance(bn, torch.nn.modules.batchnorm._BatchNorm):
+        var = bn.running_var.detach().double()
+        mean = bn.running_mean.detach().double()
+        g = torch.ones_like(var) if bn.weight is None else bn.weight.detach().double()
+        beta = torch.zeros_like(var) if bn.bias is None else bn.bias.detach().double()
+        s = g / torch.sqrt(var + bn.eps)
+        w = w * s[:, None]
+        b = (b - mean) * s + beta
+    return w, b
+
+
+def pack_mlp_params(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                    device: torch.device) -> Tuple[torch.Tensor, List[int]]:
+    """[(C_out,C_in)], [(C_out)] -> (blob fp32 on device, dims). Blob layout: W_l^T then b_l per layer."""
+    dims = [int(weights[0].shape[1])] + [int(w.shape[0]) for w in weights]
+    parts = []
+    for w, b in zip(weights, biases):
+        parts.append(w.t().contiguous().reshape(-1))
+        parts.append(b.reshape(-1))
+    blob = torch.cat([p.to(torch.float64) for p in parts]).to(torch.float32).to(device).contiguous()
+    return blob, dims
+
+
+def pack_mlp_params_bf16(params: torch.Tensor, dims: Sequence[int]) -> torch.Tensor:
+    """Device-side re-tiling of the fp32 blob into the tcgen05 stage image (uint8 tensor)."""
+    params = _need_cuda(params, "params")
+    d = _i32(dims)
+    n_bytes = _lib.lib().b200bev_pointnet_pack_bf16_bytes(d, len(dims) - 1)
+    if n_bytes == 0:
+        raise _lib.B200BevError(_lib.ERR_UNSUPPORTED, f"tensor-core path does not support layer widths {list(dims)}")
+    out = torch.empty(n_bytes, dtype=torch.uint8, device=params.device)
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.lib().b200bev_pointnet_pack_bf16(_ptr(params), d, len(dims) - 1, _ptr(out), n_bytes,
+                                                         _stream(params.device)))
+    return out
+
+
+def pointnet_encode(points: torch.Tensor, params: torch.Tensor, dims: Sequence[int],
+                    perm: Optional[torch.Tensor] = None, offsets: Optional[torch.Tensor] = None,
+                    n_cells: int = 0, precision: int = _lib.F32,
+                    tc_params: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused shared-MLP + max. Global mode -> (B, C_out); cell mode -> (B, n_cells, C_out) canvas."""
+    points = _need_cuda(points, "points")
+    params = _need_cuda(params, "params")
+    if points.dim() != 3:
+        raise ValueError("points must be (B, N, C)")
+    B, N, Cc = points.shape
+    if Cc != dims[0]:
+        raise ValueError(f"points have {Cc} channels, the MLP expects {dims[0]}")
+    dev = points.device
+    c_out = int(dims[-1])
+    if perm is not None:
+        perm = _need_cuda(perm, "perm", torch.int32)
+        offsets = _need_cuda(offsets, "offsets", torch.int32)
+        out = torch.empty((B, n_cells, c_out), dtype=torch.float32, device=dev)
+    else:
+        out = torch.empty((B, c_out), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_pointnet_encode(
+            _ptr(points), B, N, Cc, _ptr(params), _i32(dims), len(dims) - 1, _ptr(perm), _ptr(offsets), n_cells,
+            precision, _ptr(tc_params), _ptr(out), _stream(dev)))
+    return out
+
+
+def radar_encode(radar_list: Sequence[torch.Tensor], params: torch.Tensor, dims: Sequence[int], fusion: str,
+                 fc_weight: Optional[torch.Tensor], fc_bias: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """List of R tensors (B,N_r,C) -> (fused (B,F), per-radar maxima (B,R,F))."""
+    if fusion not in _lib.RADAR_FUSION:
+        raise ValueError(f"Unknown fusion method: {fusion}")  # src/encoders.py:659
+    radars = [_need_cuda(r, f"radar_list[{i}]") for i, r in enumerate(radar_list)]
+    if not radars:
+        raise ValueError("radar_list is empty")
+    params = _need_cuda(params, "params")
+    B, _, Cc = radars[0].shape
+    for r in radars:
+        if r.dim() != 3 or r.shape[0] != B or r.shape[2] != Cc:
+            raise ValueError("every radar tensor must be (B, N_r, C) with the same B and C")
+    R, F = len(radars), int(dims[-1])
+    dev = radars[0].device
+    per_radar = torch.empty((B, R, F), dtype=torch.float32, device=dev)
+    out = torch.empty((B, F), dtype=torch.float32, device=dev)
+    if fusion == "concat":
+        fc_weight = _need_cuda(fc_weight, "fc_weight")
+        fc_bias = _need_cuda(fc_bias, "fc_bias")
+        if tuple(fc_weight.shape) != (F, R * F):
+            # the reference's Linear would fail the same way
+            raise RuntimeError(f"fusion_fc expects {fc_weight.shape[1] // F} radars, got {R}")
+    ptrs = (C.c_void_p * R)(*[r.data_ptr() for r in radars])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_radar_encode(
+            ptrs, _i32([r.shape[1] for r in radars]), R, B, Cc, _ptr(params), _i32(dims), len(dims) - 1,
+            _lib.RADAR_FUSION[fusion], _ptr(fc_weight), _ptr(fc_bias), _ptr(per_radar), _ptr(out), _stream(dev)))
+    return out, per_radar
+
+
+# ------------------------------------------------------------------------------------------------
+# S2
+# ------------------------------------------------------------------------------------------------
+def camera_mean(feats: torch.Tensor) -> torch.Tensor:
+    """(B, n_cam, C, h, w) -> (B, C, h, w): camera_features.mean(dim=1) (src/fusion.py:234)."""
+    feats = _need_cuda(feats, "camera_features")
+    if feats.dim() < 3:
+        raise ValueError("camera_features must be (B, n_cam, ...)")
+    B, n_cam = feats.shape[:2]
+    out = torch.empty((B, *feats.shape[2:]), dtype=torch.float32, device=feats.device)
+    inner = out[0].numel()
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().b200bev_camera_mean(_ptr(feats), B, n_cam, inner, _ptr(out), _stream(feats.device)))
+    return out
+
+
+def bilinear_resize(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """F.interpolate(x, size=size, mode='bilinear', align_corners=False) (src/fusion.py:242-247)."""
+    x = _need_cuda(x, "input")
+    if x.dim() != 4:
+        raise ValueError("input must be (B, C, h, w)")
+    B, Cc, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().b200bev_bilinear_resize(_ptr(x), B, Cc, h, w, _ptr(out), H, W, _stream(x.device)))
+    return out
+
+
+def camera_project(feats: torch.Tensor, intrinsics: torch.Tensor, ego2cam: torch.Tensor,
+                   img_size: Tuple[float, float], bev_size: Tuple[int, int],
+                   pc_range: Sequence[float] = DEFAULT_PC_RANGE, z_plane: float = 0.0,
+                   return_table: bool = False):
+    """Geometric camera->BEV gather. feats (B,n_cam,C,h,w); intrinsics (T,n_cam,3,3); ego2cam (T,n_cam,3,4);
+    img_size = (img_w, img_h) in pixels; bev_size = (H, W). Returns (B,C,H,W) [, table (T,H*W,n_cam,3)]."""
+    feats = _need_cuda(feats, "camera_features")
+    intrinsics = _need_cuda(intrinsics, "intrinsics")
+    ego2cam = _need_cuda(ego2cam, "ego2cam")
+    if feats.dim() != 5:
+        raise ValueError("camera_features must be (B, n_cam, C, h, w)")
+    B, n_cam, Cc, h, w = feats.shape
+    if intrinsics.dim() == 3:
+        intrinsics = intrinsics.unsqueeze(0).contiguous()
+    if ego2cam.dim() == 3:
+        ego2cam = ego2cam.unsqueeze(0).contiguous()
+    T = intrinsics.shape[0]
+    if tuple(intrinsics.shape) != (T, n_cam, 3, 3) or tuple(ego2cam.shape) != (T, n_cam, 3, 4):
+        raise ValueError("intrinsics must be (T,n_cam,3,3) and ego2cam (T,n_cam,3,4)")
+    H, W = int(bev_size[0]), int(bev_size[1])
+    vx, vy = voxel_size(pc_range, W, H)
+    dev = feats.device
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=dev)
+    table = torch.empty((T, H * W, n_cam, 3), dtype=torch.float32, device=dev) if return_table else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_camera_project(
+            _ptr(feats), B, n_cam, Cc, h, w, _ptr(intrinsics), _ptr(ego2cam), T, float(img_size[0]), float(img_size[1]),
+            pc_range[0], pc_range[1], vx, vy, z_plane, W, H, _ptr(out), _ptr(table), _stream(dev)))
+    return (out, table) if return_table else out
+
+
+# ------------------------------------------------------------------------------------------------
+# S3
+# ------------------------------------------------------------------------------------------------
+def centernet_nms(heat: torch.Tensor) -> torch.Tensor:
+    """_nms(heat, kernel=3) (src/centernet_target.py:416-421)."""
+    heat = _need_cuda(heat, "heat")
+    if heat.dim() != 4:
+        raise ValueError("heat must be (B, C, H, W)")
+    B, Cc, H, W = heat.shape
+    out = torch.empty_like(heat)
+    with torch.cuda.device(heat.device):
+        _lib.check(_lib.lib().b200bev_centernet_nms(_ptr(heat), B, Cc, H, W, _ptr(out), _stream(heat.device)))
+    return out
+
+
+def _workspace(B: int, Cc: int, K: int, dev: torch.device) -> torch.Tensor:
+    n = _lib.lib().b200bev_centernet_workspace_bytes(B, Cc, K)
+    return torch.empty(max(n, 16), dtype=torch.uint8, device=dev)
+
+
+def centernet_topk(scores: torch.Tensor, K: int):
+    """_topk(scores, K) (src/centernet_target.py:424-452): (score, ind, classes, ys, xs), each (B,K)."""
+    scores = _need_cuda(scores, "scores")
+    B, Cc, H, W = scores.shape
+    dev = scores.device
+    ws = _workspace(B, Cc, K, dev)
+    top = torch.empty((B, K), dtype=torch.float32, device=dev)
+    ind, cls, ys, xs = (torch.empty((B, K), dtype=torch.int64, device=dev) for _ in range(4))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_centernet_topk(_ptr(scores), B, Cc, H, W, K, _ptr(top), _ptr(ind), _ptr(cls),
+                                                     _ptr(ys), _ptr(xs), _ptr(ws), ws.numel(), _stream(dev)))
+    return top, ind, cls, ys, xs
+
+
+def centernet_decode(heatmap: torch.Tensor, offset: torch.Tensor, size: torch.Tensor, rot: torch.Tensor,
+                     vel: torch.Tensor, K: int, voxel: float, origin: Tuple[float, float] = (-51.2, -51.2),
+                     z_value: float = -1.0, score_thresh: float = 0.0):
+    """Fused NMS + top-K + gather + box assembly. Fixed-size device outputs:
+    dict(boxes (B,K,7), scores (B,K), labels (B,K) i64, velocities (B,K,2), ys, xs, ind (B,K) i64, count (B) i32)."""
+    heatmap = _need_cuda(heatmap, "heatmap")
+    B, Cc, H, W = heatmap.shape
+    maps = {"offset": (offset, 2), "size": (size, 3), "rot": (rot, 2), "vel": (vel, 2)}
+    fixed = {}
+    for name, (t, ch) in maps.items():
+        t = _need_cuda(t, name)
+        if tuple(t.shape) != (B, ch, H, W):
+            raise ValueError(f"{name} must be {(B, ch, H, W)}, got {tuple(t.shape)}")
+        fixed[name] = t
+    dev = heatmap.device
+    ws = _workspace(B, Cc, K, dev)
+    o = {
+        "boxes": torch.empty((B, K, 7), dtype=torch.float32, device=dev),
+        "scores": torch.empty((B, K), dtype=torch.float32, device=dev),
+        "labels": torch.empty((B, K), dtype=torch.int64, device=dev),
+        "velocities": torch.empty((B, K, 2), dtype=torch.float32, device=dev),
+        "ys": torch.empty((B, K), dtype=torch.int64, device=dev),
+        "xs": torch.empty((B, K), dtype=torch.int64, device=dev),
+        "ind": torch.empty((B, K), dtype=torch.int64, device=dev),
+        "count": torch.empty((B,), dtype=torch.int32, device=dev),
+    }
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_centernet_decode(
+            _ptr(heatmap), _ptr(fixed["offset"]), _ptr(fixed["size"]), _ptr(fixed["rot"]), _ptr(fixed["vel"]),
+            B, Cc, H, W, K, voxel, origin[0], origin[1], z_value, score_thresh,
+            _ptr(o["boxes"]), _ptr(o["scores"]), _ptr(o["labels"]), _ptr(o["velocities"]),
+            _ptr(o["ys"]), _ptr(o["xs"]), _ptr(o["ind"]), _ptr(o["count"]), _ptr(ws), ws.numel(), _stream(dev)))
+    return o

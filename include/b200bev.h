@@ -1,0 +1,181 @@
+/*
+ * b200bev.h — C-ABI of libb200bev.so: hand-written sm_100a CUDA kernels for the
+ * BEV encode + decode hot path of meg89/bevfusion_multimodal_3d_object_detection.
+ *
+ * The reference has no FFI of its own (pure PyTorch); its boundary is
+ * a set of Python callables.  Each entry point below names the reference callable
+ * (file:line, relative to the reference checkout) whose arithmetic it replaces.  The
+ * Python binding a maintainer adds is one ctypes call per entry point with
+ * `tensor.data_ptr()` arguments — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - tensors are dense, row-major, in the layout written next to the argument;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no
+ *     entry point synchronises, allocates device memory or keeps global state
+ *     (re-entrant: one thread per GPU may call concurrently);
+ *   - the return value is B200BEV_OK (0) or an error code; nothing throws;
+ *     codes >= B200BEV_ERR_CUDA are (B200BEV_ERR_CUDA + cudaError_t).
+ */
+#ifndef B200BEV_H_
+#define B200BEV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BEV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B200BEV_API __attribute__((visibility("default")))
+#else
+#define B200BEV_API
+#endif
+
+enum b200bev_status {
+  B200BEV_OK = 0,
+  B200BEV_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive size, misaligned buffer */
+  B200BEV_ERR_UNSUPPORTED = 2,      /* shape outside what the kernels were built for */
+  B200BEV_ERR_K_OUT_OF_RANGE = 3,   /* K > H*W: torch.topk raises "selected index k out of range"
+                                       (src/centernet_target.py:432) */
+  B200BEV_ERR_WORKSPACE = 4,        /* caller workspace too small */
+  B200BEV_ERR_CUDA = 1000           /* + cudaError_t */
+};
+
+/* precision of the shared-MLP arithmetic (b200bev_pointnet_encode) */
+enum b200bev_precision {
+  B200BEV_F32 = 0,        /* fp32 FFMA, parity 1e-5 of max|ref| */
+  B200BEV_BF16_TENSOR = 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM; parity 1e-2 */
+};
+
+/* multi-radar fusion (src/encoders.py:650-659) */
+enum b200bev_radar_fusion { B200BEV_RADAR_CONCAT = 0, B200BEV_RADAR_MAX = 1, B200BEV_RADAR_MEAN = 2 };
+
+B200BEV_API int b200bev_abi_version(void);
+B200BEV_API const char* b200bev_error_string(int status);
+/* SM count / compute capability of the current device; any pointer may be NULL. */
+B200BEV_API int b200bev_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1a  bin-and-sort of points by BEV cell.
+ * Replaces: nothing executable in the reference; implements the cell convention of
+ *   src/centernet_target.py:222-224,250-257,285 (px=(x-x_min)/voxel, int(px), flat=iy*W+ix, reject
+ *   px<0 or px>=W) in fp32.
+ *   points  (B,N,C) f32, column 0 = x, column 1 = y (src/train_detect.py:151-155)
+ *   cell    (B,N)   i32  iy*W+ix, or -1 when the point is outside the grid (or NaN)
+ *   perm    (B,N)   i32  point indices ordered by (cell, point index) — a stable counting sort;
+ *                        the out-of-grid points follow, in index order
+ *   offsets (B,H*W+1) i32 perm[b, offsets[b,c] : offsets[b,c+1]] are the points of cell c;
+ *                        offsets[b,H*W] = number of in-grid points
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, int C,
+                     float x_min, float y_min, float voxel_x, float voxel_y, int W, int H,
+                     int32_t* cell, int32_t* perm, int32_t* offsets, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1b  fused PointNet shared-MLP + max.
+ * Replaces: PointNetLiDAREncoder.forward, src/encoders.py:271-306 (eval mode, BN folded);
+ *           RadarEncoder.forward, src/encoders.py:531-557.
+ *   points   (B,N,C) f32
+ *   params   one blob, per layer l: W_l^T (dims[l], dims[l+1]) f32 row-major, then bias_l (dims[l+1]);
+ *            BatchNorm already folded in (W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta)
+ *   dims     host array, n_layers+1 entries: C, 64, 128, ... (n_layers <= 8, every width <= 2048)
+ *   global mode  (perm == NULL): out (B, dims[n_layers]) = max over all N points (zero rows included,
+ *            SURVEY Q5) — identical to the reference's torch.max(x, 2)[0].
+ *   cell mode    (perm != NULL): perm/offsets from b200bev_bin_sort; out is the canvas
+ *            (B, n_cells, dims[n_layers]) channels-last = per-cell max, 0 for empty cells; points
+ *            outside the grid are dropped.
+ *   tc_params  only for B200BEV_BF16_TENSOR: blob made by b200bev_pointnet_pack_bf16 (else NULL)
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API int b200bev_pointnet_encode(const float* points, int B, int N, int C,
+                            const float* params, const int32_t* dims, int n_layers,
+                            const int32_t* perm, const int32_t* offsets, int n_cells,
+                            int precision, const void* tc_params,
+                            float* out, void* stream);
+
+/* Bytes of the tensor-core weight image for b200bev_pointnet_pack_bf16 (0 if dims unsupported). */
+B200BEV_API size_t b200bev_pointnet_pack_bf16_bytes(const int32_t* dims, int n_layers);
+/* Re-tiles fp32 params (layout above, device) into the bf16 swizzled stage image the tcgen05 kernel
+ * streams (device, `tc_params`). Call once per weight update. */
+B200BEV_API int b200bev_pointnet_pack_bf16(const float* params, const int32_t* dims, int n_layers,
+                               void* tc_params, size_t tc_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1c  multi-radar encoder: shared MLP + max per radar, then fusion.
+ * Replaces: MultiRadarEncoder.forward, src/encoders.py:628-661.
+ *   radar_points host array of R device pointers, radar r is (B, n_points[r], C) f32
+ *   n_points     host array, R entries (ragged radars allowed)
+ *   params/dims  as above (RadarEncoder 7-32-64-128-256)
+ *   fc_weight    (F, R*F) f32 row-major, fc_bias (F) — used when fusion == CONCAT, else may be NULL
+ *   per_radar    workspace AND output (B,R,F) f32: the stacked per-radar maxima (src/encoders.py:647)
+ *   out          (B,F) f32
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API int b200bev_radar_encode(const float* const* radar_points, const int32_t* n_points, int R, int B, int C,
+                         const float* params, const int32_t* dims, int n_layers,
+                         int fusion, const float* fc_weight, const float* fc_bias,
+                         float* per_radar, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S2  camera features -> BEV.
+ * b200bev_camera_mean: camera_features.mean(dim=1), src/fusion.py:233-234.
+ *   feats (B,n_cam,inner) f32 -> out (B,inner) f32, inner = C*h*w.  Sum in camera order, then
+ *   divide by n_cam (same association as a sequential fp32 reduction).
+ * b200bev_bilinear_resize: F.interpolate(size=(H,W), mode='bilinear', align_corners=False),
+ *   src/fusion.py:242-247.  in (B,C,h,w) f32 -> out (B,C,H,W) f32.
+ * b200bev_camera_project: the geometric form north_star describes (no counterpart in the reference,
+ *   SURVEY §0 S2): BEV cell centres (x,y,z_plane) are taken through ego->camera extrinsics and
+ *   pinhole intrinsics of each camera, the feature map is sampled bilinearly (zeros outside, the
+ *   grid_sample align_corners=False convention) and averaged over the cameras that see the cell.
+ *   feats      (B,n_cam,C,h,w) f32
+ *   intrinsics (T,n_cam,3,3) f32, ego2cam (T,n_cam,3,4) f32 [R|t]; T is 1 (shared rig) or B
+ *   img_w/img_h  pixel size the intrinsics refer to (1600x900)
+ *   out        (B,C,H,W) f32
+ *   uv_valid   optional (T,H*W,n_cam,3) f32 debug/table output: feature-map u, v and valid(0/1)
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API int b200bev_camera_mean(const float* feats, int B, int n_cam, int64_t inner, float* out, void* stream);
+B200BEV_API int b200bev_bilinear_resize(const float* in, int B, int C, int h, int w,
+                            float* out, int H, int W, void* stream);
+B200BEV_API int b200bev_camera_project(const float* feats, int B, int n_cam, int C, int h, int w,
+                           const float* intrinsics, const float* ego2cam, int T,
+                           float img_w, float img_h,
+                           float x_min, float y_min, float voxel_x, float voxel_y, float z_plane,
+                           int W, int H, float* out, float* uv_valid, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S3  CenterNet peak extraction and box decode.
+ * b200bev_centernet_nms:  _nms, src/centernet_target.py:416-421 (= src/fusion_detection.py:784-789),
+ *   kernel 3 only.  heat (B,C,H,W) f32 -> out same shape: heat * (maxpool3x3(heat) == heat).
+ * b200bev_centernet_topk: _topk, src/centernet_target.py:424-452 (= src/fusion_detection.py:792-820).
+ *   scores (B,C,H,W) f32 -> topk_score (B,K) f32 descending, topk_ind (B,K) i64 in [0,C*K),
+ *   topk_classes (B,K) i64 (identically 0 — the reference divides an index < H*W by H*W),
+ *   topk_ys/topk_xs (B,K) i64.  Ties are ordered by ascending index (torch leaves them undefined).
+ * b200bev_centernet_decode: decode_centernet_predictions, src/centernet_target.py:326-413
+ *   (= src/fusion_detection.py:695-781, which differs only in voxel_size) — NMS + both top-K stages
+ *   + gather + box assembly in one launch, fixed-size outputs:
+ *   boxes (B,K,7) f32 [x,y,z,w,l,h,yaw], scores (B,K) f32, labels (B,K) i64, velocities (B,K,2) f32,
+ *   ys/xs/ind (B,K) i64 (optional, may be NULL), count (B) i32 = #rows with score > score_thresh —
+ *   rows [0,count) of sample b are the reference's output rows, in the same order.
+ *   workspace: b200bev_centernet_workspace_bytes(B,C,K) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API int b200bev_centernet_nms(const float* heat, int B, int C, int H, int W, float* out, void* stream);
+B200BEV_API size_t b200bev_centernet_workspace_bytes(int B, int C, int K);
+B200BEV_API int b200bev_centernet_topk(const float* scores, int B, int C, int H, int W, int K,
+                           float* topk_score, int64_t* topk_ind, int64_t* topk_classes,
+                           int64_t* topk_ys, int64_t* topk_xs,
+                           void* workspace, size_t workspace_bytes, void* stream);
+B200BEV_API int b200bev_centernet_decode(const float* heatmap, const float* offset, const float* size,
+                             const float* rot, const float* vel,
+                             int B, int C, int H, int W, int K,
+                             float voxel_size, float x_origin, float y_origin, float z_value,
+                             float score_thresh,
+                             float* boxes, float* scores, int64_t* labels, float* velocities,
+                             int64_t* ys, int64_t* xs, int64_t* ind, int32_t* count,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BEV_H_ */

@@ -1,0 +1,189 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules (imported from
+/root/reference/src) on seeded synthetic inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference; tests read the committed .npz files.  Inputs and weights are not
+stored — they are regenerated from the seed by bevfusion_multimodal_3d_object_detection_b200.synthetic
+and checked against the sha256 stored here; the reference's outputs are stored.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, "/root/reference/src")
+
+from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn  # noqa: E402
+from oracle import bev_oracle as orc  # noqa: E402
+from oracle import torch_port  # noqa: E402
+
+with contextlib.redirect_stdout(io.StringIO()):
+    import centernet_target  # noqa: E402  (reference)
+    import encoders  # noqa: E402          (reference)
+    import fusion  # noqa: E402            (reference)
+    import fusion_detection  # noqa: E402  (reference)
+
+OUT = Path(__file__).resolve().parent
+torch.set_grad_enabled(False)
+
+
+def load_mlp(module, layers):
+    """Writes synthetic layer dicts into a reference PointNetLiDAREncoder / RadarEncoder."""
+    sd = module.state_dict()
+    for i, lay in enumerate(layers, start=1):
+        sd[f"conv{i}.weight"] = torch.from_numpy(lay["weight"]).unsqueeze(-1)
+        sd[f"conv{i}.bias"] = torch.from_numpy(lay["bias"])
+        sd[f"bn{i}.weight"] = torch.from_numpy(lay["bn_weight"])
+        sd[f"bn{i}.bias"] = torch.from_numpy(lay["bn_bias"])
+        sd[f"bn{i}.running_mean"] = torch.from_numpy(lay["bn_mean"])
+        sd[f"bn{i}.running_var"] = torch.from_numpy(lay["bn_var"])
+    module.load_state_dict(sd)
+    module.eval()
+
+
+def lidar_cases():
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    enc = encoders.PointNetLiDAREncoder(input_channels=4, feat_dim=1024, use_bn=True)
+    load_mlp(enc, layers)
+    out = {"weights_digest": syn.digest(*[v for lay in layers for v in lay.values()])}
+    # small batch, ragged tail (N not a multiple of the tile sizes)
+    pts = syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)
+    out["small_digest"] = syn.digest(pts)
+    out["small_global"] = enc(torch.from_numpy(pts)).numpy()
+    # (B,C,N) input layout is accepted too (src/encoders.py:282)
+    assert torch.equal(enc(torch.from_numpy(pts).transpose(1, 2).contiguous()), torch.from_numpy(out["small_global"]))
+    # full-size frame, configs[0]
+    full = syn.lidar_batch(301, 1)
+    out["full_digest"] = syn.digest(full)
+    out["full_global"] = enc(torch.from_numpy(full)).numpy()
+    # per-point features of the reference -> per-cell max (restatement of the unpinned scatter stage)
+    enc.return_point_features = True
+    feat = enc(torch.from_numpy(pts))[:, :, :1024]            # src/encoders.py:300-304
+    enc.return_point_features = False
+    W = H = 50
+    cell = orc.cell_index(pts, syn.PC_RANGE, W, H)
+    canv = []
+    for b in range(pts.shape[0]):
+        ok = torch.from_numpy(cell[b] >= 0)
+        idx = torch.from_numpy(cell[b].astype(np.int64))[ok]
+        c = torch.zeros(W * H, 1024)
+        c.scatter_reduce_(0, idx[:, None].expand(-1, 1024), feat[b][ok], reduce="amax", include_self=False)
+        canv.append(c.numpy())
+    canv = np.stack(canv)
+    np.testing.assert_allclose(
+        canv, np.stack([orc.pointnet_cell_max(pts[b], layers, cell[b], W * H) for b in range(2)]), rtol=0, atol=2e-5 * canv.max())
+    out["small_cell"] = cell
+    out["small_canvas_sub"] = canv[:, :, ::16]                # 64 of 1024 channels keeps the fixture small
+    np.savez_compressed(OUT / "lidar_encoder.npz", **out)
+
+
+def radar_cases():
+    layers = syn.mlp_weights(111, syn.RADAR_DIMS)
+    fcw, fcb = syn.linear_weights(112, 5 * 256, 256)
+    out = {"weights_digest": syn.digest(*[v for lay in layers for v in lay.values()], fcw, fcb)}
+    for method in ("concat", "max", "mean"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            enc = encoders.MultiRadarEncoder(input_channels=7, feat_dim=256, num_radars=5, fusion_method=method)
+        load_mlp(enc.radar_encoder, layers)
+        if method == "concat":
+            enc.fusion_fc.weight.copy_(torch.from_numpy(fcw))
+            enc.fusion_fc.bias.copy_(torch.from_numpy(fcb))
+        enc.eval()
+        radars = syn.radar_batch(211, 3)
+        out["digest"] = syn.digest(*radars)
+        out[f"fused_{method}"] = enc([torch.from_numpy(r) for r in radars]).numpy()
+        ragged = [r[:, : 125 - 17 * i] for i, r in enumerate(radars)]
+        out[f"ragged_{method}"] = enc([torch.from_numpy(np.ascontiguousarray(r)) for r in ragged]).numpy()
+    np.savez_compressed(OUT / "radar_encoder.npz", **out)
+
+
+def camera_cases():
+    out = {}
+    for name, (C, h, w, H, W) in {"ref28x50": (16, 28, 50, 50, 50), "hd57x100": (8, 57, 100, 50, 50),
+                                  "up7x9": (8, 7, 9, 20, 30)}.items():
+        fus = fusion.FlexibleBEVFusion(use_camera=True, use_lidar=False, use_radar=False, camera_channels=C,
+                                       bev_h=H, bev_w=W, bev_channels=8)
+        fus.eval()
+        grabbed = {}
+        fus.camera_proj.register_forward_hook(lambda m, i, o: grabbed.update(proj_in=i[0].clone(), proj_out=o.clone()))
+        fus.bev_fusion.register_forward_hook(lambda m, i, o: grabbed.update(fuse_in=i[0].clone()))
+        feats = syn.camera_features(401, 2, n_cam=6, channels=C, h=h, w=w)
+        fus(camera_features=torch.from_numpy(feats))
+        out[f"{name}_digest"] = syn.digest(feats)
+        out[f"{name}_mean"] = grabbed["proj_in"].numpy()          # camera_features.mean(dim=1), src/fusion.py:234
+        out[f"{name}_resize_in"] = grabbed["proj_out"].numpy()    # input of F.interpolate, src/fusion.py:242
+        out[f"{name}_resize_out"] = grabbed["fuse_in"].numpy()    # its output (camera-only: the concat is just it)
+    # geometric projection: cross-check the numpy restatement against torch's grid_sample
+    K, E = syn.camera_rig()
+    feats = syn.camera_features(402, 1, n_cam=6, channels=8, h=57, w=100)
+    table = orc.project_cells(K, E, (1600.0, 900.0), (57, 100), (50, 50), syn.PC_RANGE)
+    ours = orc.camera_project(feats[0], table, (50, 50))
+    ref = torch_port.camera_project(torch.from_numpy(feats), torch.from_numpy(table), (50, 50))[0].numpy()
+    np.testing.assert_allclose(ours, ref, rtol=0, atol=1e-5 * np.abs(ref).max())
+    assert table[:, :, 2].sum() > 1000, "rig sees too few cells"
+    out["project_digest"] = syn.digest(feats, K, E)
+    out["project_table"] = table
+    out["project_canvas_grid_sample"] = ref
+    np.savez_compressed(OUT / "camera_bev.npz", **out)
+
+
+def decode_cases():
+    out = {}
+    maps = syn.head_maps(501, 3)
+    pred = {k: torch.from_numpy(v) for k, v in maps.items()}
+    out["digest"] = syn.digest(*maps.values())
+    out["nms"] = centernet_target._nms(pred["heatmap"]).numpy()
+    assert torch.equal(fusion_detection._nms(pred["heatmap"]), torch.from_numpy(out["nms"]))
+    for name, val in zip(("score", "ind", "classes", "ys", "xs"), centernet_target._topk(torch.from_numpy(out["nms"]), K=100)):
+        out[f"topk_{name}"] = val.numpy()
+    for tag, mod in (("ct", centernet_target), ("fd", fusion_detection)):
+        for thr in (0.0, 0.3, 0.999):
+            dets = mod.decode_centernet_predictions(pred, score_thresh=thr, max_detections=100)
+            for b, d in enumerate(dets):
+                for k, v in d.items():
+                    out[f"{tag}_thr{thr}_b{b}_{k}"] = v.numpy()
+    # sparse map: fewer positive peaks than K in some classes
+    sparse = syn.head_maps(502, 2, peak_frac=0.02)
+    sp = {k: torch.from_numpy(v) for k, v in sparse.items()}
+    out["sparse_digest"] = syn.digest(*sparse.values())
+    for b, d in enumerate(centernet_target.decode_centernet_predictions(sp, score_thresh=0.1, max_detections=100)):
+        for k, v in d.items():
+            out[f"sparse_b{b}_{k}"] = v.numpy()
+    # 100x100 grid (stress config), K=100
+    big = syn.head_maps(503, 1, H=100, W=100)
+    bg = {k: torch.from_numpy(v) for k, v in big.items()}
+    out["big_digest"] = syn.digest(*big.values())
+    for k, v in fusion_detection.decode_centernet_predictions(bg, score_thresh=0.0, max_detections=100)[0].items():
+        out[f"big_{k}"] = v.numpy()
+    # hand-made known-answer maps: corner/edge peaks and a plateau
+    hm = np.zeros((1, 2, 6, 7), dtype=np.float32)
+    hm[0, 0, 0, 0], hm[0, 0, 0, 6], hm[0, 0, 5, 0], hm[0, 0, 5, 6], hm[0, 0, 2, 3] = 0.9, 0.8, 0.7, 0.6, 0.5
+    hm[0, 1, 3:5, 2:4] = 0.4                                   # 2x2 plateau: every cell survives _nms
+    hm[0, 1, 0, 3] = 0.95
+    out["hand_heat"] = hm
+    out["hand_nms"] = centernet_target._nms(torch.from_numpy(hm)).numpy()
+    for name, val in zip(("score", "ind", "classes", "ys", "xs"), centernet_target._topk(torch.from_numpy(out["hand_nms"]), K=6)):
+        out[f"hand_topk_{name}"] = val.numpy()
+    try:
+        centernet_target._topk(torch.from_numpy(hm), K=43)
+        raise AssertionError("expected torch.topk to reject K > H*W")
+    except RuntimeError as e:
+        out["k_too_large_message"] = np.array(str(e).splitlines()[0])
+    np.savez_compressed(OUT / "centernet_decode.npz", **out)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases):
+        fn()
+        print("wrote", fn.__name__)
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)
