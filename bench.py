@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Benchmark of the BEV encode + decode hot path (BASELINE.json metric: frames/sec, HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One STEP = one pass of every hot-path stage over a batch of FRAMES synthetic nuScenes-shaped frames
+per GPU (weak scaling; frames are independent, no collective on the data path):
+
+    S1a bin_sort            (F,35000,4) points -> cell / perm / offsets, 50x50 grid
+    S1b pointnet_encode     shared MLP 4-64-128-256-512-1024 + per-cell scatter-max canvas + global max
+    S1c radar_encode        5 x (F,125,7) -> shared MLP 7-32-64-128-256 + max + concat-FC
+    S2  camera_mean         (F,6,512,57,100) -> (F,512,57,100)           [reference drop-in]
+        bilinear_resize     (F,256,57,100) -> (F,256,50,50)              [reference drop-in]
+        camera_project      (F,6,512,57,100) -> (F,512,50,50)            [geometric form, north_star]
+    S3  centernet_decode    (F,10+9,50,50) head maps -> top-100 boxes
+
+`value` times the kernels with inputs resident in HBM; `e2e` runs the same stages through the
+package's public API from PINNED HOST buffers (H2D of every input and D2H of the results inside
+the timed region, double-buffered in chunks).  `--impl reference` times the torch-CPU port of the
+reference's implementation of the same stages (oracle/torch_port.py) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+N_POINTS, N_VALID = 35000, 34720          # base.yaml:59, src/encoders.py:834
+FEAT_H, FEAT_W, FEAT_C = 57, 100, 512     # ResNet-18 stride 16 on 900x1600
+BEV_H, BEV_W, BEV_C = 50, 50, 256         # base.yaml:54-55,216
+N_CLASSES, TOPK = 10, 100                 # src/eval.py:61
+IMG_W, IMG_H = 1600.0, 900.0
+MAC_PER_POINT = 4 * 64 + 64 * 128 + 128 * 256 + 256 * 512 + 512 * 1024   # 696,576
+L2_FLUSH_BYTES = 256 << 20
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("B200BEV_PRECISION", "auto"), choices=["auto", "f32", "bf16"])
+    ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline chunk in the e2e leg")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames per CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return {k: float(d[k]) for k in FALLBACK_PEAKS if k in d} | {"source": "measured"}
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS) | {"source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float):
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None
+        sm = [v for v in (num(r[0]) for r in rows) if v is not None]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [v for v in (num(r[2]) for r in rows) if v is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: torch-CPU port of the reference's implementation of the same stages
+# --------------------------------------------------------------------------------------------------
+class CpuWorkload:
+    def __init__(self, frames: int):
+        import numpy as np
+        import torch
+
+        from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+        from oracle import bev_oracle as orc
+        from oracle import torch_port as tp
+
+        self.tp, self.torch = tp, torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        self.frames = frames
+        g = torch.Generator().manual_seed(42)
+        self.lidar = torch.from_numpy(syn.lidar_batch(42, frames, n_valid=N_VALID, n_total=N_POINTS))
+        self.radars = [torch.from_numpy(r) for r in syn.radar_batch(43, frames)]
+        self.feats = torch.relu(torch.randn((frames, 6, FEAT_C, FEAT_H, FEAT_W), generator=g))
+        self.proj_out = torch.relu(torch.randn((frames, BEV_C, FEAT_H, FEAT_W), generator=g))
+        self.maps = {k: torch.from_numpy(v) for k, v in syn.head_maps(44, frames, N_CLASSES, BEV_H, BEV_W).items()}
+        self.lidar_layers = tp.layers_to_torch(syn.mlp_weights(101, syn.LIDAR_DIMS))
+        self.radar_layers = tp.layers_to_torch(syn.mlp_weights(111, syn.RADAR_DIMS))
+        fcw, fcb = syn.linear_weights(112, 1280, 256)
+        self.fcw, self.fcb = torch.from_numpy(fcw), torch.from_numpy(fcb)
+        K, E = syn.camera_rig(IMG_W, IMG_H)
+        self.table = torch.from_numpy(orc.project_cells(K, E, (IMG_W, IMG_H), (FEAT_H, FEAT_W), (BEV_H, BEV_W), syn.PC_RANGE))
+        self.pc_range = syn.PC_RANGE
+
+    def step(self):
+        tp = self.tp
+        cell, perm = tp.cell_index_and_sort(self.lidar, self.pc_range, BEV_W, BEV_H)
+        glob = tp.shared_mlp_max(self.lidar, self.lidar_layers)
+        radar = tp.multi_radar(self.radars, self.radar_layers, self.fcw, self.fcb)
+        mean = tp.camera_mean(self.feats)
+        cam = tp.bilinear_resize(self.proj_out, (BEV_H, BEV_W))
+        proj = tp.camera_project(self.feats, self.table, (BEV_H, BEV_W))
+        dets = tp.decode(self.maps, score_thresh=0.0, max_detections=TOPK)
+        return glob, radar, mean, cam, proj, dets, perm
+
+
+def time_cpu(frames: int, steps: int, warmup: int):
+    wl = CpuWorkload(frames)
+    for _ in range(warmup):
+        wl.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        wl.step()
+    dt = time.perf_counter() - t0
+    return wl, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl, dt = time_cpu(args.cpu_frames, args.steps, args.warmup)
+    fps = wl.frames * args.steps / dt
+    sample = (f"{wl.frames} frames/step of the same workload (full-size frames: {N_POINTS} pts, 6x{FEAT_C}x{FEAT_H}x{FEAT_W} "
+              f"features, {BEV_H}x{BEV_W} grid), torch-CPU port of the reference ops")
+    line = {
+        "impl": "reference", "metric": "bev_encode_decode_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl.frames),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, frames):
+    return {
+        "workload": ("BASELINE configs[2] 'camera+lidar fusion with CenterNet decode, batch 32 on 1 B200' plus the 5-radar "
+                     "branch of configs[3]; per GPU, so N GPUs process N x frames (configs[3] at N=2)"),
+        "frames_per_gpu": frames, "lidar_points": N_POINTS, "radars": "5x125x7",
+        "camera_features": f"6x{FEAT_C}x{FEAT_H}x{FEAT_W} (900x1600 / stride 16)", "bev_grid": f"{BEV_H}x{BEV_W}",
+        "classes": N_CLASSES, "topk": TOPK,
+        "stages": ["bin_sort", "pointnet_encode(canvas+global)", "radar_encode", "camera_mean", "bilinear_resize",
+                   "camera_project", "centernet_decode"],
+        "l2": "inputs larger than L2 (2.3 GB of camera features streamed per step) + 256 MiB flush between timed steps",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from bevfusion_multimodal_3d_object_detection_b200 import _lib, ops, runtime
+    from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+    from bevfusion_multimodal_3d_object_detection_b200.centernet_decode import decode_centernet_predictions
+    from oracle import bev_oracle as orc   # fold_layers / project table for setup and the cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    F = args.frames
+    peaks = load_peaks()
+
+    # ---- synthetic inputs, device-resident ----
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    seed = 42 + 1000 * rank
+    lidar = to(syn.lidar_batch(seed, F, n_valid=N_VALID, n_total=N_POINTS))
+    radars = [to(r) for r in syn.radar_batch(seed + 1, F)]
+    g = torch.Generator(device=dev).manual_seed(seed + 2)
+    feats = torch.relu(torch.randn((F, 6, FEAT_C, FEAT_H, FEAT_W), device=dev, generator=g))
+    maps = {k: to(v) for k, v in syn.head_maps(seed + 3, F, N_CLASSES, BEV_H, BEV_W).items()}
+    lw, lb = orc.fold_layers(syn.mlp_weights(101, syn.LIDAR_DIMS))
+    blob, dims = ops.pack_mlp_params([torch.from_numpy(w) for w in lw], [torch.from_numpy(b) for b in lb], dev)
+    rw, rb = orc.fold_layers(syn.mlp_weights(111, syn.RADAR_DIMS))
+    rblob, rdims = ops.pack_mlp_params([torch.from_numpy(w) for w in rw], [torch.from_numpy(b) for b in rb], dev)
+    fcw, fcb = (to(a) for a in syn.linear_weights(112, 1280, 256))
+    Kc, Ec = syn.camera_rig(IMG_W, IMG_H)
+    Kd, Ed = to(Kc), to(Ec)
+    table = orc.project_cells(Kc, Ec, (IMG_W, IMG_H), (FEAT_H, FEAT_W), (BEV_H, BEV_W), syn.PC_RANGE)
+    hits = int(table[:, :, 2].sum())
+
+    precision, tc = _lib.F32, None
+    dtype = "f32"
+    if args.precision in ("auto", "bf16"):
+        try:
+            tc = ops.pack_mlp_params_bf16(blob, dims)
+            precision, dtype = _lib.BF16_TENSOR, "bf16"
+        except _lib.B200BevError:
+            if args.precision == "bf16":
+                raise
+
+    stage_names = ["bin_sort", "pointnet_encode", "radar_encode", "camera_mean", "bilinear_resize", "camera_project",
+                   "centernet_decode"]
+    launches_per_step = {"bin_sort": 1, "pointnet_encode": 1, "radar_encode": 2, "camera_mean": 1, "bilinear_resize": 1,
+                         "camera_project": 1, "centernet_decode": 1}
+
+    def device_step(inp, events=None):
+        """All hot-path stages on device-resident inputs. events: list to append per-stage CUDA events to."""
+        mark = (lambda: events.append(_ev())) if events is not None else (lambda: None)
+        mark()
+        _, perm, off = ops.bin_sort(inp["lidar"], BEV_W, BEV_H)
+        mark()
+        glob, canvas = ops.pointnet_encode(inp["lidar"], blob, dims, perm=perm, offsets=off, n_cells=BEV_H * BEV_W,
+                                           precision=precision, tc_params=tc)
+        mark()
+        radar, _ = ops.radar_encode(inp["radars"], rblob, rdims, "concat", fcw, fcb)
+        mark()
+        mean = ops.camera_mean(inp["feats"])
+        mark()
+        # stand-in for the camera_proj output (the conv glue is not part of the hot path): the first
+        # F x 256 planes of the mean, a contiguous (F,256,h,w) view — no copy, right shape
+        n_f = mean.shape[0]
+        cam = ops.bilinear_resize(mean.view(n_f * (FEAT_C // BEV_C), BEV_C, FEAT_H, FEAT_W)[:n_f], (BEV_H, BEV_W))
+        mark()
+        proj = ops.camera_project(inp["feats"], Kd, Ed, (IMG_W, IMG_H), (BEV_H, BEV_W))
+        mark()
+        det = ops.centernet_decode(inp["heatmap"], inp["offset"], inp["size"], inp["rot"], inp["vel"], TOPK, 2.048)
+        mark()
+        return glob, canvas, radar, cam, proj, det
+
+    def _ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    resident = {"lidar": lidar, "radars": radars, "feats": feats, **maps}
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        device_step(resident)
+    barrier()
+    stage_ms = {n: 0.0 for n in stage_names}
+    step_ms = []
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.time()
+        for _ in range(args.steps):
+            flush.zero_()                                   # L2 flush, outside the per-step event pair
+            ev = []
+            device_step(resident, ev)
+            torch.cuda.synchronize(dev)
+            step_ms.append(ev[0].elapsed_time(ev[-1]))
+            for i, n in enumerate(stage_names):
+                stage_ms[n] += ev[i].elapsed_time(ev[i + 1])
+        barrier()
+        t_wall1 = time.time()
+        clock_summary = clocks.summary(t_wall0, t_wall1)
+    total_ms = runtime.max_over_ranks(sum(step_ms), dev)
+    ms_per_step = total_ms / args.steps
+    value = F * world * args.steps / (total_ms * 1e-3)
+    stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
+
+    # ---- per-kernel rooflines (algorithmic bytes / flops per launch; stated in DESIGN.md) ----
+    hw, HW = FEAT_H * FEAT_W, BEV_H * BEV_W
+    alg = {
+        "bin_sort": ("hbm", F * (24.0 * N_POINTS + 4.0 * (HW + 1))),
+        "pointnet_encode": ("tensor", F * N_POINTS * 2.0 * MAC_PER_POINT),
+        "radar_encode": ("tensor", F * 625 * 2.0 * (7 * 32 + 32 * 64 + 64 * 128 + 128 * 256) + F * 2.0 * 1280 * 256),
+        "camera_mean": ("hbm", F * 4.0 * FEAT_C * hw * 7),
+        "bilinear_resize": ("hbm", F * 4.0 * BEV_C * (hw + HW)),
+        "camera_project": ("hbm", F * 4.0 * FEAT_C * (min(6 * hw, 4 * hits) + HW)),
+        "centernet_decode": ("hbm", F * (4.0 * N_CLASSES * HW + 9 * 4.0 * TOPK + TOPK * (11 * 4.0 + 3 * 8.0))),
+    }
+    tensor_peak = peaks["bf16_tflops_sustained"] if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"]
+    kernels = {}
+    for n in stage_names:
+        bound, work = alg[n]
+        sec = stage_ms[n] * 1e-3
+        if bound == "hbm":
+            ach, peak, unit = work / sec / 1e9, peaks["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = work / sec / 1e12, tensor_peak, "TFLOP/s"
+        kernels[n] = {"ms": round(stage_ms[n], 4), "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit,
+                      "frac": round(ach / peak, 4)}
+    dominant = max(stage_names, key=lambda n: stage_ms[n])
+    roofline = dict(kernels[dominant])
+    roofline.pop("ms")
+    roofline.update({"kernel": dominant, "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"
+                     if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)"})
+    if dominant == "pointnet_encode" and dtype == "f32":
+        fp32_peak = 148 * 128 * 2 * (clock_summary.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        roofline["note"] = (f"fp32 FFMA path (no tensor cores): {roofline['achieved']} TFLOP/s is "
+                            f"{roofline['achieved'] / fp32_peak:.3f} of the derived fp32 FMA peak {fp32_peak:.1f} TFLOP/s; "
+                            "peak/frac above are against the measured bf16 tensor figure")
+
+    # ---- end to end through the public API, inputs in pinned host memory ----
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda t: t.cpu().pin_memory()
+        host = {"lidar": pin(lidar), "feats": pin(feats), **{k: pin(v) for k, v in maps.items()},
+                **{f"radar{i}": pin(r) for i, r in enumerate(radars)}}
+        pipe = runtime.FramePipeline(host, args.chunk, dev)
+        out_host = {
+            "glob": torch.empty((F, 1024), dtype=torch.float32).pin_memory(),
+            "radar": torch.empty((F, 256), dtype=torch.float32).pin_memory(),
+            "boxes": torch.empty((F, TOPK, 7), dtype=torch.float32).pin_memory(),
+            "scores": torch.empty((F, TOPK), dtype=torch.float32).pin_memory(),
+            "vel": torch.empty((F, TOPK, 2), dtype=torch.float32).pin_memory(),
+            "count": torch.empty((F,), dtype=torch.int32).pin_memory(),
+        }
+        d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
+
+        def chunk_step(d, b, e):
+            inp = {"lidar": d["lidar"], "radars": [d[f"radar{i}"] for i in range(5)], "feats": d["feats"],
+                   **{k: d[k] for k in maps}}
+            glob, canvas, radar, cam, proj, det = device_step(inp)
+            out_host["glob"][b:e].copy_(glob, non_blocking=True)
+            out_host["radar"][b:e].copy_(radar, non_blocking=True)
+            out_host["boxes"][b:e].copy_(det["boxes"], non_blocking=True)
+            out_host["scores"][b:e].copy_(det["scores"], non_blocking=True)
+            out_host["vel"][b:e].copy_(det["velocities"], non_blocking=True)
+            out_host["count"][b:e].copy_(det["count"], non_blocking=True)
+
+        for _ in range(max(args.warmup, 3)):
+            pipe.run(chunk_step)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pipe.run(chunk_step)
+            torch.cuda.synchronize(dev)                      # results are on the host here
+        barrier()
+        dt = runtime.max_over_ranks(time.perf_counter() - t0, dev)
+        # the reference-signature call on top of the same kernels (host sync + per-sample slicing)
+        dets = decode_centernet_predictions({k: v for k, v in maps.items()}, score_thresh=0.0, max_detections=TOPK)
+        assert len(dets) == F and int(out_host["count"][0]) == len(dets[0]["scores"])
+        e2e = {"value": F * world * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt / args.steps * 1e3, "chunk_frames": pipe.chunk,
+               "api": "ops.bin_sort/pointnet_encode/radar_encode/camera_mean/bilinear_resize/camera_project/centernet_decode "
+                      "via runtime.FramePipeline (pinned host -> device, double-buffered)"}
+        del host, pipe
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wl, dt = time_cpu(args.cpu_frames, 3, 1)
+        cpu_baseline = {"value": wl.frames * 3 / dt, "unit": "frames/s", "cores": wl.cores, "kind": "port",
+                        "sample": f"3 passes over {wl.frames} full-size frames (same stages, torch-CPU port of the reference ops), "
+                                  f"{dt:.1f} s of CPU work"}
+
+    if rank == 0:
+        line = {
+            "metric": "bev_encode_decode_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": workload_config(args, F), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": sum(launches_per_step.values()) * args.steps, "clocks": clock_summary, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

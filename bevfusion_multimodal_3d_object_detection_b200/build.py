@@ -48,7 +48,9 @@ def _fingerprint() -> str:
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200bev.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags without the checkout-dependent include paths: the .so built here must count as current
+    # on the GPU box, where the repo lives under another directory
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith(str(ROOT))).encode())
     return h.hexdigest()
 
 

@@ -4,11 +4,11 @@
 
 namespace b200bev {
 int pointnet_encode_f32(const float* points, int B, int N, int C, const float* params, const int32_t* dims,
-                        int n_layers, const int32_t* perm, const int32_t* offsets, int n_cells, float* out,
-                        cudaStream_t st);
+                        int n_layers, const int32_t* perm, const int32_t* offsets, int n_cells, float* out_global,
+                        float* out_canvas, cudaStream_t st);
 int pointnet_encode_tc(const float* points, int B, int N, int C, const float* params, const int32_t* dims,
                        int n_layers, const int32_t* perm, const int32_t* offsets, int n_cells, const void* tc_params,
-                       float* out, cudaStream_t st);
+                       float* out_global, float* out_canvas, cudaStream_t st);
 }  // namespace b200bev
 
 using namespace b200bev;
@@ -49,17 +49,20 @@ extern "C" B200BEV_API int b200bev_device_info(int* sm_count_out, int* cc_major,
 
 extern "C" B200BEV_API int b200bev_pointnet_encode(const float* points, int B, int N, int C, const float* params,
                                        const int32_t* dims, int n_layers, const int32_t* perm, const int32_t* offsets,
-                                       int n_cells, int precision, const void* tc_params, float* out, void* stream) {
-  if (!points || !params || !dims || !out || B <= 0 || C <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+                                       int n_cells, int precision, const void* tc_params, float* out_global,
+                                       float* out_canvas, void* stream) {
+  if (!points || !params || !dims || B <= 0 || C <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (!out_global && !out_canvas) return B200BEV_ERR_INVALID_ARGUMENT;
   if (N <= 0) return B200BEV_ERR_INVALID_ARGUMENT;  // torch.max over an empty point axis raises
   if ((perm == nullptr) != (offsets == nullptr)) return B200BEV_ERR_INVALID_ARGUMENT;
-  if (perm && n_cells <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (out_canvas && (!perm || n_cells <= 0)) return B200BEV_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == B200BEV_F32)
-    return pointnet_encode_f32(points, B, N, C, params, dims, n_layers, perm, offsets, n_cells, out, st);
+    return pointnet_encode_f32(points, B, N, C, params, dims, n_layers, perm, offsets, n_cells, out_global, out_canvas, st);
   if (precision == B200BEV_BF16_TENSOR) {
     if (!tc_params) return B200BEV_ERR_INVALID_ARGUMENT;
-    return pointnet_encode_tc(points, B, N, C, params, dims, n_layers, perm, offsets, n_cells, tc_params, out, st);
+    return pointnet_encode_tc(points, B, N, C, params, dims, n_layers, perm, offsets, n_cells, tc_params, out_global,
+                              out_canvas, st);
   }
   return B200BEV_ERR_INVALID_ARGUMENT;
 }

@@ -38,7 +38,8 @@ struct MlpArgs {
   const int32_t* perm;
   const int32_t* offsets;
   int n_cells;
-  float* out;
+  float* out;     // global maxima (frames, C_out) or nullptr
+  float* canvas;  // per-cell maxima (frames, n_cells, C_out) or nullptr
   int frames, tiles_per_frame, rows_a, rows_b;
   // radar mode (R > 0): frame f = b*R + r reads radar r
   int R;
@@ -78,7 +79,9 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_mlp_f32_kernel(MlpArgs a
   const int tid = threadIdx.x;
   const int tp = tid & 15, tn = tid >> 4;
   const int c_out = a.dims[a.n_layers];
-  const bool cell_mode = a.perm != nullptr;
+  const bool sorted = a.perm != nullptr;   // walk the points in cell order
+  const bool want_global = a.out != nullptr;
+  const bool want_canvas = a.canvas != nullptr;
 
   const long long total = (long long)a.frames * a.tiles_per_frame;
   const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
@@ -102,18 +105,19 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_mlp_f32_kernel(MlpArgs a
       n_pts = a.N;
       fpts = a.pts + (size_t)f * a.N * a.C;
     }
-    int n_sorted = n_pts;
+    int n_walk = n_pts, n_in_grid = 0;
     const int32_t* fperm = nullptr;
     const int32_t* foff = nullptr;
-    if (cell_mode) {
+    if (sorted) {
       fperm = a.perm + (size_t)f * a.N;
       foff = a.offsets + (size_t)f * (a.n_cells + 1);
-      n_sorted = __ldg(foff + a.n_cells);  // in-grid points only
+      n_in_grid = __ldg(foff + a.n_cells);
+      if (!want_global) n_walk = n_in_grid;  // the out-of-grid tail only matters for the global max
     }
     const int s0 = tile * kP;
-    if (s0 >= n_sorted) continue;  // uniform across the CTA
+    if (s0 >= n_walk) continue;  // uniform across the CTA
 
-    if (!cell_mode && f != cur_frame) {
+    if (want_global && f != cur_frame) {
       __syncthreads();
       if (cur_frame >= 0) {
         int* o = reinterpret_cast<int*>(a.out + (size_t)cur_frame * c_out);
@@ -130,15 +134,17 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_mlp_f32_kernel(MlpArgs a
     if (tid < kP) {
       const int s = s0 + tid;
       int src = -1, cid = -1;
-      if (s < n_sorted) {
-        if (cell_mode) {
+      if (s < n_walk) {
+        if (sorted) {
           src = __ldg(fperm + s);
-          int lo = 0, hi = a.n_cells;  // largest c with offsets[c] <= s
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(foff + mid) <= s) lo = mid; else hi = mid;
+          if (s < n_in_grid) {
+            int lo = 0, hi = a.n_cells;  // largest c with offsets[c] <= s
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (__ldg(foff + mid) <= s) lo = mid; else hi = mid;
+            }
+            cid = lo;
           }
-          cid = lo;
         } else {
           src = s;
         }
@@ -227,43 +233,49 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_mlp_f32_kernel(MlpArgs a
               v.w = fmaxf(acc[j][3] + bj, 0.0f);
               *reinterpret_cast<float4*>(outb + (size_t)(nbase + j) * kP + tp * 4) = v;
             }
-          } else if (!cell_mode) {
-            bool ok[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ok[i] = pidx[tp * 4 + i] >= 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float bj = __ldg(bias + nbase + j);
-              float m = 0.0f;  // relu floor; empty slots contribute nothing
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (ok[i]) m = fmaxf(m, acc[j][i] + bj);
-              m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 1));
-              m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 2));
-              m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 4));
-              m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, 8));
-              if (tp == 0) runmax[nbase + j] = fmaxf(runmax[nbase + j], m);
-            }
           } else {
+            bool ok[4];
             int cid[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cid[i] = cellid[tp * 4 + i];
-            float* canvas = a.out + (size_t)f * a.n_cells * c_out;
+            for (int i = 0; i < 4; ++i) {
+              ok[i] = pidx[tp * 4 + i] >= 0;
+              cid[i] = cellid[tp * 4 + i];
+            }
+            float* canvas = want_canvas ? a.canvas + (size_t)f * a.n_cells * c_out : nullptr;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float bj = __ldg(bias + nbase + j);
-              float m = 0.0f;
+              float v[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (cid[i] >= 0) {
-                  m = fmaxf(m, acc[j][i] + bj);
-                  const bool run_end = (i == 3) || (cid[i + 1 < 4 ? i + 1 : 3] != cid[i]);
-                  if (run_end) {
-                    if (m > 0.0f)
-                      atomicMax(reinterpret_cast<int*>(canvas + (size_t)cid[i] * c_out + nbase + j), __float_as_int(m));
-                    m = 0.0f;
+              for (int i = 0; i < 4; ++i) v[i] = acc[j][i] + bj;
+              if (want_canvas) {
+                float m = 0.0f;  // relu floor
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (cid[i] >= 0) {
+                    m = fmaxf(m, v[i]);
+                    const bool run_end = (i == 3) || (cid[i + 1 < 4 ? i + 1 : 3] != cid[i]);
+                    if (run_end) {
+                      if (m > 0.0f)
+                        atomicMax(reinterpret_cast<int*>(canvas + (size_t)cid[i] * c_out + nbase + j), __float_as_int(m));
+                      m = 0.0f;
+                    }
                   }
                 }
+              }
+              if (want_global) {
+                float m = 0.0f;  // relu floor; empty slots contribute nothing
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (ok[i]) m = fmaxf(m, v[i]);
+                // the two half-warps hold different channel tiles and may diverge on `nbase < Nout`
+                // (widths that are multiples of 8 but not 16): reduce within the half-warp only
+                const unsigned half = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
+                m = fmaxf(m, __shfl_xor_sync(half, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(half, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(half, m, 4));
+                m = fmaxf(m, __shfl_xor_sync(half, m, 8));
+                if (tp == 0) runmax[nbase + j] = fmaxf(runmax[nbase + j], m);
               }
             }
           }
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_mlp_f32_kernel(MlpArgs a
       __syncthreads();
     }
   }
-  if (!cell_mode) {
+  if (want_global) {
     __syncthreads();
     if (cur_frame >= 0) {
       int* o = reinterpret_cast<int*>(a.out + (size_t)cur_frame * c_out);
@@ -353,19 +365,20 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
 
 // fp32 path of b200bev_pointnet_encode (dispatch lives in api.cu)
 int pointnet_encode_f32(const float* points, int B, int N, int C, const float* params, const int32_t* dims,
-                        int n_layers, const int32_t* perm, const int32_t* offsets, int n_cells, float* out,
-                        cudaStream_t st) {
+                        int n_layers, const int32_t* perm, const int32_t* offsets, int n_cells, float* out_global,
+                        float* out_canvas, cudaStream_t st) {
   MlpArgs a{};
   const int rc = fill_layers(a, dims, n_layers, C);
   if (rc) return rc;
   if ((reinterpret_cast<uintptr_t>(params) & 15) != 0) return B200BEV_ERR_INVALID_ARGUMENT;
   a.pts = points; a.B = B; a.N = N; a.C = C; a.params = params;
-  a.perm = perm; a.offsets = offsets; a.n_cells = n_cells; a.out = out;
+  a.perm = perm; a.offsets = offsets; a.n_cells = n_cells; a.out = out_global; a.canvas = out_canvas;
   a.frames = B;
   a.tiles_per_frame = ceil_div(N, kP);
   a.R = 0;
-  const size_t out_elems = perm ? (size_t)B * n_cells * dims[n_layers] : (size_t)B * dims[n_layers];
-  B200BEV_CUDA_TRY(cudaMemsetAsync(out, 0, out_elems * sizeof(float), st));
+  const size_t c_out = (size_t)dims[n_layers];
+  if (out_global) B200BEV_CUDA_TRY(cudaMemsetAsync(out_global, 0, (size_t)B * c_out * sizeof(float), st));
+  if (out_canvas) B200BEV_CUDA_TRY(cudaMemsetAsync(out_canvas, 0, (size_t)B * n_cells * c_out * sizeof(float), st));
   return launch_mlp(a, st);
 }
 
@@ -394,7 +407,7 @@ extern "C" B200BEV_API int b200bev_radar_encode(const float* const* radar_points
     a.radar_n[r] = n_points[r];
     max_n = n_points[r] > max_n ? n_points[r] : max_n;
   }
-  a.R = R; a.B = B; a.N = max_n; a.C = C; a.params = params; a.out = per_radar;
+  a.R = R; a.B = B; a.N = max_n; a.C = C; a.params = params; a.out = per_radar; a.canvas = nullptr;
   a.frames = B * R;
   a.tiles_per_frame = ceil_div(max_n, kP);
   const int F = dims[n_layers];

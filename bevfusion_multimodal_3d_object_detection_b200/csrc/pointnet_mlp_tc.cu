@@ -6,7 +6,7 @@
 namespace b200bev {
 
 int pointnet_encode_tc(const float*, int, int, int, const float*, const int32_t*, int, const int32_t*, const int32_t*,
-                       int, const void*, float*, cudaStream_t) {
+                       int, const void*, float*, float*, cudaStream_t) {
   return B200BEV_ERR_UNSUPPORTED;
 }
 

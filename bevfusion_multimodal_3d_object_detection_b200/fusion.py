@@ -1,0 +1,123 @@
+"""BEV fusion module with the reference's interface; the camera->BEV step runs on b200bev kernels.
+
+Mirrors `FlexibleBEVFusion` (src/fusion.py:46-327): same constructor contract, same sub-module and
+state_dict names (camera_proj, lidar_init, lidar_upsample, radar_proj, radar_refine, bev_fusion),
+same forward signature and exceptions.  The hot-path piece — src/fusion.py:229-248 — is
+
+    mean over the 6 cameras  ->  [camera_proj convs, cuDNN]  ->  bilinear resize to (bev_h, bev_w)
+
+and in eval mode on CUDA the first and the last step are `b200bev_camera_mean` and
+`b200bev_bilinear_resize`.  The convolutions between and after them are the reference's own glue
+ and stay torch/cuDNN.  `project_cameras()` is the geometric form north_star
+describes: calibrated projection of the BEV cell centres and a one-pass gather of all cameras.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .encoders import load_config
+
+
+def _conv_bn_relu(c_in: int, c_out: int, k: int) -> List[nn.Module]:
+    return [nn.Conv2d(c_in, c_out, k, padding=k // 2), nn.BatchNorm2d(c_out), nn.ReLU(inplace=True)]
+
+
+def camera_branch(module: nn.Module, camera_features: torch.Tensor) -> torch.Tensor:
+    """src/fusion.py:233-247 with the mean and the resize on the b200bev kernels (eval, CUDA)."""
+    size = (module.bev_h, module.bev_w)
+    if module.training:
+        cam = camera_features.mean(dim=1) if camera_features.dim() == 5 else camera_features
+        return F.interpolate(module.camera_proj(cam), size=size, mode="bilinear", align_corners=False)
+    cam = ops.camera_mean(camera_features) if camera_features.dim() == 5 else camera_features
+    return ops.bilinear_resize(module.camera_proj(cam), size)
+
+
+def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None, radar_features=None) -> torch.Tensor:
+    """FlexibleBEVFusion.forward (src/fusion.py:209-297)."""
+    parts = []
+    B = None
+    if module.use_camera and camera_features is not None:
+        B = camera_features.shape[0]
+        parts.append(camera_branch(module, camera_features))
+    if module.use_lidar and lidar_features is not None:
+        B = lidar_features.shape[0] if B is None else B
+        s = module.lidar_start_size
+        flat = module.lidar_init(lidar_features)                       # src/fusion.py:258
+        parts.append(module.lidar_upsample(flat.view(B, 128, s, s)))   # :259-262
+    if module.use_radar and radar_features is not None:
+        B = radar_features.shape[0] if B is None else B
+        r = module.radar_proj(radar_features).view(B, module.bev_channels, 1, 1)
+        parts.append(module.radar_refine(r.expand(B, module.bev_channels, module.bev_h, module.bev_w)))  # :274-281
+    if not parts:
+        raise ValueError("No modality features provided")              # :289
+    return module.bev_fusion(torch.cat(parts, dim=1))                  # :292-295
+
+
+class FlexibleBEVFusion(nn.Module):
+    """Constructor contract of src/fusion.py:62-207."""
+
+    def __init__(self, use_camera: Optional[bool] = None, use_lidar: Optional[bool] = None,
+                 use_radar: Optional[bool] = None, camera_channels: Optional[int] = None,
+                 lidar_channels: Optional[int] = None, radar_channels: Optional[int] = None,
+                 bev_h: Optional[int] = None, bev_w: Optional[int] = None, bev_channels: Optional[int] = None,
+                 pc_range: Optional[List[float]] = None, config: Optional[Dict] = None,
+                 config_path: Optional[str] = None):
+        super().__init__()
+        pick = lambda explicit, fallback: fallback if explicit is None else explicit
+        if config is not None or config_path is not None:
+            if config is None:
+                config = load_config(config_path)
+            model = config.get("model", {})
+            bev = model.get("bev_fusion", {})
+            data = config.get("dataset", {})
+            self.use_camera = pick(use_camera, model.get("use_camera", True))
+            self.use_lidar = pick(use_lidar, model.get("use_lidar", True))
+            self.use_radar = pick(use_radar, model.get("use_radar", True))
+            camera_channels = pick(camera_channels, model.get("camera_encoder", {}).get("output_channels", 512))
+            lidar_channels = pick(lidar_channels, model.get("lidar_encoder", {}).get("feature_dim", 1024))
+            radar_channels = pick(radar_channels, model.get("radar_encoder", {}).get("feature_dim", 256))
+            self.bev_h = pick(bev_h, bev.get("bev_h", data.get("bev_h", 200)))
+            self.bev_w = pick(bev_w, bev.get("bev_w", data.get("bev_w", 200)))
+            self.bev_channels = pick(bev_channels, bev.get("bev_channels", 256))
+            self.pc_range = pick(pc_range, data.get("point_cloud_range", list(ops.DEFAULT_PC_RANGE)))
+        else:
+            self.use_camera, self.use_lidar, self.use_radar = pick(use_camera, True), pick(use_lidar, True), pick(use_radar, True)
+            camera_channels, lidar_channels, radar_channels = pick(camera_channels, 512), pick(lidar_channels, 1024), pick(radar_channels, 256)
+            self.bev_h, self.bev_w, self.bev_channels = pick(bev_h, 200), pick(bev_w, 200), pick(bev_channels, 256)
+            self.pc_range = pick(pc_range, list(ops.DEFAULT_PC_RANGE))
+        self.num_modalities = sum([self.use_camera, self.use_lidar, self.use_radar])
+        assert self.num_modalities > 0, "At least one modality must be enabled"
+        c = self.bev_channels
+        if self.use_camera:
+            self.camera_proj = nn.Sequential(*_conv_bn_relu(camera_channels, 512, 3), *_conv_bn_relu(512, c, 1))
+        if self.use_lidar:
+            self.lidar_start_size = 25   # hard-coded in the reference too (src/fusion.py:141)
+            self.lidar_init = nn.Sequential(nn.Linear(lidar_channels, 512), nn.ReLU(inplace=True),
+                                            nn.Linear(512, 128 * self.lidar_start_size ** 2))
+            self.lidar_upsample = nn.Sequential(
+                *_conv_bn_relu(128, 128, 3), nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False),
+                *_conv_bn_relu(128, c, 3))
+        if self.use_radar:
+            self.radar_proj = nn.Sequential(nn.Linear(radar_channels, c), nn.ReLU(inplace=True))
+            self.radar_refine = nn.Sequential(*_conv_bn_relu(c, c, 3), *_conv_bn_relu(c, c, 3))
+        self.bev_fusion = nn.Sequential(*_conv_bn_relu(c * self.num_modalities, c * 2, 3), *_conv_bn_relu(c * 2, c, 3))
+
+    def forward(self, camera_features: Optional[torch.Tensor] = None, lidar_features: Optional[torch.Tensor] = None,
+                radar_features: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return fusion_forward(self, camera_features, lidar_features, radar_features)
+
+    def project_cameras(self, camera_features: torch.Tensor, intrinsics: torch.Tensor, ego2cam: torch.Tensor,
+                        img_size: Tuple[float, float] = (1600.0, 900.0), z_plane: float = 0.0) -> torch.Tensor:
+        """(B,n_cam,C,h,w) -> (B,C,bev_h,bev_w) by calibrated projection (calibration layout of
+        src/data_converter.py:110-117: per-camera intrinsic 3x3 and ego->camera [R|t] 3x4)."""
+        return ops.camera_project(camera_features, intrinsics, ego2cam, img_size, (self.bev_h, self.bev_w),
+                                  self.pc_range, z_plane)
+
+    def get_config_str(self) -> str:
+        names = [n for n, on in (("camera", self.use_camera), ("lidar", self.use_lidar), ("radar", self.use_radar)) if on]
+        return "+".join(names)

@@ -114,9 +114,11 @@ def pack_mlp_params_bf16(params: torch.Tensor, dims: Sequence[int]) -> torch.Ten
 
 def pointnet_encode(points: torch.Tensor, params: torch.Tensor, dims: Sequence[int],
                     perm: Optional[torch.Tensor] = None, offsets: Optional[torch.Tensor] = None,
-                    n_cells: int = 0, precision: int = _lib.F32,
-                    tc_params: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Fused shared-MLP + max. Global mode -> (B, C_out); cell mode -> (B, n_cells, C_out) canvas."""
+                    n_cells: int = 0, precision: int = _lib.F32, tc_params: Optional[torch.Tensor] = None,
+                    want_global: bool = True, want_canvas: Optional[bool] = None):
+    """Fused shared-MLP + max.  Returns the global maxima (B, C_out) and/or the per-cell canvas
+    (B, n_cells, C_out): one tensor if one was asked for, the pair (global, canvas) if both.
+    The canvas needs perm/offsets from bin_sort; by default it is produced whenever they are given."""
     points = _need_cuda(points, "points")
     params = _need_cuda(params, "params")
     if points.dim() != 3:
@@ -124,19 +126,26 @@ def pointnet_encode(points: torch.Tensor, params: torch.Tensor, dims: Sequence[i
     B, N, Cc = points.shape
     if Cc != dims[0]:
         raise ValueError(f"points have {Cc} channels, the MLP expects {dims[0]}")
+    if want_canvas is None:
+        want_canvas = perm is not None
+    if want_canvas and perm is None:
+        raise ValueError("the per-cell canvas needs perm/offsets from bin_sort")
+    if not (want_global or want_canvas):
+        raise ValueError("nothing to compute")
     dev = points.device
     c_out = int(dims[-1])
     if perm is not None:
         perm = _need_cuda(perm, "perm", torch.int32)
         offsets = _need_cuda(offsets, "offsets", torch.int32)
-        out = torch.empty((B, n_cells, c_out), dtype=torch.float32, device=dev)
-    else:
-        out = torch.empty((B, c_out), dtype=torch.float32, device=dev)
+    glob = torch.empty((B, c_out), dtype=torch.float32, device=dev) if want_global else None
+    canvas = torch.empty((B, n_cells, c_out), dtype=torch.float32, device=dev) if want_canvas else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b200bev_pointnet_encode(
             _ptr(points), B, N, Cc, _ptr(params), _i32(dims), len(dims) - 1, _ptr(perm), _ptr(offsets), n_cells,
-            precision, _ptr(tc_params), _ptr(out), _stream(dev)))
-    return out
+            precision, _ptr(tc_params), _ptr(glob), _ptr(canvas), _stream(dev)))
+    if want_global and want_canvas:
+        return glob, canvas
+    return glob if want_global else canvas
 
 
 def radar_encode(radar_list: Sequence[torch.Tensor], params: torch.Tensor, dims: Sequence[int], fusion: str,

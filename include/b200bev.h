@@ -83,18 +83,19 @@ B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, int C,
  *   params   one blob, per layer l: W_l^T (dims[l], dims[l+1]) f32 row-major, then bias_l (dims[l+1]);
  *            BatchNorm already folded in (W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta)
  *   dims     host array, n_layers+1 entries: C, 64, 128, ... (n_layers <= 8, every width <= 2048)
- *   global mode  (perm == NULL): out (B, dims[n_layers]) = max over all N points (zero rows included,
- *            SURVEY Q5) — identical to the reference's torch.max(x, 2)[0].
- *   cell mode    (perm != NULL): perm/offsets from b200bev_bin_sort; out is the canvas
- *            (B, n_cells, dims[n_layers]) channels-last = per-cell max, 0 for empty cells; points
- *            outside the grid are dropped.
+ *   out_global (B, dims[n_layers]) or NULL: max over all N points (zero rows included) —
+ *            identical to the reference's torch.max(x, 2)[0].
+ *   out_canvas (B, n_cells, dims[n_layers]) channels-last or NULL: per-cell max, 0 for empty cells; needs
+ *            perm/offsets from b200bev_bin_sort; points outside the grid do not reach the canvas (they
+ *            still count for out_global).  With both outputs requested the MLP runs once.
+ *            perm == NULL (global only) walks the points in input order.
  *   tc_params  only for B200BEV_BF16_TENSOR: blob made by b200bev_pointnet_pack_bf16 (else NULL)
  * ------------------------------------------------------------------------------------------- */
 B200BEV_API int b200bev_pointnet_encode(const float* points, int B, int N, int C,
                             const float* params, const int32_t* dims, int n_layers,
                             const int32_t* perm, const int32_t* offsets, int n_cells,
                             int precision, const void* tc_params,
-                            float* out, void* stream);
+                            float* out_global, float* out_canvas, void* stream);
 
 /* Bytes of the tensor-core weight image for b200bev_pointnet_pack_bf16 (0 if dims unsupported). */
 B200BEV_API size_t b200bev_pointnet_pack_bf16_bytes(const int32_t* dims, int n_layers);

@@ -1,0 +1,232 @@
+"""CPU tests: the C-ABI library loads and exports exactly what include/b200bev.h declares, argument
+validation happens before any CUDA work, and the host-side mirrors keep the reference's interface."""
+import ctypes as C
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import bevfusion_multimodal_3d_object_detection_b200 as b200bev
+from bevfusion_multimodal_3d_object_detection_b200 import _lib, build, encoders, fusion, ops
+from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+from oracle import bev_oracle as orc
+from oracle import torch_port
+from tests.conftest import max_rel
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "b200bev.h"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()           # no-op when the in-tree .so is current; nvcc cross-compiles without a GPU
+    return _lib.lib()
+
+
+def declared_symbols():
+    return re.findall(r"^B200BEV_API\s+[\w\s\*]+?\b(b200bev_\w+)\s*\(", HEADER.read_text(), flags=re.M)
+
+
+def test_header_and_binding_declare_the_same_entry_points():
+    names = declared_symbols()
+    assert len(names) == len(set(names)) >= 15
+    assert set(names) == set(_lib.PROTOTYPES)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} missing from libb200bev.so"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\b(b200bev_\w+)\b", out))
+    assert exported == set(declared_symbols())          # nothing undeclared leaks out either
+
+
+def test_library_is_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "--list-elf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_version_and_error_strings(lib):
+    assert lib.b200bev_abi_version() == _lib.ABI_VERSION
+    assert lib.b200bev_error_string(0) == b"ok"
+    assert b"k out of range" in lib.b200bev_error_string(_lib.ERR_K_OUT_OF_RANGE)
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        _lib.check(_lib.ERR_K_OUT_OF_RANGE)
+    with pytest.raises(_lib.B200BevError):
+        _lib.check(_lib.ERR_INVALID_ARGUMENT)
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    null = C.c_void_p(0)
+    one = C.c_void_p(16)
+    assert lib.b200bev_bin_sort(null, 1, 1, 4, 0, 0, 1, 1, 2, 2, one, one, one, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_bin_sort(one, 1, 1, 4, 0, 0, 0.0, 1, 2, 2, one, one, one, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_centernet_nms(null, 1, 1, 1, 1, one, null) == _lib.ERR_INVALID_ARGUMENT
+    dims = (C.c_int32 * 3)(4, 8, 16)
+    assert lib.b200bev_pointnet_encode(one, 1, 0, 4, one, dims, 2, null, null, 0, 0, null, one, null, null) == _lib.ERR_INVALID_ARGUMENT
+    # K > H*W mirrors torch.topk's error; workspace too small is its own code
+    ws = lib.b200bev_centernet_workspace_bytes(1, 2, 43)
+    assert ws >= 2 * 43 * 8 + 4
+    assert lib.b200bev_centernet_topk(one, 1, 2, 6, 7, 43, one, one, one, one, one, one, ws, null) == _lib.ERR_K_OUT_OF_RANGE
+    assert lib.b200bev_centernet_topk(one, 1, 2, 6, 7, 5, one, one, one, one, one, one, 8, null) == _lib.ERR_WORKSPACE
+    assert lib.b200bev_camera_project(one, 2, 6, 8, 4, 4, one, one, 3, 1600, 900, 0, 0, 1, 1, 0, 5, 5, one, null, null) \
+        == _lib.ERR_INVALID_ARGUMENT                     # T must be 1 or B
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setenv("B200BEV_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_handle", None)
+    with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_cpu_tensors_are_rejected_not_computed():
+    enc = encoders.PointNetLiDAREncoder(input_channels=4).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.zeros(1, 8, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b200bev.decode_centernet_predictions({k: torch.zeros(1, c, 4, 4) for k, c in
+                                              (("heatmap", 2), ("offset", 2), ("size", 3), ("rot", 2), ("vel", 2))})
+
+
+# ------------------------------------------------------------------------------------------------ interface
+LIDAR_KEYS = [f"{p}{i}.{s}" for i in range(1, 6) for p, s in
+              (("conv", "weight"), ("conv", "bias"), ("bn", "weight"), ("bn", "bias"), ("bn", "running_mean"),
+               ("bn", "running_var"), ("bn", "num_batches_tracked"))]
+
+
+def test_state_dict_layout_matches_the_reference():
+    """Names and shapes of SURVEY §8b; 702,528 / 372,608 parameters as the reference reports."""
+    lid = encoders.PointNetLiDAREncoder(input_channels=4, feat_dim=1024)
+    assert sorted(lid.state_dict()) == sorted(LIDAR_KEYS)
+    assert tuple(lid.conv1.weight.shape) == (64, 4, 1) and tuple(lid.conv5.weight.shape) == (1024, 512, 1)
+    assert sum(p.numel() for p in lid.parameters()) == 702528
+    rad = encoders.MultiRadarEncoder()
+    assert tuple(rad.radar_encoder.conv1.weight.shape) == (32, 7, 1)
+    assert tuple(rad.fusion_fc.weight.shape) == (256, 1280)
+    assert sum(p.numel() for p in rad.parameters()) == 372608
+    fus = fusion.FlexibleBEVFusion(bev_h=50, bev_w=50)
+    keys = set(fus.state_dict())
+    for k in ("camera_proj.0.weight", "camera_proj.4.running_var", "lidar_init.2.weight", "lidar_upsample.5.bias",
+              "radar_proj.0.weight", "radar_refine.4.weight", "bev_fusion.3.weight"):
+        assert k in keys
+    assert tuple(fus.lidar_init[2].weight.shape) == (80000, 512)
+    assert sum(p.numel() for p in fus.parameters()) == 50468864
+
+
+def test_config_driven_construction():
+    cfg = {"model": {"lidar_encoder": {"input_channels": 4, "feature_dim": 1024, "mlp_layers": [64, 128, 256, 512, 1024]},
+                     "radar_encoder": {"input_channels": 7, "num_radars": 3, "fusion_method": "max"},
+                     "bev_fusion": {"bev_h": 50, "bev_w": 50, "bev_channels": 64}, "use_radar": False},
+           "dataset": {"point_cloud_range": [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]}}
+    assert encoders.PointNetLiDAREncoder(config=cfg).input_channels == 4
+    rad = encoders.MultiRadarEncoder(config=cfg)
+    assert rad.num_radars == 3 and rad.fusion_method == "max" and not hasattr(rad, "fusion_fc")
+    fus = fusion.FlexibleBEVFusion(config=cfg)
+    assert (fus.bev_h, fus.bev_channels, fus.use_radar, fus.num_modalities) == (50, 64, False, 2)
+    with pytest.raises(FileNotFoundError):
+        encoders.load_config("/nonexistent/base.yaml")
+    with pytest.raises(AssertionError):
+        fusion.FlexibleBEVFusion(use_camera=False, use_lidar=False, use_radar=False)
+
+
+def _load(module, layers):
+    sd = module.state_dict()
+    for i, lay in enumerate(layers, start=1):
+        sd[f"conv{i}.weight"] = torch.from_numpy(lay["weight"]).unsqueeze(-1)
+        sd[f"conv{i}.bias"] = torch.from_numpy(lay["bias"])
+        for ours, theirs in (("bn_weight", "weight"), ("bn_bias", "bias"), ("bn_mean", "running_mean"), ("bn_var", "running_var")):
+            sd[f"bn{i}.{theirs}"] = torch.from_numpy(lay[ours])
+    module.load_state_dict(sd)
+
+
+def test_batchnorm_folding_matches_the_unfolded_oracle(golden):
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    enc = encoders.PointNetLiDAREncoder(input_channels=4).eval()
+    _load(enc, layers)
+    ws, bs = [], []
+    for conv, bn in encoders._mlp_stages(enc):
+        w, b = ops.fold_batchnorm(conv.weight, conv.bias, bn)
+        ws.append(w.numpy())
+        bs.append(b.numpy())
+    ref_w, ref_b = orc.fold_layers(layers)
+    for a, b in zip(ws + bs, ref_w + ref_b):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=0)
+    # folded fp32 chain == reference output within the fp32 bound
+    pts = syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)
+    x = pts.astype(np.float32)
+    for w, b in zip(ws, bs):
+        x = np.maximum(x @ w.astype(np.float32).T + b.astype(np.float32), 0)
+    assert max_rel(x.max(axis=1), golden("lidar_encoder")["small_global"]) < 1e-5
+    # blob layout: W^T then bias, layer after layer
+    blob, dims = ops.pack_mlp_params([torch.from_numpy(w) for w in ws], [torch.from_numpy(b) for b in bs], torch.device("cpu"))
+    assert dims == list(syn.LIDAR_DIMS) and blob.numel() == sum(a * b + b for a, b in zip(dims[:-1], dims[1:]))
+    np.testing.assert_array_equal(blob[:256].view(4, 64).numpy(), ws[0].T.astype(np.float32))
+    np.testing.assert_array_equal(blob[256:320].numpy(), bs[0].astype(np.float32))
+
+
+def test_training_mode_uses_the_torch_graph_and_matches_the_reference_ops():
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    enc = encoders.PointNetLiDAREncoder(input_channels=4)
+    _load(enc, layers)
+    enc.train()
+    pts = torch.from_numpy(syn.lidar_batch(201, 2, n_valid=100, n_total=128))
+    out = enc(pts)
+    assert out.requires_grad and out.shape == (2, 1024)
+    out.sum().backward()
+    assert enc.conv1.weight.grad is not None
+    # (B,C,N) layout is accepted like the reference does
+    enc.eval()
+    enc.return_point_features = True            # forces the torch path on CPU for an eval-mode comparison
+    both = enc(pts)
+    assert both.shape == (2, 128, 2048)
+    ref = torch_port.shared_mlp_max(pts, torch_port.layers_to_torch(layers))
+    # eval BN here uses the running stats that the train-mode pass above has updated, so compare the
+    # structure only: global feature is repeated along points in the second half
+    assert torch.equal(both[:, 0, 1024:], both[:, 5, 1024:]) and ref.shape == (2, 1024)
+
+
+def test_weight_cache_follows_parameter_updates():
+    enc = encoders.PointNetLiDAREncoder(input_channels=4).eval()
+    k0 = encoders._state_key(enc, torch.device("cpu"))
+    with torch.no_grad():
+        enc.bn3.running_mean.add_(1.0)
+    k1 = encoders._state_key(enc, torch.device("cpu"))
+    enc.load_state_dict(enc.state_dict())
+    k2 = encoders._state_key(enc, torch.device("cpu"))
+    assert k0 != k1 and k1 != k2
+
+
+def test_patch_rebinds_the_reference_names():
+    ref_src = Path("/root/reference/src")
+    if not ref_src.exists():
+        pytest.skip("reference checkout not present (GPU box)")
+    code = """
+import sys, io, contextlib
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+with contextlib.redirect_stdout(io.StringIO()):
+    import encoders, fusion, centernet_target, fusion_detection, eval as ref_eval
+import bevfusion_multimodal_3d_object_detection_b200 as b
+orig = encoders.PointNetLiDAREncoder.forward
+done = b.patch()
+assert set(done) >= {'encoders', 'fusion', 'centernet_target', 'fusion_detection', 'eval'}, done
+assert encoders.PointNetLiDAREncoder.forward is not orig
+assert ref_eval.decode_centernet_predictions is fusion_detection.decode_centernet_predictions
+import torch
+enc = encoders.PointNetLiDAREncoder(input_channels=4)
+assert enc.train()(torch.zeros(2, 16, 4)).shape == (2, 1024)      # training: reference graph, CPU is fine
+try:
+    enc.eval()(torch.zeros(2, 16, 4)); raise SystemExit('eval on CPU must raise')
+except RuntimeError as e:
+    assert 'no CPU fallback' in str(e)
+b.unpatch()
+assert encoders.PointNetLiDAREncoder.forward is orig
+print('PATCH-OK')
+""" % (str(ROOT), str(ref_src))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "PATCH-OK" in r.stdout, r.stdout + r.stderr

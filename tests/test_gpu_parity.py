@@ -1,0 +1,305 @@
+"""GPU parity tests (-m gpu): every kernel, called through the C-ABI (ops -> ctypes -> libb200bev.so),
+against the numpy oracle on the same seeded inputs and against the golden vectors the reference
+produced.  Tolerances: indices / cells / permutations bit-exact; fp32 features max|d| <= 1e-5 * max|ref|
+(north_star's bound in the form SURVEY §7 derives); bf16 tensor path 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from bevfusion_multimodal_3d_object_detection_b200 import _lib, ops
+from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+from oracle import bev_oracle as orc
+from tests.conftest import max_rel
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+
+def dev_t(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def packed(layers, cuda):
+    ws, bs = orc.fold_layers(layers)
+    return ops.pack_mlp_params([torch.from_numpy(w) for w in ws], [torch.from_numpy(b) for b in bs], cuda)
+
+
+def test_library_is_loaded_and_device_is_blackwell(cuda):
+    import ctypes as C
+
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().b200bev_device_info(C.byref(sm), C.byref(major), C.byref(minor)))
+    assert major.value == 10 and sm.value >= 100
+
+
+# ------------------------------------------------------------------------------------------------ S1a
+@pytest.mark.parametrize("B,N,W,H", [(1, 35000, 50, 50), (3, 2011, 50, 50), (2, 777, 7, 5), (2, 40000, 100, 100),
+                                     (1, 31, 50, 50), (1, 300000, 100, 100)])
+def test_bin_sort_bit_exact(cuda, B, N, W, H):
+    pts = syn.lidar_batch(900 + N, B, n_valid=max(N - N // 100 - 1, 1), n_total=N)
+    # push some points outside the grid / onto edges / to NaN
+    pts[:, 3::97, 0] = 60.0
+    pts[:, 5::101, 1] = -51.2
+    pts[:, 7::103, 0] = 51.2
+    pts[:, 11::211, 1] = np.nan
+    cell, perm, off = ops.bin_sort(dev_t(pts, cuda), W, H)
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, H)
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
+    for b in range(B):
+        rp, ro = orc.bin_sort(ref_cell[b], W * H)
+        np.testing.assert_array_equal(off[b].cpu().numpy(), ro)
+        np.testing.assert_array_equal(perm[b].cpu().numpy(), rp)
+
+
+def test_bin_sort_all_points_in_one_cell_and_generic_channels(cuda):
+    pts = np.zeros((2, 5000, 5), dtype=np.float32)            # 5-channel rows: scalar load path
+    pts[1, :, 0] = np.linspace(-60, 60, 5000)
+    cell, perm, off = ops.bin_sort(dev_t(pts, cuda), 50, 50)
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, 50, 50)
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
+    for b in range(2):
+        rp, ro = orc.bin_sort(ref_cell[b], 2500)
+        np.testing.assert_array_equal(perm[b].cpu().numpy(), rp)
+        np.testing.assert_array_equal(off[b].cpu().numpy(), ro)
+
+
+def test_bin_sort_round_trip_properties_full_size(cuda):
+    """Size-independent properties at BASELINE scale: perm is a permutation, cells are sorted, stable."""
+    pts = dev_t(syn.lidar_batch(950, 4), cuda)
+    cell, perm, off = ops.bin_sort(pts, 50, 50)
+    for b in range(4):
+        p = perm[b].long()
+        assert torch.equal(torch.sort(p)[0], torch.arange(35000, device=cuda))
+        c = cell[b][p]
+        n_in = int(off[b, -1])
+        assert bool((c[:n_in] >= 0).all()) and bool((c[n_in:] == -1).all())
+        assert bool((c[1:n_in] >= c[: n_in - 1]).all())
+        same = c[1:n_in] == c[: n_in - 1]
+        assert bool((p[1:n_in][same] > p[: n_in - 1][same]).all())       # stability
+        assert torch.equal(torch.bincount(c[:n_in].long(), minlength=2500), (off[b, 1:] - off[b, :-1]).long())
+
+
+# ------------------------------------------------------------------------------------------------ S1b
+def test_lidar_global_max_vs_golden_and_oracle(cuda, golden):
+    g = golden("lidar_encoder")
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims = packed(layers, cuda)
+    small = syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)
+    got = ops.pointnet_encode(dev_t(small, cuda), blob, dims).cpu().numpy()
+    assert max_rel(got, g["small_global"]) < FP32_TOL
+    assert max_rel(got, orc.pointnet_global(small, layers)) < FP32_TOL
+    full = syn.lidar_batch(301, 1)
+    got = ops.pointnet_encode(dev_t(full, cuda), blob, dims).cpu().numpy()
+    assert max_rel(got, g["full_global"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 63), (2, 64), (3, 65), (5, 1000)])
+def test_lidar_global_ragged_sizes(cuda, B, N):
+    layers = syn.mlp_weights(102, syn.LIDAR_DIMS)
+    blob, dims = packed(layers, cuda)
+    pts = syn.lidar_batch(600 + N, B, n_valid=max(N - 2, 1), n_total=N)
+    got = ops.pointnet_encode(dev_t(pts, cuda), blob, dims).cpu().numpy()
+    assert max_rel(got, orc.pointnet_global(pts, layers)) < FP32_TOL
+
+
+def test_lidar_without_batchnorm_and_other_widths(cuda):
+    dims = (5, 32, 48, 136)
+    layers = syn.mlp_weights(103, dims, use_bn=False)
+    blob, d = packed(layers, cuda)
+    pts = syn.lidar_batch(610, 2, n_valid=300, n_total=333, channels=5)
+    got = ops.pointnet_encode(dev_t(pts, cuda), blob, d).cpu().numpy()
+    assert max_rel(got, orc.pointnet_global(pts, layers)) < FP32_TOL
+
+
+def test_lidar_cell_canvas(cuda, golden):
+    g = golden("lidar_encoder")
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims = packed(layers, cuda)
+    pts = syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)
+    pts[:, 50:60, 0] = 70.0                                     # a few points outside the grid are dropped
+    d = dev_t(pts, cuda)
+    cell, perm, off = ops.bin_sort(d, 50, 50)
+    glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=2500)
+    canvas = canvas.cpu().numpy()
+    # one pass, both outputs: the global max still sees the out-of-grid points (reference semantics)
+    assert max_rel(glob.cpu().numpy(), orc.pointnet_global(pts, layers)) < FP32_TOL
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, 50, 50)
+    for b in range(2):
+        ref = orc.pointnet_cell_max(pts[b], layers, ref_cell[b], 2500)
+        assert max_rel(canvas[b], ref) < FP32_TOL
+        empty = np.bincount(ref_cell[b][ref_cell[b] >= 0], minlength=2500) == 0
+        assert not canvas[b][empty].any()                      # empty cells are exactly zero
+    # unmodified input against the canvas the reference's per-point features give (golden)
+    pts0 = syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)
+    d0 = dev_t(pts0, cuda)
+    _, perm0, off0 = ops.bin_sort(d0, 50, 50)
+    c0 = ops.pointnet_encode(d0, blob, dims, perm=perm0, offsets=off0, n_cells=2500, want_global=False).cpu().numpy()
+    assert max_rel(c0[:, :, ::16], g["small_canvas_sub"]) < FP32_TOL
+
+
+def test_global_max_equals_max_over_canvas_full_size(cuda):
+    """Property at full size: with every point in the grid, max over cells == global max."""
+    layers = syn.mlp_weights(104, syn.LIDAR_DIMS)
+    blob, dims = packed(layers, cuda)
+    d = dev_t(syn.lidar_batch(620, 2), cuda)
+    glob = ops.pointnet_encode(d, blob, dims)
+    _, perm, off = ops.bin_sort(d, 50, 50)
+    glob2, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=2500)
+    assert torch.equal(canvas.max(dim=1)[0], glob) and torch.equal(glob2, glob)
+
+
+# ------------------------------------------------------------------------------------------------ S1c
+@pytest.mark.parametrize("method", ["concat", "max", "mean"])
+def test_multi_radar(cuda, golden, method):
+    g = golden("radar_encoder")
+    layers = syn.mlp_weights(111, syn.RADAR_DIMS)
+    fcw, fcb = syn.linear_weights(112, 5 * 256, 256)
+    blob, dims = packed(layers, cuda)
+    radars = syn.radar_batch(211, 3)
+    fused, stacked = ops.radar_encode([dev_t(r, cuda) for r in radars], blob, dims, method, dev_t(fcw, cuda), dev_t(fcb, cuda))
+    ref_fused, ref_stacked = orc.multi_radar(radars, layers, method, fcw, fcb)
+    assert max_rel(stacked.cpu().numpy(), ref_stacked) < FP32_TOL
+    assert max_rel(fused.cpu().numpy(), g[f"fused_{method}"]) < FP32_TOL
+    ragged = [np.ascontiguousarray(r[:, : 125 - 17 * i]) for i, r in enumerate(radars)]
+    fused, _ = ops.radar_encode([dev_t(r, cuda) for r in ragged], blob, dims, method, dev_t(fcw, cuda), dev_t(fcb, cuda))
+    assert max_rel(fused.cpu().numpy(), g[f"ragged_{method}"]) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------ S2
+@pytest.mark.parametrize("name,shape", [("ref28x50", (16, 28, 50, 50, 50)), ("hd57x100", (8, 57, 100, 50, 50)),
+                                        ("up7x9", (8, 7, 9, 20, 30))])
+def test_camera_mean_and_resize(cuda, golden, name, shape):
+    g = golden("camera_bev")
+    C, h, w, H, W = shape
+    feats = syn.camera_features(401, 2, n_cam=6, channels=C, h=h, w=w)
+    mean = ops.camera_mean(dev_t(feats, cuda)).cpu().numpy()
+    np.testing.assert_array_equal(mean, orc.camera_mean(feats))          # same association: bit-exact
+    assert max_rel(mean, g[f"{name}_mean"]) < 2e-7
+    out = ops.bilinear_resize(dev_t(g[f"{name}_resize_in"], cuda), (H, W)).cpu().numpy()
+    assert max_rel(out, g[f"{name}_resize_out"]) < FP32_TOL
+
+
+def test_camera_mean_odd_sizes(cuda):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 5, 3, 7, 11)).astype(np.float32)          # inner not a multiple of 4, 5 cameras
+    np.testing.assert_array_equal(ops.camera_mean(dev_t(x, cuda)).cpu().numpy(), orc.camera_mean(x))
+    y = rng.standard_normal((3, 4, 8, 4, 4)).astype(np.float32)           # vector path, n_cam != 6
+    np.testing.assert_array_equal(ops.camera_mean(dev_t(y, cuda)).cpu().numpy(), orc.camera_mean(y))
+
+
+def test_camera_projection(cuda, golden):
+    g = golden("camera_bev")
+    K, E = syn.camera_rig()
+    feats = syn.camera_features(402, 1, n_cam=6, channels=8, h=57, w=100)
+    canvas, table = ops.camera_project(dev_t(feats, cuda), dev_t(K, cuda), dev_t(E, cuda), (1600.0, 900.0), (50, 50),
+                                       return_table=True)
+    np.testing.assert_array_equal(table[0].cpu().numpy(), g["project_table"])   # (u, v, valid) bit-exact
+    assert max_rel(canvas[0].cpu().numpy(), g["project_canvas_grid_sample"]) < FP32_TOL
+    assert max_rel(canvas[0].cpu().numpy(), orc.camera_project(feats[0], g["project_table"], (50, 50))) < 1e-6
+
+
+def test_camera_projection_per_sample_rigs_and_big_grid(cuda):
+    K, E = syn.camera_rig()
+    E2 = E.copy()
+    E2[:, :, 3] += np.float32(0.25)
+    Ks, Es = np.stack([K, K]), np.stack([E, E2])
+    feats = syn.camera_features(403, 2, n_cam=6, channels=5, h=28, w=50)
+    canvas, table = ops.camera_project(dev_t(feats, cuda), dev_t(Ks, cuda), dev_t(Es, cuda), (1600.0, 900.0), (100, 100),
+                                       return_table=True)
+    for b in range(2):
+        t = orc.project_cells(Ks[b], Es[b], (1600.0, 900.0), (28, 50), (100, 100), syn.PC_RANGE)
+        np.testing.assert_array_equal(table[b].cpu().numpy(), t)
+        assert max_rel(canvas[b].cpu().numpy(), orc.camera_project(feats[b], t, (100, 100))) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ S3
+def test_nms_and_topk_vs_golden(cuda, golden):
+    g = golden("centernet_decode")
+    heat = syn.head_maps(501, 3)["heatmap"]
+    nms = ops.centernet_nms(dev_t(heat, cuda))
+    np.testing.assert_array_equal(nms.cpu().numpy(), g["nms"])
+    score, ind, cls, ys, xs = ops.centernet_topk(nms, 100)
+    np.testing.assert_array_equal(score.cpu().numpy(), g["topk_score"])
+    np.testing.assert_array_equal(ind.cpu().numpy(), g["topk_ind"])
+    np.testing.assert_array_equal(ys.cpu().numpy(), g["topk_ys"])
+    np.testing.assert_array_equal(xs.cpu().numpy(), g["topk_xs"])
+    np.testing.assert_array_equal(cls.cpu().numpy(), g["topk_classes"])
+    assert ind.dtype == torch.int64 and cls.dtype == torch.int64
+
+
+def test_hand_made_peaks_and_tie_rule(cuda, golden):
+    g = golden("centernet_decode")
+    nms = ops.centernet_nms(dev_t(g["hand_heat"], cuda))
+    np.testing.assert_array_equal(nms.cpu().numpy(), g["hand_nms"])
+    score, _, _, ys, xs = ops.centernet_topk(nms, 6)
+    np.testing.assert_array_equal(score.cpu().numpy(), g["hand_topk_score"])
+    np.testing.assert_array_equal(ys.cpu().numpy(), g["hand_topk_ys"])
+    np.testing.assert_array_equal(xs.cpu().numpy(), g["hand_topk_xs"])
+    ref = orc.topk(g["hand_nms"], 8)
+    got = ops.centernet_topk(nms, 8)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)           # includes the plateau ties: index-ascending
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        ops.centernet_topk(dev_t(g["hand_heat"], cuda), 43)
+
+
+def test_topk_on_plateaus_and_negative_scores(cuda):
+    rng = np.random.default_rng(5)
+    s = rng.integers(-3, 4, (2, 3, 9, 13)).astype(np.float32)           # massive ties, negatives, zeros
+    got = ops.centernet_topk(dev_t(s, cuda), 17)
+    for a, b in zip(got, orc.topk(s, 17)):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+
+
+def _check_decode(out, ref_dets):
+    counts = out["count"].cpu().numpy()
+    for b, ref in enumerate(ref_dets):
+        n = len(ref["scores"])
+        assert counts[b] == n
+        np.testing.assert_array_equal(out["scores"][b, :n].cpu().numpy(), ref["scores"])
+        np.testing.assert_array_equal(out["labels"][b, :n].cpu().numpy(), ref["labels"])
+        np.testing.assert_array_equal(out["velocities"][b, :n].cpu().numpy(), ref["velocities"])
+        boxes = out["boxes"][b, :n].cpu().numpy()
+        np.testing.assert_array_equal(boxes[:, :6], ref["boxes"][:, :6])
+        np.testing.assert_allclose(boxes[:, 6], ref["boxes"][:, 6], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,voxel", [("ct", 2.048), ("fd", 0.512)])
+@pytest.mark.parametrize("thr", [0.0, 0.3, 0.999])
+def test_fused_decode_vs_reference_golden(cuda, golden, tag, voxel, thr):
+    g = golden("centernet_decode")
+    maps = syn.head_maps(501, 3)
+    out = ops.centernet_decode(*[dev_t(maps[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], 100, voxel,
+                               score_thresh=thr)
+    ref = [{k: g[f"{tag}_thr{thr}_b{b}_{k}"] for k in ("boxes", "scores", "labels", "velocities")} for b in range(3)]
+    _check_decode(out, ref)
+    np.testing.assert_array_equal(out["ys"].cpu().numpy(), g["topk_ys"])
+    np.testing.assert_array_equal(out["xs"].cpu().numpy(), g["topk_xs"])
+    np.testing.assert_array_equal(out["ind"].cpu().numpy(), g["topk_ind"])
+
+
+def test_fused_decode_sparse_big_and_batch32(cuda, golden):
+    g = golden("centernet_decode")
+    sparse = syn.head_maps(502, 2, peak_frac=0.02)
+    out = ops.centernet_decode(*[dev_t(sparse[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], 100, 2.048,
+                               score_thresh=0.1)
+    _check_decode(out, [{k: g[f"sparse_b{b}_{k}"] for k in ("boxes", "scores", "labels", "velocities")} for b in range(2)])
+    big = syn.head_maps(503, 1, H=100, W=100)
+    out = ops.centernet_decode(*[dev_t(big[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], 100, 0.512)
+    _check_decode(out, [{k: g[f"big_{k}"] for k in ("boxes", "scores", "labels", "velocities")}])
+    maps = syn.head_maps(504, 32)
+    out = ops.centernet_decode(*[dev_t(maps[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], 100, 2.048)
+    _check_decode(out, orc.decode(maps, score_thresh=0.0))
+    # idempotence of the ticket counters: a second call on the same workspace pattern gives the same answer
+    out2 = ops.centernet_decode(*[dev_t(maps[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], 100, 2.048)
+    assert torch.equal(out["boxes"], out2["boxes"]) and torch.equal(out["count"], out2["count"])
+
+
+def test_decode_small_k_and_odd_grid(cuda):
+    maps = syn.head_maps(505, 2, classes=3, H=9, W=13)
+    for K in (1, 5, 64):
+        out = ops.centernet_decode(*[dev_t(maps[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], K, 2.048,
+                                   score_thresh=0.2)
+        _check_decode(out, orc.decode(maps, score_thresh=0.2, max_detections=K))
