@@ -1,0 +1,98 @@
+"""Kernel micro-timings (CUDA events, L2 flushed between runs) — a development aid, not the bench.
+
+    python tests/perf_kernels.py [mlp|binsort|camera|decode|all] [--frames 32]
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from bevfusion_multimodal_3d_object_detection_b200 import _lib, ops  # noqa: E402
+from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn  # noqa: E402
+from oracle import bev_oracle as orc  # noqa: E402
+
+dev = torch.device("cuda:0")
+flush = None
+
+
+def timeit(fn, reps=10, warm=3):
+    global flush
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--frames", type=int, default=32)
+    args = ap.parse_args()
+    F = args.frames
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if args.what in ("mlp", "all"):
+        lw, lb = orc.fold_layers(syn.mlp_weights(101, syn.LIDAR_DIMS))
+        blob, dims = ops.pack_mlp_params([torch.from_numpy(w) for w in lw], [torch.from_numpy(b) for b in lb], dev)
+        tc = ops.pack_mlp_params_bf16(blob, dims)
+        pts = to(syn.lidar_batch(42, F))
+        _, perm, off = ops.bin_sort(pts, 50, 50)
+        flops = F * 35000 * 2.0 * 696576
+        for name, fn in (
+            ("mlp f32 global", lambda: ops.pointnet_encode(pts, blob, dims)),
+            ("mlp f32 canvas+global", lambda: ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=2500)),
+            ("mlp bf16 tcgen05 global", lambda: ops.pointnet_encode(pts, blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc)),
+            ("mlp bf16 tcgen05 canvas+global", lambda: ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=2500,
+                                                                          precision=_lib.BF16_TENSOR, tc_params=tc)),
+        ):
+            try:
+                med, best = timeit(fn, reps=5 if "f32" in name else 20)
+                print(f"{name:34s} median {med:8.3f} ms  best {best:8.3f} ms  {flops / med / 1e9:8.1f} TFLOP/s", flush=True)
+            except _lib.B200BevError as e:
+                print(f"{name:34s} {e}", flush=True)
+    if args.what in ("binsort", "all"):
+        pts = to(syn.lidar_batch(42, F))
+        med, best = timeit(lambda: ops.bin_sort(pts, 50, 50), reps=20)
+        by = F * (24.0 * 35000 + 4 * 2501)
+        print(f"bin_sort {F}x35000 50x50            median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+    if args.what in ("camera", "all"):
+        g = torch.Generator(device=dev).manual_seed(1)
+        feats = torch.relu(torch.randn((F, 6, 512, 57, 100), device=dev, generator=g))
+        K, E = syn.camera_rig()
+        Kd, Ed = to(K), to(E)
+        mean = ops.camera_mean(feats)
+        x = mean.view(F * 2, 256, 57, 100)[:F]
+        table = orc.project_cells(K, E, (1600.0, 900.0), (57, 100), (50, 50), syn.PC_RANGE)
+        hits = int(table[:, :, 2].sum())
+        for name, fn, by in (
+            ("camera_mean", lambda: ops.camera_mean(feats), F * 4.0 * 512 * 5700 * 7),
+            ("bilinear_resize", lambda: ops.bilinear_resize(x, (50, 50)), F * 4.0 * 256 * (5700 + 2500)),
+            ("camera_project", lambda: ops.camera_project(feats, Kd, Ed, (1600.0, 900.0), (50, 50)),
+             F * 4.0 * 512 * (min(6 * 5700, 4 * hits) + 2500)),
+        ):
+            med, best = timeit(fn, reps=20)
+            print(f"{name:34s} median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+    if args.what in ("decode", "all"):
+        maps = {k: to(v) for k, v in syn.head_maps(44, F).items()}
+        med, best = timeit(lambda: ops.centernet_decode(maps["heatmap"], maps["offset"], maps["size"], maps["rot"], maps["vel"],
+                                                        100, 2.048), reps=20)
+        by = F * (4.0 * 10 * 2500 + 3600 + 6800)
+        print(f"centernet_decode {F}x10x50x50       median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -303,3 +303,40 @@ def test_decode_small_k_and_odd_grid(cuda):
         out = ops.centernet_decode(*[dev_t(maps[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], K, 2.048,
                                    score_thresh=0.2)
         _check_decode(out, orc.decode(maps, score_thresh=0.2, max_detections=K))
+
+
+# ------------------------------------------------------------------------------------------------ S1b, tcgen05 path
+def _tc(cuda, layers):
+    blob, dims = packed(layers, cuda)
+    return blob, dims, ops.pack_mlp_params_bf16(blob, dims)
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 128), (2, 129), (2, 2011), (5, 1000), (3, 35000)])
+def test_tensor_core_global_max(cuda, B, N):
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, tc = _tc(cuda, layers)
+    pts = syn.lidar_batch(700 + N, B, n_valid=max(N - N // 50 - 1, 1), n_total=N)
+    got = ops.pointnet_encode(dev_t(pts, cuda), blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc).cpu().numpy()
+    ref = orc.pointnet_global(pts, layers)
+    assert max_rel(got, ref) < BF16_TOL
+    # the fp32 kernel on the same input is the tighter cross-check of everything but the rounding
+    f32 = ops.pointnet_encode(dev_t(pts, cuda), blob, dims).cpu().numpy()
+    assert max_rel(got, f32) < BF16_TOL
+
+
+def test_tensor_core_is_deterministic_and_matches_golden(cuda, golden):
+    g = golden("lidar_encoder")
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, tc = _tc(cuda, layers)
+    d = dev_t(syn.lidar_batch(301, 1), cuda)
+    a = ops.pointnet_encode(d, blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc)
+    b = ops.pointnet_encode(d, blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc)
+    assert torch.equal(a, b)
+    assert max_rel(a.cpu().numpy(), g["full_global"]) < BF16_TOL
+
+
+def test_tensor_core_rejects_other_widths(cuda):
+    layers = syn.mlp_weights(103, (5, 32, 48, 136), use_bn=False)
+    blob, dims = packed(layers, cuda)
+    with pytest.raises(_lib.B200BevError):
+        ops.pack_mlp_params_bf16(blob, dims)
