@@ -18,7 +18,8 @@
 //   warp 0      producer: cp.async.bulk global -> smem ring, mbarrier expect_tx / complete_tx
 //   warp 1      MMA issuer: one thread, 4 x tcgen05.mma (128x128x16) per stage, tcgen05.commit
 //               releases the stage and publishes the accumulator
-//   warps 2..5  epilogue: layer 1 (K = 4) on CUDA cores, layers 2-4 TMEM -> bias/ReLU/bf16 -> TMEM,
+//   warps 2..17 epilogue (4 warps per TMEM lane quadrant, each owning a quarter of the columns):
+//               layer 1 (K = 4) on CUDA cores, layers 2-4 TMEM -> bias/ReLU/bf16 -> TMEM,
 //               layer 5: max over the 128 points of the tile.  Points are TMEM lanes, so this is a
 //               cross-lane reduction: a 31-shuffle transposing butterfly per 32 channels leaves lane l
 //               with channel l's maximum; it is folded into 32 running-max registers per thread and
@@ -28,6 +29,9 @@
 // tile), [256,384) act3, which becomes accumulator 0 for layer 5, [384,512) accumulator 1.
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200bev {
@@ -35,8 +39,11 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kStageBytes = 16384;  // 128 rows x 64 bf16
-constexpr int kStages = 12;
-constexpr int kTcThreads = 192;
+constexpr int kStagesGlobal = 12;   // ring depth when shared memory holds nothing but weights
+constexpr int kStagesCell = 8;      // cell mode gives 66 KB to the transposing tile below
+constexpr int kTStride = 132;       // floats per channel row of the tile: 16-B aligned, conflict-free both ways
+constexpr int kEpiThreads = 512;     // 16 epilogue warps: 4 per TMEM lane quadrant
+constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kStagesPerTile = 1 + 4 + 16 + 64;
 constexpr int kBiasFloats = 128 + 256 + 512 + 1024;
 constexpr int kMaxCin = 16;
@@ -47,10 +54,27 @@ struct TcArgs {
   const float* pts;
   int B, N, C;
   const uint8_t* tc;  // [85 stages][W1^T (C x 64) f32][b1 64][bias L2..L5]
-  float* out_global;
+  float* out_global;  // (B,1024) or nullptr
+  // cell mode
+  const int32_t* perm;     // (B,N) points ordered by cell
+  const int32_t* offsets;  // (B,n_cells+1)
+  int n_cells;
+  float* out_canvas;       // (B,n_cells,1024)
   int tiles_per_frame;
   long long total_tiles;
+  int cluster;             // CTAs per cluster sharing each weight stage by multicast (1, 2 or 4)
+  unsigned long long* trace;  // debug only (B200BEV_TC_TRACE): clock stamps of CTA 0, else nullptr
+  int debug;                  // debug only (B200BEV_TC_DEBUG): bit 0 = skip the weight copies after the first tile
 };
+
+// Debug timeline: (event id << 48 | clock) appended by one thread per role of CTA 0.
+constexpr int kTraceMma = 0, kTraceEpi = 8192, kTraceLen = 16384;
+__device__ __forceinline__ void trace_ev(const TcArgs& a, int& idx, int base, unsigned id) {
+  if (a.trace != nullptr && blockIdx.x == 0 && idx < 8192) {
+    a.trace[base + idx] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
+    ++idx;
+  }
+}
 
 __host__ __device__ inline size_t tc_blob_bytes(int C) {
   return (size_t)kStagesPerTile * kStageBytes + ((size_t)C * 64 + 64 + kBiasFloats) * sizeof(float);
@@ -84,6 +108,40 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// Same copy, delivered to the same shared-memory offset (and signalled on the barrier at the same offset)
+// of every CTA of the cluster named in `mask`: one L2 read feeds several SMs.
+__device__ __forceinline__ void bulk_copy_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// One lane of a fully converged warp (elect.sync): the branch stays warp-uniform for the compiler.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -127,6 +185,11 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
       "r"(r[o + 14]), "r"(r[o + 15])                                                                                       \
       : "memory")
 
+#define TC_ST8(taddr, r)                                                                                      \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), \
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                    \
+               : "memory")
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   // element with the even k index in the low half (verified on hardware by tests/cuda/umma_probe.cu)
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -146,10 +209,17 @@ __device__ __forceinline__ void butterfly_level(float* v, int lane) {
   }
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <bool CELL>
 __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a) {
+  constexpr int kStages = CELL ? kStagesCell : kStagesGlobal;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B: 1024-B aligned tiles
-  float* bias_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);  // L2 | L3 | L4 | L5
+  float* tile_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);   // CELL: [128 channels][kTStride]
+  int* cid_s = reinterpret_cast<int*>(tile_s + (CELL ? 128 * kTStride : 0));        // CELL: cell id of each tile slot
+  uint32_t* endmask_s = reinterpret_cast<uint32_t*>(cid_s + (CELL ? 128 : 0));      // CELL: run-end flags, one word per warp
+  float* bias_s = reinterpret_cast<float*>(endmask_s + (CELL ? 4 : 0));             // L2 | L3 | L4 | L5
   float* w1_s = bias_s + kBiasFloats;                                               // W1^T (C x 64), then b1 (64)
   uint64_t* bars = reinterpret_cast<uint64_t*>(w1_s + kMaxCin * 64 + 64);
   uint64_t* full = bars;                    // [kStages]  weights landed
@@ -167,13 +237,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], a.cluster);   // every CTA of the cluster must have retired the stage
     }
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], kTileM);
-    mbar_init(&acc_empty[1], kTileM);
-    mbar_init(act_ready, kTileM);
+    mbar_init(&acc_empty[0], kEpiThreads);
+    mbar_init(&acc_empty[1], kEpiThreads);
+    mbar_init(act_ready, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -182,12 +252,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   }
   tc_fence_before();
   __syncthreads();
+  if (a.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Every CTA runs the same number of tile slots: the CTAs of a cluster consume the multicast weight
+  // stream in lock step.  Slots past the end of the work list are dummy tiles (MMAs run, nothing is stored).
   const long long per_cta = (a.total_tiles + gridDim.x - 1) / gridDim.x;
   const long long t_begin = per_cta * blockIdx.x;
-  const long long t_end = t_begin + per_cta < a.total_tiles ? t_begin + per_cta : a.total_tiles;
+  const long long t_end = t_begin + per_cta;
+  const uint32_t cta_rank = a.cluster > 1 ? cluster_ctarank() : 0;
+  const uint16_t cta_mask = (uint16_t)((1u << a.cluster) - 1u);
 
   if (warp == 0) {
     // ================================ producer ================================
@@ -196,92 +271,187 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       for (long long t = t_begin; t < t_end; ++t) {
         for (int s = 0; s < kStagesPerTile; ++s) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if ((a.debug & 1) && t > t_begin) {   // experiment: how fast is the kernel when weights cost nothing?
+            mbar_arrive(&full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[stage], kStageBytes);
-          bulk_copy_g2s(ring + (size_t)stage * kStageBytes, a.tc + (size_t)s * kStageBytes, kStageBytes, &full[stage]);
+          if (a.cluster == 1) {
+            bulk_copy_g2s(ring + (size_t)stage * kStageBytes, a.tc + (size_t)s * kStageBytes, kStageBytes, &full[stage]);
+          } else {
+            // this CTA fetches its 1/cluster slice of the stage and multicasts it to all peers
+            const uint32_t part = kStageBytes / a.cluster, o = cta_rank * part;
+            bulk_copy_g2s_multicast(ring + (size_t)stage * kStageBytes + o, a.tc + (size_t)s * kStageBytes + o, part,
+                                    &full[stage], cta_mask);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop and one elected lane issues: with warp-uniform control flow the
+    // operands of tcgen05.mma / tcgen05.commit sit in uniform registers.  Run from a single divergent
+    // lane instead, every UTCHMMA was wrapped in an ELECT + 4x R2UR.BROADCAST "waterfall" loop and
+    // took ~140 clk to issue — more than the 64 clk it executes (timeline in profiles/r01_tc_timeline.md).
+    {
       // instruction descriptor: D f32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major, N=128, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(FULL_MASK, tmem, 0);                        // provably uniform
+      const uint32_t ring_u = __shfl_sync(FULL_MASK, smem_u32(ring), 0);
       uint32_t stage = 0, phase = 0, act_phase = 0;
       uint32_t acc_parity = 0;  // bit b: parity of the next use of accumulator b
+      int tr = 0;
       for (long long t = t_begin; t < t_end; ++t) {
 #pragma unroll 1
         for (int layer = 0; layer < 4; ++layer) {  // network layers 2..5
           const int kchunks = 1 << layer;          // K / 64
           const int nchunks = 1 << layer;          // N / 128
           const uint32_t a_col = layer == 0 ? kColAct1 : layer == 1 ? kColAct2 : layer == 2 ? kColAct3 : kColAct4;
+          if (lane == 0) trace_ev(a, tr, kTraceMma, 0x100 + layer);            // waiting for the A operand
           mbar_wait(act_ready, act_phase);
           act_phase ^= 1;
           tc_fence_after();
+          if (lane == 0) trace_ev(a, tr, kTraceMma, 0x110 + layer);            // A operand ready
 #pragma unroll 1
           for (int c = 0; c < nchunks; ++c) {
             const int buf = (layer == 3) ? (c & 1) : 1;
             mbar_wait(&acc_empty[buf], ((acc_parity >> buf) & 1) ^ 1);
             acc_parity ^= 1u << buf;
             tc_fence_after();
-            const uint32_t d_addr = tmem + (buf ? kColAcc1 : kColAcc0);
+            if (lane == 0) trace_ev(a, tr, kTraceMma, 0x120 + layer * 8 + c);  // accumulator free, issuing
+            const uint32_t d_addr = tmem_u + (buf ? kColAcc1 : kColAcc0);
 #pragma unroll 1
-            for (int kc = 0; kc < kchunks; ++kc) {
-              mbar_wait(&full[stage], phase);
+            for (int kc = 0; kc < kchunks; kc += 2) {
+              // two stages (8 MMAs = 512 clk of tensor work) per trip: the fixed cost of a trip (barrier
+              // poll, fence, descriptor arithmetic, commits: ~350 clk) no longer exceeds the work it issues
+              const bool two = kc + 1 < kchunks;
+              const uint32_t st0 = stage, ph0 = phase;
+              uint32_t st1 = stage + 1, ph1 = phase;
+              if (st1 == kStages) { st1 = 0; ph1 ^= 1; }
+              mbar_wait(&full[st0], ph0);
+              if (two) mbar_wait(&full[st1], ph1);
               tc_fence_after();
-              const uint64_t bdesc = make_b_desc(smem_u32(ring + (size_t)stage * kStageBytes));
+              const uint64_t bdesc0 = make_b_desc(ring_u + st0 * kStageBytes);
+              const uint64_t bdesc1 = make_b_desc(ring_u + st1 * kStageBytes);
+              const uint32_t a_addr = tmem_u + a_col + kc * 32;
+              if (elect_one()) {
 #pragma unroll
-              for (int s = 0; s < 4; ++s)
-                umma_ts(d_addr, tmem + a_col + kc * 32 + s * 8, bdesc + (uint64_t)(s * 2), idesc, (kc | s) != 0);
-              tc_commit(&empty[stage]);
+                for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + s * 8, bdesc0 + (uint64_t)(s * 2), idesc, (kc | s) != 0);
+                if (a.cluster == 1) tc_commit(&empty[st0]);
+                else tc_commit_multicast(&empty[st0], cta_mask);
+                if (two) {
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + 32 + s * 8, bdesc1 + (uint64_t)(s * 2), idesc, 1u);
+                  if (a.cluster == 1) tc_commit(&empty[st1]);
+                  else tc_commit_multicast(&empty[st1], cta_mask);
+                }
+                if (kc + 2 >= kchunks) tc_commit(&acc_full[buf]);
+              }
+              __syncwarp();
+              if (two) { stage = st1; phase = ph1; }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            tc_commit(&acc_full[buf]);
+            if (lane == 0) trace_ev(a, tr, kTraceMma, 0x160 + layer * 8 + c);  // chunk issued
           }
         }
       }
     }
   } else {
-    // ================================ epilogue (128 threads) ================================
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    // ================================ epilogue (16 warps, 512 threads) ================================
+    // Four warps share each TMEM lane quadrant and split the accumulator columns four ways ("part"):
+    // with one epilogue warp per scheduler the dependent ALU/shuffle chains ran at ~5 clk per
+    // instruction and the tensor pipe idled two thirds of the time (profiles/r01_tc_*); four warps
+    // per scheduler hide that latency.
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch (hardware: warp id % 4)
+    const int part = (warp - 2) >> 2;          // which quarter of the columns / of the tile's points this warp owns
     const int row = quad * 32 + lane;          // point within the tile = TMEM lane
     const uint32_t tm = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t full_phase[2] = {0, 0};
-    float rmax[32];
+    // running maximum of the raw layer-5 accumulators of the current frame, one value per 128-channel chunk c:
+    //   global mode: rmax[c] <-> channel c*128 + part*32 + lane (what the butterfly leaves in this lane)
+    //   cell mode  : rmax[c] <-> channel c*128 + row, over the 32 tile slots [part*32, part*32+32) this thread walks
+    float rmax[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) rmax[i] = -INFINITY;
+    for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
     int cur_frame = -1;
+    int tr = 0;
+    const bool vec4_points = a.C == 4 && (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0;
+    float4 xpre = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile's point, prefetched under layer 5
+    bool have_pre = false;
     const int c_out = 1024;
     const float* b5 = bias_s + 128 + 256 + 512;
 
     auto flush = [&](int frame) {
+      if (a.out_global == nullptr) return;
       int* o = reinterpret_cast<int*>(a.out_global + (size_t)frame * c_out);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = i * 32 + lane;
+      for (int i = 0; i < 8; ++i) {
+        const int col = CELL ? i * 128 + row : i * 128 + part * 32 + lane;
         const float v = fmaxf(rmax[i] + b5[col], 0.0f);   // bias + ReLU commute with the max
         atomicMax(o + col, __float_as_int(v));
         rmax[i] = -INFINITY;
       }
     };
 
+    // (frame, tile-in-frame) of the running tile slot, advanced incrementally: one 64-bit division per
+    // kernel instead of four per tile in each of the 16 warps
+    int tf = (int)(t_begin / a.tiles_per_frame), tt = (int)(t_begin % a.tiles_per_frame);
     for (long long t = t_begin; t < t_end; ++t) {
-      const int f = (int)(t / a.tiles_per_frame);
-      const int s0 = (int)(t % a.tiles_per_frame) * kTileM;
+      const bool tracer = (tid == 64);
+      if (tracer) trace_ev(a, tr, kTraceEpi, 0x200);          // tile start
+      const bool dummy = t >= a.total_tiles;
+      const int f = dummy ? cur_frame : tf;
+      const int s0 = dummy ? a.N : tt * kTileM;
+      // the slot after this one, for the prefetch below
+      int tf_next = tf, tt_next = tt + 1;
+      if (tt_next == a.tiles_per_frame) { tt_next = 0; ++tf_next; }
       if (f != cur_frame) {
         if (cur_frame >= 0) flush(cur_frame);
         cur_frame = f;
       }
-      const int p = s0 + row;
-      const bool valid = p < a.N;
+      const int slot = s0 + row;                // position in input order (global) or in cell order (CELL)
+      const bool valid = slot < a.N;            // a dummy tile has no valid slot
       const bool partial = s0 + kTileM > a.N;
+      int p = slot;
+      if (CELL) {
+        // slot -> source point (every part needs it for layer 1) and cell id (part 0 looks it up for all)
+        if (valid) p = __ldg(a.perm + (size_t)f * a.N + slot);
+        if (part == 0) {
+          int cid = -1;
+          if (valid) {
+            const int32_t* foff = a.offsets + (size_t)f * (a.n_cells + 1);
+            if (slot < __ldg(foff + a.n_cells)) {   // in-grid points come first in perm
+              int lo = 0, hi = a.n_cells;           // largest c with offsets[c] <= slot
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(foff + mid) <= slot) lo = mid; else hi = mid;
+              }
+              cid = lo;
+            }
+          }
+          cid_s[row] = cid;
+        }
+        epi_bar_sync();
+        if (part == 0) {
+          // run ends: one flag word per 32 slots.  The last slot of a word never carries a flag for a run
+          // that goes on in the next word; the walker of that word hands such a run over with an atomic.
+          const int cid = cid_s[row];
+          const int next = row < kTileM - 1 ? cid_s[row + 1] : -2;
+          const unsigned ends = __ballot_sync(FULL_MASK, cid >= 0 && next != cid);
+          if (lane == 0) endmask_s[quad] = ends;
+        }
+        // endmask_s becomes visible to the walkers at the barrier after the first tile store below
+      }
 
       // ---- layer 1 on CUDA cores (K = C_in is 4): act1 = relu(W1 x + b1) -> bf16 -> TMEM [0,32) ----
       {
         float x[kMaxCin];
         const float* src = a.pts + ((size_t)f * a.N + (valid ? p : 0)) * a.C;
-        if (a.C == 4 && (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0) {
-          const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec4_points) {
+          float4 v = xpre;   // fetched while the previous tile's layer 5 ran
+          if (!have_pre) v = valid ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
           x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
 #pragma unroll
           for (int k = 4; k < kMaxCin; ++k) x[k] = 0.0f;
@@ -289,24 +459,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 #pragma unroll
           for (int k = 0; k < kMaxCin; ++k) x[k] = (k < a.C && valid) ? __ldg(src + k) : 0.0f;
         }
-        uint32_t packed[32];
+        // this part's 16 of the 64 channels; weights and bias of a part are contiguous: 128-bit broadcast loads
+        float acc[16];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(w1_s + a.C * 64 + part * 16);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v0 = w1_s[a.C * 64 + 2 * j], v1 = w1_s[a.C * 64 + 2 * j + 1];
-#pragma unroll
-          for (int k = 0; k < kMaxCin; ++k) {
-            if (k < a.C) {
-              v0 = fmaf(w1_s[k * 64 + 2 * j], x[k], v0);
-              v1 = fmaf(w1_s[k * 64 + 2 * j + 1], x[k], v1);
-            }
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = bp[q];
+            acc[4 * q] = b4.x; acc[4 * q + 1] = b4.y; acc[4 * q + 2] = b4.z; acc[4 * q + 3] = b4.w;
           }
-          packed[j] = pack_bf16x2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f));
         }
-        TC_ST16(tm + kColAct1, packed, 0);
-        TC_ST16(tm + kColAct1 + 16, packed, 16);
+        auto add_k = [&](int k, float xk) {
+          const float4* wp = reinterpret_cast<const float4*>(w1_s + k * 64 + part * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w4 = wp[q];
+            acc[4 * q] = fmaf(w4.x, xk, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(w4.y, xk, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w4.z, xk, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(w4.w, xk, acc[4 * q + 3]);
+          }
+        };
+        if (a.C == 4) {
+          add_k(0, x[0]); add_k(1, x[1]); add_k(2, x[2]); add_k(3, x[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kMaxCin; ++k)
+            if (k < a.C) add_k(k, x[k]);
+        }
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) packed[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
+        if (tracer) trace_ev(a, tr, kTraceEpi, 0x203);        // layer 1 computed
+        TC_ST8(tm + kColAct1 + part * 8, packed);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(act_ready);
+        if (tracer) trace_ev(a, tr, kTraceEpi, 0x201);        // layer 1 stored
       }
 
       // ---- layers 2..4: accumulator -> bias, ReLU, bf16 -> next A operand in TMEM ----
@@ -320,8 +509,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           mbar_wait(&acc_full[1], full_phase[1]);
           full_phase[1] ^= 1;
           tc_fence_after();
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
+          if (tracer) trace_ev(a, tr, kTraceEpi, 0x210 + layer * 8 + c);   // accumulator seen
+          {
+            const int q = part;   // this warp's 32 of the chunk's 128 columns
             uint32_t r[32];
             TC_LD32(r, tm + kColAcc1 + q * 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -339,7 +529,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           tc_fence_before();
           mbar_arrive(&acc_empty[1]);
           if (c == nchunks - 1) mbar_arrive(act_ready);
+          if (tracer) trace_ev(a, tr, kTraceEpi, 0x230 + layer * 8 + c);   // next operand stored
         }
+      }
+
+      // ---- prefetch the next tile's point: its DRAM latency hides under layer 5 ----
+      have_pre = false;
+      if (vec4_points && t + 1 < t_end) {
+        const bool dn = t + 1 >= a.total_tiles;
+        const int fn = dn ? 0 : tf_next;
+        const int slotn = dn ? a.N : tt_next * kTileM + row;
+        xpre = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slotn < a.N) {
+          const int pn = CELL ? __ldg(a.perm + (size_t)fn * a.N + slotn) : slotn;
+          xpre = __ldg(reinterpret_cast<const float4*>(a.pts + ((size_t)fn * a.N + pn) * 4));
+        }
+        have_pre = true;
       }
 
       // ---- layer 5: max over the tile's points, channel chunk by channel chunk ----
@@ -349,16 +554,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         mbar_wait(&acc_full[buf], full_phase[buf]);
         full_phase[buf] ^= 1;
         tc_fence_after();
+        if (tracer) trace_ev(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
         const uint32_t acc_col = buf ? kColAcc1 : kColAcc0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        {
+          const int g = part;   // this warp's 32 of the chunk's 128 channels
           uint32_t r[32];
           TC_LD32(r, tm + acc_col + g * 32);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (g == 3) {  // the whole chunk is in registers: hand the accumulator back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
-          }
+          // this warp's share of the chunk is in registers: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -366,20 +571,74 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
           }
-          butterfly_level<16>(v, lane);
-          butterfly_level<8>(v, lane);
-          butterfly_level<4>(v, lane);
-          butterfly_level<2>(v, lane);
-          butterfly_level<1>(v, lane);
-          rmax[c * 4 + g] = fmaxf(rmax[c * 4 + g], v[0]);  // lane l holds channel c*128 + g*32 + l
+          if (!CELL) {
+            butterfly_level<16>(v, lane);
+            butterfly_level<8>(v, lane);
+            butterfly_level<4>(v, lane);
+            butterfly_level<2>(v, lane);
+            butterfly_level<1>(v, lane);
+            rmax[c] = fmaxf(rmax[c], v[0]);  // lane l holds channel c*128 + g*32 + l
+            if (tracer) trace_ev(a, tr, kTraceEpi, 0x260 + c);  // layer-5 chunk reduced
+          } else {
+            // transpose through shared memory: tile_s[channel][point]; lanes are consecutive points
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile_s[(g * 32 + j) * kTStride + row] = v[j];
+          }
+        }
+        if (CELL) {
+          epi_bar_sync();
+          // Thread (row, part) now owns channel c*128 + row over the 32 tile slots [part*32, part*32+32),
+          // which are in cell order: the maximum of each run of equal cell ids goes to the canvas.  A run
+          // that touches the first or the last slot of this stretch may continue in a neighbouring
+          // stretch or tile -> atomic max; any other run is the cell's only writer -> plain store.  The 32
+          // lanes of a warp see the same run boundaries and write 128 contiguous bytes of a canvas row.
+          const int ch = c * 128 + row;
+          const float bias = b5[ch];
+          float* canvas = a.out_canvas + (size_t)f * a.n_cells * c_out + ch;
+          const float* trow = tile_s + row * kTStride + part * 32;
+          const int* cids = cid_s + part * 32;
+          const uint32_t ends = endmask_s[part];
+          float m = -INFINITY, gm = rmax[c];
+          bool first_run = true;
+#pragma unroll
+          for (int b4 = 0; b4 < 8; ++b4) {
+            const float4 q4 = *reinterpret_cast<const float4*>(trow + b4 * 4);
+            const float e[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              m = fmaxf(m, e[k]);
+              if (ends & (1u << (b4 * 4 + k))) {
+                const int pt = b4 * 4 + k;
+                const float val = fmaxf(m + bias, 0.0f);
+                if (val > 0.0f) {
+                  float* dst = canvas + (size_t)cids[pt] * c_out;
+                  if (first_run || pt == 31) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
+                  else *dst = val;
+                }
+                gm = fmaxf(gm, m);
+                m = -INFINITY;
+                first_run = false;
+              }
+            }
+          }
+          // a run still open at the last slot goes on in the next stretch: hand its partial maximum over
+          if (!(ends >> 31) && cids[31] >= 0) {
+            const float val = fmaxf(m + bias, 0.0f);
+            if (val > 0.0f) atomicMax(reinterpret_cast<int*>(canvas + (size_t)cids[31] * c_out), __float_as_int(val));
+          }
+          rmax[c] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
+          epi_bar_sync();           // tile_s, cid_s and endmask_s are free again
         }
       }
+      tf = tf_next;
+      tt = tt_next;
     }
     if (cur_frame >= 0) flush(cur_frame);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (a.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still write its shared memory
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -439,9 +698,23 @@ bool tc_dims_supported(const int32_t* dims, int n_layers) {
          dims[4] == 512 && dims[5] == 1024;
 }
 
-size_t tc_smem_bytes() {
-  return 1024 + (size_t)kStages * kStageBytes + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
-         (2 * kStages + 5) * sizeof(uint64_t) + 16;
+// Cluster size of the tensor-core kernel; B200BEV_TC_CLUSTER (1, 2 or 4) overrides the default for experiments.
+// Measured on B200 (32 x 35,000 points): cluster 1 1.50 ms, cluster 2 1.58 ms, cluster 4 ~2x slower (fewer
+// co-resident clusters).  Multicast does not pay because the weight stream is not the limiter (a run with the
+// copies disabled takes the same time), so the default is 1; the multicast path stays for larger weight sets.
+int tc_cluster_size() {
+  const char* e = getenv("B200BEV_TC_CLUSTER");
+  if (e) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) return v;
+  }
+  return 1;
+}
+
+size_t tc_smem_bytes(bool cell) {
+  const int stages = cell ? kStagesCell : kStagesGlobal;
+  return 1024 + (size_t)stages * kStageBytes + (cell ? (128 * kTStride + 128 + 4) * sizeof(float) : 0) +
+         (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) + (2 * stages + 5) * sizeof(uint64_t) + 16;
 }
 
 }  // namespace
@@ -449,22 +722,68 @@ size_t tc_smem_bytes() {
 int pointnet_encode_tc(const float* points, int B, int N, int C, const float* params, const int32_t* dims, int n_layers,
                        const int32_t* perm, const int32_t* offsets, int n_cells, const void* tc_params, float* out_global,
                        float* out_canvas, cudaStream_t st) {
-  (void)params; (void)offsets; (void)n_cells;
+  (void)params;
   if (!tc_dims_supported(dims, n_layers) || dims[0] != C) return B200BEV_ERR_UNSUPPORTED;
-  if (perm || out_canvas || !out_global) return B200BEV_ERR_UNSUPPORTED;  // per-cell canvas: fp32 path for now
   if ((reinterpret_cast<uintptr_t>(tc_params) & 15) != 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  const bool cell = out_canvas != nullptr;   // perm without a canvas: the order does not matter for a global max
   TcArgs a{};
   a.pts = points; a.B = B; a.N = N; a.C = C;
   a.tc = reinterpret_cast<const uint8_t*>(tc_params);
   a.out_global = out_global;
+  a.perm = perm; a.offsets = offsets; a.n_cells = n_cells; a.out_canvas = out_canvas;
   a.tiles_per_frame = ceil_div(N, kTileM);
   a.total_tiles = (long long)B * a.tiles_per_frame;
-  const size_t smem = tc_smem_bytes();
-  B200BEV_CUDA_TRY(cudaFuncSetAttribute(pointnet_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B200BEV_CUDA_TRY(cudaMemsetAsync(out_global, 0, (size_t)B * 1024 * sizeof(float), st));
-  long long grid = sm_count();
-  if (grid > a.total_tiles) grid = a.total_tiles;
-  pointnet_mlp_tc_kernel<<<(int)grid, kTcThreads, smem, st>>>(a);
+  const size_t smem = tc_smem_bytes(cell);
+  if (out_global) B200BEV_CUDA_TRY(cudaMemsetAsync(out_global, 0, (size_t)B * 1024 * sizeof(float), st));
+  if (out_canvas) B200BEV_CUDA_TRY(cudaMemsetAsync(out_canvas, 0, (size_t)B * n_cells * 1024 * sizeof(float), st));
+  // cluster size: weight stages are multicast to `cluster` SMs, dividing the L2 read traffic of the
+  // 1.39 MB-per-tile weight stream (the kernel's bottleneck at cluster 1) by that factor
+  int cluster = tc_cluster_size();
+  while (cluster > 1 && a.total_tiles < 2LL * cluster) cluster >>= 1;
+  a.cluster = cluster;
+  // debug timeline: B200BEV_TC_TRACE=<file> dumps CTA 0's clock stamps after a (synchronous) launch
+  if (const char* dbg = getenv("B200BEV_TC_DEBUG")) a.debug = atoi(dbg);
+  const char* trace_path = getenv("B200BEV_TC_TRACE");
+  unsigned long long* d_trace = nullptr;
+  if (trace_path) {
+    B200BEV_CUDA_TRY(cudaMalloc(&d_trace, kTraceLen * sizeof(unsigned long long)));
+    B200BEV_CUDA_TRY(cudaMemsetAsync(d_trace, 0, kTraceLen * sizeof(unsigned long long), st));
+    a.trace = d_trace;
+  }
+  long long grid = (sm_count() / cluster) * cluster;
+  const long long need = ceil_div64(a.total_tiles, cluster) * cluster;
+  if (grid > need) grid = need;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cell) {
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(pointnet_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, pointnet_mlp_tc_kernel<true>, a));
+  } else {
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(pointnet_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, pointnet_mlp_tc_kernel<false>, a));
+  }
+  if (d_trace) {
+    B200BEV_CUDA_TRY(cudaStreamSynchronize(st));
+    unsigned long long* h = (unsigned long long*)malloc(kTraceLen * sizeof(unsigned long long));
+    B200BEV_CUDA_TRY(cudaMemcpy(h, d_trace, kTraceLen * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* fp = fopen(trace_path, "w")) {
+      for (int i = 0; i < kTraceLen; ++i)
+        if (h[i]) fprintf(fp, "%d %llx %llu\n", i < kTraceEpi ? 0 : 1, h[i] >> 48, h[i] & 0xffffffffffffull);
+      fclose(fp);
+    }
+    free(h);
+    cudaFree(d_trace);
+  }
   return launch_status();
 }
 

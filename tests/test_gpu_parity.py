@@ -340,3 +340,27 @@ def test_tensor_core_rejects_other_widths(cuda):
     blob, dims = packed(layers, cuda)
     with pytest.raises(_lib.B200BevError):
         ops.pack_mlp_params_bf16(blob, dims)
+
+
+@pytest.mark.parametrize("B,N,W", [(2, 2011, 50), (1, 35000, 50), (2, 5000, 100)])
+def test_tensor_core_cell_canvas(cuda, B, N, W):
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, tc = _tc(cuda, layers)
+    pts = syn.lidar_batch(800 + N, B, n_valid=max(N - N // 50 - 1, 1), n_total=N)
+    pts[:, 7::53, 0] = 75.0                                    # out-of-grid points: global max only
+    d = dev_t(pts, cuda)
+    _, perm, off = ops.bin_sort(d, W, W)
+    glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.BF16_TENSOR,
+                                       tc_params=tc)
+    g32, c32 = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W)
+    scale = float(c32.max())
+    assert float((canvas - c32).abs().max()) < BF16_TOL * scale
+    assert float((glob - g32).abs().max()) < BF16_TOL * float(g32.max())
+    empty_cells = (off[:, 1:] - off[:, :-1]) == 0
+    assert not bool(canvas[empty_cells].any())                  # untouched cells stay exactly zero
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, W)
+    ref = orc.pointnet_cell_max(pts[0], layers, ref_cell[0], W * W)
+    assert max_rel(canvas[0].cpu().numpy(), ref) < BF16_TOL
+    only = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.BF16_TENSOR, tc_params=tc,
+                               want_global=False)
+    assert torch.equal(only, canvas)                            # deterministic, with or without the global output
