@@ -2,12 +2,13 @@
 //
 //   camera_mean      camera_features.mean(dim=1)                       src/fusion.py:233-234
 //   bilinear_resize  F.interpolate(size, 'bilinear', align_corners=False)  src/fusion.py:242-247
-//   camera_project   BEV cell centres -> pinhole projection -> bilinear gather -> mean over the
-//                    cameras that see the cell (north_star S2; the reference has no geometric
-//                    projection, SURVEY §0 — oracle/bev_oracle.py holds the restatement)
+//   (camera_project, the geometric form, lives in camera_project.cu)
 //
 // All three are HBM-bound streaming/gather kernels: 16-byte accesses where the layout allows,
 // every output written exactly once, no intermediate tensors.
+#include <algorithm>
+
+#include "async_copy.cuh"
 #include "common.cuh"
 
 namespace b200bev {
@@ -104,130 +105,72 @@ __global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __res
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// geometric projection + gather.
-// ---------------------------------------------------------------------------------------------
-constexpr int kMaxCams = 8;
-constexpr int kCellsPerBlock = 64;
-constexpr float kNearPlane = 0.1f;  // metres in front of the camera
-
-struct ProjArgs {
-  const float* feats;
-  int B, n_cam, C, h, w;
-  const float* K;   // (T,n_cam,3,3)
-  const float* E;   // (T,n_cam,3,4)
-  int T;
-  float img_w, img_h, x_min, y_min, vx, vy, z_plane;
-  int W, H;
-  float* out;
-  float* uv_valid;
+// Staged form of the same arithmetic: a persistent CTA double-buffers whole input planes in shared
+// memory with cp.async.bulk (one elected thread issues, an mbarrier counts the bytes), so HBM sees
+// only sequential full-line reads; the taps come out of shared memory, the x/y coordinate tables are
+// computed once per CTA, and every output row is written coalesced.
+struct ResizeAxis {
+  int i0, i1;
+  float l0, l1;
 };
 
-// Feature-map coordinates (u,v) of BEV cell (ix,iy) in camera `cam`; every operation is a single
-// correctly-rounded fp32 op in a fixed order so that numpy float32 reproduces it bit for bit.
-__device__ __forceinline__ bool project_cell(const ProjArgs& a, const float* __restrict__ Kc, const float* __restrict__ Ec,
-                                             int ix, int iy, float& u, float& v) {
-  const float X = __fadd_rn(a.x_min, __fmul_rn(__fadd_rn((float)ix, 0.5f), a.vx));
-  const float Y = __fadd_rn(a.y_min, __fmul_rn(__fadd_rn((float)iy, 0.5f), a.vy));
-  const float Z = a.z_plane;
-  float pc[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(Ec[r * 4 + 0], X), __fmul_rn(Ec[r * 4 + 1], Y)), __fmul_rn(Ec[r * 4 + 2], Z));
-    pc[r] = __fadd_rn(s, Ec[r * 4 + 3]);
-  }
-  const bool front = pc[2] > kNearPlane;
-  const float zs = front ? pc[2] : 1.0f;
-  const float xn = __fdiv_rn(pc[0], zs), yn = __fdiv_rn(pc[1], zs);
-  const float U = __fadd_rn(__fadd_rn(__fmul_rn(Kc[0], xn), __fmul_rn(Kc[1], yn)), Kc[2]);
-  const float V = __fadd_rn(__fadd_rn(__fmul_rn(Kc[3], xn), __fmul_rn(Kc[4], yn)), Kc[5]);
-  const bool inside = front && (U >= 0.0f) && (U < a.img_w) && (V >= 0.0f) && (V < a.img_h);
-  // pixel -> feature coordinate, grid_sample(align_corners=False): u = U * (w / img_w) - 0.5
-  u = __fsub_rn(__fmul_rn(U, __fdiv_rn((float)a.w, a.img_w)), 0.5f);
-  v = __fsub_rn(__fmul_rn(V, __fdiv_rn((float)a.h, a.img_h)), 0.5f);
-  return inside;
-}
-
-struct Tap {
-  int o00, o01, o10, o11;   // clamped offsets inside one (h,w) plane
-  float w00, w01, w10, w11; // bilinear weights, 0 for taps outside the map (padding_mode='zeros')
-};
-
-__global__ void __launch_bounds__(256) camera_project_kernel(ProjArgs a) {
-  __shared__ Tap taps[kCellsPerBlock][kMaxCams];
-  __shared__ int cam_of[kCellsPerBlock][kMaxCams];
-  __shared__ int n_vis[kCellsPerBlock];
-
-  const int b = blockIdx.y;
-  const int cell0 = blockIdx.x * kCellsPerBlock;
-  const int HW = a.H * a.W;
+__global__ void __launch_bounds__(256) bilinear_resize_staged_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                     long long planes, int h, int w, int H, int W) {
+  extern __shared__ __align__(128) uint8_t rs_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(rs_smem);                 // [2]
+  ResizeAxis* xtab = reinterpret_cast<ResizeAxis*>(rs_smem + 16);        // [W]
+  ResizeAxis* ytab = xtab + W;                                           // [H]
+  const int plane = h * w;
+  float* buf = reinterpret_cast<float*>(rs_smem + ((16 + (size_t)(W + H) * sizeof(ResizeAxis) + 127) & ~(size_t)127));  // [2][plane]
   const int tid = threadIdx.x;
-  const int t = a.T == 1 ? 0 : b;
-
-  // stage 1: per-cell tap table (64 cells x n_cam), visible cameras compacted in camera order
-  if (tid < kCellsPerBlock) {
-    const int cell = cell0 + tid;
-    int nv = 0;
-    if (cell < HW) {
-      const int iy = cell / a.W, ix = cell % a.W;
-      for (int cam = 0; cam < a.n_cam; ++cam) {
-        const float* Kc = a.K + ((size_t)t * a.n_cam + cam) * 9;
-        const float* Ec = a.E + ((size_t)t * a.n_cam + cam) * 12;
-        float u, v;
-        const bool vis = project_cell(a, Kc, Ec, ix, iy, u, v);
-        if (a.uv_valid && (a.T != 1 || b == 0)) {
-          float* o = a.uv_valid + (((size_t)t * HW + cell) * a.n_cam + cam) * 3;
-          o[0] = u; o[1] = v; o[2] = vis ? 1.0f : 0.0f;
-        }
-        if (vis) {
-          const float fx = floorf(u), fy = floorf(v);
-          const int x0 = (int)fx, y0 = (int)fy;
-          const float ax = __fsub_rn(u, fx), ay = __fsub_rn(v, fy);  // weight of the +1 tap
-          const float bx = __fsub_rn(__fadd_rn(fx, 1.0f), u), by = __fsub_rn(__fadd_rn(fy, 1.0f), v);
-          const bool x0ok = x0 >= 0 && x0 < a.w, x1ok = x0 + 1 >= 0 && x0 + 1 < a.w;
-          const bool y0ok = y0 >= 0 && y0 < a.h, y1ok = y0 + 1 >= 0 && y0 + 1 < a.h;
-          const int cx0 = min(max(x0, 0), a.w - 1), cx1 = min(max(x0 + 1, 0), a.w - 1);
-          const int cy0 = min(max(y0, 0), a.h - 1), cy1 = min(max(y0 + 1, 0), a.h - 1);
-          Tap tp;
-          tp.o00 = cy0 * a.w + cx0; tp.o01 = cy0 * a.w + cx1;
-          tp.o10 = cy1 * a.w + cx0; tp.o11 = cy1 * a.w + cx1;
-          tp.w00 = (x0ok && y0ok) ? __fmul_rn(bx, by) : 0.0f;
-          tp.w01 = (x1ok && y0ok) ? __fmul_rn(ax, by) : 0.0f;
-          tp.w10 = (x0ok && y1ok) ? __fmul_rn(bx, ay) : 0.0f;
-          tp.w11 = (x1ok && y1ok) ? __fmul_rn(ax, ay) : 0.0f;
-          taps[tid][nv] = tp;
-          cam_of[tid][nv] = cam;
-          ++nv;
-        }
-      }
-    }
-    n_vis[tid] = nv;
+  const float sy = __fdiv_rn((float)h, (float)H), sx = __fdiv_rn((float)w, (float)W);
+  for (int i = tid; i < W; i += blockDim.x) resize_coord(i, sx, w, xtab[i].i0, xtab[i].i1, xtab[i].l0, xtab[i].l1);
+  for (int i = tid; i < H; i += blockDim.x) {
+    ResizeAxis r;
+    resize_coord(i, sy, h, r.i0, r.i1, r.l0, r.l1);
+    r.i0 *= w;   // row offsets
+    r.i1 *= w;
+    ytab[i] = r;
+  }
+  if (tid == 0) {
+    mbarrier_init(&full[0], 1);
+    mbarrier_init(&full[1], 1);
+    mbarrier_init_fence();
   }
   __syncthreads();
-
-  // stage 2: lanes <-> cells (coalesced canvas writes), warps stride over channels
-  const int lane_cell = tid & (kCellsPerBlock - 1);
-  const int cgroup = tid / kCellsPerBlock;              // 0..3
-  constexpr int kGroups = 256 / kCellsPerBlock;
-  const int cell = cell0 + lane_cell;
-  if (cell >= HW) return;
-  const int nv = n_vis[lane_cell];
-  const size_t plane = (size_t)a.h * a.w;
-  const float* fb = a.feats + (size_t)b * a.n_cam * a.C * plane;
-  float* ob = a.out + (size_t)b * a.C * HW + cell;
-  const float inv_den = (float)(nv > 0 ? nv : 1);
-  for (int c = cgroup; c < a.C; c += kGroups) {
-    float s = 0.0f;
-    for (int k = 0; k < nv; ++k) {
-      const Tap& tp = taps[lane_cell][k];
-      const float* src = fb + ((size_t)cam_of[lane_cell][k] * a.C + c) * plane;
-      float val = __fmul_rn(tp.w00, __ldg(src + tp.o00));
-      val = __fadd_rn(val, __fmul_rn(tp.w01, __ldg(src + tp.o01)));
-      val = __fadd_rn(val, __fmul_rn(tp.w10, __ldg(src + tp.o10)));
-      val = __fadd_rn(val, __fmul_rn(tp.w11, __ldg(src + tp.o11)));
-      s = __fadd_rn(s, val);
+  const uint32_t bytes = (uint32_t)plane * sizeof(float);
+  long long p = blockIdx.x;
+  if (tid == 0 && p < planes) {
+    mbarrier_expect_tx(&full[0], bytes);
+    bulk_copy_global_to_shared(buf, in + p * plane, bytes, &full[0]);
+  }
+  const int HW = H * W;
+  uint32_t parity[2] = {0, 0};
+  for (int s = 0; p < planes; p += gridDim.x, s ^= 1) {
+    const long long pn = p + gridDim.x;
+    // the other buffer was read in the previous trip; every thread passed the barrier at its end
+    if (tid == 0 && pn < planes) {
+      mbarrier_expect_tx(&full[s ^ 1], bytes);
+      bulk_copy_global_to_shared(buf + (size_t)(s ^ 1) * plane, in + pn * plane, bytes, &full[s ^ 1]);
     }
-    ob[(size_t)c * HW] = __fdiv_rn(s, inv_den);
+    mbarrier_wait(&full[s], parity[s]);
+    parity[s] ^= 1;
+    const float* src = buf + (size_t)s * plane;
+    float* dst = out + p * HW;
+    int x = tid % W, y = tid / W;
+    const int dx = blockDim.x % W, dy = blockDim.x / W;
+    for (int i = tid; i < HW; i += blockDim.x) {
+      const ResizeAxis cx = xtab[x], cy = ytab[y];
+      const float v00 = src[cy.i0 + cx.i0], v01 = src[cy.i0 + cx.i1];
+      const float v10 = src[cy.i1 + cx.i0], v11 = src[cy.i1 + cx.i1];
+      const float top = __fadd_rn(__fmul_rn(cx.l0, v00), __fmul_rn(cx.l1, v01));
+      const float bot = __fadd_rn(__fmul_rn(cx.l0, v10), __fmul_rn(cx.l1, v11));
+      dst[i] = __fadd_rn(__fmul_rn(cy.l0, top), __fmul_rn(cy.l1, bot));
+      x += dx;
+      y += dy;
+      if (x >= W) { x -= W; ++y; }
+    }
+    __syncthreads();   // buffer s may be refilled two trips from now, by the copy issued in the next one
   }
 }
 
@@ -266,24 +209,17 @@ extern "C" B200BEV_API int b200bev_camera_mean(const float* feats, int B, int n_
 extern "C" B200BEV_API int b200bev_bilinear_resize(const float* in, int B, int C, int h, int w, float* out, int H, int W, void* stream) {
   if (!in || !out || B <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
   const long long planes = (long long)B * C;
-  bilinear_resize_kernel<<<grid_for(planes * H * W, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, h, w, H, W);
-  return launch_status();
-}
-
-extern "C" B200BEV_API int b200bev_camera_project(const float* feats, int B, int n_cam, int C, int h, int w, const float* intrinsics,
-                                      const float* ego2cam, int T, float img_w, float img_h, float x_min, float y_min,
-                                      float voxel_x, float voxel_y, float z_plane, int W, int H, float* out,
-                                      float* uv_valid, void* stream) {
-  if (!feats || !intrinsics || !ego2cam || !out || B <= 0 || n_cam <= 0 || C <= 0 || h <= 0 || w <= 0 || W <= 0 || H <= 0)
-    return B200BEV_ERR_INVALID_ARGUMENT;
-  if (T != 1 && T != B) return B200BEV_ERR_INVALID_ARGUMENT;
-  if (!(img_w > 0.0f) || !(img_h > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
-  if (n_cam > kMaxCams || B > 65535) return B200BEV_ERR_UNSUPPORTED;
-  ProjArgs a{};
-  a.feats = feats; a.B = B; a.n_cam = n_cam; a.C = C; a.h = h; a.w = w;
-  a.K = intrinsics; a.E = ego2cam; a.T = T;
-  a.img_w = img_w; a.img_h = img_h; a.x_min = x_min; a.y_min = y_min; a.vx = voxel_x; a.vy = voxel_y; a.z_plane = z_plane;
-  a.W = W; a.H = H; a.out = out; a.uv_valid = uv_valid;
-  camera_project_kernel<<<dim3(ceil_div(H * W, kCellsPerBlock), B), 256, 0, (cudaStream_t)stream>>>(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long plane = (long long)h * w;
+  const size_t smem = ((16 + (size_t)(W + H) * sizeof(ResizeAxis) + 127) & ~(size_t)127) + 2 * (size_t)plane * sizeof(float);
+  // staged path: planes are whole 16-byte units, two of them (plus the tables) fit a quarter of an SM's shared memory
+  if (plane % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && smem <= 56 * 1024) {
+    if (smem > 48 * 1024)
+      B200BEV_CUDA_TRY(cudaFuncSetAttribute(bilinear_resize_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<long long>(planes, (long long)sm_count() * 4);
+    bilinear_resize_staged_kernel<<<grid, 256, smem, st>>>(in, out, planes, h, w, H, W);
+  } else {
+    bilinear_resize_kernel<<<grid_for(planes * H * W, 256), 256, 0, st>>>(in, out, planes, h, w, H, W);
+  }
   return launch_status();
 }

@@ -1,0 +1,433 @@
+// S2 (geometric form) — camera features -> BEV canvas by calibrated projection.
+//
+// north_star S2: "projects BEV cell centres through per-camera intrinsics/extrinsics and bilinearly
+// gathers ResNet-18 image features".  The reference has no geometric projection; the
+// arithmetic is the restatement in oracle/bev_oracle.py (project_cells / camera_project): pinhole
+// projection of the cell centre on the z = z_plane ground plane, grid_sample(align_corners=False,
+// padding_mode='zeros') taps, mean over the cameras that see the cell.  Calibration layout as written
+// by src/data_converter.py:110-117 (per camera: 3x3 intrinsic, ego->camera [R|t]).
+//
+// Two kernels compute the same bits:
+//
+//   camera_project_staged_kernel   the fast path.  The features are NCHW, so the rows of one (camera,
+//       channel) plane that any BEV cell samples form ONE contiguous byte range ("band": ground cells
+//       project below the horizon, ~40 % of the plane).  A persistent CTA per SM walks (frame, channel
+//       group) items; a producer thread streams the bands of the item's cameras into a shared-memory
+//       ring with cp.async.bulk (TMA 1-D) + mbarrier expect_tx, 16 consumer warps gather the bilinear
+//       taps out of shared memory.  Each consumer thread owns fixed cells (lane <-> consecutive cells),
+//       keeps their camera-visibility masks and accumulators in registers, reads the (u,v) table the
+//       CTA built once in shared memory, and writes every canvas value exactly once, coalesced.
+//       HBM sees only full-line sequential reads and coalesced writes.
+//   camera_project_gather_kernel   the general fallback (any shape): taps read straight from global
+//       memory, lanes <-> cells.
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+
+#include "async_copy.cuh"
+#include "common.cuh"
+
+namespace b200bev {
+namespace {
+
+constexpr int kMaxCams = 8;
+constexpr float kNearPlane = 0.1f;  // metres in front of the camera
+
+struct ProjArgs {
+  const float* feats;
+  int B, n_cam, C, h, w;
+  const float* K;   // (T,n_cam,3,3)
+  const float* E;   // (T,n_cam,3,4)
+  int T;
+  float img_w, img_h, x_min, y_min, vx, vy, z_plane;
+  int W, H;
+  float* out;
+  float* uv_valid;
+};
+
+// Feature-map coordinates (u,v) of BEV cell (ix,iy) in one camera; every operation is a single
+// correctly-rounded fp32 op in a fixed order so that numpy float32 reproduces it bit for bit.
+__device__ __forceinline__ bool project_cell(const ProjArgs& a, const float* __restrict__ Kc, const float* __restrict__ Ec,
+                                             int ix, int iy, float& u, float& v) {
+  const float X = __fadd_rn(a.x_min, __fmul_rn(__fadd_rn((float)ix, 0.5f), a.vx));
+  const float Y = __fadd_rn(a.y_min, __fmul_rn(__fadd_rn((float)iy, 0.5f), a.vy));
+  const float Z = a.z_plane;
+  float pc[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(Ec[r * 4 + 0], X), __fmul_rn(Ec[r * 4 + 1], Y)), __fmul_rn(Ec[r * 4 + 2], Z));
+    pc[r] = __fadd_rn(s, Ec[r * 4 + 3]);
+  }
+  const bool front = pc[2] > kNearPlane;
+  const float zs = front ? pc[2] : 1.0f;
+  const float xn = __fdiv_rn(pc[0], zs), yn = __fdiv_rn(pc[1], zs);
+  const float U = __fadd_rn(__fadd_rn(__fmul_rn(Kc[0], xn), __fmul_rn(Kc[1], yn)), Kc[2]);
+  const float V = __fadd_rn(__fadd_rn(__fmul_rn(Kc[3], xn), __fmul_rn(Kc[4], yn)), Kc[5]);
+  const bool inside = front && (U >= 0.0f) && (U < a.img_w) && (V >= 0.0f) && (V < a.img_h);
+  // pixel -> feature coordinate, grid_sample(align_corners=False): u = U * (w / img_w) - 0.5
+  u = __fsub_rn(__fmul_rn(U, __fdiv_rn((float)a.w, a.img_w)), 0.5f);
+  v = __fsub_rn(__fmul_rn(V, __fdiv_rn((float)a.h, a.img_h)), 0.5f);
+  return inside;
+}
+
+struct Tap {
+  int o00, o01, o10, o11;   // clamped offsets inside one (h,w) plane; o00 is the smallest, o11 the largest
+  float w00, w01, w10, w11; // bilinear weights, 0 for taps outside the map (padding_mode='zeros')
+};
+
+__device__ __forceinline__ Tap make_tap(float u, float v, int h, int w) {
+  const float fx = floorf(u), fy = floorf(v);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float ax = __fsub_rn(u, fx), ay = __fsub_rn(v, fy);  // weight of the +1 tap
+  const float bx = __fsub_rn(__fadd_rn(fx, 1.0f), u), by = __fsub_rn(__fadd_rn(fy, 1.0f), v);
+  const bool x0ok = x0 >= 0 && x0 < w, x1ok = x0 + 1 >= 0 && x0 + 1 < w;
+  const bool y0ok = y0 >= 0 && y0 < h, y1ok = y0 + 1 >= 0 && y0 + 1 < h;
+  const int cx0 = min(max(x0, 0), w - 1), cx1 = min(max(x0 + 1, 0), w - 1);
+  const int cy0 = min(max(y0, 0), h - 1), cy1 = min(max(y0 + 1, 0), h - 1);
+  Tap tp;
+  tp.o00 = cy0 * w + cx0; tp.o01 = cy0 * w + cx1;
+  tp.o10 = cy1 * w + cx0; tp.o11 = cy1 * w + cx1;
+  tp.w00 = (x0ok && y0ok) ? __fmul_rn(bx, by) : 0.0f;
+  tp.w01 = (x1ok && y0ok) ? __fmul_rn(ax, by) : 0.0f;
+  tp.w10 = (x0ok && y1ok) ? __fmul_rn(bx, ay) : 0.0f;
+  tp.w11 = (x1ok && y1ok) ? __fmul_rn(ax, ay) : 0.0f;
+  return tp;
+}
+
+// value of one camera at one cell: ((w00*v00 + w01*v01) + w10*v10) + w11*v11, each op rounded
+__device__ __forceinline__ float tap_value(const Tap& tp, const float* __restrict__ plane) {
+  float val = __fmul_rn(tp.w00, plane[tp.o00]);
+  val = __fadd_rn(val, __fmul_rn(tp.w01, plane[tp.o01]));
+  val = __fadd_rn(val, __fmul_rn(tp.w10, plane[tp.o10]));
+  val = __fadd_rn(val, __fmul_rn(tp.w11, plane[tp.o11]));
+  return val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optional table output (T, H*W, n_cam, 3): u, v, valid
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) camera_project_table_kernel(ProjArgs a) {
+  const int HW = a.H * a.W;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (cell >= HW) return;
+  const int iy = cell / a.W, ix = cell % a.W;
+  for (int cam = 0; cam < a.n_cam; ++cam) {
+    float u, v;
+    const bool vis = project_cell(a, a.K + ((size_t)t * a.n_cam + cam) * 9, a.E + ((size_t)t * a.n_cam + cam) * 12, ix, iy, u, v);
+    float* o = a.uv_valid + (((size_t)t * HW + cell) * a.n_cam + cam) * 3;
+    o[0] = u; o[1] = v; o[2] = vis ? 1.0f : 0.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fallback: gather straight from global memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kCellsPerBlock = 64;
+
+__global__ void __launch_bounds__(256) camera_project_gather_kernel(ProjArgs a) {
+  __shared__ Tap taps[kCellsPerBlock][kMaxCams];
+  __shared__ int cam_of[kCellsPerBlock][kMaxCams];
+  __shared__ int n_vis[kCellsPerBlock];
+
+  const int b = blockIdx.y;
+  const int cell0 = blockIdx.x * kCellsPerBlock;
+  const int HW = a.H * a.W;
+  const int tid = threadIdx.x;
+  const int t = a.T == 1 ? 0 : b;
+
+  // stage 1: per-cell tap table (64 cells x n_cam), visible cameras compacted in camera order
+  if (tid < kCellsPerBlock) {
+    const int cell = cell0 + tid;
+    int nv = 0;
+    if (cell < HW) {
+      const int iy = cell / a.W, ix = cell % a.W;
+      for (int cam = 0; cam < a.n_cam; ++cam) {
+        float u, v;
+        if (project_cell(a, a.K + ((size_t)t * a.n_cam + cam) * 9, a.E + ((size_t)t * a.n_cam + cam) * 12, ix, iy, u, v)) {
+          taps[tid][nv] = make_tap(u, v, a.h, a.w);
+          cam_of[tid][nv] = cam;
+          ++nv;
+        }
+      }
+    }
+    n_vis[tid] = nv;
+  }
+  __syncthreads();
+
+  // stage 2: lanes <-> cells (coalesced canvas writes), warps stride over channels
+  const int lane_cell = tid & (kCellsPerBlock - 1);
+  const int cgroup = tid / kCellsPerBlock;              // 0..3
+  constexpr int kGroups = 256 / kCellsPerBlock;
+  const int cell = cell0 + lane_cell;
+  if (cell >= HW) return;
+  const int nv = n_vis[lane_cell];
+  const size_t plane = (size_t)a.h * a.w;
+  const float* fb = a.feats + (size_t)b * a.n_cam * a.C * plane;
+  float* ob = a.out + (size_t)b * a.C * HW + cell;
+  const float den = (float)(nv > 0 ? nv : 1);
+  for (int c = cgroup; c < a.C; c += kGroups) {
+    float s = 0.0f;
+    for (int k = 0; k < nv; ++k) s = __fadd_rn(s, tap_value(taps[lane_cell][k], fb + ((size_t)cam_of[lane_cell][k] * a.C + c) * plane));
+    ob[(size_t)c * HW] = __fdiv_rn(s, den);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast path: bands staged in shared memory by the copy engine
+// ---------------------------------------------------------------------------------------------
+constexpr int kConsumers = 512;                 // 16 gather warps
+constexpr int kStagedThreads = kConsumers + 32; // + the producer warp
+constexpr int kMaxStages = 8;
+constexpr int kCtrlBytes = 1024;                // barriers, band bounds, calibration
+constexpr int kMaxSmemOptin = 232448;           // 227 KB
+
+struct StagedCtrl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  int n_entries;
+  int band_lo[kMaxCams];   // first / one-past-last float of the plane any visible cell taps
+  int band_hi[kMaxCams];
+  float K[kMaxCams * 9];
+  float E[kMaxCams * 12];
+};
+static_assert(sizeof(StagedCtrl) <= kCtrlBytes, "control block must fit its slot");
+
+template <int CPT, int CG>
+__global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kernel(ProjArgs a, int tab_cap, int ring_floats) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  StagedCtrl* ctrl = reinterpret_cast<StagedCtrl*>(smem);
+  float2* tab = reinterpret_cast<float2*>(smem + kCtrlBytes);                         // (u,v) of every visible (cell,camera)
+  float* ring = reinterpret_cast<float*>(smem + kCtrlBytes + (size_t)tab_cap * sizeof(float2));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = a.H * a.W;
+  const int plane = a.h * a.w;
+  const int n_groups = ceil_div(a.C, CG);
+  const long long items = (long long)a.B * n_groups;
+  const long long per = ceil_div64(items, (long long)gridDim.x);
+  long long it = per * blockIdx.x;
+  const long long it_end = min(items, it + per);
+  bool first_segment = true;
+
+  // One pass of this loop per calibration in use: the whole item range when the rig is shared (T == 1),
+  // one frame at a time when every frame brings its own.
+  while (it < it_end) {
+    const int b0 = (int)(it / n_groups);
+    const long long seg_end = a.T == 1 ? it_end : min(it_end, (long long)(b0 + 1) * n_groups);
+    const int t = a.T == 1 ? 0 : b0;
+
+    // ---- calibration, barriers ----
+    if (tid < a.n_cam * 9) ctrl->K[tid] = __ldg(a.K + (size_t)t * a.n_cam * 9 + tid);
+    if (tid >= 128 && tid < 128 + a.n_cam * 12) ctrl->E[tid - 128] = __ldg(a.E + (size_t)t * a.n_cam * 12 + tid - 128);
+    if (tid == 0) {
+      for (int s = 0; s < kMaxStages; ++s) {
+        if (!first_segment) { mbarrier_inval(&ctrl->full[s]); mbarrier_inval(&ctrl->empty[s]); }
+        mbarrier_init(&ctrl->full[s], 1);
+        mbarrier_init(&ctrl->empty[s], kConsumers / 32);
+      }
+      ctrl->n_entries = 0;
+      for (int c = 0; c < kMaxCams; ++c) { ctrl->band_lo[c] = INT_MAX; ctrl->band_hi[c] = 0; }
+      mbarrier_init_fence();
+    }
+    first_segment = false;
+    __syncthreads();
+
+    // ---- table: visibility masks and entry bases in registers, (u,v) in shared memory ----
+    uint32_t info[CPT];   // bits 0..7: cameras that see the cell; bits 8..31: index of the cell's first table entry
+    if (tid < kConsumers) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int cell = tid + j * kConsumers;
+        uint32_t vis = 0;
+        float us[kMaxCams], vs[kMaxCams];
+        if (cell < HW) {
+          const int iy = cell / a.W, ix = cell % a.W;
+#pragma unroll
+          for (int cam = 0; cam < kMaxCams; ++cam) {
+            us[cam] = 0.0f; vs[cam] = 0.0f;
+            if (cam < a.n_cam && project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, ix, iy, us[cam], vs[cam])) vis |= 1u << cam;
+          }
+        }
+        const int nv = __popc(vis);
+        const int base = nv ? atomicAdd(&ctrl->n_entries, nv) : 0;
+        info[j] = vis | ((uint32_t)base << 8);
+        int k = 0;
+#pragma unroll
+        for (int cam = 0; cam < kMaxCams; ++cam) {
+          const bool on = (vis >> cam) & 1u;
+          int lo = INT_MAX, hi = 0;
+          if (on) {
+            if (base + k < tab_cap) tab[base + k] = make_float2(us[cam], vs[cam]);
+            ++k;
+            const Tap tp = make_tap(us[cam], vs[cam], a.h, a.w);
+            lo = tp.o00;
+            hi = tp.o11 + 1;
+          }
+          if (cam < a.n_cam) {   // warp-uniform
+            lo = __reduce_min_sync(FULL_MASK, lo);
+            hi = __reduce_max_sync(FULL_MASK, hi);
+            if (lane == 0 && hi > 0) {
+              atomicMin(&ctrl->band_lo[cam], lo);
+              atomicMax(&ctrl->band_hi[cam], hi);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // bands are copied in 16-byte units: round to multiples of 4 floats (plane % 4 == 0, checked by the host)
+    int stage_floats = 4;
+    for (int cam = 0; cam < a.n_cam; ++cam) {
+      const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
+      if (hi > lo) stage_floats = max(stage_floats, hi - lo);
+    }
+    const int n_stages = min(kMaxStages, ring_floats / (CG * stage_floats));   // >= 2: the host sized the ring for two whole planes
+    uint32_t stage = 0, phase = 0;
+
+    if (warp == kConsumers / 32) {
+      // ================================ producer ================================
+      if (lane == 0) {
+        for (long long item = it; item < seg_end; ++item) {
+          const int b = (int)(item / n_groups);
+          const int g0 = (int)(item % n_groups) * CG;
+          const int ncg = min(CG, a.C - g0);
+          for (int cam = 0; cam < a.n_cam; ++cam) {
+            const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
+            if (hi <= lo) continue;   // no cell sees this camera
+            const uint32_t bytes = (uint32_t)(hi - lo) * sizeof(float);
+            mbarrier_wait(&ctrl->empty[stage], phase ^ 1);
+            mbarrier_expect_tx(&ctrl->full[stage], bytes * ncg);
+            const float* src = a.feats + (((size_t)b * a.n_cam + cam) * a.C + g0) * plane + lo;
+            float* dst = ring + (size_t)stage * CG * stage_floats;
+            for (int g = 0; g < ncg; ++g) bulk_copy_global_to_shared(dst + (size_t)g * stage_floats, src + (size_t)g * plane, bytes, &ctrl->full[stage]);
+            if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else {
+      // ================================ consumers ================================
+      float acc[CG][CPT];
+#pragma unroll
+      for (int g = 0; g < CG; ++g)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[g][j] = 0.0f;
+      for (long long item = it; item < seg_end; ++item) {
+        const int b = (int)(item / n_groups);
+        const int g0 = (int)(item % n_groups) * CG;
+        const int ncg = min(CG, a.C - g0);
+        for (int cam = 0; cam < a.n_cam; ++cam) {
+          const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
+          if (hi <= lo) continue;
+          mbarrier_wait(&ctrl->full[stage], phase);
+          const float* sb = ring + (size_t)stage * CG * stage_floats - lo;   // tap offsets are plane-relative
+          const uint32_t below = (1u << cam) - 1u;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            if ((info[j] >> cam) & 1u) {
+              const int idx = (int)(info[j] >> 8) + __popc(info[j] & below);
+              float2 uv;
+              if (idx < tab_cap) {
+                uv = tab[idx];
+              } else {   // table overflow (more visible pairs than the host budgeted for): recompute
+                const int cell = tid + j * kConsumers;
+                project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, cell % a.W, cell / a.W, uv.x, uv.y);
+              }
+              const Tap tp = make_tap(uv.x, uv.y, a.h, a.w);
+#pragma unroll
+              for (int g = 0; g < CG; ++g) acc[g][j] = __fadd_rn(acc[g][j], tap_value(tp, sb + (size_t)g * stage_floats));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbarrier_arrive(&ctrl->empty[stage]);
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+        }
+        // every canvas value written once; a warp writes 128 contiguous bytes per (channel, j)
+        float* ob = a.out + ((size_t)b * a.C + g0) * HW;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int cell = tid + j * kConsumers;
+          const int nv = __popc(info[j] & 0xffu);
+          const float den = (float)(nv > 0 ? nv : 1);
+#pragma unroll
+          for (int g = 0; g < CG; ++g) {
+            if (cell < HW && g < ncg) ob[(size_t)g * HW + cell] = __fdiv_rn(acc[g][j], den);
+            acc[g][j] = 0.0f;
+          }
+        }
+      }
+    }
+    it = seg_end;
+    if (it < it_end) __syncthreads();   // the table and the barriers are about to be rebuilt
+  }
+}
+
+// "gather" | "staged" | nullptr: B200BEV_PROJECT_IMPL forces one implementation (tests, experiments)
+const char* forced_impl() { return getenv("B200BEV_PROJECT_IMPL"); }
+
+}  // namespace
+}  // namespace b200bev
+
+using namespace b200bev;
+
+extern "C" B200BEV_API int b200bev_camera_project(const float* feats, int B, int n_cam, int C, int h, int w, const float* intrinsics,
+                                      const float* ego2cam, int T, float img_w, float img_h, float x_min, float y_min,
+                                      float voxel_x, float voxel_y, float z_plane, int W, int H, float* out,
+                                      float* uv_valid, void* stream) {
+  if (!feats || !intrinsics || !ego2cam || !out || B <= 0 || n_cam <= 0 || C <= 0 || h <= 0 || w <= 0 || W <= 0 || H <= 0)
+    return B200BEV_ERR_INVALID_ARGUMENT;
+  if (T != 1 && T != B) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (!(img_w > 0.0f) || !(img_h > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (n_cam > kMaxCams || B > 65535) return B200BEV_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProjArgs a{};
+  a.feats = feats; a.B = B; a.n_cam = n_cam; a.C = C; a.h = h; a.w = w;
+  a.K = intrinsics; a.E = ego2cam; a.T = T;
+  a.img_w = img_w; a.img_h = img_h; a.x_min = x_min; a.y_min = y_min; a.vx = voxel_x; a.vy = voxel_y; a.z_plane = z_plane;
+  a.W = W; a.H = H; a.out = out; a.uv_valid = uv_valid;
+  const long long HW = (long long)H * W;
+
+  if (uv_valid) {
+    camera_project_table_kernel<<<dim3((unsigned)ceil_div64(HW, 256), T), 256, 0, st>>>(a);
+    B200BEV_CUDA_TRY(cudaGetLastError());
+  }
+
+  // staged path: whole 16-byte units per band, every cell owned by one consumer thread, two full planes per
+  // channel of a group must fit the ring next to the table
+  const long long plane = (long long)h * w;
+  const bool small_grid = HW <= (long long)kConsumers * 5;
+  const int CG = small_grid ? 4 : 1;   // 20 cells per thread leave registers for one channel
+  bool staged = (plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0) && HW <= (long long)kConsumers * 20;
+  int tab_cap = 0, ring_bytes = 0;
+  if (staged) {
+    const long long two_stages = 2LL * CG * plane * (long long)sizeof(float);
+    const long long room = (long long)kMaxSmemOptin - kCtrlBytes - two_stages;
+    const long long want = ((HW * n_cam + 15) / 16) * 16;
+    const long long cap = std::min(want, (room / (long long)sizeof(float2)) / 16 * 16);
+    if (room <= 0 || cap < HW) staged = false;   // would recompute most projections per channel: not a fast path
+    else {
+      tab_cap = (int)cap;
+      ring_bytes = kMaxSmemOptin - kCtrlBytes - tab_cap * (int)sizeof(float2);
+    }
+  }
+  if (const char* f = forced_impl()) {
+    if (f[0] == 'g') staged = false;
+    else if (f[0] == 's' && !staged) return B200BEV_ERR_UNSUPPORTED;
+  }
+  if (staged) {
+    const long long items = (long long)B * ceil_div(C, CG);
+    const int grid = (int)std::min<long long>(items, sm_count());
+    const int ring_floats = ring_bytes / (int)sizeof(float);
+    if (small_grid) {
+      B200BEV_CUDA_TRY(cudaFuncSetAttribute(camera_project_staged_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+      camera_project_staged_kernel<5, 4><<<grid, kStagedThreads, kMaxSmemOptin, st>>>(a, tab_cap, ring_floats);
+    } else {
+      B200BEV_CUDA_TRY(cudaFuncSetAttribute(camera_project_staged_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+      camera_project_staged_kernel<20, 1><<<grid, kStagedThreads, kMaxSmemOptin, st>>>(a, tab_cap, ring_floats);
+    }
+  } else {
+    camera_project_gather_kernel<<<dim3(ceil_div((int)HW, kCellsPerBlock), B), 256, 0, st>>>(a);
+  }
+  return launch_status();
+}

@@ -97,6 +97,22 @@ def mlp_weights(seed: int, dims: Sequence[int], use_bn: bool = True) -> List[Dic
     return layers
 
 
+def fold_mlp(layers: Sequence[Dict[str, np.ndarray]]) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """Eval-mode BatchNorm folded into the k=1 convolutions, in float64 (the numpy twin of
+    ops.fold_batchnorm): W' = W*s, b' = (b - mean)*s + beta with s = gamma / sqrt(var + eps)."""
+    ws, bs = [], []
+    for lay in layers:
+        w = lay["weight"].astype(np.float64)
+        b = lay["bias"].astype(np.float64)
+        if "bn_var" in lay:
+            s = lay["bn_weight"].astype(np.float64) / np.sqrt(lay["bn_var"].astype(np.float64) + float(BN_EPS))
+            w = w * s[:, None]
+            b = (b - lay["bn_mean"].astype(np.float64)) * s + lay["bn_bias"].astype(np.float64)
+        ws.append(w)
+        bs.append(b)
+    return ws, bs
+
+
 def linear_weights(seed: int, c_in: int, c_out: int) -> Tuple[np.ndarray, np.ndarray]:
     g = _rng(seed)
     bound = 1.0 / np.sqrt(c_in)

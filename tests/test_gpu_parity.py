@@ -189,7 +189,14 @@ def test_camera_mean_odd_sizes(cuda):
     np.testing.assert_array_equal(ops.camera_mean(dev_t(y, cuda)).cpu().numpy(), orc.camera_mean(y))
 
 
-def test_camera_projection(cuda, golden):
+@pytest.fixture(params=["staged", "gather"])
+def project_impl(request, monkeypatch):
+    """Both camera_project kernels (TMA-staged bands / plain global gather) must give the same bits."""
+    monkeypatch.setenv("B200BEV_PROJECT_IMPL", request.param)
+    return request.param
+
+
+def test_camera_projection(cuda, golden, project_impl):
     g = golden("camera_bev")
     K, E = syn.camera_rig()
     feats = syn.camera_features(402, 1, n_cam=6, channels=8, h=57, w=100)
@@ -200,7 +207,7 @@ def test_camera_projection(cuda, golden):
     assert max_rel(canvas[0].cpu().numpy(), orc.camera_project(feats[0], g["project_table"], (50, 50))) < 1e-6
 
 
-def test_camera_projection_per_sample_rigs_and_big_grid(cuda):
+def test_camera_projection_per_sample_rigs_and_big_grid(cuda, project_impl):
     K, E = syn.camera_rig()
     E2 = E.copy()
     E2[:, :, 3] += np.float32(0.25)
@@ -212,6 +219,35 @@ def test_camera_projection_per_sample_rigs_and_big_grid(cuda):
         t = orc.project_cells(Ks[b], Es[b], (1600.0, 900.0), (28, 50), (100, 100), syn.PC_RANGE)
         np.testing.assert_array_equal(table[b].cpu().numpy(), t)
         assert max_rel(canvas[b].cpu().numpy(), orc.camera_project(feats[b], t, (100, 100))) < 1e-6
+
+
+def test_camera_projection_staged_equals_gather_full_size(cuda, monkeypatch):
+    """BASELINE-size features (6x512x57x100, 3 frames, ragged channel tail): the staged kernel and the
+    gather kernel agree bit for bit, and a blind camera / an all-blind rig give zeros, not garbage."""
+    K, E = syn.camera_rig()
+    g = torch.Generator(device=cuda).manual_seed(9)
+    feats = torch.relu(torch.randn((3, 6, 510, 57, 100), device=cuda, generator=g))
+    Kd, Ed = dev_t(K, cuda), dev_t(E, cuda)
+    outs = {}
+    for impl in ("staged", "gather"):
+        monkeypatch.setenv("B200BEV_PROJECT_IMPL", impl)
+        outs[impl] = ops.camera_project(feats, Kd, Ed, (1600.0, 900.0), (50, 50))
+        outs[impl + "_big"] = ops.camera_project(feats[:1, :, :37].contiguous(), Kd, Ed, (1600.0, 900.0), (100, 100))
+    assert torch.equal(outs["staged"], outs["gather"])
+    assert torch.equal(outs["staged_big"], outs["gather_big"])
+    assert float(outs["staged"].abs().max()) > 0
+    # camera 3 looks at the sky (pitch it up by 90 degrees): nothing on the ground plane projects into it
+    E_sky = E.copy()
+    E_sky[3, :, :3] = E[3, [2, 0, 1], :3]
+    E_far = E.copy()
+    E_far[:, 2, 3] = -1.0e6                      # every cell ends up behind every camera
+    for rig in (E_sky, E_far):
+        res = {}
+        for impl in ("staged", "gather"):
+            monkeypatch.setenv("B200BEV_PROJECT_IMPL", impl)
+            res[impl] = ops.camera_project(feats[:2, :, :9].contiguous(), Kd, dev_t(rig, cuda), (1600.0, 900.0), (50, 50))
+        assert torch.equal(res["staged"], res["gather"])
+    assert float(res["staged"].abs().max()) == 0.0
 
 
 # ------------------------------------------------------------------------------------------------ S3
