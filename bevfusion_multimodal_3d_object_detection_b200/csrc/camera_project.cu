@@ -13,7 +13,7 @@
 //       channel) plane that any BEV cell samples form ONE contiguous byte range ("band": ground cells
 //       project below the horizon, ~40 % of the plane).  A persistent CTA per SM walks (frame, channel
 //       group) items; a producer thread streams the bands of the item's cameras into a shared-memory
-//       ring with cp.async.bulk (TMA 1-D) + mbarrier expect_tx, 16 consumer warps gather the bilinear
+//       ring with cp.async.bulk (TMA 1-D) + mbarrier expect_tx, 15 consumer warps gather the bilinear
 //       taps out of shared memory.  Each consumer thread owns fixed cells (lane <-> consecutive cells),
 //       keeps their camera-visibility masks and accumulators in registers, reads the (u,v) table the
 //       CTA built once in shared memory, and writes every canvas value exactly once, coalesced.
@@ -103,6 +103,10 @@ __device__ __forceinline__ float tap_value(const Tap& tp, const float* __restric
   return val;
 }
 
+__device__ __forceinline__ uint32_t pack_offsets(const Tap& tp) {
+  return (uint32_t)tp.o00 | ((uint32_t)(tp.o01 - tp.o00) << 30) | ((uint32_t)(tp.o10 != tp.o00) << 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // optional table output (T, H*W, n_cam, 3): u, v, valid
 // ---------------------------------------------------------------------------------------------
@@ -176,50 +180,70 @@ __global__ void __launch_bounds__(256) camera_project_gather_kernel(ProjArgs a) 
 // ---------------------------------------------------------------------------------------------
 // fast path: bands staged in shared memory by the copy engine
 // ---------------------------------------------------------------------------------------------
-constexpr int kConsumers = 512;                 // 16 gather warps
+constexpr int kConsumers = 480;                 // 15 gather warps: with the producer warp 16 warps, 4 per scheduler -> 128 registers each
 constexpr int kStagedThreads = kConsumers + 32; // + the producer warp
-constexpr int kMaxStages = 8;
+constexpr int kCPT = 6;                         // cells per consumer thread
+constexpr int kPartCells = kConsumers * kCPT;   // cells one CTA owns at a time (2880); larger grids are cut into parts
+constexpr int kMaxStages = 16;
 constexpr int kCtrlBytes = 1024;                // barriers, band bounds, calibration
+constexpr int kEntryBytes = 20;                 // table entry: four tap weights + packed offsets
 constexpr int kMaxSmemOptin = 232448;           // 227 KB
 
 struct StagedCtrl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   int n_entries;
-  int band_lo[kMaxCams];   // first / one-past-last float of the plane any visible cell taps
+  int band_lo[kMaxCams];   // first / one-past-last float of the plane any visible cell of the part taps
   int band_hi[kMaxCams];
   float K[kMaxCams * 9];
   float E[kMaxCams * 12];
 };
 static_assert(sizeof(StagedCtrl) <= kCtrlBytes, "control block must fit its slot");
 
-template <int CPT, int CG>
-__global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kernel(ProjArgs a, int tab_cap, int ring_floats) {
+// Work item = (cell part, frame, group of CG channels); a CTA walks a contiguous range of items.
+template <int CG>
+__global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kernel(ProjArgs a, int n_parts, int part_cells, int tab_cap,
+                                                                                   int ring_floats) {
+  constexpr int CPT = kCPT;
   extern __shared__ __align__(128) uint8_t smem[];
   StagedCtrl* ctrl = reinterpret_cast<StagedCtrl*>(smem);
-  float2* tab = reinterpret_cast<float2*>(smem + kCtrlBytes);                         // (u,v) of every visible (cell,camera)
-  float* ring = reinterpret_cast<float*>(smem + kCtrlBytes + (size_t)tab_cap * sizeof(float2));
+  // table of every visible (cell, camera) pair: the four bilinear weights and the packed tap offsets
+  // (bits 0..29 offset of the top-left tap, bit 30: the right taps are one float on, bit 31: the lower taps one row on)
+  float4* wtab = reinterpret_cast<float4*>(smem + kCtrlBytes);
+  uint32_t* otab = reinterpret_cast<uint32_t*>(smem + kCtrlBytes + (size_t)tab_cap * sizeof(float4));
+  float* ring = reinterpret_cast<float*>(smem + kCtrlBytes + (size_t)tab_cap * kEntryBytes);
+  // scratch of the table build, aliased onto the (then idle) ring
+  int* hist = reinterpret_cast<int*>(ring);                               // [256] cells per visibility mask, then cursors
+  uint16_t* order = reinterpret_cast<uint16_t*>(hist + 256);              // [kPartCells] cells sorted by visibility mask
+  uint8_t* mask_of = reinterpret_cast<uint8_t*>(order + kPartCells);      // [kPartCells]
+  float2* uv_of = reinterpret_cast<float2*>(mask_of + kPartCells);        // [part cells][n_cam] (u,v), when it fits
+  constexpr int kScratchFixed = 256 * 4 + kPartCells * 3;                 // multiple of 8
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = a.H * a.W;
   const int plane = a.h * a.w;
   const int n_groups = ceil_div(a.C, CG);
-  const long long items = (long long)a.B * n_groups;
+  const long long per_part = (long long)a.B * n_groups;
+  const long long items = per_part * n_parts;
   const long long per = ceil_div64(items, (long long)gridDim.x);
   long long it = per * blockIdx.x;
   const long long it_end = min(items, it + per);
   bool first_segment = true;
 
-  // One pass of this loop per calibration in use: the whole item range when the rig is shared (T == 1),
-  // one frame at a time when every frame brings its own.
+  // One pass of this loop per (cell part, calibration) in use.
   while (it < it_end) {
-    const int b0 = (int)(it / n_groups);
-    const long long seg_end = a.T == 1 ? it_end : min(it_end, (long long)(b0 + 1) * n_groups);
+    const int part = (int)(it / per_part);
+    const int b0 = (int)((it % per_part) / n_groups);
+    const long long seg_end = a.T == 1 ? min(it_end, (long long)(part + 1) * per_part)
+                                       : min(it_end, (long long)part * per_part + (long long)(b0 + 1) * n_groups);
     const int t = a.T == 1 ? 0 : b0;
+    const int cell_lo = part * part_cells;
+    const int n_cells = min(part_cells, HW - cell_lo);
 
     // ---- calibration, barriers ----
     if (tid < a.n_cam * 9) ctrl->K[tid] = __ldg(a.K + (size_t)t * a.n_cam * 9 + tid);
     if (tid >= 128 && tid < 128 + a.n_cam * 12) ctrl->E[tid - 128] = __ldg(a.E + (size_t)t * a.n_cam * 12 + tid - 128);
+    if (tid >= 256) hist[tid - 256] = 0;
     if (tid == 0) {
       for (int s = 0; s < kMaxStages; ++s) {
         if (!first_segment) { mbarrier_inval(&ctrl->full[s]); mbarrier_inval(&ctrl->empty[s]); }
@@ -233,49 +257,84 @@ __global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kerne
     first_segment = false;
     __syncthreads();
 
-    // ---- table: visibility masks and entry bases in registers, (u,v) in shared memory ----
-    uint32_t info[CPT];   // bits 0..7: cameras that see the cell; bits 8..31: index of the cell's first table entry
+    // ---- cells sorted by visibility mask: the 32 cells of a warp then (mostly) see the same camera, so a
+    //      gather step runs with all lanes on instead of a few ----
+    const bool uv_cached = kScratchFixed + (long long)n_cells * a.n_cam * (long long)sizeof(float2) <= (long long)ring_floats * 4;
     if (tid < kConsumers) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int cell = tid + j * kConsumers;
+      for (int i = tid; i < n_cells; i += kConsumers) {
+        const int cell = cell_lo + i, iy = cell / a.W, ix = cell % a.W;
         uint32_t vis = 0;
-        float us[kMaxCams], vs[kMaxCams];
-        if (cell < HW) {
-          const int iy = cell / a.W, ix = cell % a.W;
-#pragma unroll
-          for (int cam = 0; cam < kMaxCams; ++cam) {
-            us[cam] = 0.0f; vs[cam] = 0.0f;
-            if (cam < a.n_cam && project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, ix, iy, us[cam], vs[cam])) vis |= 1u << cam;
-          }
+        for (int cam = 0; cam < a.n_cam; ++cam) {
+          float u, v;
+          if (project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, ix, iy, u, v)) vis |= 1u << cam;
+          if (uv_cached) uv_of[i * a.n_cam + cam] = make_float2(u, v);
         }
-        const int nv = __popc(vis);
-        const int base = nv ? atomicAdd(&ctrl->n_entries, nv) : 0;
-        info[j] = vis | ((uint32_t)base << 8);
-        int k = 0;
-#pragma unroll
-        for (int cam = 0; cam < kMaxCams; ++cam) {
-          const bool on = (vis >> cam) & 1u;
-          int lo = INT_MAX, hi = 0;
-          if (on) {
-            if (base + k < tab_cap) tab[base + k] = make_float2(us[cam], vs[cam]);
-            ++k;
-            const Tap tp = make_tap(us[cam], vs[cam], a.h, a.w);
-            lo = tp.o00;
-            hi = tp.o11 + 1;
-          }
-          if (cam < a.n_cam) {   // warp-uniform
-            lo = __reduce_min_sync(FULL_MASK, lo);
-            hi = __reduce_max_sync(FULL_MASK, hi);
-            if (lane == 0 && hi > 0) {
-              atomicMin(&ctrl->band_lo[cam], lo);
-              atomicMax(&ctrl->band_hi[cam], hi);
-            }
-          }
-        }
+        mask_of[i] = (uint8_t)vis;
+        atomicAdd(&hist[vis], 1);
       }
     }
     __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 256 bins, 8 per lane
+      int v[8], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { v[k] = hist[lane * 8 + k]; sum += v[k]; }
+      int run = warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { hist[lane * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    if (tid < kConsumers)
+      for (int i = tid; i < n_cells; i += kConsumers) order[atomicAdd(&hist[mask_of[i]], 1)] = (uint16_t)i;
+    __syncthreads();
+
+    // ---- table: visibility masks, entry bases, cell ids and mean factors in registers; taps in shared memory ----
+    uint32_t info[CPT];   // bits 0..7: cameras that see the cell; bits 8..31: index of the cell's first table entry
+    int cell_of[CPT];     // cell owned in slot j, -1 if none
+    float scale[CPT];     // 1/n for n = 0, 1 or a power of two cameras (exact); 0 = "needs the IEEE division"
+    if (tid < kConsumers) {
+      int lo_r[kMaxCams], hi_r[kMaxCams];
+#pragma unroll
+      for (int cam = 0; cam < kMaxCams; ++cam) { lo_r[cam] = INT_MAX; hi_r[cam] = 0; }
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int slot = tid + j * kConsumers;
+        const int i = slot < n_cells ? (int)order[slot] : -1;
+        const int cell = i >= 0 ? cell_lo + i : -1;
+        cell_of[j] = cell;
+        const uint32_t vis = i >= 0 ? (uint32_t)mask_of[i] : 0u;
+        const int nv = __popc(vis);
+        const int base = nv ? atomicAdd(&ctrl->n_entries, nv) : 0;
+        info[j] = vis | ((uint32_t)base << 8);
+        scale[j] = nv <= 1 ? 1.0f : ((nv & (nv - 1)) == 0 ? __fdiv_rn(1.0f, (float)nv) : 0.0f);
+        int k = 0;
+#pragma unroll
+        for (int cam = 0; cam < kMaxCams; ++cam) {
+          if ((vis >> cam) & 1u) {
+            float2 uv;
+            if (uv_cached) uv = uv_of[i * a.n_cam + cam];
+            else project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, cell % a.W, cell / a.W, uv.x, uv.y);
+            const Tap tp = make_tap(uv.x, uv.y, a.h, a.w);
+            if (base + k < tab_cap) {
+              wtab[base + k] = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
+              otab[base + k] = pack_offsets(tp);
+            }
+            ++k;
+            lo_r[cam] = min(lo_r[cam], tp.o00);
+            hi_r[cam] = max(hi_r[cam], tp.o11 + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int cam = 0; cam < kMaxCams; ++cam) {
+        const int lo = __reduce_min_sync(FULL_MASK, lo_r[cam]);
+        const int hi = __reduce_max_sync(FULL_MASK, hi_r[cam]);
+        if (lane == 0 && hi > 0) {
+          atomicMin(&ctrl->band_lo[cam], lo);
+          atomicMax(&ctrl->band_hi[cam], hi);
+        }
+      }
+    }
+    __syncthreads();   // table complete; the scratch on the ring is dead from here on
 
     // bands are copied in 16-byte units: round to multiples of 4 floats (plane % 4 == 0, checked by the host)
     int stage_floats = 4;
@@ -283,19 +342,52 @@ __global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kerne
       const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
       if (hi > lo) stage_floats = max(stage_floats, hi - lo);
     }
-    const int n_stages = min(kMaxStages, ring_floats / (CG * stage_floats));   // >= 2: the host sized the ring for two whole planes
+    const int n_stages = min(kMaxStages, ring_floats / (CG * stage_floats));   // >= 1: the host sized the ring for CG whole planes
     uint32_t stage = 0, phase = 0;
 
-    if (warp == kConsumers / 32) {
+    if (ctrl->n_entries > tab_cap) {
+      // More visible (cell, camera) pairs than the table holds (cameras overlapping almost everywhere): this
+      // part is gathered straight from global memory, cell by cell — same arithmetic, no staging.
+      if (tid < kConsumers) {
+        for (long long item = it; item < seg_end; ++item) {
+          const long long r = item % per_part;
+          const int b = (int)(r / n_groups);
+          const int g0 = (int)(r % n_groups) * CG;
+          const int ncg = min(CG, a.C - g0);
+          for (int slot = tid; slot < n_cells; slot += kConsumers) {
+            const int cell = cell_lo + (int)order[slot];
+            float sum[CG];
+#pragma unroll
+            for (int g = 0; g < CG; ++g) sum[g] = 0.0f;
+            int nv = 0;
+            for (int cam = 0; cam < a.n_cam; ++cam) {
+              float u, v;
+              if (!project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, cell % a.W, cell / a.W, u, v)) continue;
+              ++nv;
+              const Tap tp = make_tap(u, v, a.h, a.w);
+              const float* pl = a.feats + (((size_t)b * a.n_cam + cam) * a.C + g0) * plane;
+#pragma unroll
+              for (int g = 0; g < CG; ++g)
+                if (g < ncg) sum[g] = __fadd_rn(sum[g], tap_value(tp, pl + (size_t)g * plane));
+            }
+            const float den = (float)(nv > 0 ? nv : 1);
+#pragma unroll
+            for (int g = 0; g < CG; ++g)
+              if (g < ncg) a.out[((size_t)b * a.C + g0 + g) * HW + cell] = __fdiv_rn(sum[g], den);
+          }
+        }
+      }
+    } else if (warp == kConsumers / 32) {
       // ================================ producer ================================
       if (lane == 0) {
         for (long long item = it; item < seg_end; ++item) {
-          const int b = (int)(item / n_groups);
-          const int g0 = (int)(item % n_groups) * CG;
+          const long long r = item % per_part;
+          const int b = (int)(r / n_groups);
+          const int g0 = (int)(r % n_groups) * CG;
           const int ncg = min(CG, a.C - g0);
           for (int cam = 0; cam < a.n_cam; ++cam) {
             const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
-            if (hi <= lo) continue;   // no cell sees this camera
+            if (hi <= lo) continue;   // no cell of the part sees this camera
             const uint32_t bytes = (uint32_t)(hi - lo) * sizeof(float);
             mbarrier_wait(&ctrl->empty[stage], phase ^ 1);
             mbarrier_expect_tx(&ctrl->full[stage], bytes * ncg);
@@ -314,8 +406,9 @@ __global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kerne
 #pragma unroll
         for (int j = 0; j < CPT; ++j) acc[g][j] = 0.0f;
       for (long long item = it; item < seg_end; ++item) {
-        const int b = (int)(item / n_groups);
-        const int g0 = (int)(item % n_groups) * CG;
+        const long long r = item % per_part;
+        const int b = (int)(r / n_groups);
+        const int g0 = (int)(r % n_groups) * CG;
         const int ncg = min(CG, a.C - g0);
         for (int cam = 0; cam < a.n_cam; ++cam) {
           const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
@@ -327,32 +420,43 @@ __global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kerne
           for (int j = 0; j < CPT; ++j) {
             if ((info[j] >> cam) & 1u) {
               const int idx = (int)(info[j] >> 8) + __popc(info[j] & below);
-              float2 uv;
-              if (idx < tab_cap) {
-                uv = tab[idx];
-              } else {   // table overflow (more visible pairs than the host budgeted for): recompute
-                const int cell = tid + j * kConsumers;
-                project_cell(a, ctrl->K + cam * 9, ctrl->E + cam * 12, cell % a.W, cell / a.W, uv.x, uv.y);
-              }
-              const Tap tp = make_tap(uv.x, uv.y, a.h, a.w);
+              const float4 wt = wtab[idx];
+              const uint32_t po = otab[idx];
+              const float* p00 = sb + (po & 0x3fffffffu);
+              const int dx = (int)((po >> 30) & 1u), dy = (po >> 31) ? a.w : 0;
 #pragma unroll
-              for (int g = 0; g < CG; ++g) acc[g][j] = __fadd_rn(acc[g][j], tap_value(tp, sb + (size_t)g * stage_floats));
+              for (int g = 0; g < CG; ++g) {
+                const float* pl = p00 + (size_t)g * stage_floats;
+                float val = __fmul_rn(wt.x, pl[0]);
+                val = __fadd_rn(val, __fmul_rn(wt.y, pl[dx]));
+                val = __fadd_rn(val, __fmul_rn(wt.z, pl[dy]));
+                val = __fadd_rn(val, __fmul_rn(wt.w, pl[dy + dx]));
+                acc[g][j] = __fadd_rn(acc[g][j], val);
+              }
             }
           }
           __syncwarp();
           if (lane == 0) mbarrier_arrive(&ctrl->empty[stage]);
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
-        // every canvas value written once; a warp writes 128 contiguous bytes per (channel, j)
+        // every canvas value written once; cells of equal visibility are runs of neighbours, so a warp's
+        // stores fall into a few contiguous stretches
         float* ob = a.out + ((size_t)b * a.C + g0) * HW;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-          const int cell = tid + j * kConsumers;
-          const int nv = __popc(info[j] & 0xffu);
-          const float den = (float)(nv > 0 ? nv : 1);
+          // mean over the cameras that see the cell: s / n.  n = 1 is the common case and a power of two
+          // divides exactly by multiplication; only n = 3, 5, 6, 7 takes the IEEE division.
+          float sc = scale[j];
+          if (sc == 0.0f) {
+            const float den = (float)__popc(info[j] & 0xffu);
+#pragma unroll
+            for (int g = 0; g < CG; ++g) acc[g][j] = __fdiv_rn(acc[g][j], den);
+            sc = 1.0f;
+          }
+          float* oj = ob + cell_of[j];
 #pragma unroll
           for (int g = 0; g < CG; ++g) {
-            if (cell < HW && g < ncg) ob[(size_t)g * HW + cell] = __fdiv_rn(acc[g][j], den);
+            if (cell_of[j] >= 0 && g < ncg) oj[(size_t)g * HW] = __fmul_rn(acc[g][j], sc);
             acc[g][j] = 0.0f;
           }
         }
@@ -393,39 +497,45 @@ extern "C" B200BEV_API int b200bev_camera_project(const float* feats, int B, int
     B200BEV_CUDA_TRY(cudaGetLastError());
   }
 
-  // staged path: whole 16-byte units per band, every cell owned by one consumer thread, two full planes per
-  // channel of a group must fit the ring next to the table
+  // staged path: bands are whole 16-byte units.  Shared-memory budget: the table holds up to ~1.25 visible
+  // cameras per owned cell (a surround rig overlaps little; pairs beyond that are recomputed on the fly), the
+  // ring gets the rest and must hold at least one stage of CG whole planes — bands are normally well under
+  // half a plane, which is what gives the ring its depth.
   const long long plane = (long long)h * w;
-  const bool small_grid = HW <= (long long)kConsumers * 5;
-  const int CG = small_grid ? 4 : 1;   // 20 cells per thread leave registers for one channel
-  bool staged = (plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0) && HW <= (long long)kConsumers * 20;
-  int tab_cap = 0, ring_bytes = 0;
+  const int n_parts = (int)ceil_div64(HW, kPartCells);
+  const int part_cells = (int)ceil_div64(HW, n_parts);
+  bool staged = (plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0) && plane < (1LL << 30) && n_parts <= 64;
+  int CG = 0, tab_cap = 0, ring_bytes = 0;
   if (staged) {
-    const long long two_stages = 2LL * CG * plane * (long long)sizeof(float);
-    const long long room = (long long)kMaxSmemOptin - kCtrlBytes - two_stages;
-    const long long want = ((HW * n_cam + 15) / 16) * 16;
-    const long long cap = std::min(want, (room / (long long)sizeof(float2)) / 16 * 16);
-    if (room <= 0 || cap < HW) staged = false;   // would recompute most projections per channel: not a fast path
-    else {
-      tab_cap = (int)cap;
-      ring_bytes = kMaxSmemOptin - kCtrlBytes - tab_cap * (int)sizeof(float2);
+    const long long want = std::min<long long>((long long)part_cells * n_cam, part_cells + part_cells / 4 + 64);
+    tab_cap = (int)((want + 15) / 16 * 16);
+    ring_bytes = kMaxSmemOptin - kCtrlBytes - tab_cap * kEntryBytes;
+    int cg_max = 4;
+    if (const char* e = getenv("B200BEV_PROJECT_CG")) {   // experiments: 1, 2 or 4
+      const int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4) cg_max = v;
     }
+    const long long scratch = 256 * 4 + kPartCells * 3;   // table-build scratch aliased onto the ring
+    for (int cg = cg_max; cg >= 1; cg >>= 1)
+      if ((long long)cg * plane * (long long)sizeof(float) <= ring_bytes && scratch <= ring_bytes) { CG = cg; break; }
+    if (CG == 0) staged = false;
   }
   if (const char* f = forced_impl()) {
     if (f[0] == 'g') staged = false;
     else if (f[0] == 's' && !staged) return B200BEV_ERR_UNSUPPORTED;
   }
   if (staged) {
-    const long long items = (long long)B * ceil_div(C, CG);
+    const long long items = (long long)n_parts * B * ceil_div(C, CG);
     const int grid = (int)std::min<long long>(items, sm_count());
     const int ring_floats = ring_bytes / (int)sizeof(float);
-    if (small_grid) {
-      B200BEV_CUDA_TRY(cudaFuncSetAttribute(camera_project_staged_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-      camera_project_staged_kernel<5, 4><<<grid, kStagedThreads, kMaxSmemOptin, st>>>(a, tab_cap, ring_floats);
-    } else {
-      B200BEV_CUDA_TRY(cudaFuncSetAttribute(camera_project_staged_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-      camera_project_staged_kernel<20, 1><<<grid, kStagedThreads, kMaxSmemOptin, st>>>(a, tab_cap, ring_floats);
-    }
+    auto launch = [&](auto kernel) -> int {
+      B200BEV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+      kernel<<<grid, kStagedThreads, kMaxSmemOptin, st>>>(a, n_parts, part_cells, tab_cap, ring_floats);
+      return B200BEV_OK;
+    };
+    const int rc = CG == 4 ? launch(camera_project_staged_kernel<4>) : CG == 2 ? launch(camera_project_staged_kernel<2>)
+                                                                              : launch(camera_project_staged_kernel<1>);
+    if (rc != B200BEV_OK) return rc;
   } else {
     camera_project_gather_kernel<<<dim3(ceil_div((int)HW, kCellsPerBlock), B), 256, 0, st>>>(a);
   }

@@ -42,8 +42,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--grid", type=int, default=50)
     args = ap.parse_args()
     F = args.frames
+    G = args.grid
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     if args.what in ("mlp", "all"):
         lw, lb = orc.fold_layers(syn.mlp_weights(101, syn.LIDAR_DIMS))
@@ -76,13 +78,13 @@ def main():
         Kd, Ed = to(K), to(E)
         mean = ops.camera_mean(feats)
         x = mean.view(F * 2, 256, 57, 100)[:F]
-        table = orc.project_cells(K, E, (1600.0, 900.0), (57, 100), (50, 50), syn.PC_RANGE)
+        table = orc.project_cells(K, E, (1600.0, 900.0), (57, 100), (G, G), syn.PC_RANGE)
         hits = int(table[:, :, 2].sum())
         for name, fn, by in (
             ("camera_mean", lambda: ops.camera_mean(feats), F * 4.0 * 512 * 5700 * 7),
-            ("bilinear_resize", lambda: ops.bilinear_resize(x, (50, 50)), F * 4.0 * 256 * (5700 + 2500)),
-            ("camera_project", lambda: ops.camera_project(feats, Kd, Ed, (1600.0, 900.0), (50, 50)),
-             F * 4.0 * 512 * (min(6 * 5700, 4 * hits) + 2500)),
+            ("bilinear_resize", lambda: ops.bilinear_resize(x, (G, G)), F * 4.0 * 256 * (5700 + G * G)),
+            ("camera_project", lambda: ops.camera_project(feats, Kd, Ed, (1600.0, 900.0), (G, G)),
+             F * 4.0 * 512 * (min(6 * 5700, 4 * hits) + G * G)),
         ):
             med, best = timeit(fn, reps=20)
             print(f"{name:34s} median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)

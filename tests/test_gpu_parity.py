@@ -250,6 +250,31 @@ def test_camera_projection_staged_equals_gather_full_size(cuda, monkeypatch):
     assert float(res["staged"].abs().max()) == 0.0
 
 
+def test_camera_projection_overlapping_cameras(cuda, monkeypatch):
+    """Means over 3 and 6 cameras (not powers of two: the IEEE-division branch) and a rig whose cameras all
+    see most of the grid, which overflows the staged kernel's shared-memory table and takes its
+    gather-from-global segment path.  All against the oracle, and staged == gather bit for bit."""
+    K, E = syn.camera_rig()
+    E3 = E.copy()
+    E3[1] = E[0]
+    E3[2] = E[0]                                  # the forward wedge is seen by cameras 0, 1 and 2
+    down = np.array([[0.0, -1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)   # looking straight down
+    t = -(down @ np.array([0.0, 0.0, 100.0], dtype=np.float32))
+    E6 = np.stack([np.concatenate([down, t[:, None]], axis=1)] * 6).astype(np.float32)
+    feats = syn.camera_features(404, 2, n_cam=6, channels=7, h=57, w=100)
+    d = dev_t(feats, cuda)
+    for rig, bev, min_overlap in ((E3, (50, 50), 3), (E6, (50, 50), 6), (E6, (100, 100), 6)):
+        table = orc.project_cells(K, rig, (1600.0, 900.0), (57, 100), bev, syn.PC_RANGE)
+        assert int(table[:, :, 2].sum(axis=1).max()) == min_overlap
+        res = {}
+        for impl in ("staged", "gather"):
+            monkeypatch.setenv("B200BEV_PROJECT_IMPL", impl)
+            res[impl] = ops.camera_project(d, dev_t(K, cuda), dev_t(rig, cuda), (1600.0, 900.0), bev)
+        assert torch.equal(res["staged"], res["gather"])
+        for b in range(2):
+            assert max_rel(res["staged"][b].cpu().numpy(), orc.camera_project(feats[b], table, bev)) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------------ S3
 def test_nms_and_topk_vs_golden(cuda, golden):
     g = golden("centernet_decode")
