@@ -451,7 +451,7 @@ def run_b200_arm(args):
     if rank == 0:
         line = {
             "metric": "bev_encode_decode_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "warmup_run": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": workload_config(args, F), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": sum(launches_per_step.values()) * args.steps, "clocks": clock_summary, "kernels": kernels,

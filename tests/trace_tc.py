@@ -20,7 +20,12 @@ pts = torch.from_numpy(syn.lidar_batch(42, 32)).to(dev)
 for _ in range(3):
     ops.pointnet_encode(pts, blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc)
 torch.cuda.synchronize()
-os.environ["B200BEV_TC_TRACE"] = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace.txt"
+out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace.txt"
+os.environ["B200BEV_TC_TRACE"] = out
 ops.pointnet_encode(pts, blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc)
+torch.cuda.synchronize()
+_, perm, off = ops.bin_sort(pts, 50, 50)
+os.environ["B200BEV_TC_TRACE"] = out.replace(".txt", "_cell.txt")
+ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=2500, precision=_lib.BF16_TENSOR, tc_params=tc)
 torch.cuda.synchronize()
 print("trace written")
