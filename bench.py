@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the fp32-path side measurement (for ncu launch lists)")
     return ap.parse_args()
 
 
@@ -72,6 +73,17 @@ def load_peaks():
         except Exception:
             pass
     return dict(FALLBACK_PEAKS) | {"source": "fallback"}
+
+
+def load_traffic(stage: str, dtype: str, frames: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json); None when no capture matches this workload."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        entry = json.loads(p.read_text())[f"{stage}:{dtype}"]
+        return float(entry["bytes_per_launch"]) if int(entry["frames"]) == frames else None
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -363,7 +375,7 @@ def run_b200_arm(args):
     dominant = max(stage_names, key=lambda n: stage_ms[n])
     roofline = dict(kernels[dominant])
     roofline.pop("ms")
-    roofline.update({"kernel": dominant, "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"
+    roofline.update({"kernel": dominant, "traffic": load_traffic(dominant, dtype, F), "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"
                      if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)"})
     if dominant == "pointnet_encode" and dtype == "f32":
         fp32_peak = 148 * 128 * 2 * 1965.0 * 1e6 / 1e12
@@ -373,7 +385,7 @@ def run_b200_arm(args):
 
     # ---- the fp32-parity path of the dominant stage, for the record (outside the timed region) ----
     alt = None
-    if dtype == "bf16":
+    if dtype == "bf16" and not args.no_alt:
         def f32_mlp():
             _, perm, off = ops.bin_sort(lidar, BEV_W, BEV_H)
             return ops.pointnet_encode(lidar, blob, dims, perm=perm, offsets=off, n_cells=BEV_H * BEV_W)

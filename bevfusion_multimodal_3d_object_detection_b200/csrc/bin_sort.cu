@@ -17,7 +17,17 @@
 //              the lanes that hit the same cell, the group takes `count` consecutive slots from the
 //              cell's cursor in shared memory — a stable counting sort, no global atomics, no
 //              second pass over the points, deterministic output.
+//
+// bin_sort_ranked_kernel is the fast form of the same sort (bin_sort_kernel stays as the any-size
+// fallback).  The serial phase-3 walk is gone: in phase 1 every warp walks its OWN contiguous
+// sub-slice in point order and, with the same match.any grouping, gives each point its rank among
+// the points of (cell, CTA, warp) while counting into a per-warp 16-bit histogram; the scan of phase 2
+// then runs over (cell, CTA) with the eight per-warp counts of a cell fetched as ONE 16-byte
+// distributed-shared-memory read; and the placement is a fully parallel pass:
+//     perm[ base(cell, CTA) + sum of counts(cell, CTA, warps before mine) + rank ] = point.
 #include <cooperative_groups.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -180,6 +190,191 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_kernel(BinArgs a) {
   cluster.sync();
 }
 
+// ---------------------------------------------------------------------------------------------
+// ranked form: all warps rank their own sub-slice in phase 1, placement is parallel
+// ---------------------------------------------------------------------------------------------
+struct RankedArgs {
+  BinArgs a;
+  int NW;   // warps (sub-slices) per CTA that walk points: 8, 4, 2 or 1
+  int sub;  // points per sub-slice, multiple of 32, <= 65535
+};
+
+// sum of the 16-bit counts [0, upto) of one cell row (NW entries, 2*NW bytes, naturally aligned)
+__device__ __forceinline__ uint32_t row_prefix(const uint16_t* row, int NW, int upto) {
+  uint32_t s = 0;
+  if (NW == 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(row);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (2 * k < upto) s += w[k] & 0xffffu;
+      if (2 * k + 1 < upto) s += w[k] >> 16;
+    }
+  } else {
+    for (int k = 0; k < upto; ++k) s += row[k];
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs ra) {
+  const BinArgs& a = ra.a;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = kBinThreads / 32;
+  const int HW = a.W * a.H;
+  const int nb = HW + 1;
+  const int NW = ra.NW;
+
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* base = smem;                    // nb: start of (cell, this CTA) in perm
+  uint32_t* cta_tot = base + nb;            // kMaxCluster
+  uint32_t* wsum = cta_tot + kMaxCluster;   // nwarps
+  uint16_t* whist = reinterpret_cast<uint16_t*>(smem + (((size_t)nb + kMaxCluster + nwarps + 3) & ~(size_t)3));  // [nb][NW]
+  uint16_t* rank_s = whist + (((size_t)nb * NW + 7) & ~(size_t)7);   // [slice]
+  int32_t* cells_s = reinterpret_cast<int32_t*>(rank_s + (((size_t)a.slice + 1) & ~(size_t)1));  // [slice] if cached
+
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(whist);
+    const int nz = (nb * NW + 1) / 2;
+    for (int i = tid; i < nz; i += kBinThreads) z[i] = 0;
+  }
+  __syncthreads();
+
+  const int start = rank * a.slice;
+  const int end = min(a.N, start + a.slice);
+  const float* pts = a.pts + (size_t)b * a.N * a.C;
+  int32_t* cell_out = a.cell + (size_t)b * a.N;
+
+  // ---- phase 1: cell ids, rank within (cell, warp), per-warp histogram; sub-slice walked in order ----
+  if (warp < NW) {
+    const bool vec2 = ((a.C & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.pts) & 7) == 0);
+    const int s0 = start + warp * ra.sub;
+    const int s1 = min(end, s0 + ra.sub);
+    uint16_t* wh = whist + warp;
+    constexpr int U = 4;
+    for (int i0 = s0; i0 < s1; i0 += 32 * U) {
+      float x[U], y[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 32 + lane;
+        x[u] = 0.0f;
+        y[u] = 0.0f;
+        if (i < s1) {
+          if (vec2) {
+            const float2 xy = __ldg(reinterpret_cast<const float2*>(pts + (size_t)i * a.C));
+            x[u] = xy.x;
+            y[u] = xy.y;
+          } else {
+            x[u] = __ldg(pts + (size_t)i * a.C);
+            y[u] = __ldg(pts + (size_t)i * a.C + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 32 + lane;
+        const bool valid = i < s1;
+        const int c = cell_of(x[u], y[u], a);
+        const int bin = c < 0 ? HW : c;
+        const unsigned peers = __match_any_sync(FULL_MASK, valid ? bin : (0x40000000 | lane));
+        const int rk = __popc(peers & lanemask_lt());
+        const uint32_t cur = valid ? wh[(size_t)bin * NW] : 0u;
+        __syncwarp();
+        if (valid && rk == 0) wh[(size_t)bin * NW] = (uint16_t)(cur + (uint32_t)__popc(peers));
+        __syncwarp();
+        if (valid) {
+          cell_out[i] = c;
+          rank_s[i - start] = (uint16_t)(cur + (uint32_t)rk);
+          if (a.cache_cells) cells_s[i - start] = c;
+        }
+      }
+    }
+  }
+  cluster.sync();
+
+  // ---- phase 2: exclusive scan over (cell, CTA), cells dealt out to the CTAs ----
+  auto count_of = [&](int q, int bin) -> uint32_t {
+    const uint16_t* row = cluster.map_shared_rank(whist, q) + (size_t)bin * NW;
+    return row_prefix(row, NW, NW);
+  };
+  const int share = ceil_div(nb, CL);
+  const int lo = rank * share, hi = min(nb, lo + share);
+  uint32_t cnt_keep[kMaxCluster];   // counts of this thread's first bin (the common case: share <= 256)
+  {
+    uint32_t mine = 0;
+    for (int bin = lo + tid; bin < hi; bin += kBinThreads) {
+      const bool first = bin < lo + kBinThreads;
+#pragma unroll
+      for (int q = 0; q < kMaxCluster; ++q) {
+        const uint32_t c = q < CL ? count_of(q, bin) : 0u;
+        if (first) cnt_keep[q] = c;
+        mine += c;
+      }
+    }
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, d);
+    if (lane == 0) wsum[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < nwarps; ++w) t += wsum[w];
+      for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cta_tot, q)[rank] = t;
+    }
+  }
+  cluster.sync();
+  uint32_t carry = 0;
+  for (int q = 0; q < rank; ++q) carry += cta_tot[q];
+  int32_t* offsets = a.offsets + (size_t)b * nb;
+  for (int bs = lo; bs < hi; bs += kBinThreads) {
+    const int bin = bs + tid;
+    const bool ok = bin < hi;
+    uint32_t cnt[kMaxCluster];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int q = 0; q < kMaxCluster; ++q) {
+      cnt[q] = (bs == lo) ? (ok ? cnt_keep[q] : 0u) : ((ok && q < CL) ? count_of(q, bin) : 0u);
+      tot += cnt[q];
+    }
+    const uint32_t incl = (uint32_t)warp_incl_scan((int)tot, lane);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < nwarps; ++w) {
+      const uint32_t v = wsum[w];
+      if (w < warp) before += v;
+      total += v;
+    }
+    if (ok) {
+      uint32_t run = carry + before + incl - tot;
+      offsets[bin] = (int32_t)run;
+#pragma unroll
+      for (int q = 0; q < kMaxCluster; ++q) {
+        if (q < CL) {
+          cluster.map_shared_rank(base, q)[bin] = run;
+          run += cnt[q];
+        }
+      }
+    }
+    carry += total;
+    __syncthreads();
+  }
+  cluster.sync();   // every base[] is written; no remote access after this point
+
+  // ---- phase 3: parallel placement ----
+  int32_t* perm = a.perm + (size_t)b * a.N;
+  for (int i = start + tid; i < end; i += kBinThreads) {
+    const int li = i - start;
+    const int c = a.cache_cells ? cells_s[li] : cell_out[i];
+    const int bin = c < 0 ? HW : c;
+    const int w = li / ra.sub;
+    const uint32_t pos = base[bin] + row_prefix(whist + (size_t)bin * NW, NW, w) + rank_s[li];
+    perm[pos] = i;
+  }
+}
+
 }  // namespace
 }  // namespace b200bev
 
@@ -200,20 +395,11 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
   int CL = 1;
   while (CL < kMaxCluster && N / (CL * 2) >= 1024) CL *= 2;
   a.slice = ceil_div(ceil_div(N, CL), 32) * 32;
-  const size_t fixed = ((size_t)W * H + 1 + kMaxCluster + kBinThreads / 32) * sizeof(uint32_t);
-  size_t smem = fixed + (size_t)a.slice * sizeof(int32_t);
-  a.cache_cells = 1;
-  if (smem > 200 * 1024) {
-    a.cache_cells = 0;
-    smem = fixed;
-  }
-  if (smem > 48 * 1024)
-    B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t nb = (size_t)W * H + 1;
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(CL, B, 1);
   cfg.blockDim = dim3(kBinThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -222,6 +408,41 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+
+  // ranked form: the widest per-warp histogram that fits shared memory (and 16-bit counts)
+  const char* force = getenv("B200BEV_BINSORT");
+  const bool legacy = force && force[0] == 'l';
+  if (!legacy) {
+    const size_t kLimit = 220 * 1024;
+    for (int NW = kBinThreads / 32; NW >= 1; NW >>= 1) {
+      const int sub = ceil_div(ceil_div(a.slice, NW), 32) * 32;
+      if (sub > 65535) break;   // halving NW only makes it larger
+      const size_t head = ((nb + kMaxCluster + kBinThreads / 32 + 3) & ~(size_t)3) * sizeof(uint32_t);
+      const size_t hist = ((nb * NW + 7) & ~(size_t)7) * sizeof(uint16_t);
+      const size_t ranks = (((size_t)a.slice + 1) & ~(size_t)1) * sizeof(uint16_t);
+      size_t smem = head + hist + ranks;
+      if (smem > kLimit) continue;
+      a.cache_cells = smem + (size_t)a.slice * sizeof(int32_t) <= 100 * 1024 ? 1 : 0;   // keep two CTAs per SM
+      if (a.cache_cells) smem += (size_t)a.slice * sizeof(int32_t);
+      RankedArgs ra{a, NW, sub};
+      if (smem > 48 * 1024)
+        B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg.dynamicSmemBytes = smem;
+      B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, bin_sort_ranked_kernel, ra));
+      return launch_status();
+    }
+  }
+
+  const size_t fixed = (nb + kMaxCluster + kBinThreads / 32) * sizeof(uint32_t);
+  size_t smem = fixed + (size_t)a.slice * sizeof(int32_t);
+  a.cache_cells = 1;
+  if (smem > 200 * 1024) {
+    a.cache_cells = 0;
+    smem = fixed;
+  }
+  if (smem > 48 * 1024)
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cfg.dynamicSmemBytes = smem;
   B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, bin_sort_kernel, a));
   return launch_status();
 }
