@@ -34,6 +34,10 @@
 
 #include "common.cuh"
 
+#ifndef B200BEV_TC_TRIP
+#define B200BEV_TC_TRIP 0   // 0: per-mode default; 1 or 2 forces the ring pairs per MMA trip (experiments)
+#endif
+
 namespace b200bev {
 namespace {
 
@@ -44,11 +48,29 @@ constexpr int kStagesCell = 8;      // cell mode gives 66 KB to the transposing 
 constexpr int kTStride = 132;       // floats per channel row of the tile: 16-B aligned, conflict-free both ways
 constexpr int kEpiThreads = 512;     // 16 epilogue warps: 4 per TMEM lane quadrant
 constexpr int kTcThreads = 64 + kEpiThreads;
-constexpr int kStagesPerTile = 1 + 4 + 16 + 64;
+constexpr int kPairBytes = 2 * kStageBytes;
+// Weight stream of one tile, in PAIRS of 16 KB stages (one 32 KB bulk copy, one full/empty barrier each):
+// layer 2 has a single stage, so its pair carries a padding stage that nothing reads.
+constexpr int kPairsPerTile = 1 + 2 + 8 + 32;
+constexpr int kStagesPerTile = 2 * kPairsPerTile;   // 86: 85 weight stages + 1 padding stage
 constexpr int kBiasFloats = 128 + 256 + 512 + 1024;
 constexpr int kMaxCin = 16;
 
 constexpr uint32_t kColAct1 = 0, kColAct2 = 64, kColAct4 = 0, kColAct3 = 256, kColAcc0 = 256, kColAcc1 = 384;
+// third accumulator: the upper half of the act4 region, free until layer 4 writes its chunks 2 and 3
+constexpr uint32_t kColAccX = 128;
+constexpr int kEpiWarps = kEpiThreads / 32;
+
+// Accumulator of chunk c of network layer 2 + `layer` (0..3); the MMA issuer and the epilogue must agree.
+//   layer 2: acc1.  layer 3: acc1, accX.  layer 4: acc1, accX, acc1, acc1 (accX is overwritten by the
+//   activations of chunks 2 and 3).  layer 5: acc0 / acc1 alternating (act3, which acc0 aliases, is dead).
+__device__ __forceinline__ int acc_buffer(int layer, int c) {
+  if (layer == 3) return c & 1;
+  if (layer == 0) return 1;
+  if (layer == 1) return c == 0 ? 1 : 2;
+  return c == 1 ? 2 : 1;
+}
+__device__ __forceinline__ uint32_t acc_column(int buf) { return buf == 0 ? kColAcc0 : buf == 1 ? kColAcc1 : kColAccX; }
 
 struct TcArgs {
   const float* pts;
@@ -64,7 +86,8 @@ struct TcArgs {
   long long total_tiles;
   int cluster;             // CTAs per cluster sharing each weight stage by multicast (1, 2 or 4)
   unsigned long long* trace;  // debug only (B200BEV_TC_TRACE): clock stamps of CTA 0, else nullptr
-  int debug;                  // debug only (B200BEV_TC_DEBUG): bit 0 = skip the weight copies after the first tile
+  int debug;                  // debug only (B200BEV_TC_DEBUG): bit 0 = skip the weight copies after the first tile,
+                              // bit 1 = skip the layer-5 epilogue, bit 2 = issue MMAs without waiting for weights
 };
 
 // Debug timeline: (event id << 48 | clock) appended by one thread per role of CTA 0.
@@ -76,8 +99,9 @@ __device__ __forceinline__ void trace_ev(const TcArgs& a, int& idx, int base, un
   }
 }
 
+constexpr int kImageStages = kStagesPerTile;
 __host__ __device__ inline size_t tc_blob_bytes(int C) {
-  return (size_t)kStagesPerTile * kStageBytes + ((size_t)C * 64 + 64 + kBiasFloats) * sizeof(float);
+  return (size_t)kImageStages * kStageBytes + ((size_t)C * 64 + 64 + kBiasFloats) * sizeof(float);
 }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -219,19 +243,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   float* tile_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);   // CELL: [128 channels][kTStride]
   int* cid_s = reinterpret_cast<int*>(tile_s + (CELL ? 128 * kTStride : 0));        // CELL: cell id of each tile slot
   uint32_t* endmask_s = reinterpret_cast<uint32_t*>(cid_s + (CELL ? 128 : 0));      // CELL: run-end flags, one word per warp
-  float* bias_s = reinterpret_cast<float*>(endmask_s + (CELL ? 4 : 0));             // L2 | L3 | L4 | L5
+  int* scan_s = reinterpret_cast<int*>(endmask_s + (CELL ? 4 : 0));                 // CELL: [0,4) warp maxima, [4,6) "more cells" flags
+  float* bias_s = reinterpret_cast<float*>(scan_s + (CELL ? 8 : 0));                // L2 | L3 | L4 | L5
   float* w1_s = bias_s + kBiasFloats;                                               // W1^T (C x 64), then b1 (64)
   uint64_t* bars = reinterpret_cast<uint64_t*>(w1_s + kMaxCin * 64 + 64);
-  uint64_t* full = bars;                    // [kStages]  weights landed
-  uint64_t* empty = bars + kStages;         // [kStages]  MMAs that read the stage retired
-  uint64_t* acc_full = empty + kStages;     // [2]        accumulator complete
-  uint64_t* acc_empty = acc_full + 2;       // [2]        accumulator drained by the epilogue
-  uint64_t* act_ready = acc_empty + 2;      // [1]        next layer's A operand is in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
+  uint64_t* full = bars;                    // [kStages/2 used] weights of a pair of ring slots landed
+  uint64_t* empty = bars + kStages;         // [kStages/2 used] MMAs that read the pair retired
+  uint64_t* acc_full = empty + kStages;     // [3]        accumulator complete
+  uint64_t* acc_empty = acc_full + 3;       // [3]        accumulator drained by the epilogue (one arrival per warp)
+  uint64_t* act_ready = acc_empty + 3;      // [4]        K-pair kp (128 channels) of the next A operand is in TMEM (one arrival per warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const float* tail = reinterpret_cast<const float*>(a.tc + (size_t)kStagesPerTile * kStageBytes);
+  const float* tail = reinterpret_cast<const float*>(a.tc + (size_t)kImageStages * kStageBytes);
   for (int i = tid; i < a.C * 64 + 64; i += kTcThreads) w1_s[i] = __ldg(tail + i);
   for (int i = tid; i < kBiasFloats; i += kTcThreads) bias_s[i] = __ldg(tail + a.C * 64 + 64 + i);
   if (tid == 0) {
@@ -239,11 +264,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], a.cluster);   // every CTA of the cluster must have retired the stage
     }
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], kEpiThreads);
-    mbar_init(&acc_empty[1], kEpiThreads);
-    mbar_init(act_ready, kEpiThreads);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -266,27 +291,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 
   if (warp == 0) {
     // ================================ producer ================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        for (int s = 0; s < kStagesPerTile; ++s) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if ((a.debug & 1) && t > t_begin) {   // experiment: how fast is the kernel when weights cost nothing?
-            mbar_arrive(&full[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          mbar_expect_tx(&full[stage], kStageBytes);
-          if (a.cluster == 1) {
-            bulk_copy_g2s(ring + (size_t)stage * kStageBytes, a.tc + (size_t)s * kStageBytes, kStageBytes, &full[stage]);
+    // The stream moves PAIRS of stages: one 32 KB bulk copy and one full/empty barrier per pair of ring slots
+    // (one thread can start a bulk copy only every ~380 clk whatever its size, tests/cuda/bulk_rate.cu, and every
+    // barrier the MMA warp polls costs it issue time).
+    // The whole warp runs the loop and one elected lane issues, as in the MMA warp: issued from a single
+    // divergent lane, every UBLKCP sat in an ELECT + 4x R2UR.BROADCAST waterfall and cost ~380 clk.
+    {
+      const long long n_pairs = (t_end - t_begin) * kPairsPerTile;
+      constexpr int kRingPairs = kStages / 2;
+      const bool free_weights = (a.debug & 1) != 0;   // experiment: how fast is the kernel when weights cost nothing?
+      const bool single_cta = a.cluster == 1;
+      const uint32_t part = kPairBytes / a.cluster, part_off = cta_rank * part;
+      uint32_t pair = 0, phase = 0;
+      int img = 0;   // pair within the tile's stream
+      for (long long j = 0; j < n_pairs; ++j) {
+        mbar_wait(&empty[pair], phase ^ 1);
+        uint8_t* dst = ring + (size_t)pair * kPairBytes;
+        const uint8_t* src = a.tc + (size_t)img * kPairBytes;
+        if (elect_one()) {
+          if (free_weights && j >= kPairsPerTile) {
+            mbar_arrive(&full[pair]);
           } else {
-            // this CTA fetches its 1/cluster slice of the stage and multicasts it to all peers
-            const uint32_t part = kStageBytes / a.cluster, o = cta_rank * part;
-            bulk_copy_g2s_multicast(ring + (size_t)stage * kStageBytes + o, a.tc + (size_t)s * kStageBytes + o, part,
-                                    &full[stage], cta_mask);
+            mbar_expect_tx(&full[pair], kPairBytes);
+            if (single_cta) bulk_copy_g2s(dst, src, kPairBytes, &full[pair]);
+            // else: this CTA fetches its 1/cluster slice of the pair and multicasts it to all peers
+            else bulk_copy_g2s_multicast(dst + part_off, src + part_off, part, &full[pair], cta_mask);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++img == kPairsPerTile) img = 0;
+        if (++pair == kRingPairs) { pair = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -300,58 +334,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(FULL_MASK, tmem, 0);                        // provably uniform
       const uint32_t ring_u = __shfl_sync(FULL_MASK, smem_u32(ring), 0);
-      uint32_t stage = 0, phase = 0, act_phase = 0;
+      constexpr int kRingPairs = kStages / 2;
+      // ring pairs per trip: two where the ring is deep enough (global mode, 6 pairs); with the 4 pairs the
+      // cell mode has room for, a trip that needs half the ring at once stalls the weight stream
+      constexpr int kTrip = (B200BEV_TC_TRIP) ? (B200BEV_TC_TRIP) : (CELL ? 1 : 2);
+      uint32_t pair = 0, phase = 0;   // ring pair slot and the parity of its round
+      uint32_t act_phase = 0;         // bit kp: parity of the next phase of act_ready[kp]
       uint32_t acc_parity = 0;  // bit b: parity of the next use of accumulator b
       int tr = 0;
+      const bool wait_weights = !(a.debug & 4);      // debug bit 2: issue without waiting for the weights
+      const bool single_cta = a.cluster == 1;
+      // 8 MMAs over one ring pair (K = 128): D[d_addr] (+)= A[a_addr .. a_addr+64 columns) . B[pair]^T
+      auto issue_pair = [&](uint32_t d_addr, uint32_t a_addr, uint32_t pr, bool first, bool half) {
+        const uint64_t bdesc0 = make_b_desc(ring_u + pr * kPairBytes);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + s * 8, bdesc0 + (uint64_t)(s * 2), idesc, !(first && s == 0));
+        if (!half) {
+          const uint64_t bdesc1 = make_b_desc(ring_u + pr * kPairBytes + kStageBytes);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + 32 + s * 8, bdesc1 + (uint64_t)(s * 2), idesc, 1u);
+        }
+        if (single_cta) tc_commit(&empty[pr]);
+        else tc_commit_multicast(&empty[pr], cta_mask);
+      };
       for (long long t = t_begin; t < t_end; ++t) {
 #pragma unroll 1
         for (int layer = 0; layer < 4; ++layer) {  // network layers 2..5
-          const int kchunks = 1 << layer;          // K / 64
-          const int nchunks = 1 << layer;          // N / 128
+          const int kpairs = layer == 0 ? 1 : (1 << layer) >> 1;   // K / 128 (layer 2: half a pair)
+          const int nchunks = 1 << layer;                           // N / 128
           const uint32_t a_col = layer == 0 ? kColAct1 : layer == 1 ? kColAct2 : layer == 2 ? kColAct3 : kColAct4;
-          if (lane == 0) trace_ev(a, tr, kTraceMma, 0x100 + layer);            // waiting for the A operand
-          mbar_wait(act_ready, act_phase);
-          act_phase ^= 1;
-          tc_fence_after();
-          if (lane == 0) trace_ev(a, tr, kTraceMma, 0x110 + layer);            // A operand ready
+          if (lane == 0) trace_ev(a, tr, kTraceMma, 0x100 + layer);            // first MMA of the layer
 #pragma unroll 1
           for (int c = 0; c < nchunks; ++c) {
-            const int buf = (layer == 3) ? (c & 1) : 1;
+            const int buf = acc_buffer(layer, c);
             mbar_wait(&acc_empty[buf], ((acc_parity >> buf) & 1) ^ 1);
             acc_parity ^= 1u << buf;
             tc_fence_after();
             if (lane == 0) trace_ev(a, tr, kTraceMma, 0x120 + layer * 8 + c);  // accumulator free, issuing
-            const uint32_t d_addr = tmem_u + (buf ? kColAcc1 : kColAcc0);
+            const uint32_t d_addr = tmem_u + acc_column(buf);
 #pragma unroll 1
-            for (int kc = 0; kc < kchunks; kc += 2) {
-              // two stages (8 MMAs = 512 clk of tensor work) per trip: the fixed cost of a trip (barrier
-              // poll, fence, descriptor arithmetic, commits: ~350 clk) no longer exceeds the work it issues
-              const bool two = kc + 1 < kchunks;
-              const uint32_t st0 = stage, ph0 = phase;
-              uint32_t st1 = stage + 1, ph1 = phase;
-              if (st1 == kStages) { st1 = 0; ph1 ^= 1; }
-              mbar_wait(&full[st0], ph0);
-              if (two) mbar_wait(&full[st1], ph1);
-              tc_fence_after();
-              const uint64_t bdesc0 = make_b_desc(ring_u + st0 * kStageBytes);
-              const uint64_t bdesc1 = make_b_desc(ring_u + st1 * kStageBytes);
-              const uint32_t a_addr = tmem_u + a_col + kc * 32;
-              if (elect_one()) {
-#pragma unroll
-                for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + s * 8, bdesc0 + (uint64_t)(s * 2), idesc, (kc | s) != 0);
-                if (a.cluster == 1) tc_commit(&empty[st0]);
-                else tc_commit_multicast(&empty[st0], cta_mask);
+            for (int kp = 0; kp < kpairs; kp += kTrip) {
+              // up to two ring pairs (16 MMAs = 1024 clk of tensor work) per trip: the issue side of a trip (barrier
+              // polls, fence, descriptor arithmetic in the uniform datapath, releases) must stay below the time the
+              // MMAs it issues take, or the tensor pipe starves
+              const bool two = kTrip == 2 && kp + 1 < kpairs;
+              uint32_t pr1 = pair + 1, ph1 = phase;
+              if (pr1 == kRingPairs) { pr1 = 0; ph1 ^= 1; }
+              // The A operand arrives chunk by chunk: K-pair kp of this layer is the 128 channels that chunk kp of
+              // the layer before produced, so the first chunk of a layer starts while the pipe still works on the
+              // previous layer's last chunks.  One barrier per K-pair index: on each of them production and
+              // consumption alternate strictly (a single barrier would let the epilogue get two phases ahead of
+              // this warp, which a parity wait cannot tell from zero phases ahead).
+              if (c == 0) {
+                mbar_wait(&act_ready[kp], (act_phase >> kp) & 1);
+                act_phase ^= 1u << kp;
                 if (two) {
-#pragma unroll
-                  for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + 32 + s * 8, bdesc1 + (uint64_t)(s * 2), idesc, 1u);
-                  if (a.cluster == 1) tc_commit(&empty[st1]);
-                  else tc_commit_multicast(&empty[st1], cta_mask);
+                  mbar_wait(&act_ready[kp + 1], (act_phase >> (kp + 1)) & 1);
+                  act_phase ^= 1u << (kp + 1);
                 }
-                if (kc + 2 >= kchunks) tc_commit(&acc_full[buf]);
+              }
+              if (wait_weights) {
+                mbar_wait(&full[pair], phase);
+                if (two) mbar_wait(&full[pr1], ph1);
+              }
+              tc_fence_after();
+              const uint32_t a_addr = tmem_u + a_col + kp * 64;
+              if (elect_one()) {
+                issue_pair(d_addr, a_addr, pair, kp == 0, layer == 0);
+                if (two) issue_pair(d_addr, a_addr + 64, pr1, false, false);
+                if (kp + kTrip >= kpairs) tc_commit(&acc_full[buf]);
               }
               __syncwarp();
-              if (two) { stage = st1; phase = ph1; }
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              if (two) { pair = pr1; phase = ph1; }
+              if (++pair == kRingPairs) { pair = 0; phase ^= 1; }
             }
             if (lane == 0) trace_ev(a, tr, kTraceMma, 0x160 + layer * 8 + c);  // chunk issued
           }
@@ -368,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     const int part = (warp - 2) >> 2;          // which quarter of the columns / of the tile's points this warp owns
     const int row = quad * 32 + lane;          // point within the tile = TMEM lane
     const uint32_t tm = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t full_phase[2] = {0, 0};
+    uint32_t full_phase = 0;                   // bit b: parity of the next completion of accumulator b
     // running maximum of the raw layer-5 accumulators of the current frame, one value per 128-channel chunk c:
     //   global mode: rmax[c] <-> channel c*128 + part*32 + lane (what the butterfly leaves in this lane)
     //   cell mode  : rmax[c] <-> channel c*128 + row, over the 32 tile slots [part*32, part*32+32) this thread walks
@@ -382,6 +437,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     bool have_pre = false;
     const int c_out = 1024;
     const float* b5 = bias_s + 128 + 256 + 512;
+    // cell mode, part 0 only: cell of the tile's first slot, carried from tile to tile, and the in-grid count
+    int c_carry = 0, n_in = 0;
+    bool carry_valid = false;
+
+    // one arrival per warp: every lane has fenced its tensor-memory accesses, __syncwarp orders them
+    // before lane 0's arrive (512 per-thread arrivals on one barrier word cost more than the work they guard)
+    auto warp_arrive = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    auto acc_wait = [&](int buf) {
+      mbar_wait(&acc_full[buf], (full_phase >> buf) & 1);
+      full_phase ^= 1u << buf;
+      tc_fence_after();
+    };
 
     auto flush = [&](int frame) {
       if (a.out_global == nullptr) return;
@@ -395,9 +466,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       }
     };
 
+    // the point of tile slot `slot_` of frame `f_` (zeros for a slot past the end of the frame)
+    auto load_point = [&](int f_, int slot_, float* x) {
+      const bool ok = slot_ < a.N;
+      int p_ = slot_;
+      if (CELL && ok) p_ = __ldg(a.perm + (size_t)f_ * a.N + slot_);
+      const float* src = a.pts + ((size_t)f_ * a.N + (ok ? p_ : 0)) * a.C;
+      if (vec4_points) {
+        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+#pragma unroll
+        for (int k = 4; k < kMaxCin; ++k) x[k] = 0.0f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxCin; ++k) x[k] = (k < a.C && ok) ? __ldg(src + k) : 0.0f;
+      }
+    };
+    // layer 1 on CUDA cores (K = C_in is 4): this part's 16 of the 64 channels of relu(W1 x + b1), as bf16 pairs.
+    // Weights and bias of a part are contiguous: 128-bit broadcast loads.
+    auto layer1 = [&](const float* x, uint32_t* packed) {
+      float acc[16];
+      {
+        const float4* bp = reinterpret_cast<const float4*>(w1_s + a.C * 64 + part * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b4 = bp[q];
+          acc[4 * q] = b4.x; acc[4 * q + 1] = b4.y; acc[4 * q + 2] = b4.z; acc[4 * q + 3] = b4.w;
+        }
+      }
+      auto add_k = [&](int k, float xk) {
+        const float4* wp = reinterpret_cast<const float4*>(w1_s + k * 64 + part * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wp[q];
+          acc[4 * q] = fmaf(w4.x, xk, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(w4.y, xk, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(w4.z, xk, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(w4.w, xk, acc[4 * q + 3]);
+        }
+      };
+      if (a.C == 4) {
+        add_k(0, x[0]); add_k(1, x[1]); add_k(2, x[2]); add_k(3, x[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxCin; ++k)
+          if (k < a.C) add_k(k, x[k]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) packed[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
+    };
+    // act1 -> TMEM [0,32) and tell the MMA warp.  Legal only while no MMA reads act4 (which aliases act1):
+    // before the first tile, or after the last layer-5 accumulator of the previous tile has completed.
+    auto publish_act1 = [&](const uint32_t* packed) {
+      TC_ST8(tm + kColAct1 + part * 8, packed);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      warp_arrive(&act_ready[0]);
+    };
+
     // (frame, tile-in-frame) of the running tile slot, advanced incrementally: one 64-bit division per
     // kernel instead of four per tile in each of the 16 warps
     int tf = (int)(t_begin / a.tiles_per_frame), tt = (int)(t_begin % a.tiles_per_frame);
+    {
+      // layer 1 of the first tile; every later tile's layer 1 is computed under the previous tile's layer 5
+      const bool dummy0 = t_begin >= a.total_tiles;
+      float x[kMaxCin];
+      load_point(dummy0 ? 0 : tf, dummy0 ? a.N : tt * kTileM + row, x);
+      uint32_t packed[8];
+      layer1(x, packed);
+      publish_act1(packed);
+    }
     for (long long t = t_begin; t < t_end; ++t) {
       const bool tracer = (tid == 64);
       if (tracer) trace_ev(a, tr, kTraceEpi, 0x200);          // tile start
@@ -407,95 +544,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       // the slot after this one, for the prefetch below
       int tf_next = tf, tt_next = tt + 1;
       if (tt_next == a.tiles_per_frame) { tt_next = 0; ++tf_next; }
-      if (f != cur_frame) {
+      const bool new_frame = f != cur_frame;
+      if (new_frame) {
         if (cur_frame >= 0) flush(cur_frame);
         cur_frame = f;
       }
       const int slot = s0 + row;                // position in input order (global) or in cell order (CELL)
       const bool valid = slot < a.N;            // a dummy tile has no valid slot
       const bool partial = s0 + kTileM > a.N;
-      int p = slot;
       if (CELL) {
-        // slot -> source point (every part needs it for layer 1) and cell id (part 0 looks it up for all)
-        if (valid) p = __ldg(a.perm + (size_t)f * a.N + slot);
+        // Cell id of every tile slot (part 0, 128 threads <-> 128 slots).  The slots are in cell order, so
+        // cid(slot) = largest c with offsets[c] <= slot: every cell that starts inside the tile drops its
+        // index at its first slot (atomicMax: of several cells starting at one slot, all but the last are
+        // empty), a prefix maximum fills the runs, and the cell of the last slot is carried to the next
+        // tile — one coalesced read of `offsets` per tile instead of a 12-step binary search per slot.
         if (part == 0) {
-          int cid = -1;
-          if (valid) {
-            const int32_t* foff = a.offsets + (size_t)f * (a.n_cells + 1);
-            if (slot < __ldg(foff + a.n_cells)) {   // in-grid points come first in perm
-              int lo = 0, hi = a.n_cells;           // largest c with offsets[c] <= slot
+          auto bar128 = [] { asm volatile("bar.sync 2, 128;" ::: "memory"); };
+          const int32_t* foff = a.offsets + (size_t)(f < 0 ? 0 : f) * (a.n_cells + 1);
+          if (!dummy && (new_frame || !carry_valid)) {
+            n_in = __ldg(foff + a.n_cells);       // in-grid points come first in perm
+            int lo = 0;
+            if (s0 > 0 && s0 < n_in) {            // a CTA that starts in the middle of a frame: search once
+              int hi = a.n_cells;
               while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (__ldg(foff + mid) <= slot) lo = mid; else hi = mid;
+                if (__ldg(foff + mid) <= s0) lo = mid; else hi = mid;
               }
-              cid = lo;
             }
+            c_carry = lo;
+            carry_valid = true;
           }
+          const bool in_grid = !dummy && s0 < n_in;   // uniform over the 128 threads
+          int v = -1;
+          if (in_grid) {
+            cid_s[row] = row == 0 ? c_carry : -1;
+            bar128();
+            int c_scan = c_carry, it = 0;
+            while (true) {
+              const int c = c_scan + row;
+              const int o = c < a.n_cells ? __ldg(foff + c) : 0x7fffffff;
+              if (o >= s0 && o < s0 + kTileM && o < n_in) atomicMax(&cid_s[o - s0], c);
+              if (row == kTileM - 1) scan_s[4 + (it & 1)] = (o < s0 + kTileM) && (c + 1 < a.n_cells);
+              bar128();
+              if (!scan_s[4 + (it & 1)]) break;
+              c_scan += kTileM;
+              ++it;
+            }
+            v = cid_s[row];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) v = max(v, __shfl_up_sync(FULL_MASK, v, d));   // -1 is the identity
+            if (lane == 31) scan_s[quad] = v;
+            bar128();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < quad) v = max(v, scan_s[q]);
+            c_carry = max(max(scan_s[0], scan_s[1]), max(scan_s[2], scan_s[3]));   // cell of the tile's last slot
+          }
+          const int cid = (in_grid && valid && slot < n_in) ? v : -1;
           cid_s[row] = cid;
-        }
-        epi_bar_sync();
-        if (part == 0) {
+          bar128();
           // run ends: one flag word per 32 slots.  The last slot of a word never carries a flag for a run
           // that goes on in the next word; the walker of that word hands such a run over with an atomic.
-          const int cid = cid_s[row];
           const int next = row < kTileM - 1 ? cid_s[row + 1] : -2;
           const unsigned ends = __ballot_sync(FULL_MASK, cid >= 0 && next != cid);
           if (lane == 0) endmask_s[quad] = ends;
         }
-        // endmask_s becomes visible to the walkers at the barrier after the first tile store below
-      }
-
-      // ---- layer 1 on CUDA cores (K = C_in is 4): act1 = relu(W1 x + b1) -> bf16 -> TMEM [0,32) ----
-      {
-        float x[kMaxCin];
-        const float* src = a.pts + ((size_t)f * a.N + (valid ? p : 0)) * a.C;
-        if (vec4_points) {
-          float4 v = xpre;   // fetched while the previous tile's layer 5 ran
-          if (!have_pre) v = valid ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-#pragma unroll
-          for (int k = 4; k < kMaxCin; ++k) x[k] = 0.0f;
-        } else {
-#pragma unroll
-          for (int k = 0; k < kMaxCin; ++k) x[k] = (k < a.C && valid) ? __ldg(src + k) : 0.0f;
-        }
-        // this part's 16 of the 64 channels; weights and bias of a part are contiguous: 128-bit broadcast loads
-        float acc[16];
-        {
-          const float4* bp = reinterpret_cast<const float4*>(w1_s + a.C * 64 + part * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b4 = bp[q];
-            acc[4 * q] = b4.x; acc[4 * q + 1] = b4.y; acc[4 * q + 2] = b4.z; acc[4 * q + 3] = b4.w;
-          }
-        }
-        auto add_k = [&](int k, float xk) {
-          const float4* wp = reinterpret_cast<const float4*>(w1_s + k * 64 + part * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 w4 = wp[q];
-            acc[4 * q] = fmaf(w4.x, xk, acc[4 * q]);
-            acc[4 * q + 1] = fmaf(w4.y, xk, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(w4.z, xk, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(w4.w, xk, acc[4 * q + 3]);
-          }
-        };
-        if (a.C == 4) {
-          add_k(0, x[0]); add_k(1, x[1]); add_k(2, x[2]); add_k(3, x[3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < kMaxCin; ++k)
-            if (k < a.C) add_k(k, x[k]);
-        }
-        uint32_t packed[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) packed[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
-        if (tracer) trace_ev(a, tr, kTraceEpi, 0x203);        // layer 1 computed
-        TC_ST8(tm + kColAct1 + part * 8, packed);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(act_ready);
-        if (tracer) trace_ev(a, tr, kTraceEpi, 0x201);        // layer 1 stored
+        // cid_s / endmask_s become visible to the walkers at the barrier after the first tile store of layer 5
       }
 
       // ---- layers 2..4: accumulator -> bias, ReLU, bf16 -> next A operand in TMEM ----
@@ -506,15 +620,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         const float* bl = bias_s + (layer == 0 ? 0 : layer == 1 ? 128 : 384);
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&acc_full[1], full_phase[1]);
-          full_phase[1] ^= 1;
-          tc_fence_after();
+          const int buf = acc_buffer(layer, c);
+          acc_wait(buf);
           if (tracer) trace_ev(a, tr, kTraceEpi, 0x210 + layer * 8 + c);   // accumulator seen
           {
             const int q = part;   // this warp's 32 of the chunk's 128 columns
             uint32_t r[32];
-            TC_LD32(r, tm + kColAcc1 + q * 32);
+            TC_LD32(r, tm + acc_column(buf) + q * 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            warp_arrive(&acc_empty[buf]);   // the values are in registers: the next chunk may overwrite the accumulator
             uint32_t packed[16];
             const float* bq = bl + c * 128 + q * 32;
 #pragma unroll
@@ -523,22 +637,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
               const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bq[2 * j + 1], 0.0f);
               packed[j] = pack_bf16x2(v0, v1);
             }
+            // chunks 2 and 3 of layer 4 land on accX: every warp must have drained it (layer 4, chunk 1) first.
+            // accX completes two drain phases per tile (layer 3 chunk 1, layer 4 chunk 1): this is the odd one.
+            if (layer == 2 && c == 2) mbar_wait(&acc_empty[2], 1);
             TC_ST16(tm + out_col + c * 64 + q * 16, packed, 0);
           }
+          // chunk c is K-pair c of the next layer: tell the MMA warp these 128 channels are in place
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          mbar_arrive(&acc_empty[1]);
-          if (c == nchunks - 1) mbar_arrive(act_ready);
+          warp_arrive(&act_ready[c]);
           if (tracer) trace_ev(a, tr, kTraceEpi, 0x230 + layer * 8 + c);   // next operand stored
         }
       }
 
       // ---- prefetch the next tile's point: its DRAM latency hides under layer 5 ----
+      const bool more = t + 1 < t_end;
+      const bool dn = t + 1 >= a.total_tiles;
+      const int fn = dn ? 0 : tf_next;
+      const int slotn = dn ? a.N : tt_next * kTileM + row;
       have_pre = false;
-      if (vec4_points && t + 1 < t_end) {
-        const bool dn = t + 1 >= a.total_tiles;
-        const int fn = dn ? 0 : tf_next;
-        const int slotn = dn ? a.N : tt_next * kTileM + row;
+      if (vec4_points && more) {
         xpre = make_float4(0.f, 0.f, 0.f, 0.f);
         if (slotn < a.N) {
           const int pn = CELL ? __ldg(a.perm + (size_t)fn * a.N + slotn) : slotn;
@@ -551,19 +668,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int buf = c & 1;
-        mbar_wait(&acc_full[buf], full_phase[buf]);
-        full_phase[buf] ^= 1;
-        tc_fence_after();
+        uint32_t packed1[8];
+        if (c == 7 && more) {
+          // layer 1 of the NEXT tile, computed while the tensor pipe works on this tile's last chunk
+          float x[kMaxCin];
+          if (have_pre) {
+            x[0] = xpre.x; x[1] = xpre.y; x[2] = xpre.z; x[3] = xpre.w;
+#pragma unroll
+            for (int k = 4; k < kMaxCin; ++k) x[k] = 0.0f;
+          } else {
+            load_point(fn, slotn, x);
+          }
+          layer1(x, packed1);
+        }
+        acc_wait(buf);
         if (tracer) trace_ev(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
+        // every MMA of this tile has completed (the pipe retires in order): act4 is dead, act1 may be replaced
+        if (c == 7 && more) publish_act1(packed1);
         const uint32_t acc_col = buf ? kColAcc1 : kColAcc0;
+        if (a.debug & 2) {   // debug bit 1: no layer-5 epilogue at all (results are garbage; timing experiment)
+          warp_arrive(&acc_empty[buf]);
+          continue;
+        }
         {
           const int g = part;   // this warp's 32 of the chunk's 128 channels
           uint32_t r[32];
           TC_LD32(r, tm + acc_col + g * 32);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           // this warp's share of the chunk is in registers: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
+          warp_arrive(&acc_empty[buf]);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -650,7 +783,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 // swizzled with (r & 7) exactly as SWIZZLE_128B reads them.
 __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict__ params, int C, uint8_t* __restrict__ tc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (stage, row, chunk)
-  const int total = kStagesPerTile * 128 * 8;
+  const int total = kImageStages * 128 * 8;
   // fp32 blob offsets of layers 1..5
   long long w_off[5], b_off[5];
   const int dims[6] = {C, 64, 128, 256, 512, 1024};
@@ -662,23 +795,28 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
     off += dims[l + 1];
   }
   if (idx < total) {
-    const int s = idx / (128 * 8), r = (idx / 8) % 128, ch = idx % 8;
-    int layer, i;
-    if (s < 1) { layer = 1; i = s; }
-    else if (s < 5) { layer = 2; i = s - 1; }
-    else if (s < 21) { layer = 3; i = s - 5; }
-    else { layer = 4; i = s - 21; }
-    const int kchunks = dims[layer] / 64;
-    const int n0 = (i / kchunks) * 128, k0 = (i % kchunks) * 64;
-    const int Nout = dims[layer + 1];
-    const float* wt = params + w_off[layer];
-    __align__(16) __nv_bfloat16 v[8];
+    const int s_img = idx / (128 * 8), r = (idx / 8) % 128, ch = idx % 8;
+    if (s_img == 1) {   // padding stage of the layer-2 pair (no early return: every thread serves the tail loop below)
+      *reinterpret_cast<uint4*>(tc + (size_t)s_img * kStageBytes + r * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      const int s = s_img == 0 ? 0 : s_img - 1;
+      int layer, i;
+      if (s < 1) { layer = 1; i = s; }
+      else if (s < 5) { layer = 2; i = s - 1; }
+      else if (s < 21) { layer = 3; i = s - 5; }
+      else { layer = 4; i = s - 21; }
+      const int kchunks = dims[layer] / 64;
+      const int n0 = (i / kchunks) * 128, k0 = (i % kchunks) * 64;
+      const int Nout = dims[layer + 1];
+      const float* wt = params + w_off[layer];
+      __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(wt[(size_t)(k0 + ch * 8 + j) * Nout + n0 + r]);
-    *reinterpret_cast<uint4*>(tc + (size_t)s * kStageBytes + r * 128 + ((ch ^ (r & 7)) * 16)) = *reinterpret_cast<uint4*>(v);
+      for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(wt[(size_t)(k0 + ch * 8 + j) * Nout + n0 + r]);
+      *reinterpret_cast<uint4*>(tc + (size_t)s_img * kStageBytes + r * 128 + ((ch ^ (r & 7)) * 16)) = *reinterpret_cast<uint4*>(v);
+    }
   }
   // tail: W1^T, b1, then the biases of layers 2..5, fp32
-  float* tailp = reinterpret_cast<float*>(tc + (size_t)kStagesPerTile * kStageBytes);
+  float* tailp = reinterpret_cast<float*>(tc + (size_t)kImageStages * kStageBytes);
   const int n_w1 = C * 64 + 64;
   for (int i = idx; i < n_w1 + kBiasFloats; i += gridDim.x * blockDim.x) {
     float v;
@@ -714,7 +852,8 @@ int tc_cluster_size() {
 size_t tc_smem_bytes(bool cell) {
   const int stages = cell ? kStagesCell : kStagesGlobal;
   return 1024 + (size_t)stages * kStageBytes + (cell ? (128 * kTStride + 128 + 4) * sizeof(float) : 0) +
-         (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) + (2 * stages + 5) * sizeof(uint64_t) + 16;
+         (cell ? 8 * sizeof(int) : 0) + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
+         (2 * stages + 10) * sizeof(uint64_t) + 16;
 }
 
 }  // namespace
@@ -801,7 +940,7 @@ extern "C" B200BEV_API int b200bev_pointnet_pack_bf16(const float* params, const
   if (!params || !tc_params) return B200BEV_ERR_INVALID_ARGUMENT;
   if (!tc_dims_supported(dims, n_layers)) return B200BEV_ERR_UNSUPPORTED;
   if (tc_bytes < tc_blob_bytes(dims[0]) || (reinterpret_cast<uintptr_t>(tc_params) & 15) != 0) return B200BEV_ERR_WORKSPACE;
-  const int total = kStagesPerTile * 128 * 8;
+  const int total = kImageStages * 128 * 8;
   pack_bf16_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, dims[0], reinterpret_cast<uint8_t*>(tc_params));
   return launch_status();
 }

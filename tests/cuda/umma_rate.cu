@@ -221,7 +221,7 @@ int main() {
   CK(cudaMalloc(&d_str, sms * 8));
   const size_t smem = 1024 + (size_t)kStages * kStageBytes + 16384;
   CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  struct Case { const char* name; Mode m; };
+  struct Case { const char* name; Mode m; int grid; };
   const Case cases[] = {
       {"TS N=128 1 acc            ", {128, 1, 4, 0, 0, 8, 0}},
       {"TS N=128 2 acc alternating", {128, 2, 4, 0, 0, 8, 0}},
@@ -237,25 +237,35 @@ int main() {
       {"TS N=128 1 acc, 1 B stage ", {128, 1, 1, 0, 0, 1, 0}},
       {"TS N=128 1 acc + free stream", {128, 1, 1, 0, 2, 6, 0}},
       {"tiny MMAs: N=16 + free stream", {16, 1, 1, 0, 2, 6, 0}},
+      {"N=128 free stream window 11, 148 CTAs", {128, 1, 4, 0, 2, 1, 0}, 0},
+      {"N=128 free stream window 8,  148 CTAs", {128, 1, 4, 0, 2, 4, 0}, 0},
+      {"N=128 free stream window 4,  148 CTAs", {128, 1, 4, 0, 2, 8, 0}, 0},
+      {"N=128 free stream window 2,  148 CTAs", {128, 1, 4, 0, 2, 10, 0}, 0},
+      {"N=128 free stream window 11, 74 CTAs ", {128, 1, 4, 0, 2, 1, 0}, 74},
+      {"N=128 free stream window 11, 16 CTAs ", {128, 1, 4, 0, 2, 1, 0}, 16},
+      {"N=128 free stream window 4,  16 CTAs ", {128, 1, 4, 0, 2, 8, 0}, 16},
+      {"N=128 free stream window 11, 1 CTA   ", {128, 1, 4, 0, 2, 1, 0}, 1},
   };
   const int n_mma = 8192;
   std::vector<unsigned long long> clk(sms), str(sms);
-  for (const Case& c : cases) {
+  for (const Case& c0 : cases) {
+    Case c = c0;
+    if (c.grid <= 0) c.grid = sms;
     CK(cudaMemset(d_str, 0, sms * 8));
     for (int rep = 0; rep < 2; ++rep) {
-      rate_kernel<<<sms, 192, smem>>>(wimg, n_img, c.m, n_mma, d_clk, d_str);
+      rate_kernel<<<c.grid, 192, smem>>>(wimg, n_img, c.m, n_mma, d_clk, d_str);
       CK(cudaDeviceSynchronize());
     }
     CK(cudaMemcpy(clk.data(), d_clk, sms * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(str.data(), d_str, sms * 8, cudaMemcpyDeviceToHost));
     double sum = 0, mx = 0, mn = 1e30, ssum = 0;
-    for (int i = 0; i < sms; ++i) {
+    for (int i = 0; i < c.grid; ++i) {
       const double v = (double)clk[i] / n_mma;
       sum += v; mx = std::max(mx, v); mn = std::min(mn, v);
       ssum += (double)str[i];
     }
-    printf("%s clk/MMA avg %.1f min %.1f max %.1f (ideal %d)  stream: %.2f stages per 4 MMAs\n", c.name, sum / sms, mn, mx, c.m.n / 2,
-           ssum / sms / (n_mma / 4.0));
+    printf("%s clk/MMA avg %.1f min %.1f max %.1f (ideal %d)  stream: %.2f stages per 4 MMAs\n", c.name, sum / c.grid, mn, mx, c.m.n / 2,
+           ssum / c.grid / (n_mma / 4.0));
   }
   return 0;
 }

@@ -1,3 +1,8 @@
 mkdir -p gpurun_out
-timeout 120 tests/cuda/_build/umma_rate > gpurun_out/umma_rate.log 2>&1; echo "umma_rate rc=$?" >> gpurun_out/rc.txt
-cat gpurun_out/umma_rate.log
+step() { echo "== $*"; timeout 40 "$@"; rc=$?; echo "rc=$rc"; if [ $rc -eq 124 ]; then echo "HANG: $*"; exit 3; fi; }
+step python -m pytest tests -m gpu -q -x -k "tensor_core" -p no:cacheprovider 2>&1 | tail -3
+[ ${PIPESTATUS[0]} -eq 3 ] && exit 3
+echo default; timeout 60 python tests/perf_kernels.py mlp 2>&1 | grep "tcgen05" || exit 3
+for v in 1 2; do
+echo "trip=$v"; B200BEV_LIB=$PWD/gpurun_variants_trip$v.so timeout 60 python tests/perf_kernels.py mlp 2>&1 | grep "tcgen05" || exit 3
+done
