@@ -44,6 +44,43 @@ def voxel_size(pc_range: Sequence[float], W: int, H: int) -> Tuple[float, float]
 
 
 # ------------------------------------------------------------------------------------------------
+# N3: the step in front of S1
+# ------------------------------------------------------------------------------------------------
+def lidar_prepare(raw: torch.Tensor, frame_offsets: torch.Tensor, max_points: int,
+                  pc_range: Sequence[float] = DEFAULT_PC_RANGE, select: Optional[torch.Tensor] = None,
+                  max_frame_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Range filter + pad / subsample of a batch of raw sweeps (src/train_detect.py:147-189).
+
+    raw (total_rows, C) f32 with the frames back to back, frame_offsets (B+1) i64 -> (points (B, max_points, C),
+    count (B) i32).  `select` (B, max_points) i32 picks output rows by their index among the in-range points
+    (the reference's np.random.choice draw); without it the in-range points keep their file order."""
+    raw = _need_cuda(raw, "raw")
+    frame_offsets = _need_cuda(frame_offsets, "frame_offsets", torch.int64)
+    if raw.dim() != 2 or raw.shape[1] < 3:
+        raise ValueError("raw must be (total_rows, C) with C >= 3")
+    if frame_offsets.dim() != 1 or frame_offsets.numel() < 2:
+        raise ValueError("frame_offsets must be (B + 1,)")
+    B = frame_offsets.numel() - 1
+    Cc = int(raw.shape[1])
+    if max_frame_rows is None:
+        max_frame_rows = int(raw.shape[0])     # a bound that needs no host sync
+    dev = raw.device
+    if select is not None:
+        select = _need_cuda(select, "select", torch.int32)
+        if tuple(select.shape) != (B, max_points):
+            raise ValueError(f"select must be {(B, max_points)}, got {tuple(select.shape)}")
+    n_ws = _lib.lib().b200bev_lidar_prepare_workspace_bytes(B, max_frame_rows, 1 if select is not None else 0)
+    ws = torch.empty(max(n_ws, 16), dtype=torch.uint8, device=dev)
+    out = torch.empty((B, max_points, Cc), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    rng = (C.c_float * 6)(*[float(v) for v in pc_range])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_lidar_prepare(_ptr(raw), _ptr(frame_offsets), B, Cc, max_frame_rows, rng, max_points,
+                                                    _ptr(select), _ptr(out), _ptr(count), _ptr(ws), ws.numel(), _stream(dev)))
+    return out, count
+
+
+# ------------------------------------------------------------------------------------------------
 # S1a
 # ------------------------------------------------------------------------------------------------
 def bin_sort(points: torch.Tensor, W: int, H: int,

@@ -56,6 +56,27 @@ def lidar_points(seed: int, n_valid: int = 34720, n_total: int = 35000, channels
     return pts
 
 
+def raw_sweep(seed: int, n_rows: int, channels: int = 4) -> np.ndarray:
+    """A raw sweep as it sits in a nuScenes .bin file before NuScenesDataset._load_lidar_points filters it
+    (src/train_detect.py:151): about a fifth of the rows fall outside the range, a few sit exactly on a
+    boundary (the filter is strict) and a few are NaN."""
+    g = _rng(seed)
+    p = np.empty((n_rows, channels), dtype=np.float32)
+    p[:, 0] = (28.0 * g.standard_normal(n_rows)).astype(np.float32)
+    p[:, 1] = (28.0 * g.standard_normal(n_rows)).astype(np.float32)
+    p[:, 2] = g.uniform(-5.6, 3.6, n_rows).astype(np.float32)
+    for c in range(3, channels):
+        p[:, c] = g.uniform(0.0, 255.0, n_rows).astype(np.float32)
+    edges = np.float32([-51.2, 51.2])
+    p[3::997, 0] = edges[0]
+    p[5::991, 0] = edges[1]
+    p[7::983, 1] = edges[1]
+    p[11::977, 2] = np.float32(-5.0)
+    p[13::971, 2] = np.float32(3.0)
+    p[17::1999, 1] = np.nan
+    return p
+
+
 def lidar_batch(seed: int, batch: int, **kw) -> np.ndarray:
     return np.stack([lidar_points(seed + i, **kw) for i in range(batch)])
 

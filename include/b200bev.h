@@ -60,6 +60,27 @@ B200BEV_API const char* b200bev_error_string(int status);
 B200BEV_API int b200bev_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---------------------------------------------------------------------------------------------
+ * N3 (the step in front of S1)  range filter + pad / subsample of raw LiDAR sweeps.
+ * Replaces: NuScenesDataset._load_lidar_points + _pad_or_subsample, src/train_detect.py:147-189
+ *   (mask = strictly inside pc_range on x, y, z; points[mask] in file order; zero rows up to max_points,
+ *   or points[np.random.choice(N, max_points, replace=False)] when N >= max_points), for a whole batch.
+ *   raw            (total_rows, C) f32: the rows of all frames back to back (C >= 3; columns 0..2 = x, y, z)
+ *   frame_offsets  (B+1) i64, device: frame b is rows [frame_offsets[b], frame_offsets[b+1])
+ *   max_frame_rows upper bound of the rows of one frame (sizes the launch and the workspace)
+ *   pc_range       HOST array of 6 floats [x_min, y_min, z_min, x_max, y_max, z_max] (configs/base.yaml:48)
+ *   select         optional (B, max_points) i32: output row j = the select[b,j]-th in-range point of frame b
+ *                  (the caller's np.random.choice draw; an index >= count gives a zero row).  NULL: in-range
+ *                  points in file order, truncated to max_points, zero rows after them.
+ *   out            (B, max_points, C) f32;  count (B) i32 = in-range points of each frame (before truncation)
+ *   workspace      b200bev_lidar_prepare_workspace_bytes(B, max_frame_rows, select != NULL) bytes, 16-byte aligned
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API size_t b200bev_lidar_prepare_workspace_bytes(int B, int64_t max_frame_rows, int with_select);
+B200BEV_API int b200bev_lidar_prepare(const float* raw, const int64_t* frame_offsets, int B, int C,
+                          int64_t max_frame_rows, const float* pc_range, int max_points,
+                          const int32_t* select, float* out, int32_t* count,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * S1a  bin-and-sort of points by BEV cell.
  * Replaces: nothing executable in the reference; implements the cell convention of
  *   src/centernet_target.py:222-224,250-257,285 (px=(x-x_min)/voxel, int(px), flat=iy*W+ix, reject

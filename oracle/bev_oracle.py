@@ -92,6 +92,24 @@ def voxel_size(pc_range, W: int, H: int) -> Tuple[np.float32, np.float32]:
     return F32((float(x_max) - float(x_min)) / W), F32((float(y_max) - float(y_min)) / H)
 
 
+def lidar_prepare(raw: np.ndarray, max_points: int, pc_range, indices: Optional[np.ndarray] = None) -> Tuple[np.ndarray, int]:
+    """[pinned] One sweep (M, C) -> ((max_points, C), n_in_range): NuScenesDataset._load_lidar_points and
+    _pad_or_subsample, src/train_detect.py:152-158,181-189.  Strict open-interval mask on x, y, z; points[mask];
+    zero rows up to max_points, or points[indices] when N >= max_points — `indices` being the draw the reference
+    takes from np.random.choice(N, max_points, replace=False) (None: the first max_points, for want of a draw)."""
+    p = np.asarray(raw, dtype=F32)
+    with np.errstate(invalid="ignore"):
+        mask = ((p[:, 0] > F32(pc_range[0])) & (p[:, 0] < F32(pc_range[3])) & (p[:, 1] > F32(pc_range[1])) &
+                (p[:, 1] < F32(pc_range[4])) & (p[:, 2] > F32(pc_range[2])) & (p[:, 2] < F32(pc_range[5])))
+    kept = p[mask]
+    n = kept.shape[0]
+    if n >= max_points:
+        out = kept[indices] if indices is not None else kept[:max_points]
+    else:
+        out = np.concatenate([kept, np.zeros((max_points - n, p.shape[1]), dtype=F32)], axis=0)
+    return out.astype(F32), n
+
+
 def cell_index(points: np.ndarray, pc_range, W: int, H: int) -> np.ndarray:
     """[unpinned] (..., C) -> int32 cell ids iy*W+ix, -1 outside.  px=(x-x_min)/voxel; reject px<0 or
     px>=W; ix=int(px); flat=iy*W+ix — src/centernet_target.py:250-257,285, evaluated in fp32."""

@@ -180,9 +180,43 @@ def decode_cases():
     np.savez_compressed(OUT / "centernet_decode.npz", **out)
 
 
+def lidar_prepare_cases():
+    """N3: the reference's own NuScenesDataset._load_lidar_points (src/train_detect.py:147-189) on sweeps written
+    to .bin files, pad branch and subsample branch.  The subsample draw is np.random.choice without a seed in the
+    reference; here numpy's global generator is seeded before each call and the same draw is repeated to store
+    the indices next to the output."""
+    import tempfile
+
+    import train_detect  # noqa: E402  (reference)
+
+    ds = object.__new__(train_detect.NuScenesDataset)      # no pkl / images needed for this method
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (rows, max_points) in {"pad": (3000, 2600), "pad_exact_empty": (64, 80), "subsample": (5000, 2048)}.items():
+            raw = syn.raw_sweep(601 + rows, rows)
+            if name == "pad_exact_empty":
+                raw[:, 0] = 60.0                            # nothing in range: all zero rows
+            path = f"{tmp}/{name}.bin"
+            raw.tofile(path)
+            ds.max_points = max_points
+            np.random.seed(1234)
+            got = ds._load_lidar_points({"lidar_path": path}).numpy()
+            ref, n_in = orc.lidar_prepare(raw, max_points, syn.PC_RANGE, None)
+            out[f"{name}_digest"] = syn.digest(raw)
+            out[f"{name}_count"] = np.int32(n_in)
+            if n_in >= max_points:
+                np.random.seed(1234)
+                idx = np.random.choice(n_in, max_points, replace=False)
+                ref, _ = orc.lidar_prepare(raw, max_points, syn.PC_RANGE, idx)
+                out[f"{name}_indices"] = idx.astype(np.int32)
+            assert got.shape == (max_points, 4) and np.array_equal(got, ref), name
+            out[f"{name}_out"] = got
+    np.savez_compressed(OUT / "lidar_prepare.npz", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases):
+    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases):
         fn()
         print("wrote", fn.__name__)
     for f in sorted(OUT.glob("*.npz")):

@@ -71,6 +71,14 @@ def main():
         med, best = timeit(lambda: ops.bin_sort(pts, 50, 50), reps=20)
         by = F * (24.0 * 35000 + 4 * 2501)
         print(f"bin_sort {F}x35000 50x50            median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+    if args.what in ("prepare", "all"):
+        rows = 43000                                            # ~35k in range after the filter
+        sweeps = [syn.raw_sweep(900 + i, rows) for i in range(F)]
+        raw = to(np.concatenate(sweeps, axis=0))
+        off = torch.tensor([rows * i for i in range(F + 1)], dtype=torch.int64, device=dev)
+        med, best = timeit(lambda: ops.lidar_prepare(raw, off, 35000, syn.PC_RANGE, max_frame_rows=rows), reps=20)
+        by = F * 16.0 * (rows + 35000)
+        print(f"lidar_prepare {F}x{rows} -> 35000     median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
     if args.what in ("camera", "all"):
         g = torch.Generator(device=dev).manual_seed(1)
         feats = torch.relu(torch.randn((F, 6, 512, 57, 100), device=dev, generator=g))

@@ -54,6 +54,11 @@ def main():
                                             precision=_lib.BF16_TENSOR, tc_params=tc))
         if want("mlp_f32"):
             run(lambda: ops.pointnet_encode(pts[:2], blob, dims, perm=perm[:2], offsets=off[:2], n_cells=G * G))
+    if want("prepare"):
+        rows = 43000
+        raw = to(np.concatenate([syn.raw_sweep(900 + i, rows) for i in range(F)], axis=0))
+        off = torch.tensor([rows * i for i in range(F + 1)], dtype=torch.int64, device=dev)
+        run(lambda: ops.lidar_prepare(raw, off, 35000, syn.PC_RANGE, max_frame_rows=rows))
     if want("radar"):
         rw, rb = syn.fold_mlp(syn.mlp_weights(111, syn.RADAR_DIMS))
         rblob, rdims = ops.pack_mlp_params([torch.from_numpy(w) for w in rw], [torch.from_numpy(b) for b in rb], dev)

@@ -34,6 +34,69 @@ def test_library_is_loaded_and_device_is_blackwell(cuda):
     assert major.value == 10 and sm.value >= 100
 
 
+# ------------------------------------------------------------------------------------------------ N3
+def test_lidar_prepare_vs_reference_golden(cuda, golden):
+    """Range filter + pad / subsample, against what the reference's own dataset code produced."""
+    g = golden("lidar_prepare")
+    cases = {"pad": (3000, 2600), "pad_exact_empty": (64, 80), "subsample": (5000, 2048)}
+    for name, (rows, max_points) in cases.items():
+        raw = syn.raw_sweep(601 + rows, rows)
+        if name == "pad_exact_empty":
+            raw[:, 0] = 60.0
+        off = torch.tensor([0, rows], dtype=torch.int64, device=cuda)
+        sel = None
+        if f"{name}_indices" in g:
+            sel = torch.from_numpy(g[f"{name}_indices"]).to(cuda).view(1, -1)
+        out, count = ops.lidar_prepare(dev_t(raw, cuda), off, max_points, syn.PC_RANGE, select=sel)
+        assert int(count[0]) == int(g[f"{name}_count"])
+        np.testing.assert_array_equal(out[0].cpu().numpy(), g[f"{name}_out"])       # bit-exact: it is a copy
+
+
+@pytest.mark.parametrize("rows,C,max_points", [([35211, 0, 1, 40000, 777], 4, 35000), ([3000, 2999], 5, 1024),
+                                                ([300000, 280000], 4, 300000)])
+def test_lidar_prepare_ragged_batches(cuda, rows, C, max_points):
+    """Whole batches with empty, tiny and over-full frames, 4- and 5-channel rows, against the oracle."""
+    sweeps = [syn.raw_sweep(700 + i, r, channels=C) for i, r in enumerate(rows)]
+    raw = np.concatenate(sweeps, axis=0) if sum(rows) else np.zeros((0, C), np.float32)
+    off = torch.tensor([0] + list(np.cumsum(rows)), dtype=torch.int64, device=cuda)
+    out, count = ops.lidar_prepare(dev_t(raw, cuda), off, max_points, syn.PC_RANGE, max_frame_rows=max(rows))
+    for b, s in enumerate(sweeps):
+        ref, n = orc.lidar_prepare(s, max_points, syn.PC_RANGE)
+        assert int(count[b]) == n
+        np.testing.assert_array_equal(out[b].cpu().numpy(), ref)
+    # the subsample branch with a caller-supplied draw, for the frames that overflow
+    counts = count.tolist()
+    over = [b for b, n in enumerate(counts) if n >= max_points]
+    if over:
+        rng = np.random.default_rng(5)
+        sel = np.full((len(rows), max_points), -1, dtype=np.int32)
+        for b in over:
+            sel[b] = rng.choice(counts[b], max_points, replace=False)
+        got, _ = ops.lidar_prepare(dev_t(raw, cuda), off, max_points, syn.PC_RANGE, select=dev_t(sel, cuda), max_frame_rows=max(rows))
+        for b in over:
+            ref, _ = orc.lidar_prepare(sweeps[b], max_points, syn.PC_RANGE, sel[b])
+            np.testing.assert_array_equal(got[b].cpu().numpy(), ref)
+
+
+def test_prepare_lidar_batch_feeds_the_encoder_path(cuda, tmp_path):
+    """dataset.prepare_lidar_batch: .bin files -> filtered/padded batch -> bin_sort accepts every kept point."""
+    from bevfusion_multimodal_3d_object_detection_b200 import dataset
+
+    paths = []
+    for i, r in enumerate((5000, 1200)):
+        p = tmp_path / f"sweep{i}.bin"
+        syn.raw_sweep(800 + i, r).tofile(p)
+        paths.append(p)
+    pts, count = dataset.prepare_lidar_batch(paths, cuda, max_points=2048, rng=np.random.default_rng(3))
+    assert tuple(pts.shape) == (2, 2048, 4) and count.tolist()[1] < 2048 <= count.tolist()[0]
+    cell, _, off = ops.bin_sort(pts, 50, 50)
+    n1 = int(count[1])
+    assert bool((cell[0] >= 0).all()) and bool((cell[1, :n1] >= 0).all())     # in-range points are all in the grid
+    assert not bool(pts[1, n1:].any())                                         # zero padding (SURVEY Q5)
+    ref_rows = {tuple(r) for r in orc.lidar_prepare(dataset.read_sweep(paths[0]), 10**6, syn.PC_RANGE)[0][: int(count[0])].tolist()}
+    assert all(tuple(r) in ref_rows for r in pts[0].cpu().numpy().tolist())     # a subset of the in-range points
+
+
 # ------------------------------------------------------------------------------------------------ S1a
 @pytest.mark.parametrize("B,N,W,H", [(1, 35000, 50, 50), (3, 2011, 50, 50), (2, 777, 7, 5), (2, 40000, 100, 100),
                                      (1, 31, 50, 50), (1, 300000, 100, 100)])

@@ -30,6 +30,25 @@ def test_lidar_points_respect_the_reference_filter():
     assert not pts[34720:].any()                                  # zero padding, src/train_detect.py:188
 
 
+def test_lidar_prepare_matches_the_reference_dataset(golden):
+    """N3: oracle vs the reference's NuScenesDataset._load_lidar_points (pad branch and seeded subsample branch)."""
+    g = golden("lidar_prepare")
+    for name, (rows, max_points) in {"pad": (3000, 2600), "pad_exact_empty": (64, 80), "subsample": (5000, 2048)}.items():
+        raw = syn.raw_sweep(601 + rows, rows)
+        if name == "pad_exact_empty":
+            raw[:, 0] = 60.0
+        assert syn.digest(raw) == str(g[f"{name}_digest"])
+        idx = g.get(f"{name}_indices")
+        out, n = orc.lidar_prepare(raw, max_points, syn.PC_RANGE, idx)
+        assert n == int(g[f"{name}_count"])
+        np.testing.assert_array_equal(out, g[f"{name}_out"])
+    # boundary and NaN rows never pass the strict filter
+    edge = np.array([[-51.2, 0, 0, 1], [51.2, 0, 0, 1], [0, 51.2, 0, 1], [0, 0, -5.0, 1], [0, 0, 3.0, 1], [np.nan, 0, 0, 1],
+                     [0, 0, 0, 7]], dtype=np.float32)
+    out, n = orc.lidar_prepare(edge, 3, syn.PC_RANGE)
+    assert n == 1 and out[0, 3] == 7 and not out[1:].any()
+
+
 def test_lidar_global_max(golden):
     g = golden("lidar_encoder")
     layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
