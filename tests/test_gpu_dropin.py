@@ -1,0 +1,222 @@
+"""GPU (-m gpu): the drop-in layer itself — the mirror modules and functions with the reference's signatures
+(encoders.py, fusion.py, centernet_decode.py, the same code patch() installs on the reference's classes) —
+in eval mode on CUDA, against (1) the outputs the REFERENCE's modules produced for the same state_dict and
+inputs (tests/golden) and (2) the plain torch graph of the same module on the same device.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import bevfusion_multimodal_3d_object_detection_b200 as b200bev
+from bevfusion_multimodal_3d_object_detection_b200 import encoders as enc_mod
+from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+from oracle import bev_oracle as orc
+from tests.conftest import max_rel
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_torch():
+    """The torch side of every comparison must be real fp32 (no TF32 in cuDNN / cuBLAS)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def load_mlp(module, layers):
+    """Synthetic layer dicts -> the reference's state_dict names (conv{i}.*, bn{i}.*), as make_golden.py does."""
+    sd = module.state_dict()
+    for i, lay in enumerate(layers, start=1):
+        sd[f"conv{i}.weight"] = torch.from_numpy(lay["weight"]).unsqueeze(-1)
+        sd[f"conv{i}.bias"] = torch.from_numpy(lay["bias"])
+        sd[f"bn{i}.weight"] = torch.from_numpy(lay["bn_weight"])
+        sd[f"bn{i}.bias"] = torch.from_numpy(lay["bn_bias"])
+        sd[f"bn{i}.running_mean"] = torch.from_numpy(lay["bn_mean"])
+        sd[f"bn{i}.running_var"] = torch.from_numpy(lay["bn_var"])
+    module.load_state_dict(sd)
+    return module.eval()
+
+
+def test_lidar_encoder_module_reproduces_the_reference_outputs(cuda, golden):
+    g = golden("lidar_encoder")
+    enc = load_mlp(b200bev.PointNetLiDAREncoder(input_channels=4, feat_dim=1024, use_bn=True),
+                   syn.mlp_weights(101, syn.LIDAR_DIMS)).to(cuda)
+    pts = torch.from_numpy(syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)).to(cuda)
+    with torch.no_grad():
+        out = enc(pts)
+        assert out.is_cuda and tuple(out.shape) == (2, 1024)
+        assert max_rel(out.cpu().numpy(), g["small_global"]) < FP32_TOL                      # vs the reference itself
+        assert torch.equal(enc(pts.transpose(1, 2).contiguous()), out)                       # (B,C,N) layout, src/encoders.py:282
+        torch_graph = torch.max(enc_mod._torch_mlp(enc, pts.transpose(1, 2)), 2)[0]          # same module, plain ATen ops
+        assert max_rel(out.cpu().numpy(), torch_graph.cpu().numpy()) < FP32_TOL
+        full = torch.from_numpy(syn.lidar_batch(301, 1)).to(cuda)
+        assert max_rel(enc(full).cpu().numpy(), g["full_global"]) < FP32_TOL
+        enc.b200_precision = "bf16"
+        assert max_rel(enc(full).cpu().numpy(), g["full_global"]) < BF16_TOL                 # tcgen05 path behind the same call
+        enc.b200_precision = None
+        canvas = enc.cell_canvas(pts, (50, 50))                                              # north_star S1, extended mode
+        assert tuple(canvas.shape) == (2, 1024, 50, 50)
+        sub = canvas.permute(0, 2, 3, 1).reshape(2, 2500, 1024)[:, :, ::16]
+        assert max_rel(sub.cpu().numpy(), g["small_canvas_sub"]) < FP32_TOL
+
+
+def test_lidar_encoder_follows_state_dict_updates_and_training_mode(cuda):
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    enc = load_mlp(b200bev.PointNetLiDAREncoder(input_channels=4), layers).to(cuda)
+    pts = torch.from_numpy(syn.lidar_batch(205, 2, n_valid=500, n_total=512)).to(cuda)
+    with torch.no_grad():
+        a = enc(pts)
+        other = syn.mlp_weights(177, syn.LIDAR_DIMS)
+        load_mlp(enc, other)                                   # load_state_dict -> the folded-weight cache must be rebuilt
+        b = enc(pts)
+        assert max_rel(b.cpu().numpy(), orc.pointnet_global(pts.cpu().numpy(), other)) < FP32_TOL
+        assert not torch.allclose(a, b)
+    enc.train()                                                # training: torch graph with batch statistics + autograd
+    out = enc(pts.requires_grad_(True))
+    out.sum().backward()
+    assert pts.grad is not None and out.requires_grad
+    with pytest.raises(RuntimeError):
+        enc.eval()(pts.detach().cpu())                         # no CPU path
+
+
+@pytest.mark.parametrize("method", ["concat", "max", "mean"])
+def test_multi_radar_module_reproduces_the_reference_outputs(cuda, golden, method):
+    g = golden("radar_encoder")
+    m = b200bev.MultiRadarEncoder(input_channels=7, feat_dim=256, num_radars=5, fusion_method=method)
+    load_mlp(m.radar_encoder, syn.mlp_weights(111, syn.RADAR_DIMS))
+    if method == "concat":
+        fcw, fcb = syn.linear_weights(112, 5 * 256, 256)
+        with torch.no_grad():
+            m.fusion_fc.weight.copy_(torch.from_numpy(fcw))
+            m.fusion_fc.bias.copy_(torch.from_numpy(fcb))
+    m = m.eval().to(cuda)
+    radars = [torch.from_numpy(r).to(cuda) for r in syn.radar_batch(211, 3)]
+    with torch.no_grad():
+        assert max_rel(m(radars).cpu().numpy(), g[f"fused_{method}"]) < FP32_TOL
+        ragged = [r[:, : 125 - 17 * i].contiguous() for i, r in enumerate(radars)]
+        assert max_rel(m(ragged).cpu().numpy(), g[f"ragged_{method}"]) < FP32_TOL
+    m.fusion_method = "bogus"
+    with pytest.raises(ValueError, match="Unknown fusion method"):
+        m(radars)
+
+
+@pytest.mark.parametrize("name,shape", [("ref28x50", (16, 28, 50, 50, 50)), ("hd57x100", (8, 57, 100, 50, 50)),
+                                        ("up7x9", (8, 7, 9, 20, 30))])
+def test_fusion_module_camera_branch_vs_the_same_module_in_torch(cuda, golden, name, shape):
+    """FlexibleBEVFusion.forward in eval mode on CUDA: mean and resize on the kernels, convs on cuDNN, against the
+    module's own torch graph (the training-mode branch evaluated with eval-mode BatchNorm)."""
+    C, h, w, H, W = shape
+    torch.manual_seed(11)
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=C, lidar_channels=64,
+                                    radar_channels=32, bev_h=H, bev_w=W, bev_channels=8)
+    if (H, W) != (50, 50):
+        fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=False, use_radar=True, camera_channels=C,
+                                        radar_channels=32, bev_h=H, bev_w=W, bev_channels=8)   # lidar BEV is fixed at 50x50 (src/fusion.py:141)
+    for mod in fus.modules():                                   # BatchNorm statistics away from the identity
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+    fus = fus.eval().to(cuda)
+    feats = torch.from_numpy(syn.camera_features(401, 2, n_cam=6, channels=C, h=h, w=w)).to(cuda)
+    lidar = torch.randn(2, 64, device=cuda) if fus.use_lidar else None
+    radar = torch.randn(2, 32, device=cuda)
+    with torch.no_grad():
+        got = fus(camera_features=feats, lidar_features=lidar, radar_features=radar)
+        # the same module through plain torch ops
+        cam = F.interpolate(fus.camera_proj(feats.mean(dim=1)), size=(H, W), mode="bilinear", align_corners=False)
+        parts = [cam]
+        if fus.use_lidar:
+            parts.append(fus.lidar_upsample(fus.lidar_init(lidar).view(2, 128, 25, 25)))
+        r = fus.radar_proj(radar).view(2, 8, 1, 1).expand(2, 8, H, W)
+        parts.append(fus.radar_refine(r))
+        ref = fus.bev_fusion(torch.cat(parts, dim=1))
+        assert tuple(got.shape) == (2, 8, H, W)
+        assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < FP32_TOL
+        # the two kernel steps against what the reference's module fed / produced around F.interpolate
+        g = golden("camera_bev")
+        mean = b200bev.ops.camera_mean(feats).cpu().numpy()
+        assert max_rel(mean, g[f"{name}_mean"]) < 2e-7
+        if name != "up7x9":          # ATen's scalar path for tiny planes associates differently (1 ulp in <1 % of elements)
+            assert np.array_equal(mean, g[f"{name}_mean"])
+        rs = b200bev.ops.bilinear_resize(torch.from_numpy(g[f"{name}_resize_in"]).to(cuda), (H, W))
+        assert max_rel(rs.cpu().numpy(), g[f"{name}_resize_out"]) < FP32_TOL
+        with pytest.raises(ValueError, match="No modality features provided"):
+            fus()
+        # 4-D camera input (already averaged) is accepted, src/fusion.py:233-236
+        got4 = fus(camera_features=feats.mean(dim=1), lidar_features=lidar, radar_features=radar)
+        assert max_rel(got4.cpu().numpy(), ref.cpu().numpy()) < FP32_TOL
+
+
+@pytest.mark.parametrize("tag,fn,voxel", [("ct", "decode_centernet_predictions", 2.048),
+                                          ("fd", "decode_centernet_predictions_fusion_detection", 0.512)])
+def test_decode_function_returns_the_reference_lists(cuda, golden, tag, fn, voxel):
+    """The list-of-dicts interface (data-dependent lengths, dtypes, the CPU tensors of an empty sample)."""
+    g = golden("centernet_decode")
+    maps = {k: torch.from_numpy(v).to(cuda) for k, v in syn.head_maps(501, 3).items()}
+    decode = getattr(b200bev, fn)
+    for thr in (0.0, 0.3, 0.999):
+        dets = decode(maps, score_thresh=thr, max_detections=100)
+        assert len(dets) == 3
+        for b, d in enumerate(dets):
+            ref_scores = g[f"{tag}_thr{thr}_b{b}_scores"]
+            assert d["labels"].dtype == torch.int64 and d["boxes"].dtype == torch.float32
+            np.testing.assert_array_equal(d["scores"].cpu().numpy(), ref_scores)
+            np.testing.assert_allclose(d["boxes"].cpu().numpy(), g[f"{tag}_thr{thr}_b{b}_boxes"], rtol=0, atol=1e-5)
+            np.testing.assert_array_equal(d["labels"].cpu().numpy(), g[f"{tag}_thr{thr}_b{b}_labels"])
+            np.testing.assert_array_equal(d["velocities"].cpu().numpy(), g[f"{tag}_thr{thr}_b{b}_velocities"])
+    empty = decode(maps, score_thresh=2.0, max_detections=100)           # nothing passes: CPU tensors
+    assert all(d["boxes"].device.type == "cpu" and tuple(d["boxes"].shape) == (0, 7) and d["labels"].dtype == torch.int64
+               for d in empty)
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        decode({k: v[:, :, :3, :3].contiguous() for k, v in maps.items()}, max_detections=100)   # K > H*W (Q7)
+
+
+def test_encode_fuse_head_decode_chain_on_device(cuda):
+    """The whole inference chain the pipelines run (src/fusion.py:1090-1137 + decode), mirror modules with kernels
+    against the same modules through torch ops: identical boxes."""
+    torch.manual_seed(5)
+    lidar_enc = load_mlp(b200bev.PointNetLiDAREncoder(input_channels=4), syn.mlp_weights(101, syn.LIDAR_DIMS)).to(cuda)
+    radar_enc = b200bev.MultiRadarEncoder(input_channels=7, feat_dim=256, num_radars=5, fusion_method="concat")
+    load_mlp(radar_enc.radar_encoder, syn.mlp_weights(111, syn.RADAR_DIMS))
+    radar_enc = radar_enc.eval().to(cuda)
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=32, bev_h=50, bev_w=50,
+                                    bev_channels=16).eval().to(cuda)
+    head = torch.nn.ModuleDict({k: torch.nn.Sequential(torch.nn.Conv2d(16, 16, 3, padding=1), torch.nn.ReLU(),
+                                                       torch.nn.Conv2d(16, c, 1))
+                                for k, c in (("heatmap", 10), ("offset", 2), ("size", 3), ("rot", 2), ("vel", 2))}).eval().to(cuda)
+    B = 2
+    pts = torch.from_numpy(syn.lidar_batch(901, B, n_valid=3000, n_total=3072)).to(cuda)
+    radars = [torch.from_numpy(r).to(cuda) for r in syn.radar_batch(902, B)]
+    feats = torch.from_numpy(syn.camera_features(903, B, channels=32, h=28, w=50)).to(cuda)
+
+    def run(kernels: bool):
+        with torch.no_grad():
+            if kernels:
+                lf, rf = lidar_enc(pts), radar_enc(radars)
+                bev = fus(camera_features=feats, lidar_features=lf, radar_features=rf)
+            else:
+                lf = torch.max(enc_mod._torch_mlp(lidar_enc, pts.transpose(1, 2)), 2)[0]
+                per = torch.stack([torch.max(enc_mod._torch_mlp(radar_enc.radar_encoder, r.transpose(1, 2)), 2)[0] for r in radars], 1)
+                rf = radar_enc.fusion_fc(per.view(B, -1))
+                cam = F.interpolate(fus.camera_proj(feats.mean(dim=1)), size=(50, 50), mode="bilinear", align_corners=False)
+                li = fus.lidar_upsample(fus.lidar_init(lf).view(B, 128, 25, 25))
+                ra = fus.radar_refine(fus.radar_proj(rf).view(B, 16, 1, 1).expand(B, 16, 50, 50))
+                bev = fus.bev_fusion(torch.cat([cam, li, ra], dim=1))
+            pred = {k: m(bev) for k, m in head.items()}
+            pred["heatmap"] = torch.sigmoid(pred["heatmap"])                 # src/fusion.py:871
+            return pred
+
+    pk, pt = run(True), run(False)
+    for k in pk:
+        assert max_rel(pk[k].cpu().numpy(), pt[k].cpu().numpy()) < 1e-4, k   # conv stacks amplify the 1e-5 of the inputs a little
+    dets = b200bev.decode_centernet_predictions(pk, score_thresh=0.0, max_detections=50)
+    ref = orc.decode({k: v.cpu().numpy() for k, v in pk.items()}, score_thresh=0.0, max_detections=50)
+    for d, r in zip(dets, ref):
+        np.testing.assert_array_equal(d["scores"].cpu().numpy(), r["scores"])
+        np.testing.assert_allclose(d["boxes"].cpu().numpy(), r["boxes"], rtol=0, atol=1e-5)
