@@ -69,3 +69,54 @@ def prepare_lidar_batch(sweeps: Sequence[Union[np.ndarray, torch.Tensor, str, Pa
         idx = torch.tensor(over, device=device)
         points[idx] = gathered[idx]
     return points, count
+
+
+# ------------------------------------------------------------------------------------------------
+# N4: calibration plumbing for the geometric camera projection
+# ------------------------------------------------------------------------------------------------
+CAMERA_ORDER = ("CAM_FRONT", "CAM_FRONT_RIGHT", "CAM_FRONT_LEFT", "CAM_BACK", "CAM_BACK_LEFT", "CAM_BACK_RIGHT")
+
+
+def quaternion_to_matrix(q: Sequence[float]) -> np.ndarray:
+    """nuScenes quaternion (w, x, y, z) -> 3x3 rotation, float64."""
+    w, x, y, z = (float(v) for v in q)
+    n = np.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def calibration_from_info(info: dict, cameras: Sequence[str] = CAMERA_ORDER, frame: str = "lidar") -> Tuple[np.ndarray, np.ndarray]:
+    """One sample's info dict, as ConfigDrivenNuScenesConverter writes it (src/data_converter.py:110-117,
+    145-152), -> (intrinsics (n_cam,3,3) f32, ego2cam (n_cam,3,4) f32) in the layout b200bev_camera_project takes.
+
+    `calibrated_sensor` holds sensor->ego transforms (translation, rotation quaternion w,x,y,z).  The BEV grid of
+    the reference lives in the LiDAR frame (boxes are moved there, src/data_converter.py:237-247), so with
+    frame == "lidar" the returned [R|t] maps LiDAR-frame points to each camera: p_cam = R_c^T (R_l p + t_l - t_c).
+    frame == "ego" maps ego-frame points.  NuScenesDataset never reads these fields; this is the
+    plumbing the geometric projection needs on real data."""
+    if frame not in ("lidar", "ego"):
+        raise ValueError("frame must be 'lidar' or 'ego'")
+    if frame == "lidar":
+        lc = info["lidar_calibrated_sensor"]
+        R_l, t_l = quaternion_to_matrix(lc["rotation"]), np.asarray(lc["translation"], dtype=np.float64)
+    else:
+        R_l, t_l = np.eye(3), np.zeros(3)
+    Ks, Es = [], []
+    for cam in cameras:
+        cs = info["cams"][cam]["calibrated_sensor"]
+        R_c, t_c = quaternion_to_matrix(cs["rotation"]), np.asarray(cs["translation"], dtype=np.float64)
+        R = R_c.T @ R_l
+        t = R_c.T @ (t_l - t_c)
+        Ks.append(np.asarray(cs["camera_intrinsic"], dtype=np.float64).reshape(3, 3))
+        Es.append(np.concatenate([R, t[:, None]], axis=1))
+    return np.stack(Ks).astype(np.float32), np.stack(Es).astype(np.float32)
+
+
+def calibration_batch(infos: Sequence[dict], device: torch.device, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(intrinsics (B,n_cam,3,3), ego2cam (B,n_cam,3,4)) on `device` for a batch of info dicts (T = B rigs)."""
+    pairs = [calibration_from_info(i, **kw) for i in infos]
+    K = torch.from_numpy(np.stack([p[0] for p in pairs])).to(device)
+    E = torch.from_numpy(np.stack([p[1] for p in pairs])).to(device)
+    return K, E

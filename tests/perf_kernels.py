@@ -43,7 +43,9 @@ def main():
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--grid", type=int, default=50)
+    ap.add_argument("--points", type=int, default=35000, help="points per frame (300000 = the 10-sweep stress config)")
     args = ap.parse_args()
+    NP = args.points
     F = args.frames
     G = args.grid
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -51,14 +53,14 @@ def main():
         lw, lb = orc.fold_layers(syn.mlp_weights(101, syn.LIDAR_DIMS))
         blob, dims = ops.pack_mlp_params([torch.from_numpy(w) for w in lw], [torch.from_numpy(b) for b in lb], dev)
         tc = ops.pack_mlp_params_bf16(blob, dims)
-        pts = to(syn.lidar_batch(42, F))
-        _, perm, off = ops.bin_sort(pts, 50, 50)
-        flops = F * 35000 * 2.0 * 696576
+        pts = to(syn.lidar_batch(42, F, n_valid=NP - NP // 125, n_total=NP))
+        _, perm, off = ops.bin_sort(pts, G, G)
+        flops = F * NP * 2.0 * 696576
         for name, fn in (
             ("mlp f32 global", lambda: ops.pointnet_encode(pts, blob, dims)),
-            ("mlp f32 canvas+global", lambda: ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=2500)),
+            ("mlp f32 canvas+global", lambda: ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=G * G)),
             ("mlp bf16 tcgen05 global", lambda: ops.pointnet_encode(pts, blob, dims, precision=_lib.BF16_TENSOR, tc_params=tc)),
-            ("mlp bf16 tcgen05 canvas+global", lambda: ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=2500,
+            ("mlp bf16 tcgen05 canvas+global", lambda: ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=off, n_cells=G * G,
                                                                           precision=_lib.BF16_TENSOR, tc_params=tc)),
         ):
             try:
@@ -67,10 +69,10 @@ def main():
             except _lib.B200BevError as e:
                 print(f"{name:34s} {e}", flush=True)
     if args.what in ("binsort", "all"):
-        pts = to(syn.lidar_batch(42, F))
-        med, best = timeit(lambda: ops.bin_sort(pts, 50, 50), reps=20)
-        by = F * (24.0 * 35000 + 4 * 2501)
-        print(f"bin_sort {F}x35000 50x50            median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+        pts = to(syn.lidar_batch(42, F, n_valid=NP - NP // 125, n_total=NP))
+        med, best = timeit(lambda: ops.bin_sort(pts, G, G), reps=20)
+        by = F * (24.0 * NP + 4 * (G * G + 1))
+        print(f"bin_sort {F}x{NP} {G}x{G}            median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
     if args.what in ("prepare", "all"):
         rows = 43000                                            # ~35k in range after the filter
         sweeps = [syn.raw_sweep(900 + i, rows) for i in range(F)]
@@ -97,11 +99,11 @@ def main():
             med, best = timeit(fn, reps=20)
             print(f"{name:34s} median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
     if args.what in ("decode", "all"):
-        maps = {k: to(v) for k, v in syn.head_maps(44, F).items()}
+        maps = {k: to(v) for k, v in syn.head_maps(44, F, 10, G, G).items()}
         med, best = timeit(lambda: ops.centernet_decode(maps["heatmap"], maps["offset"], maps["size"], maps["rot"], maps["vel"],
                                                         100, 2.048), reps=20)
-        by = F * (4.0 * 10 * 2500 + 3600 + 6800)
-        print(f"centernet_decode {F}x10x50x50       median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+        by = F * (4.0 * 10 * G * G + 3600 + 6800)
+        print(f"centernet_decode {F}x10x{G}x{G}       median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -230,3 +230,48 @@ print('PATCH-OK')
 """ % (str(ROOT), str(ref_src))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "PATCH-OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_calibration_plumbing_round_trip():
+    """N4: info dicts in the converter's layout (src/data_converter.py:110-117) -> the [R|t] the projection kernel takes."""
+    from bevfusion_multimodal_3d_object_detection_b200 import dataset
+    from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+
+    def to_quat(R):                                              # rotation matrix -> (w, x, y, z), w >= 0 branch and the others
+        t = np.trace(R)
+        if t > 0:
+            s = np.sqrt(t + 1.0) * 2
+            return [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = [0.0] * 4
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+        return q
+
+    K, E = syn.camera_rig()
+    # a lidar mounted 0.9 m forward, 1.8 m up, yawed by -90 degrees as on the nuScenes car
+    yaw = -np.pi / 2
+    R_l = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+    t_l = np.array([0.9, 0.0, 1.8])
+    info = {"lidar_calibrated_sensor": {"translation": t_l.tolist(), "rotation": to_quat(R_l)}, "cams": {}}
+    for name, k, e in zip(dataset.CAMERA_ORDER, K, E):
+        R_ec, t_ec = e[:, :3].astype(np.float64), e[:, 3].astype(np.float64)   # ego -> camera
+        R_c, t_c = R_ec.T, -R_ec.T @ t_ec                                        # sensor -> ego, what nuScenes stores
+        info["cams"][name] = {"filename": "x.jpg", "calibrated_sensor": {
+            "translation": t_c.tolist(), "rotation": to_quat(R_c), "camera_intrinsic": k.tolist()}}
+    K2, E_ego = dataset.calibration_from_info(info, frame="ego")
+    np.testing.assert_array_equal(K2, K)
+    np.testing.assert_allclose(E_ego, E, atol=2e-6)
+    _, E_lidar = dataset.calibration_from_info(info, frame="lidar")
+    p = np.array([3.0, -7.0, 0.5])                                # a point in the lidar frame, through both routes
+    for e_l, e_e in zip(E_lidar, E):
+        via_ego = e_e[:, :3] @ (R_l @ p + t_l) + e_e[:, 3]
+        np.testing.assert_allclose(e_l[:, :3] @ p + e_l[:, 3], via_ego, atol=1e-5)
+    Kb, Eb = dataset.calibration_batch([info, info], torch.device("cpu"))
+    assert tuple(Kb.shape) == (2, 6, 3, 3) and tuple(Eb.shape) == (2, 6, 3, 4)
+    with pytest.raises(ValueError):
+        dataset.calibration_from_info(info, frame="world")
