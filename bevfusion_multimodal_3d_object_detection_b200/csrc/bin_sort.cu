@@ -286,9 +286,16 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
         if (valid && rk == 0) wh[(size_t)bin * NW] = (uint16_t)(cur + (uint32_t)__popc(peers));
         __syncwarp();
         if (valid) {
-          cell_out[i] = c;
-          rank_s[i - start] = (uint16_t)(cur + (uint32_t)rk);
-          if (a.cache_cells) cells_s[i - start] = c;
+          const uint32_t rnk = cur + (uint32_t)rk;
+          if (a.cache_cells) {
+            cell_out[i] = c;
+            rank_s[i - start] = (uint16_t)rnk;
+            cells_s[i - start] = c;
+          } else {
+            // no room in shared memory (big grids / long sweeps): the rank rides in the upper half of the cell word
+            // until phase 3 (cell ids fit 16 bits: W*H <= 48000; -1 <-> 0xffff)
+            cell_out[i] = (int32_t)(((uint32_t)c & 0xffffu) | (rnk << 16));
+          }
         }
       }
     }
@@ -367,10 +374,20 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
   int32_t* perm = a.perm + (size_t)b * a.N;
   for (int i = start + tid; i < end; i += kBinThreads) {
     const int li = i - start;
-    const int c = a.cache_cells ? cells_s[li] : cell_out[i];
+    int c;
+    uint32_t rnk;
+    if (a.cache_cells) {
+      c = cells_s[li];
+      rnk = rank_s[li];
+    } else {
+      const uint32_t packed = (uint32_t)cell_out[i];
+      c = (int)(int16_t)(packed & 0xffffu);
+      rnk = packed >> 16;
+      cell_out[i] = c;
+    }
     const int bin = c < 0 ? HW : c;
     const int w = li / ra.sub;
-    const uint32_t pos = base[bin] + row_prefix(whist + (size_t)bin * NW, NW, w) + rank_s[li];
+    const uint32_t pos = base[bin] + row_prefix(whist + (size_t)bin * NW, NW, w) + rnk;
     perm[pos] = i;
   }
 }
@@ -419,11 +436,14 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
       if (sub > 65535) break;   // halving NW only makes it larger
       const size_t head = ((nb + kMaxCluster + kBinThreads / 32 + 3) & ~(size_t)3) * sizeof(uint32_t);
       const size_t hist = ((nb * NW + 7) & ~(size_t)7) * sizeof(uint16_t);
-      const size_t ranks = (((size_t)a.slice + 1) & ~(size_t)1) * sizeof(uint16_t);
-      size_t smem = head + hist + ranks;
+      const size_t cache = (((size_t)a.slice + 1) & ~(size_t)1) * sizeof(uint16_t) + (size_t)a.slice * sizeof(int32_t);
+      size_t smem = head + hist;
       if (smem > kLimit) continue;
-      a.cache_cells = smem + (size_t)a.slice * sizeof(int32_t) <= 100 * 1024 ? 1 : 0;   // keep two CTAs per SM
-      if (a.cache_cells) smem += (size_t)a.slice * sizeof(int32_t);
+      // ranks and cell ids of the slice stay in shared memory when two CTAs per SM still fit; otherwise they
+      // travel packed in the `cell` output (16 + 16 bits) and all of shared memory goes to the per-warp histograms
+      a.cache_cells = (smem + cache <= 100 * 1024 && (long long)W * H < 0xffff) ? 1 : 0;
+      if (a.cache_cells) smem += cache;
+      else if ((long long)W * H >= 0xffff) break;   // cell ids would not fit the packed form: legacy kernel
       RankedArgs ra{a, NW, sub};
       if (smem > 48 * 1024)
         B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

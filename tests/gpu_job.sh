@@ -4,13 +4,14 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus.txt; nproc >> gpurun_out/gpus.txt
-tests/run_gpu_groups.sh gpurun_out
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/rc.txt
-python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/rc.txt
+timeout 500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1; echo "pytest -m gpu rc=$?" >> gpurun_out/rc.txt
+tail -3 gpurun_out/gpu_tests.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/rc.txt
+timeout 600 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/rc.txt
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "benchref rc=$?" >> gpurun_out/rc.txt
-python tests/perf_kernels.py all > gpurun_out/perf_all.log 2>&1
-B200BEV_BINSORT=legacy python tests/perf_kernels.py binsort > gpurun_out/perf_binsort_legacy.log 2>&1
-python tests/trace_tc.py gpurun_out/trace_tc.txt > gpurun_out/trace_tc.log 2>&1
+timeout 300 python tests/perf_kernels.py all > gpurun_out/perf_all.log 2>&1
+timeout 300 python tests/perf_kernels.py all --frames 8 --grid 100 --points 300000 > gpurun_out/perf_stress.log 2>&1
+timeout 120 python tests/trace_tc.py gpurun_out/trace_tc.txt > gpurun_out/trace_tc.log 2>&1
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-alt > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?" >> gpurun_out/rc.txt
 ncu --set full --clock-control none -o gpurun_out/prof_stages -f python tests/prof_stages.py --reps 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" >> gpurun_out/rc.txt
