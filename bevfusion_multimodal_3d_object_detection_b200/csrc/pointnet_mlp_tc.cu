@@ -31,6 +31,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -92,8 +93,9 @@ struct TcArgs {
 
 // Debug timeline: (event id << 48 | clock) appended by one thread per role of CTA 0.
 constexpr int kTraceMma = 0, kTraceEpi = 8192, kTraceLen = 16384;
+template <bool TRACE>
 __device__ __forceinline__ void trace_ev(const TcArgs& a, int& idx, int base, unsigned id) {
-  if (a.trace != nullptr && blockIdx.x == 0 && idx < 8192) {
+  if (TRACE && a.trace != nullptr && blockIdx.x == 0 && idx < 8192) {
     a.trace[base + idx] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
     ++idx;
   }
@@ -235,7 +237,7 @@ __device__ __forceinline__ void butterfly_level(float* v, int lane) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <bool CELL>
+template <bool CELL, bool TRACE>
 __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a) {
   constexpr int kStages = CELL ? kStagesCell : kStagesGlobal;
   extern __shared__ uint8_t smem_raw[];
@@ -335,9 +337,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       const uint32_t tmem_u = __shfl_sync(FULL_MASK, tmem, 0);                        // provably uniform
       const uint32_t ring_u = __shfl_sync(FULL_MASK, smem_u32(ring), 0);
       constexpr int kRingPairs = kStages / 2;
-      // ring pairs per trip: two where the ring is deep enough (global mode, 6 pairs); with the 4 pairs the
-      // cell mode has room for, a trip that needs half the ring at once stalls the weight stream
-      constexpr int kTrip = (B200BEV_TC_TRIP) ? (B200BEV_TC_TRIP) : (CELL ? 1 : 2);
+      // ring pairs per trip: one (8 MMAs).  Two per trip halve the polls, but measured slower once the layer shapes
+      // became compile-time constants (global mode 1.02 vs 1.05 ms) and stall a 4-pair ring (cell mode)
+      constexpr int kTrip = (B200BEV_TC_TRIP) ? (B200BEV_TC_TRIP) : 1;
       uint32_t pair = 0, phase = 0;   // ring pair slot and the parity of its round
       uint32_t act_phase = 0;         // bit kp: parity of the next phase of act_ready[kp]
       uint32_t acc_parity = 0;  // bit b: parity of the next use of accumulator b
@@ -357,60 +359,77 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         if (single_cta) tc_commit(&empty[pr]);
         else tc_commit_multicast(&empty[pr], cta_mask);
       };
-      for (long long t = t_begin; t < t_end; ++t) {
-#pragma unroll 1
-        for (int layer = 0; layer < 4; ++layer) {  // network layers 2..5
-          const int kpairs = layer == 0 ? 1 : (1 << layer) >> 1;   // K / 128 (layer 2: half a pair)
-          const int nchunks = 1 << layer;                           // N / 128
-          const uint32_t a_col = layer == 0 ? kColAct1 : layer == 1 ? kColAct2 : layer == 2 ? kColAct3 : kColAct4;
-          if (lane == 0) trace_ev(a, tr, kTraceMma, 0x100 + layer);            // first MMA of the layer
-#pragma unroll 1
-          for (int c = 0; c < nchunks; ++c) {
-            const int buf = acc_buffer(layer, c);
-            mbar_wait(&acc_empty[buf], ((acc_parity >> buf) & 1) ^ 1);
-            acc_parity ^= 1u << buf;
-            tc_fence_after();
-            if (lane == 0) trace_ev(a, tr, kTraceMma, 0x120 + layer * 8 + c);  // accumulator free, issuing
-            const uint32_t d_addr = tmem_u + acc_column(buf);
-#pragma unroll 1
-            for (int kp = 0; kp < kpairs; kp += kTrip) {
-              // up to two ring pairs (16 MMAs = 1024 clk of tensor work) per trip: the issue side of a trip (barrier
-              // polls, fence, descriptor arithmetic in the uniform datapath, releases) must stay below the time the
-              // MMAs it issues take, or the tensor pipe starves
-              const bool two = kTrip == 2 && kp + 1 < kpairs;
-              uint32_t pr1 = pair + 1, ph1 = phase;
-              if (pr1 == kRingPairs) { pr1 = 0; ph1 ^= 1; }
-              // The A operand arrives chunk by chunk: K-pair kp of this layer is the 128 channels that chunk kp of
-              // the layer before produced, so the first chunk of a layer starts while the pipe still works on the
-              // previous layer's last chunks.  One barrier per K-pair index: on each of them production and
-              // consumption alternate strictly (a single barrier would let the epilogue get two phases ahead of
-              // this warp, which a parity wait cannot tell from zero phases ahead).
-              if (c == 0) {
-                mbar_wait(&act_ready[kp], (act_phase >> kp) & 1);
-                act_phase ^= 1u << kp;
-                if (two) {
-                  mbar_wait(&act_ready[kp + 1], (act_phase >> (kp + 1)) & 1);
-                  act_phase ^= 1u << (kp + 1);
-                }
+      // One network layer, its shape a compile-time constant: chunks and trips are fully unrolled, so the accumulator
+      // choice, the A-operand columns and the loop tests cost the issuing thread nothing at run time — every
+      // instruction on this path delays the tensor pipe (tests/cuda/umma_rate.cu: a handful of extra integer
+      // instructions per 4 MMAs take the pipe from 64 to 80 clk per MMA).
+      auto issue_layer = [&](auto layer_tag) {
+        constexpr int layer = decltype(layer_tag)::value;           // 0..3 = network layers 2..5
+        constexpr int kpairs = layer == 0 ? 1 : (1 << layer) >> 1;   // K / 128 (layer 2: half a pair)
+        constexpr int nchunks = 1 << layer;                          // N / 128
+        constexpr uint32_t a_col = layer == 0 ? kColAct1 : layer == 1 ? kColAct2 : layer == 2 ? kColAct3 : kColAct4;
+        if (lane == 0) trace_ev<TRACE>(a, tr, kTraceMma, 0x100 + layer);            // first MMA of the layer
+        auto issue_chunk = [&](int c) {
+          const int buf = acc_buffer(layer, c);
+          mbar_wait(&acc_empty[buf], ((acc_parity >> buf) & 1) ^ 1);
+          acc_parity ^= 1u << buf;
+          tc_fence_after();
+          if (lane == 0) trace_ev<TRACE>(a, tr, kTraceMma, 0x120 + layer * 8 + c);  // accumulator free, issuing
+          const uint32_t d_addr = tmem_u + acc_column(buf);
+#pragma unroll
+          for (int kp = 0; kp < kpairs; kp += kTrip) {
+            // up to two ring pairs (16 MMAs = 1024 clk of tensor work) per trip: the issue side of a trip (barrier
+            // polls, fence, descriptor arithmetic in the uniform datapath, releases) must stay below the time the
+            // MMAs it issues take, or the tensor pipe starves
+            const bool two = kTrip == 2 && kp + 1 < kpairs;
+            uint32_t pr1 = pair + 1, ph1 = phase;
+            if (pr1 == kRingPairs) { pr1 = 0; ph1 ^= 1; }
+            // The A operand arrives chunk by chunk: K-pair kp of this layer is the 128 channels that chunk kp of
+            // the layer before produced, so the first chunk of a layer starts while the pipe still works on the
+            // previous layer's last chunks.  One barrier per K-pair index: on each of them production and
+            // consumption alternate strictly (a single barrier would let the epilogue get two phases ahead of
+            // this warp, which a parity wait cannot tell from zero phases ahead).
+            if (c == 0) {
+              mbar_wait(&act_ready[kp], (act_phase >> kp) & 1);
+              act_phase ^= 1u << kp;
+              if (two) {
+                mbar_wait(&act_ready[kp + 1], (act_phase >> (kp + 1)) & 1);
+                act_phase ^= 1u << (kp + 1);
               }
-              if (wait_weights) {
-                mbar_wait(&full[pair], phase);
-                if (two) mbar_wait(&full[pr1], ph1);
-              }
-              tc_fence_after();
-              const uint32_t a_addr = tmem_u + a_col + kp * 64;
-              if (elect_one()) {
-                issue_pair(d_addr, a_addr, pair, kp == 0, layer == 0);
-                if (two) issue_pair(d_addr, a_addr + 64, pr1, false, false);
-                if (kp + kTrip >= kpairs) tc_commit(&acc_full[buf]);
-              }
-              __syncwarp();
-              if (two) { pair = pr1; phase = ph1; }
-              if (++pair == kRingPairs) { pair = 0; phase ^= 1; }
             }
-            if (lane == 0) trace_ev(a, tr, kTraceMma, 0x160 + layer * 8 + c);  // chunk issued
+            if (wait_weights) {
+              mbar_wait(&full[pair], phase);
+              if (two) mbar_wait(&full[pr1], ph1);
+            }
+            tc_fence_after();
+            const uint32_t a_addr = tmem_u + a_col + kp * 64;
+            if (elect_one()) {
+              issue_pair(d_addr, a_addr, pair, kp == 0, layer == 0);
+              if (two) issue_pair(d_addr, a_addr + 64, pr1, false, false);
+              if (kp + kTrip >= kpairs) tc_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+            if (two) { pair = pr1; phase = ph1; }
+            if (++pair == kRingPairs) { pair = 0; phase ^= 1; }
           }
+          if (lane == 0) trace_ev<TRACE>(a, tr, kTraceMma, 0x160 + layer * 8 + c);  // chunk issued
+        };
+        // Global mode unrolls the chunks too (accumulator choice and the c == 0 tests fold away: 1.10 -> 1.05 ms).
+        // Cell mode keeps them rolled: its epilogue is the bottleneck and lives on instruction fetch — with
+        // the chunks unrolled here the issuer got faster and the epilogue 40 % slower.
+        if constexpr (CELL) {
+#pragma unroll 1
+          for (int c = 0; c < nchunks; ++c) issue_chunk(c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < nchunks; ++c) issue_chunk(c);
         }
+      };
+      for (long long t = t_begin; t < t_end; ++t) {
+        issue_layer(std::integral_constant<int, 0>{});
+        issue_layer(std::integral_constant<int, 1>{});
+        issue_layer(std::integral_constant<int, 2>{});
+        issue_layer(std::integral_constant<int, 3>{});
       }
     }
   } else {
@@ -537,7 +556,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     }
     for (long long t = t_begin; t < t_end; ++t) {
       const bool tracer = (tid == 64);
-      if (tracer) trace_ev(a, tr, kTraceEpi, 0x200);          // tile start
+      if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x200);          // tile start
       const bool dummy = t >= a.total_tiles;
       const int f = dummy ? cur_frame : tf;
       const int s0 = dummy ? a.N : tt * kTileM;
@@ -622,7 +641,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         for (int c = 0; c < nchunks; ++c) {
           const int buf = acc_buffer(layer, c);
           acc_wait(buf);
-          if (tracer) trace_ev(a, tr, kTraceEpi, 0x210 + layer * 8 + c);   // accumulator seen
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x210 + layer * 8 + c);   // accumulator seen
           {
             const int q = part;   // this warp's 32 of the chunk's 128 columns
             uint32_t r[32];
@@ -645,7 +664,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           // chunk c is K-pair c of the next layer: tell the MMA warp these 128 channels are in place
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           warp_arrive(&act_ready[c]);
-          if (tracer) trace_ev(a, tr, kTraceEpi, 0x230 + layer * 8 + c);   // next operand stored
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x230 + layer * 8 + c);   // next operand stored
         }
       }
 
@@ -665,7 +684,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       }
 
       // ---- layer 5: max over the tile's points, channel chunk by channel chunk ----
-#pragma unroll
+      // The loop stays ROLLED (the unrolled cell-mode kernel was 164 KB of code and its epilogue warps starved on
+      // instruction fetch); the eight running maxima live in registers all the same: rmax[0] is always the
+      // current chunk's, and the array is rotated by one after every chunk — back in place after the eighth.
+#pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         const int buf = c & 1;
         uint32_t packed1[8];
@@ -682,7 +704,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           layer1(x, packed1);
         }
         acc_wait(buf);
-        if (tracer) trace_ev(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
+        if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
         // every MMA of this tile has completed (the pipe retires in order): act4 is dead, act1 may be replaced
         if (c == 7 && more) publish_act1(packed1);
         const uint32_t acc_col = buf ? kColAcc1 : kColAcc0;
@@ -710,8 +732,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             butterfly_level<4>(v, lane);
             butterfly_level<2>(v, lane);
             butterfly_level<1>(v, lane);
-            rmax[c] = fmaxf(rmax[c], v[0]);  // lane l holds channel c*128 + g*32 + l
-            if (tracer) trace_ev(a, tr, kTraceEpi, 0x260 + c);  // layer-5 chunk reduced
+            rmax[0] = fmaxf(rmax[0], v[0]);  // lane l holds channel c*128 + g*32 + l
+            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x260 + c);  // layer-5 chunk reduced
           } else {
             // transpose through shared memory: tile_s[channel][point]; lanes are consecutive points
 #pragma unroll
@@ -731,7 +753,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           const float* trow = tile_s + row * kTStride + part * 32;
           const int* cids = cid_s + part * 32;
           const uint32_t ends = endmask_s[part];
-          float m = -INFINITY, gm = rmax[c];
+          float m = -INFINITY, gm = rmax[0];
           bool first_run = true;
 #pragma unroll
           for (int b4 = 0; b4 < 8; ++b4) {
@@ -759,8 +781,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             const float val = fmaxf(m + bias, 0.0f);
             if (val > 0.0f) atomicMax(reinterpret_cast<int*>(canvas + (size_t)cids[31] * c_out), __float_as_int(val));
           }
-          rmax[c] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
+          rmax[0] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
           epi_bar_sync();           // tile_s, cid_s and endmask_s are free again
+        }
+        {
+          const float r0 = rmax[0];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) rmax[i] = rmax[i + 1];
+          rmax[7] = r0;
         }
       }
       tf = tf_next;
@@ -904,13 +932,11 @@ int pointnet_encode_tc(const float* points, int B, int N, int C, const float* pa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cell) {
-    B200BEV_CUDA_TRY(cudaFuncSetAttribute(pointnet_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, pointnet_mlp_tc_kernel<true>, a));
-  } else {
-    B200BEV_CUDA_TRY(cudaFuncSetAttribute(pointnet_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, pointnet_mlp_tc_kernel<false>, a));
-  }
+  // the clock-stamp instrumentation is compiled out of the production instantiations
+  void (*kern)(TcArgs) = cell ? (d_trace ? pointnet_mlp_tc_kernel<true, true> : pointnet_mlp_tc_kernel<true, false>)
+                              : (d_trace ? pointnet_mlp_tc_kernel<false, true> : pointnet_mlp_tc_kernel<false, false>);
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
   if (d_trace) {
     B200BEV_CUDA_TRY(cudaStreamSynchronize(st));
     unsigned long long* h = (unsigned long long*)malloc(kTraceLen * sizeof(unsigned long long));

@@ -78,6 +78,10 @@ struct Mode {
   int stream;     // 1: a producer thread streams 16 KB stages into the ring while the MMAs run
   int b_stages;   // how many ring stages the MMAs read from (cycled every 4 MMAs)
   int epi;        // 1: four warps hammer shared memory with st.shared/ld.shared meanwhile (epilogue transposes)
+  int fence;      // 1: tcgen05.fence::after_thread_sync before every group of 4 MMAs (as after a barrier wait)
+  int poll;       // 1: an mbarrier try_wait on an already completed barrier before every group
+  int ldtm;       // 1: the four other warps read the accumulators with tcgen05.ld all the time (layer-5 epilogue)
+  int a_walk;     // 1: the A operand walks over 256 TMEM columns (K = 512) instead of staying on 32
 };
 
 __global__ void __launch_bounds__(192, 1) rate_kernel(const uint8_t* wimg, int n_img_stages, Mode m, int n_mma,
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) rate_kernel(const uint8_t* wimg, int n
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* scratch = ring + (size_t)kStages * kStageBytes;   // 16 KB for the epi traffic
-  __shared__ uint64_t bar_done, bar_full[kStages], bar_dummy;
+  __shared__ uint64_t bar_done, bar_full[kStages], bar_dummy, bar_ready;
   __shared__ uint32_t tmem_slot;
   __shared__ volatile int stop_flag;
   __shared__ volatile int mma_progress;   // stages consumed by the MMA thread: the stream is rate-matched to it
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(192, 1) rate_kernel(const uint8_t* wimg, int n
   }
   if (tid == 0) {
     mbar_init(&bar_done, 1);
+    mbar_init(&bar_ready, 1);
     mbar_init(&bar_dummy, (1 << 20) - 1);
     for (int i = 0; i < kStages; ++i) mbar_init(&bar_full[i], 1);
     stop_flag = 0;
@@ -109,6 +114,8 @@ __global__ void __launch_bounds__(192, 1) rate_kernel(const uint8_t* wimg, int n
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_ready)) : "memory");   // phase 0 of bar_ready is complete
+  __syncthreads();
 
   if (warp == 0) {
     // producer: keeps `depth` bulk copies in flight into ring stages [b_stages, kStages)
@@ -158,13 +165,16 @@ __global__ void __launch_bounds__(192, 1) rate_kernel(const uint8_t* wimg, int n
       const uint32_t d = tmem_u + 512 - (uint32_t)(acc + 1) * m.n;
       const uint64_t bdesc = make_desc(ring_u + bst * kStageBytes);
       const uint64_t adesc = make_desc(ring_u + ((bst + 1) % m.b_stages) * kStageBytes);
+      if (m.poll) mbar_wait(&bar_ready, 0);
+      if (m.fence) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_col = m.a_walk ? (uint32_t)((i & 63) * 8 / 4 * 4) % 256u : 0u;
       if (elect_one()) {
         if (m.ss) {
 #pragma unroll
           for (int s = 0; s < 4; ++s) umma_ss(d, adesc + (uint64_t)(s * 2), bdesc + (uint64_t)(s * 2), idesc, 1u);
         } else {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) umma_ts(d, tmem_u + s * 8, bdesc + (uint64_t)(s * 2), idesc, 1u);
+          for (int s = 0; s < 4; ++s) umma_ts(d, tmem_u + a_col + s * 8, bdesc + (uint64_t)(s * 2), idesc, 1u);
         }
         tc_commit(&bar_dummy);
         mma_progress = (i + 4) >> 2;
@@ -185,6 +195,28 @@ __global__ void __launch_bounds__(192, 1) rate_kernel(const uint8_t* wimg, int n
       out_clk[blockIdx.x] = t1 - t0;
       stop_flag = 1;
     }
+  } else if (m.ldtm) {
+    // warps 2..5 <-> TMEM lane quadrants 2,3,0,1: read 32 accumulator columns over and over
+    const uint32_t tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t sink = 0;
+    while (!stop_flag) {
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+            "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(tm + 256 + q * 32)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        sink ^= r[lane & 31];
+      }
+    }
+    if (sink == 0x12345678u) out_clk[1] = 0;
   } else if (m.epi) {
     // 4 warps: conflict-free 128-bit st.shared + ld.shared on a 16 KB scratch until told to stop
     float4* s4 = reinterpret_cast<float4*>(scratch);
@@ -237,6 +269,11 @@ int main() {
       {"TS N=128 1 acc, 1 B stage ", {128, 1, 1, 0, 0, 1, 0}},
       {"TS N=128 1 acc + free stream", {128, 1, 1, 0, 2, 6, 0}},
       {"tiny MMAs: N=16 + free stream", {16, 1, 1, 0, 2, 6, 0}},
+      {"TS N=128 2x32 + fence per 4   ", {128, 2, 32, 0, 0, 8, 0, 1, 0, 0, 0}, 0},
+      {"TS N=128 2x32 + poll+fence    ", {128, 2, 32, 0, 0, 8, 0, 1, 1, 0, 0}, 0},
+      {"TS N=128 2x32 + A walks 256col", {128, 2, 32, 0, 0, 8, 0, 0, 0, 0, 1}, 0},
+      {"TS N=128 2x32 + tcgen05.ld    ", {128, 2, 32, 0, 0, 8, 0, 0, 0, 1, 0}, 0},
+      {"TS N=128 2x32 + ld+stream+walk+poll+fence", {128, 2, 32, 0, 1, 6, 0, 1, 1, 1, 1}, 0},
       {"N=128 free stream window 11, 148 CTAs", {128, 1, 4, 0, 2, 1, 0}, 0},
       {"N=128 free stream window 8,  148 CTAs", {128, 1, 4, 0, 2, 4, 0}, 0},
       {"N=128 free stream window 4,  148 CTAs", {128, 1, 4, 0, 2, 8, 0}, 0},

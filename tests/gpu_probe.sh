@@ -1,4 +1,4 @@
-timeout 100 python -m pytest tests -m gpu -q -x -k "bin_sort or cell_canvas" -p no:cacheprovider 2>&1 | tail -3
-timeout 100 python tests/perf_kernels.py binsort 2>&1 | tail -1
-timeout 100 python tests/perf_kernels.py binsort --frames 8 --grid 100 --points 300000 2>&1 | tail -1
-timeout 100 python tests/perf_kernels.py binsort --frames 32 --grid 100 --points 300000 2>&1 | tail -1
+step() { echo "== $*"; timeout 40 "$@"; rc=$?; echo "rc=$rc"; if [ $rc -eq 124 ]; then echo "HANG: $*"; exit 3; fi; }
+step python -m pytest tests -m gpu -q -x -k "tensor_core" -p no:cacheprovider 2>&1 | tail -3
+[ ${PIPESTATUS[0]} -eq 3 ] && exit 3
+timeout 60 python tests/perf_kernels.py mlp 2>&1 | grep "tcgen05" || exit 3
