@@ -736,12 +736,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x260 + c);  // layer-5 chunk reduced
           } else {
             // transpose through shared memory: tile_s[channel][point]; lanes are consecutive points
+            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x270);   // accumulator in registers
 #pragma unroll
             for (int j = 0; j < 32; ++j) tile_s[(g * 32 + j) * kTStride + row] = v[j];
+            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x271);   // transposed tile stored
           }
         }
         if (CELL) {
           epi_bar_sync();
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x272);     // everyone's stores visible
           // Thread (row, part) now owns channel c*128 + row over the 32 tile slots [part*32, part*32+32),
           // which are in cell order: the maximum of each run of equal cell ids goes to the canvas.  A run
           // that touches the first or the last slot of this stretch may continue in a neighbouring
@@ -752,13 +755,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           float* canvas = a.out_canvas + (size_t)f * a.n_cells * c_out + ch;
           const float* trow = tile_s + row * kTStride + part * 32;
           const int* cids = cid_s + part * 32;
-          const uint32_t ends = endmask_s[part];
+          // the same word in every lane: broadcast through a shuffle so that the compiler knows the branches on its
+          // bits are warp-uniform (a possibly-divergent branch per slot costs a BSSY/BSYNC pair and its resolve latency)
+          const uint32_t ends = __shfl_sync(FULL_MASK, endmask_s[part], 0);
           float m = -INFINITY, gm = rmax[0];
           bool first_run = true;
+          // all 32 values first (one shared-memory latency, not eight), then four slots at a time: a group without a
+          // run end — most of them — is four maxima and ONE warp-uniform branch
+          float4 q[8];
+#pragma unroll
+          for (int b4 = 0; b4 < 8; ++b4) q[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
 #pragma unroll
           for (int b4 = 0; b4 < 8; ++b4) {
-            const float4 q4 = *reinterpret_cast<const float4*>(trow + b4 * 4);
-            const float e[4] = {q4.x, q4.y, q4.z, q4.w};
+            const float e[4] = {q[b4].x, q[b4].y, q[b4].z, q[b4].w};
+            if (((ends >> (b4 * 4)) & 0xfu) == 0u) {
+              m = fmaxf(fmaxf(m, fmaxf(e[0], e[1])), fmaxf(e[2], e[3]));
+              continue;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               m = fmaxf(m, e[k]);
@@ -782,7 +795,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             if (val > 0.0f) atomicMax(reinterpret_cast<int*>(canvas + (size_t)cids[31] * c_out), __float_as_int(val));
           }
           rmax[0] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x273);     // runs walked
           epi_bar_sync();           // tile_s, cid_s and endmask_s are free again
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x274);     // tile free
         }
         {
           const float r0 = rmax[0];
