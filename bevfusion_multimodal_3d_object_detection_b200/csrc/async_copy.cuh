@@ -40,6 +40,19 @@ __device__ __forceinline__ void bulk_copy_global_to_shared(void* dst, const void
                "l"(src), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
+// One lane of a fully converged warp.  Issue bulk copies from inside `if (elect_one())` with the WHOLE warp running
+// the surrounding loop: the copy's operands then live in uniform registers.  Issued from a lane that diverged long
+// before (`if (lane == 0) { loop }`), every UBLKCP sits in an ELECT + R2UR.BROADCAST waterfall and costs ~380 clk
+// whatever its size (tests/cuda/bulk_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // shared -> global bulk store; completion tracked by the bulk async-group of the issuing thread
 __device__ __forceinline__ void bulk_copy_shared_to_global(void* dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes)

@@ -140,18 +140,25 @@ __global__ void __launch_bounds__(256) bilinear_resize_staged_kernel(const float
   __syncthreads();
   const uint32_t bytes = (uint32_t)plane * sizeof(float);
   long long p = blockIdx.x;
-  if (tid == 0 && p < planes) {
-    mbarrier_expect_tx(&full[0], bytes);
-    bulk_copy_global_to_shared(buf, in + p * plane, bytes, &full[0]);
+  // copies are issued by an elected lane of the (converged) first warp: see elect_one()
+  if (tid < 32 && p < planes) {
+    if (elect_one()) {
+      mbarrier_expect_tx(&full[0], bytes);
+      bulk_copy_global_to_shared(buf, in + p * plane, bytes, &full[0]);
+    }
+    __syncwarp();
   }
   const int HW = H * W;
   uint32_t parity[2] = {0, 0};
   for (int s = 0; p < planes; p += gridDim.x, s ^= 1) {
     const long long pn = p + gridDim.x;
     // the other buffer was read in the previous trip; every thread passed the barrier at its end
-    if (tid == 0 && pn < planes) {
-      mbarrier_expect_tx(&full[s ^ 1], bytes);
-      bulk_copy_global_to_shared(buf + (size_t)(s ^ 1) * plane, in + pn * plane, bytes, &full[s ^ 1]);
+    if (tid < 32 && pn < planes) {
+      if (elect_one()) {
+        mbarrier_expect_tx(&full[s ^ 1], bytes);
+        bulk_copy_global_to_shared(buf + (size_t)(s ^ 1) * plane, in + pn * plane, bytes, &full[s ^ 1]);
+      }
+      __syncwarp();
     }
     mbarrier_wait(&full[s], parity[s]);
     parity[s] ^= 1;

@@ -379,23 +379,27 @@ __global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kerne
       }
     } else if (warp == kConsumers / 32) {
       // ================================ producer ================================
-      if (lane == 0) {
-        for (long long item = it; item < seg_end; ++item) {
-          const long long r = item % per_part;
-          const int b = (int)(r / n_groups);
-          const int g0 = (int)(r % n_groups) * CG;
-          const int ncg = min(CG, a.C - g0);
-          for (int cam = 0; cam < a.n_cam; ++cam) {
-            const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
-            if (hi <= lo) continue;   // no cell of the part sees this camera
-            const uint32_t bytes = (uint32_t)(hi - lo) * sizeof(float);
-            mbarrier_wait(&ctrl->empty[stage], phase ^ 1);
+      // the whole warp runs the loop, one elected lane issues (see elect_one)
+      for (long long item = it; item < seg_end; ++item) {
+        const long long r = item % per_part;
+        const int b = (int)(r / n_groups);
+        const int g0 = (int)(r % n_groups) * CG;
+        const int ncg = min(CG, a.C - g0);
+        for (int cam = 0; cam < a.n_cam; ++cam) {
+          const int lo = ctrl->band_lo[cam] & ~3, hi = (ctrl->band_hi[cam] + 3) & ~3;
+          if (hi <= lo) continue;   // no cell of the part sees this camera
+          const uint32_t bytes = (uint32_t)(hi - lo) * sizeof(float);
+          mbarrier_wait(&ctrl->empty[stage], phase ^ 1);
+          const float* src = a.feats + (((size_t)b * a.n_cam + cam) * a.C + g0) * plane + lo;
+          float* dst = ring + (size_t)stage * CG * stage_floats;
+          if (elect_one()) {
             mbarrier_expect_tx(&ctrl->full[stage], bytes * ncg);
-            const float* src = a.feats + (((size_t)b * a.n_cam + cam) * a.C + g0) * plane + lo;
-            float* dst = ring + (size_t)stage * CG * stage_floats;
-            for (int g = 0; g < ncg; ++g) bulk_copy_global_to_shared(dst + (size_t)g * stage_floats, src + (size_t)g * plane, bytes, &ctrl->full[stage]);
-            if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int g = 0; g < CG; ++g)
+              if (g < ncg) bulk_copy_global_to_shared(dst + (size_t)g * stage_floats, src + (size_t)g * plane, bytes, &ctrl->full[stage]);
           }
+          __syncwarp();
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
     } else {
