@@ -1,3 +1,2 @@
-timeout 100 python -m pytest tests -m gpu -q -x -k "camera" -p no:cacheprovider 2>&1 | tail -3
-timeout 100 python tests/perf_kernels.py camera 2>&1 | tail -3
-timeout 100 python tests/perf_kernels.py camera --grid 100 2>&1 | tail -3
+timeout 200 python -m pytest tests -m gpu -q -x -k "random_shapes" -p no:cacheprovider 2>&1 | tail -15
+timeout 100 python __graft_entry__.py smoke 2>&1 | tail -2

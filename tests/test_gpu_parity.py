@@ -488,3 +488,48 @@ def test_tensor_core_cell_canvas(cuda, B, N, W):
     only = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.BF16_TENSOR, tc_params=tc,
                                want_global=False)
     assert torch.equal(only, canvas)                            # deterministic, with or without the global output
+
+
+# ------------------------------------------------------------------------------------------------ randomised shapes
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_bin_sort_prepare_decode(cuda, seed):
+    """Shapes drawn at random (odd sizes, tiny and large grids, K near H*W): integer outputs stay bit-exact."""
+    rng = np.random.default_rng(1000 + seed)
+    # bin_sort
+    B, N = int(rng.integers(1, 5)), int(rng.integers(1, 9000))
+    W, H = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+    pts = np.zeros((B, N, 4), dtype=np.float32)
+    pts[..., 0] = rng.uniform(-60, 60, (B, N))
+    pts[..., 1] = rng.uniform(-60, 60, (B, N))
+    cell, perm, off = ops.bin_sort(dev_t(pts, cuda), W, H)
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, H)
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
+    for b in range(B):
+        rp, ro = orc.bin_sort(ref_cell[b], W * H)
+        np.testing.assert_array_equal(perm[b].cpu().numpy(), rp)
+        np.testing.assert_array_equal(off[b].cpu().numpy(), ro)
+    # lidar_prepare
+    rows = [int(rng.integers(0, 6000)) for _ in range(int(rng.integers(1, 5)))]
+    C = int(rng.integers(3, 7))
+    max_points = int(rng.integers(1, 5000))
+    sweeps = [syn.raw_sweep(2000 + seed * 10 + i, r, channels=C) for i, r in enumerate(rows)]
+    raw = np.concatenate(sweeps, axis=0) if sum(rows) else np.zeros((1, C), np.float32)[:0]
+    offs = torch.tensor([0] + list(np.cumsum(rows)), dtype=torch.int64, device=cuda)
+    if raw.shape[0]:
+        out, count = ops.lidar_prepare(dev_t(raw, cuda), offs, max_points, syn.PC_RANGE, max_frame_rows=max(max(rows), 1))
+        for b, s in enumerate(sweeps):
+            ref, n = orc.lidar_prepare(s, max_points, syn.PC_RANGE)
+            assert int(count[b]) == n
+            np.testing.assert_array_equal(out[b].cpu().numpy(), ref)
+    # decode: odd grids, few classes, K close to H*W
+    Hh, Ww, Cc = int(rng.integers(3, 40)), int(rng.integers(3, 40)), int(rng.integers(1, 12))
+    K = int(rng.integers(1, min(Hh * Ww, 300) + 1))
+    maps = syn.head_maps(3000 + seed, 2, Cc, Hh, Ww)
+    got = ops.centernet_decode(*[dev_t(maps[k], cuda) for k in ("heatmap", "offset", "size", "rot", "vel")], K, 2.048)
+    ref = orc.decode(maps, score_thresh=0.0, max_detections=K)
+    cnt = got["count"].cpu().numpy()
+    for b, r in enumerate(ref):
+        n = len(r["scores"])
+        assert cnt[b] == n
+        np.testing.assert_array_equal(got["scores"][b, :n].cpu().numpy(), r["scores"])
+        np.testing.assert_allclose(got["boxes"][b, :n].cpu().numpy(), r["boxes"], rtol=0, atol=1e-5)
