@@ -84,9 +84,10 @@ __global__ void __launch_bounds__(kThreads, 1) pointnet_mlp_f32_kernel(MlpArgs a
   const bool want_canvas = a.canvas != nullptr;
 
   const long long total = (long long)a.frames * a.tiles_per_frame;
-  const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
-  const long long t_begin = per_cta * blockIdx.x;
-  const long long t_end = t_begin + per_cta < total ? t_begin + per_cta : total;
+  // contiguous shares that differ by at most one tile (the first `extra` CTAs take one more)
+  const long long base_share = total / gridDim.x, extra = total % gridDim.x;
+  const long long t_begin = base_share * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
+  const long long t_end = t_begin + base_share + (blockIdx.x < extra ? 1 : 0);
 
   for (int n = tid; n < c_out; n += kThreads) runmax[n] = 0.0f;
   int cur_frame = -1;
@@ -355,7 +356,12 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024)
     B200BEV_CUDA_TRY(cudaFuncSetAttribute(pointnet_mlp_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)a.frames * a.tiles_per_frame;
-  long long grid = sm_count();
+  // persistent grid: as many CTAs as can be resident at once (the narrow radar MLP fits three per SM; with one per
+  // SM its 320 tiles took three rounds on 107 SMs), each walking a contiguous share of the tiles
+  int resident = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pointnet_mlp_f32_kernel, kThreads, smem) != cudaSuccess || resident < 1)
+    resident = 1;
+  long long grid = (long long)sm_count() * resident;
   if (grid > total) grid = total;
   pointnet_mlp_f32_kernel<<<(int)grid, kThreads, smem, st>>>(a);
   return launch_status();

@@ -81,6 +81,14 @@ def main():
         med, best = timeit(lambda: ops.lidar_prepare(raw, off, 35000, syn.PC_RANGE, max_frame_rows=rows), reps=20)
         by = F * 16.0 * (rows + 35000)
         print(f"lidar_prepare {F}x{rows} -> 35000     median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+    if args.what in ("radar", "all"):
+        rw, rb = orc.fold_layers(syn.mlp_weights(111, syn.RADAR_DIMS))
+        rblob, rdims = ops.pack_mlp_params([torch.from_numpy(w) for w in rw], [torch.from_numpy(b) for b in rb], dev)
+        fcw, fcb = (to(a) for a in syn.linear_weights(112, 1280, 256))
+        radars = [to(r) for r in syn.radar_batch(43, F)]
+        med, best = timeit(lambda: ops.radar_encode(radars, rblob, rdims, "concat", fcw, fcb), reps=20)
+        fl = F * 625 * 2.0 * (7 * 32 + 32 * 64 + 64 * 128 + 128 * 256) + F * 2.0 * 1280 * 256
+        print(f"radar_encode {F}x5x125               median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {fl / med / 1e9:8.2f} TFLOP/s", flush=True)
     if args.what in ("camera", "all"):
         g = torch.Generator(device=dev).manual_seed(1)
         feats = torch.relu(torch.randn((F, 6, 512, 57, 100), device=dev, generator=g))
