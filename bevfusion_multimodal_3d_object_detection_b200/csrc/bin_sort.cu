@@ -27,6 +27,7 @@
 //     perm[ base(cell, CTA) + sum of counts(cell, CTA, warps before mine) + rank ] = point.
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -197,6 +198,7 @@ struct RankedArgs {
   BinArgs a;
   int NW;   // warps (sub-slices) per CTA that walk points: 8, 4, 2 or 1
   int sub;  // points per sub-slice, multiple of 32, <= 65535
+  unsigned long long* dbg;  // debug only (B200BEV_BINSORT_TRACE): clock stamps of CTA (0,0), thread 0
 };
 
 // sum of the 16-bit counts [0, upto) of one cell row (NW entries, 2*NW bytes, naturally aligned)
@@ -218,6 +220,9 @@ __device__ __forceinline__ uint32_t row_prefix(const uint16_t* row, int NW, int 
 
 __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs ra) {
   const BinArgs& a = ra.a;
+  int dbg_n = 0;
+  auto stamp = [&]() { if (ra.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ra.dbg[dbg_n++] = clock64(); };
+  stamp();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
     for (int i = tid; i < nz; i += kBinThreads) z[i] = 0;
   }
   __syncthreads();
+  stamp();
 
   const int start = rank * a.slice;
   const int end = min(a.N, start + a.slice);
@@ -300,7 +306,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
       }
     }
   }
+  stamp();
   cluster.sync();
+  stamp();
 
   // ---- phase 2: exclusive scan over (cell, CTA), cells dealt out to the CTAs ----
   auto count_of = [&](int q, int bin) -> uint32_t {
@@ -330,7 +338,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
       for (int q = 0; q < CL; ++q) cluster.map_shared_rank(cta_tot, q)[rank] = t;
     }
   }
+  stamp();
   cluster.sync();
+  stamp();
   uint32_t carry = 0;
   for (int q = 0; q < rank; ++q) carry += cta_tot[q];
   int32_t* offsets = a.offsets + (size_t)b * nb;
@@ -368,7 +378,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
     carry += total;
     __syncthreads();
   }
+  stamp();
   cluster.sync();   // every base[] is written; no remote access after this point
+  stamp();
 
   // ---- phase 3: parallel placement ----
   int32_t* perm = a.perm + (size_t)b * a.N;
@@ -390,6 +402,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
     const uint32_t pos = base[bin] + row_prefix(whist + (size_t)bin * NW, NW, w) + rnk;
     perm[pos] = i;
   }
+  stamp();
 }
 
 }  // namespace
@@ -444,11 +457,20 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
       a.cache_cells = (smem + cache <= 100 * 1024 && (long long)W * H < 0xffff) ? 1 : 0;
       if (a.cache_cells) smem += cache;
       else if ((long long)W * H >= 0xffff) break;   // cell ids would not fit the packed form: legacy kernel
-      RankedArgs ra{a, NW, sub};
+      RankedArgs ra{a, NW, sub, nullptr};
+      if (getenv("B200BEV_BINSORT_TRACE")) B200BEV_CUDA_TRY(cudaMalloc(&ra.dbg, 16 * sizeof(unsigned long long)));
       if (smem > 48 * 1024)
         B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cfg.dynamicSmemBytes = smem;
       B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, bin_sort_ranked_kernel, ra));
+      if (ra.dbg) {   // debug: phase boundaries of CTA (0,0) in SM clocks since its start
+        unsigned long long h[16];
+        B200BEV_CUDA_TRY(cudaStreamSynchronize(cfg.stream));
+        B200BEV_CUDA_TRY(cudaMemcpy(h, ra.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "bin_sort trace (clk since start): zero %llu | phase1 %llu | sync %llu | mine %llu | sync %llu | scan %llu | sync %llu | place %llu\n",
+                h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+        cudaFree(ra.dbg);
+      }
       return launch_status();
     }
   }
