@@ -85,7 +85,7 @@ struct TcArgs {
   float* out_canvas;       // (B,n_cells,1024)
   int tiles_per_frame;
   long long total_tiles;
-  int cluster;             // CTAs per cluster sharing each weight stage by multicast (1, 2 or 4)
+  int cluster;             // 1: one CTA per tile stream (cta_group::1); 2: CTA pairs (cta_group::2), each CTA holding half of every weight stage
   unsigned long long* trace;  // debug only (B200BEV_TC_TRACE): clock stamps of CTA 0, else nullptr
   int debug;                  // debug only (B200BEV_TC_DEBUG): bit 0 = skip the weight copies after the first tile,
                               // bit 1 = skip the layer-5 epilogue, bit 2 = issue MMAs without waiting for weights
@@ -102,9 +102,14 @@ __device__ __forceinline__ void trace_ev(const TcArgs& a, int& idx, int base, un
 }
 
 constexpr int kImageStages = kStagesPerTile;
-__host__ __device__ inline size_t tc_blob_bytes(int C) {
-  return (size_t)kImageStages * kStageBytes + ((size_t)C * 64 + 64 + kBiasFloats) * sizeof(float);
+// blob: [single-CTA stage image][fp32 tail: W1^T, b1, biases][pair image: rank 0 stream, rank 1 stream]
+// The pair image holds, per CTA of a cta_group::2 pair, the 64 of every stage's 128 channel rows that CTA feeds to the
+// MMA (rank r: rows 64r .. 64r+63), stage after stage, so a ring pair is one contiguous 16 KB copy per CTA.
+__host__ __device__ inline size_t tc_pair_image_offset(int C) {
+  const size_t tail_end = (size_t)kImageStages * kStageBytes + ((size_t)C * 64 + 64 + kBiasFloats) * sizeof(float);
+  return (tail_end + 1023) & ~(size_t)1023;
 }
+__host__ __device__ inline size_t tc_blob_bytes(int C) { return tc_pair_image_offset(C) + (size_t)kImageStages * kStageBytes; }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,21 +140,31 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// Same copy, delivered to the same shared-memory offset (and signalled on the barrier at the same offset)
-// of every CTA of the cluster named in `mask`: one L2 read feeds several SMs.
-__device__ __forceinline__ void bulk_copy_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+// tcgen05.commit of a CTA pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
       : "memory");
 }
-// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
+// Same, without release semantics: for the relay, which forwards the completion of a bulk copy (the copy's bytes are
+// in shared memory before its mbarrier completes; the relay itself has written nothing that needs publishing)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
 }
 // One lane of a fully converged warp (elect.sync): the branch stays warp-uniform for the compiler.
 __device__ __forceinline__ bool elect_one() {
@@ -174,13 +189,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T, 128 x 128 x 16, bf16 -> f32
+// D[tmem] (+)= A[tmem] . B[smem]^T, 128 x 128 x 16 per CTA, bf16 -> f32.  CG = 2: one instruction of the leader CTA
+// drives both CTAs of the pair (M = 256), each with its own A and D and half of B (tests/cuda/umma2_probe.cu).
+template <int CG>
 __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
-      "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+        "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+        "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -237,9 +262,11 @@ __device__ __forceinline__ void butterfly_level(float* v, int lane) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <bool CELL, bool TRACE>
+template <bool CELL, bool TRACE, int CG>
 __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a) {
   constexpr int kStages = CELL ? kStagesCell : kStagesGlobal;
+  constexpr int kSlotBytes = kPairBytes / CG;                    // bytes of one ring pair in THIS CTA's shared memory
+  constexpr int kRingPairs = kStages * kStageBytes / kSlotBytes;  // a pair of CTAs keeps twice as many pairs in flight
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B: 1024-B aligned tiles
   float* tile_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);   // CELL: [128 channels][kTStride]
@@ -249,12 +276,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   float* bias_s = reinterpret_cast<float*>(scan_s + (CELL ? 8 : 0));                // L2 | L3 | L4 | L5
   float* w1_s = bias_s + kBiasFloats;                                               // W1^T (C x 64), then b1 (64)
   uint64_t* bars = reinterpret_cast<uint64_t*>(w1_s + kMaxCin * 64 + 64);
-  uint64_t* full = bars;                    // [kStages/2 used] weights of a pair of ring slots landed
-  uint64_t* empty = bars + kStages;         // [kStages/2 used] MMAs that read the pair retired
-  uint64_t* acc_full = empty + kStages;     // [3]        accumulator complete
+  uint64_t* full = bars;                    // [kRingPairs used] this CTA's weights of a ring pair landed
+  uint64_t* empty = bars + kStages;         // [kRingPairs used] MMAs that read the pair retired
+  uint64_t* peer_full = empty + kStages;    // [kRingPairs used] CG = 2, leader only: the follower's half landed too
+  uint64_t* acc_full = peer_full + kStages; // [3]        accumulator complete
   uint64_t* acc_empty = acc_full + 3;       // [3]        accumulator drained by the epilogue (one arrival per warp)
   uint64_t* act_ready = acc_empty + 3;      // [4]        K-pair kp (128 channels) of the next A operand is in TMEM (one arrival per warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 4);
+  uint64_t* accx = act_ready + 4;           // [1]        this CTA's warps have drained accX (layer 4, chunk 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accx + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -264,32 +293,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], a.cluster);   // every CTA of the cluster must have retired the stage
+      mbar_init(&empty[i], 1);
+      mbar_init(&peer_full[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiWarps);
+      mbar_init(&acc_empty[i], kEpiWarps * CG);   // the epilogue warps of BOTH CTAs report to the leader
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps * CG);
+    mbar_init(accx, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (a.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // Every CTA runs the same number of tile slots: the CTAs of a cluster consume the multicast weight
-  // stream in lock step.  Slots past the end of the work list are dummy tiles (MMAs run, nothing is stored).
-  const long long per_cta = (a.total_tiles + gridDim.x - 1) / gridDim.x;
-  const long long t_begin = per_cta * blockIdx.x;
+  // Work is dealt out in tile SLOTS of CG tiles: slot t of a cluster is tile t*CG + rank for its CTA `rank`.  Every
+  // cluster runs the same number of slots; tiles past the end of the work list are dummies (MMAs run, nothing is
+  // stored).  With CG = 2 the two CTAs of a pair walk their tiles in lock step: one MMA instruction stream, issued
+  // by the leader, serves both.
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+  const long long n_slots = (a.total_tiles + CG - 1) / CG;
+  const long long n_clusters = gridDim.x / CG;
+  const long long per_cta = (n_slots + n_clusters - 1) / n_clusters;
+  const long long t_begin = per_cta * (blockIdx.x / CG);
   const long long t_end = t_begin + per_cta;
-  const uint32_t cta_rank = a.cluster > 1 ? cluster_ctarank() : 0;
-  const uint16_t cta_mask = (uint16_t)((1u << a.cluster) - 1u);
 
   if (warp == 0) {
     // ================================ producer ================================
@@ -300,30 +339,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     // divergent lane, every UBLKCP sat in an ELECT + 4x R2UR.BROADCAST waterfall and cost ~380 clk.
     {
       const long long n_pairs = (t_end - t_begin) * kPairsPerTile;
-      constexpr int kRingPairs = kStages / 2;
       const bool free_weights = (a.debug & 1) != 0;   // experiment: how fast is the kernel when weights cost nothing?
-      const bool single_cta = a.cluster == 1;
-      const uint32_t part = kPairBytes / a.cluster, part_off = cta_rank * part;
+      // CG = 1: the whole 32 KB pair; CG = 2: this CTA's 16 KB of it, from its own stream of the pair image
+      const uint8_t* image = CG == 1 ? a.tc : a.tc + tc_pair_image_offset(a.C) + (size_t)cta_rank * kPairsPerTile * kSlotBytes;
       uint32_t pair = 0, phase = 0;
       int img = 0;   // pair within the tile's stream
       for (long long j = 0; j < n_pairs; ++j) {
         mbar_wait(&empty[pair], phase ^ 1);
-        uint8_t* dst = ring + (size_t)pair * kPairBytes;
-        const uint8_t* src = a.tc + (size_t)img * kPairBytes;
+        uint8_t* dst = ring + (size_t)pair * kSlotBytes;
+        const uint8_t* src = image + (size_t)img * kSlotBytes;
         if (elect_one()) {
           if (free_weights && j >= kPairsPerTile) {
             mbar_arrive(&full[pair]);
           } else {
-            mbar_expect_tx(&full[pair], kPairBytes);
-            if (single_cta) bulk_copy_g2s(dst, src, kPairBytes, &full[pair]);
-            // else: this CTA fetches its 1/cluster slice of the pair and multicasts it to all peers
-            else bulk_copy_g2s_multicast(dst + part_off, src + part_off, part, &full[pair], cta_mask);
+            mbar_expect_tx(&full[pair], kSlotBytes);
+            bulk_copy_g2s(dst, src, kSlotBytes, &full[pair]);
           }
         }
         __syncwarp();
         if (++img == kPairsPerTile) img = 0;
         if (++pair == kRingPairs) { pair = 0; phase ^= 1; }
       }
+    }
+  } else if (warp == 1 && CG == 2 && cta_rank != 0) {
+    // ================================ follower of a pair: relay ================================
+    // The leader issues the MMAs for both CTAs and must know that THIS CTA's half of a ring pair has landed: a
+    // bulk copy can only signal a barrier of the CTA it writes to, so this warp forwards every completion.
+    const long long n_pairs = (t_end - t_begin) * kPairsPerTile;
+    uint32_t pair = 0, phase = 0;
+    for (long long j = 0; j < n_pairs; ++j) {
+      mbar_wait(&full[pair], phase);
+      if (lane == 0) mbar_arrive_remote_relaxed(&peer_full[pair], 0);
+      __syncwarp();
+      if (++pair == kRingPairs) { pair = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -332,11 +380,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     // lane instead, every UTCHMMA was wrapped in an ELECT + 4x R2UR.BROADCAST "waterfall" loop and
     // took ~140 clk to issue — more than the 64 clk it executes (timeline in profiles/r01_tc_timeline.md).
     {
-      // instruction descriptor: D f32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major, N=128, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      // instruction descriptor: D f32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major, N = 128, M = 128 per CTA
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | (((128u * CG) >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(FULL_MASK, tmem, 0);                        // provably uniform
       const uint32_t ring_u = __shfl_sync(FULL_MASK, smem_u32(ring), 0);
-      constexpr int kRingPairs = kStages / 2;
       // ring pairs per trip: one (8 MMAs).  Two per trip halve the polls, but measured slower once the layer shapes
       // became compile-time constants (global mode 1.02 vs 1.05 ms) and stall a 4-pair ring (cell mode)
       constexpr int kTrip = (B200BEV_TC_TRIP) ? (B200BEV_TC_TRIP) : 1;
@@ -345,19 +392,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       uint32_t acc_parity = 0;  // bit b: parity of the next use of accumulator b
       int tr = 0;
       const bool wait_weights = !(a.debug & 4);      // debug bit 2: issue without waiting for the weights
-      const bool single_cta = a.cluster == 1;
       // 8 MMAs over one ring pair (K = 128): D[d_addr] (+)= A[a_addr .. a_addr+64 columns) . B[pair]^T
       auto issue_pair = [&](uint32_t d_addr, uint32_t a_addr, uint32_t pr, bool first, bool half) {
-        const uint64_t bdesc0 = make_b_desc(ring_u + pr * kPairBytes);
+        const uint64_t bdesc0 = make_b_desc(ring_u + pr * kSlotBytes);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + s * 8, bdesc0 + (uint64_t)(s * 2), idesc, !(first && s == 0));
+        for (int s = 0; s < 4; ++s) umma_ts<CG>(d_addr, a_addr + s * 8, bdesc0 + (uint64_t)(s * 2), idesc, !(first && s == 0));
         if (!half) {
-          const uint64_t bdesc1 = make_b_desc(ring_u + pr * kPairBytes + kStageBytes);
+          const uint64_t bdesc1 = make_b_desc(ring_u + pr * kSlotBytes + kSlotBytes / 2);
 #pragma unroll
-          for (int s = 0; s < 4; ++s) umma_ts(d_addr, a_addr + 32 + s * 8, bdesc1 + (uint64_t)(s * 2), idesc, 1u);
+          for (int s = 0; s < 4; ++s) umma_ts<CG>(d_addr, a_addr + 32 + s * 8, bdesc1 + (uint64_t)(s * 2), idesc, 1u);
         }
-        if (single_cta) tc_commit(&empty[pr]);
-        else tc_commit_multicast(&empty[pr], cta_mask);
+        if constexpr (CG == 1) tc_commit(&empty[pr]);
+        else tc_commit_pair(&empty[pr]);
+      };
+      auto commit_acc = [&](int buf) {
+        if constexpr (CG == 1) tc_commit(&acc_full[buf]);
+        else tc_commit_pair(&acc_full[buf]);
       };
       // One network layer, its shape a compile-time constant: chunks and trips are fully unrolled, so the accumulator
       // choice, the A-operand columns and the loop tests cost the issuing thread nothing at run time — every
@@ -399,14 +449,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             }
             if (wait_weights) {
               mbar_wait(&full[pair], phase);
-              if (two) mbar_wait(&full[pr1], ph1);
+              if constexpr (CG == 2) mbar_wait(&peer_full[pair], phase);
+              if (two) {
+                mbar_wait(&full[pr1], ph1);
+                if constexpr (CG == 2) mbar_wait(&peer_full[pr1], ph1);
+              }
             }
             tc_fence_after();
             const uint32_t a_addr = tmem_u + a_col + kp * 64;
             if (elect_one()) {
               issue_pair(d_addr, a_addr, pair, kp == 0, layer == 0);
               if (two) issue_pair(d_addr, a_addr + 64, pr1, false, false);
-              if (kp + kTrip >= kpairs) tc_commit(&acc_full[buf]);
+              if (kp + kTrip >= kpairs) commit_acc(buf);
             }
             __syncwarp();
             if (two) { pair = pr1; phase = ph1; }
@@ -462,11 +516,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 
     // one arrival per warp: every lane has fenced its tensor-memory accesses, __syncwarp orders them
     // before lane 0's arrive (512 per-thread arrivals on one barrier word cost more than the work they guard)
+    // (CG = 2: acc_empty and act_ready live in the leader, whose MMA warp waits on them; the follower arrives remotely)
     auto warp_arrive = [&](uint64_t* bar) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar);
+      if (lane == 0) {
+        if (CG == 1 || cta_rank == 0) mbar_arrive(bar);
+        // relaxed: what the leader's MMA warp needs is that this warp's tensor-memory accesses have COMPLETED
+        // (tcgen05.wait::ld / wait::st above) — tensor memory is not part of the generic memory model a release
+        // would order, and a release.cluster arrive stalls the warp for ~1,000 clk
+        else mbar_arrive_remote_relaxed(bar, 0);
+      }
     };
+    uint32_t accx_parity = 0;
     auto acc_wait = [&](int buf) {
       mbar_wait(&acc_full[buf], (full_phase >> buf) & 1);
       full_phase ^= 1u << buf;
@@ -544,10 +606,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 
     // (frame, tile-in-frame) of the running tile slot, advanced incrementally: one 64-bit division per
     // kernel instead of four per tile in each of the 16 warps
-    int tf = (int)(t_begin / a.tiles_per_frame), tt = (int)(t_begin % a.tiles_per_frame);
+    const long long tile0 = t_begin * CG + cta_rank;   // this CTA's first tile
+    int tf = (int)(tile0 / a.tiles_per_frame), tt = (int)(tile0 % a.tiles_per_frame);
     {
       // layer 1 of the first tile; every later tile's layer 1 is computed under the previous tile's layer 5
-      const bool dummy0 = t_begin >= a.total_tiles;
+      const bool dummy0 = tile0 >= a.total_tiles;
       float x[kMaxCin];
       load_point(dummy0 ? 0 : tf, dummy0 ? a.N : tt * kTileM + row, x);
       uint32_t packed[8];
@@ -557,12 +620,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     for (long long t = t_begin; t < t_end; ++t) {
       const bool tracer = (tid == 64);
       if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x200);          // tile start
-      const bool dummy = t >= a.total_tiles;
+      const long long tile = t * CG + cta_rank;
+      const bool dummy = tile >= a.total_tiles;
       const int f = dummy ? cur_frame : tf;
       const int s0 = dummy ? a.N : tt * kTileM;
-      // the slot after this one, for the prefetch below
-      int tf_next = tf, tt_next = tt + 1;
-      if (tt_next == a.tiles_per_frame) { tt_next = 0; ++tf_next; }
+      // this CTA's next tile, for the prefetch below
+      int tf_next = tf, tt_next = tt + CG;
+      while (tt_next >= a.tiles_per_frame) { tt_next -= a.tiles_per_frame; ++tf_next; }
       const bool new_frame = f != cur_frame;
       if (new_frame) {
         if (cur_frame >= 0) flush(cur_frame);
@@ -602,7 +666,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             while (true) {
               const int c = c_scan + row;
               const int o = c < a.n_cells ? __ldg(foff + c) : 0x7fffffff;
-              if (o >= s0 && o < s0 + kTileM && o < n_in) atomicMax(&cid_s[o - s0], c);
+              // a cell that starts before the tile (the carried one, or — for a CTA of a pair, which skips its peer's
+              // tile — any cell that started in between) competes for slot 0
+              if (o < s0 + kTileM && o < n_in) atomicMax(&cid_s[o > s0 ? o - s0 : 0], c);
               if (row == kTileM - 1) scan_s[4 + (it & 1)] = (o < s0 + kTileM) && (c + 1 < a.n_cells);
               bar128();
               if (!scan_s[4 + (it & 1)]) break;
@@ -648,6 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             TC_LD32(r, tm + acc_column(buf) + q * 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             warp_arrive(&acc_empty[buf]);   // the values are in registers: the next chunk may overwrite the accumulator
+            if (layer == 2 && c == 1 && lane == 0) mbar_arrive(accx);   // ... and, locally: this warp is done with accX
             uint32_t packed[16];
             const float* bq = bl + c * 128 + q * 32;
 #pragma unroll
@@ -656,9 +723,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
               const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bq[2 * j + 1], 0.0f);
               packed[j] = pack_bf16x2(v0, v1);
             }
-            // chunks 2 and 3 of layer 4 land on accX: every warp must have drained it (layer 4, chunk 1) first.
-            // accX completes two drain phases per tile (layer 3 chunk 1, layer 4 chunk 1): this is the odd one.
-            if (layer == 2 && c == 2) mbar_wait(&acc_empty[2], 1);
+            // chunks 2 and 3 of layer 4 land on accX: every warp of this CTA must have drained it (layer 4, chunk 1) first
+            if (layer == 2 && c == 2) {
+              mbar_wait(accx, accx_parity);
+              accx_parity ^= 1;
+            }
             TC_ST16(tm + out_col + c * 64 + q * 16, packed, 0);
           }
           // chunk c is K-pair c of the next layer: tell the MMA warp these 128 channels are in place
@@ -670,7 +739,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 
       // ---- prefetch the next tile's point: its DRAM latency hides under layer 5 ----
       const bool more = t + 1 < t_end;
-      const bool dn = t + 1 >= a.total_tiles;
+      const bool dn = tile + CG >= a.total_tiles;
       const int fn = dn ? 0 : tf_next;
       const int slotn = dn ? a.N : tt_next * kTileM + row;
       have_pre = false;
@@ -814,10 +883,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
 
   tc_fence_before();
   __syncthreads();
-  if (a.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still write its shared memory
+  if constexpr (CG == 2) cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its peer may still signal or compute
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -839,9 +909,8 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
   }
   if (idx < total) {
     const int s_img = idx / (128 * 8), r = (idx / 8) % 128, ch = idx % 8;
-    if (s_img == 1) {   // padding stage of the layer-2 pair (no early return: every thread serves the tail loop below)
-      *reinterpret_cast<uint4*>(tc + (size_t)s_img * kStageBytes + r * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
-    } else {
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);   // s_img == 1: the padding stage of the layer-2 pair
+    if (s_img != 1) {
       const int s = s_img == 0 ? 0 : s_img - 1;
       int layer, i;
       if (s < 1) { layer = 1; i = s; }
@@ -855,8 +924,14 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
       __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(wt[(size_t)(k0 + ch * 8 + j) * Nout + n0 + r]);
-      *reinterpret_cast<uint4*>(tc + (size_t)s_img * kStageBytes + r * 128 + ((ch ^ (r & 7)) * 16)) = *reinterpret_cast<uint4*>(v);
+      val = *reinterpret_cast<uint4*>(v);
     }
+    // single-CTA image: 128 rows per stage
+    *reinterpret_cast<uint4*>(tc + (size_t)s_img * kStageBytes + r * 128 + ((ch ^ (r & 7)) * 16)) = val;
+    // pair image (cta_group::2): rank h of a pair streams rows 64h .. 64h+63 of every stage, 8 KB per stage
+    const int h = r / 64, rr = r % 64;
+    *reinterpret_cast<uint4*>(tc + tc_pair_image_offset(C) + ((size_t)h * kImageStages + s_img) * (kStageBytes / 2) + rr * 128 +
+                              ((ch ^ (rr & 7)) * 16)) = val;
   }
   // tail: W1^T, b1, then the biases of layers 2..5, fp32
   float* tailp = reinterpret_cast<float*>(tc + (size_t)kImageStages * kStageBytes);
@@ -879,24 +954,23 @@ bool tc_dims_supported(const int32_t* dims, int n_layers) {
          dims[4] == 512 && dims[5] == 1024;
 }
 
-// Cluster size of the tensor-core kernel; B200BEV_TC_CLUSTER (1, 2 or 4) overrides the default for experiments.
-// Measured on B200 (32 x 35,000 points): cluster 1 1.50 ms, cluster 2 1.58 ms, cluster 4 ~2x slower (fewer
-// co-resident clusters).  Multicast does not pay because the weight stream is not the limiter (a run with the
-// copies disabled takes the same time), so the default is 1; the multicast path stays for larger weight sets.
+// 1: every CTA runs its own MMA stream (cta_group::1).  2: CTA pairs (cta_group::2) — the leader's one instruction
+// stream drives both SMs, each CTA keeps half of every weight stage, so the shared-memory traffic of the B operand
+// and of the weight stream, and the MMA instructions issued per tile, are halved.  B200BEV_TC_CLUSTER=1|2 overrides.
 int tc_cluster_size() {
   const char* e = getenv("B200BEV_TC_CLUSTER");
   if (e) {
     const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) return v;
+    if (v == 1 || v == 2) return v;
   }
-  return 1;
+  return 2;   // measured on B200 (32 x 35,000 points): pairs 0.98 ms global / 1.43 ms cell, single CTAs 1.03 / 1.53
 }
 
 size_t tc_smem_bytes(bool cell) {
   const int stages = cell ? kStagesCell : kStagesGlobal;
   return 1024 + (size_t)stages * kStageBytes + (cell ? (128 * kTStride + 128 + 4) * sizeof(float) : 0) +
          (cell ? 8 * sizeof(int) : 0) + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
-         (2 * stages + 10) * sizeof(uint64_t) + 16;
+         (3 * stages + 11) * sizeof(uint64_t) + 16;
 }
 
 }  // namespace
@@ -918,10 +992,9 @@ int pointnet_encode_tc(const float* points, int B, int N, int C, const float* pa
   const size_t smem = tc_smem_bytes(cell);
   if (out_global) B200BEV_CUDA_TRY(cudaMemsetAsync(out_global, 0, (size_t)B * 1024 * sizeof(float), st));
   if (out_canvas) B200BEV_CUDA_TRY(cudaMemsetAsync(out_canvas, 0, (size_t)B * n_cells * 1024 * sizeof(float), st));
-  // cluster size: weight stages are multicast to `cluster` SMs, dividing the L2 read traffic of the
-  // 1.39 MB-per-tile weight stream (the kernel's bottleneck at cluster 1) by that factor
+  // CTA pairs (cta_group::2) when asked for and there are at least two tiles
   int cluster = tc_cluster_size();
-  while (cluster > 1 && a.total_tiles < 2LL * cluster) cluster >>= 1;
+  if (a.total_tiles < 2) cluster = 1;
   a.cluster = cluster;
   // debug timeline: B200BEV_TC_TRACE=<file> dumps CTA 0's clock stamps after a (synchronous) launch
   if (const char* dbg = getenv("B200BEV_TC_DEBUG")) a.debug = atoi(dbg);
@@ -948,8 +1021,13 @@ int pointnet_encode_tc(const float* points, int B, int N, int C, const float* pa
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // the clock-stamp instrumentation is compiled out of the production instantiations
-  void (*kern)(TcArgs) = cell ? (d_trace ? pointnet_mlp_tc_kernel<true, true> : pointnet_mlp_tc_kernel<true, false>)
-                              : (d_trace ? pointnet_mlp_tc_kernel<false, true> : pointnet_mlp_tc_kernel<false, false>);
+  void (*kern)(TcArgs);
+  if (cluster == 2)
+    kern = cell ? (d_trace ? pointnet_mlp_tc_kernel<true, true, 2> : pointnet_mlp_tc_kernel<true, false, 2>)
+                : (d_trace ? pointnet_mlp_tc_kernel<false, true, 2> : pointnet_mlp_tc_kernel<false, false, 2>);
+  else
+    kern = cell ? (d_trace ? pointnet_mlp_tc_kernel<true, true, 1> : pointnet_mlp_tc_kernel<true, false, 1>)
+                : (d_trace ? pointnet_mlp_tc_kernel<false, true, 1> : pointnet_mlp_tc_kernel<false, false, 1>);
   B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
   if (d_trace) {

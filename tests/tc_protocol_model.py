@@ -1,12 +1,16 @@
 """Executable model of the synchronisation protocol of csrc/pointnet_mlp_tc.cu (test infrastructure).
 
-Three agents — the weight producer, the MMA issuer and the epilogue — talk through mbarriers whose waiters
-only see a PHASE PARITY (mbarrier.try_wait.parity): a waiter that falls two phases behind, or a barrier
-that is re-armed before a waiter's second look at it, deadlocks or reads stale data.  Two such bugs were
-found on the GPU the expensive way (a hung box); this model replays the protocol under random schedules with
-asynchronous completions (bulk copies land in any order, the tensor pipe retires MMAs in issue order at
-arbitrary times) and reports deadlocks and data hazards.  It mirrors the loops of the kernel one to one:
-change both together.
+The kernel's agents — weight producer(s), the MMA issuer, the epilogue(s) and, for a cta_group::2 pair, the
+follower's relay — talk through mbarriers whose waiters only see a PHASE PARITY (mbarrier.try_wait.parity): a
+waiter that falls two phases behind, or a barrier that is re-armed before a waiter's second look at it,
+deadlocks or reads stale data.  Two such bugs were found on the GPU the expensive way (a hung box); this model
+replays the protocol under random schedules with asynchronous completions (bulk copies land in any order, the
+tensor pipe retires MMAs in issue order at arbitrary times) and reports deadlocks and data hazards.  It mirrors
+the loops of the kernel one to one: change both together.
+
+cg = 1: one CTA.  cg = 2: a CTA pair — two producers (each fills its own half of every ring pair), the relay
+(follower: full -> leader's peer_full), ONE issuer (the leader's) whose commits reach the barriers of both CTAs,
+two epilogues whose acc_empty / act_ready arrivals all go to the leader's barriers (count 2 here: one per CTA).
 """
 from __future__ import annotations
 
@@ -30,34 +34,51 @@ def acc_buffer(layer: int, c: int) -> int:
 
 
 class Bar:
-    def __init__(self):
+    def __init__(self, count: int = 1):
         self.bit = 0
+        self.count = count
+        self.pending = 0
 
     def done(self, parity: int) -> bool:      # mbarrier.try_wait.parity
         return self.bit != parity
 
-    def complete(self):
-        self.bit ^= 1
+    def arrive(self):
+        self.pending += 1
+        if self.pending == self.count:
+            self.pending = 0
+            self.bit ^= 1
+
+    complete = arrive                          # a barrier with count 1
 
 
-def producer(n_tiles, ring_pairs, bars, inflight):
+def producer(n_tiles, ring_pairs, full, empty, inflight, who):
     pair = phase = 0
-    img = 0
     for j in range(n_tiles * PAIRS_PER_TILE):
-        yield ("wait", bars["empty"][pair], phase ^ 1)
-        inflight.append((pair, j))             # expect_tx + cp.async.bulk
+        yield ("wait", empty[pair], phase ^ 1)
+        inflight.append((who, pair, j))        # expect_tx + cp.async.bulk
         yield ("step",)
-        img = (img + 1) % PAIRS_PER_TILE
         pair += 1
         if pair == ring_pairs:
             pair, phase = 0, phase ^ 1
 
 
-def issuer(n_tiles, ring_pairs, bars, pipe, state, trip=2):
+def relay(n_tiles, ring_pairs, full, peer_full):
+    pair = phase = 0
+    for _ in range(n_tiles * PAIRS_PER_TILE):
+        yield ("wait", full[pair], phase)
+        peer_full[pair].arrive()               # mbarrier.arrive on the leader's barrier
+        yield ("step",)
+        pair += 1
+        if pair == ring_pairs:
+            pair, phase = 0, phase ^ 1
+
+
+def issuer(n_tiles, ring_pairs, bars, pipe, state, trip, cg):
     pair = phase = 0
     act_phase = [0, 0, 0, 0]
     acc_parity = [0, 0, 0]
     stream = 0
+    full = bars["full"][0]
     for t in range(n_tiles):
         for layer in range(4):
             for c in range(N_CHUNKS[layer]):
@@ -76,15 +97,20 @@ def issuer(n_tiles, ring_pairs, bars, pipe, state, trip=2):
                         if two:
                             yield ("wait", bars["act_ready"][kp + 1], act_phase[kp + 1])
                             act_phase[kp + 1] ^= 1
-                    yield ("wait", bars["full"][pair], phase)
+                    yield ("wait", full[pair], phase)
+                    if cg == 2:
+                        yield ("wait", bars["peer_full"][pair], phase)
                     if two:
-                        yield ("wait", bars["full"][pr1], ph1)
-                    # data checks at issue time
-                    assert state["ring"][pair] == stream, f"ring pair {pair} holds {state['ring'][pair]}, wanted {stream}"
-                    if two:
-                        assert state["ring"][pr1] == stream + 1, "second ring pair holds the wrong weights"
-                    assert state["acc_owner"][buf] in (None, (t, layer, c)), f"accumulator {buf} overwritten before it was drained"
-                    state["acc_owner"][buf] = (t, layer, c)
+                        yield ("wait", full[pr1], ph1)
+                        if cg == 2:
+                            yield ("wait", bars["peer_full"][pr1], ph1)
+                    # data checks at issue time, for every CTA the instruction touches
+                    for r in range(cg):
+                        assert state["ring"][r][pair] == stream, f"CTA {r}: ring pair {pair} holds {state['ring'][r][pair]}, wanted {stream}"
+                        if two:
+                            assert state["ring"][r][pr1] == stream + 1, f"CTA {r}: second ring pair holds the wrong weights"
+                        assert state["acc_owner"][r][buf] in (None, (t, layer, c)), f"CTA {r}: accumulator {buf} overwritten before it was drained"
+                        state["acc_owner"][r][buf] = (t, layer, c)
                     last = kp + trip >= K_PAIRS[layer]
                     pipe.append(("mma", pair, (buf, (t, layer, c)) if (last and not two) else None))
                     if two:
@@ -99,58 +125,71 @@ def issuer(n_tiles, ring_pairs, bars, pipe, state, trip=2):
                     kp += trip
 
 
-def epilogue(n_tiles, bars, state):
+def epilogue(n_tiles, bars, state, r):
+    """Epilogue of CTA r: waits on ITS acc_full / accx, arrives on the LEADER's acc_empty / act_ready."""
     full_phase = [0, 0, 0]
-    bars["act_ready"][0].complete()            # layer 1 of the first tile
+    accx_parity = 0
+    acc_full, accx = bars["acc_full"][r], bars["accx"][r]
+    bars["act_ready"][0].arrive()              # layer 1 of the first tile
     yield ("step",)
     for t in range(n_tiles):
         more = t + 1 < n_tiles
         for layer in range(3):
             for c in range(N_CHUNKS[layer]):
                 buf = acc_buffer(layer, c)
-                yield ("wait", bars["acc_full"][buf], full_phase[buf])
+                yield ("wait", acc_full[buf], full_phase[buf])
                 full_phase[buf] ^= 1
-                assert state["acc_done"][buf] == (t, layer, c), "epilogue drains an accumulator that holds another chunk"
-                state["acc_owner"][buf] = None
-                bars["acc_empty"][buf].complete()
+                assert state["acc_done"][r][buf] == (t, layer, c), "epilogue drains an accumulator that holds another chunk"
+                state["acc_owner"][r][buf] = None
+                bars["acc_empty"][buf].arrive()
+                if layer == 2 and c == 1:
+                    accx.arrive()
                 yield ("step",)
                 if layer == 2 and c == 2:
-                    yield ("wait", bars["acc_empty"][2], 1)
-                bars["act_ready"][c].complete()
+                    yield ("wait", accx, accx_parity)
+                    accx_parity ^= 1
+                bars["act_ready"][c].arrive()
                 yield ("step",)
         for c in range(8):
             buf = c & 1
-            yield ("wait", bars["acc_full"][buf], full_phase[buf])
+            yield ("wait", acc_full[buf], full_phase[buf])
             full_phase[buf] ^= 1
-            assert state["acc_done"][buf] == (t, 3, c)
+            assert state["acc_done"][r][buf] == (t, 3, c)
             if c == 7 and more:
-                bars["act_ready"][0].complete()   # layer 1 of the next tile
+                bars["act_ready"][0].arrive()   # layer 1 of the next tile
                 yield ("step",)
-            state["acc_owner"][buf] = None
-            bars["acc_empty"][buf].complete()
+            state["acc_owner"][r][buf] = None
+            bars["acc_empty"][buf].arrive()
             yield ("step",)
 
 
-def run(n_tiles: int, ring_pairs: int, seed: int, max_steps: int = 2_000_000, trip: int = 2):
-    """Returns 'ok' or a description of the failure."""
+def make_bars(ring_pairs: int, cg: int):
+    return {"full": [[Bar() for _ in range(ring_pairs)] for _ in range(cg)],
+            "empty": [[Bar() for _ in range(ring_pairs)] for _ in range(cg)],
+            "peer_full": [Bar() for _ in range(ring_pairs)],
+            "acc_full": [[Bar() for _ in range(3)] for _ in range(cg)],
+            "accx": [Bar() for _ in range(cg)],
+            "acc_empty": [Bar(cg) for _ in range(3)],
+            "act_ready": [Bar(cg) for _ in range(4)]}
+
+
+def run(n_tiles: int, ring_pairs: int, seed: int, max_steps: int = 4_000_000, trip: int = 1, cg: int = 1, bars=None):
+    """Returns 'ok' or a description of the failure.  n_tiles = tile slots per cluster."""
     rnd = random.Random(seed)
-    bars = {"full": [Bar() for _ in range(ring_pairs)], "empty": [Bar() for _ in range(ring_pairs)],
-            "acc_full": [Bar() for _ in range(3)], "acc_empty": [Bar() for _ in range(3)],
-            "act_ready": [Bar() for _ in range(4)]}
+    bars = bars if bars is not None else make_bars(ring_pairs, cg)
     inflight, pipe = [], deque()
-    state = {"ring": [None] * ring_pairs, "acc_owner": [None] * 3, "acc_done": [None] * 3}
-    agents = {"producer": producer(n_tiles, ring_pairs, bars, inflight),
-              "issuer": issuer(n_tiles, ring_pairs, bars, pipe, state, trip),
-              "epilogue": epilogue(n_tiles, bars, state)}
-    pending = {}
-    for name, g in list(agents.items()):
-        pending[name] = next(g)
+    state = {"ring": [[None] * ring_pairs for _ in range(cg)], "acc_owner": [[None] * 3 for _ in range(cg)],
+             "acc_done": [[None] * 3 for _ in range(cg)]}
+    agents = {"issuer": issuer(n_tiles, ring_pairs, bars, pipe, state, trip, cg)}
+    for r in range(cg):
+        agents[f"producer{r}"] = producer(n_tiles, ring_pairs, bars["full"][r], bars["empty"][r], inflight, r)
+        agents[f"epilogue{r}"] = epilogue(n_tiles, bars, state, r)
+    if cg == 2:
+        agents["relay"] = relay(n_tiles, ring_pairs, bars["full"][1], bars["peer_full"])
+    pending = {name: next(g) for name, g in agents.items()}
     try:
         for _ in range(max_steps):
-            choices = []
-            for name, req in pending.items():
-                if req[0] == "step" or (req[0] == "wait" and req[1].done(req[2])):
-                    choices.append(name)
+            choices = [name for name, req in pending.items() if req[0] == "step" or req[1].done(req[2])]
             if inflight:
                 choices.append("land")
             if pipe:
@@ -159,15 +198,16 @@ def run(n_tiles: int, ring_pairs: int, seed: int, max_steps: int = 2_000_000, tr
                 return "ok" if not pending else f"deadlock: waiting {sorted(pending)}"
             pick = rnd.choice(choices)
             if pick == "land":
-                pair, j = inflight.pop(rnd.randrange(len(inflight)))
-                state["ring"][pair] = j
-                bars["full"][pair].complete()
+                who, pair, j = inflight.pop(rnd.randrange(len(inflight)))
+                state["ring"][who][pair] = j
+                bars["full"][who][pair].arrive()
             elif pick == "retire":
                 _, pair, acc = pipe.popleft()
-                bars["empty"][pair].complete()     # tcgen05.commit -> empty[pair]
-                if acc is not None:
-                    state["acc_done"][acc[0]] = acc[1]
-                    bars["acc_full"][acc[0]].complete()
+                for r in range(cg):                # tcgen05.commit (multicast for a pair) -> every CTA's barriers
+                    bars["empty"][r][pair].arrive()
+                    if acc is not None:
+                        state["acc_done"][r][acc[0]] = acc[1]
+                        bars["acc_full"][r][acc[0]].arrive()
             else:
                 try:
                     pending[pick] = next(agents[pick])
