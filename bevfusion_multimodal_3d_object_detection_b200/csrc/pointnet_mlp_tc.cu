@@ -46,6 +46,8 @@ constexpr int kTileM = 128;
 constexpr int kStageBytes = 16384;  // 128 rows x 64 bf16
 constexpr int kStagesGlobal = 12;   // ring depth when shared memory holds nothing but weights
 constexpr int kStagesCell = 8;      // cell mode gives 66 KB to the transposing tile below
+constexpr int kStagesCellPair = 4;  // cell mode of a CTA pair: half the ring bytes carry the same number of pairs, the
+                                    // other half holds a SECOND transposing tile (stores of chunk c+1 overlap the walk of c)
 constexpr int kTStride = 132;       // floats per channel row of the tile: 16-B aligned, conflict-free both ways
 constexpr int kEpiThreads = 512;     // 16 epilogue warps: 4 per TMEM lane quadrant
 constexpr int kTcThreads = 64 + kEpiThreads;
@@ -264,13 +266,14 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;"
 
 template <bool CELL, bool TRACE, int CG>
 __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a) {
-  constexpr int kStages = CELL ? kStagesCell : kStagesGlobal;
+  constexpr int kStages = CELL ? (CG == 2 ? kStagesCellPair : kStagesCell) : kStagesGlobal;
+  constexpr int kTileBufs = (CELL && CG == 2) ? 2 : 1;   // transposing tiles
   constexpr int kSlotBytes = kPairBytes / CG;                    // bytes of one ring pair in THIS CTA's shared memory
   constexpr int kRingPairs = kStages * kStageBytes / kSlotBytes;  // a pair of CTAs keeps twice as many pairs in flight
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B: 1024-B aligned tiles
   float* tile_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);   // CELL: [128 channels][kTStride]
-  int* cid_s = reinterpret_cast<int*>(tile_s + (CELL ? 128 * kTStride : 0));        // CELL: cell id of each tile slot
+  int* cid_s = reinterpret_cast<int*>(tile_s + (CELL ? kTileBufs * 128 * kTStride : 0));   // CELL: cell id of each tile slot
   uint32_t* endmask_s = reinterpret_cast<uint32_t*>(cid_s + (CELL ? 128 : 0));      // CELL: run-end flags, one word per warp
   int* scan_s = reinterpret_cast<int*>(endmask_s + (CELL ? 4 : 0));                 // CELL: [0,4) warp maxima, [4,6) "more cells" flags
   float* bias_s = reinterpret_cast<float*>(scan_s + (CELL ? 8 : 0));                // L2 | L3 | L4 | L5
@@ -807,7 +810,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             // transpose through shared memory: tile_s[channel][point]; lanes are consecutive points
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x270);   // accumulator in registers
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tile_s[(g * 32 + j) * kTStride + row] = v[j];
+            for (int j = 0; j < 32; ++j) tile_s[(kTileBufs == 2 ? (c & 1) * 128 * kTStride : 0) + (g * 32 + j) * kTStride + row] = v[j];
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x271);   // transposed tile stored
           }
         }
@@ -822,7 +825,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           const int ch = c * 128 + row;
           const float bias = b5[ch];
           float* canvas = a.out_canvas + (size_t)f * a.n_cells * c_out + ch;
-          const float* trow = tile_s + row * kTStride + part * 32;
+          const float* trow = tile_s + (kTileBufs == 2 ? (c & 1) * 128 * kTStride : 0) + row * kTStride + part * 32;
           const int* cids = cid_s + part * 32;
           // the same word in every lane: broadcast through a shuffle so that the compiler knows the branches on its
           // bits are warp-uniform (a possibly-divergent branch per slot costs a BSSY/BSYNC pair and its resolve latency)
@@ -865,7 +868,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           }
           rmax[0] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
           if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x273);     // runs walked
-          epi_bar_sync();           // tile_s, cid_s and endmask_s are free again
+          // One tile: it is free again when everyone has walked it.  Two tiles: the barrier after the NEXT chunk's
+          // stores already proves that (a thread gets there only after this walk), so warps that finish early go
+          // straight on to the next chunk; cid_s / endmask_s are protected once per tile, below.
+          if (kTileBufs == 1 || c == 7) epi_bar_sync();
           if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x274);     // tile free
         }
         {
@@ -966,9 +972,10 @@ int tc_cluster_size() {
   return 2;   // measured on B200 (32 x 35,000 points): pairs 0.98 ms global / 1.43 ms cell, single CTAs 1.03 / 1.53
 }
 
-size_t tc_smem_bytes(bool cell) {
-  const int stages = cell ? kStagesCell : kStagesGlobal;
-  return 1024 + (size_t)stages * kStageBytes + (cell ? (128 * kTStride + 128 + 4) * sizeof(float) : 0) +
+size_t tc_smem_bytes(bool cell, int cluster) {
+  const int stages = cell ? (cluster == 2 ? kStagesCellPair : kStagesCell) : kStagesGlobal;
+  const int tile_bufs = (cell && cluster == 2) ? 2 : 1;
+  return 1024 + (size_t)stages * kStageBytes + (cell ? (tile_bufs * 128 * kTStride + 128 + 4) * sizeof(float) : 0) +
          (cell ? 8 * sizeof(int) : 0) + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
          (3 * stages + 11) * sizeof(uint64_t) + 16;
 }
@@ -989,13 +996,13 @@ int pointnet_encode_tc(const float* points, int B, int N, int C, const float* pa
   a.perm = perm; a.offsets = offsets; a.n_cells = n_cells; a.out_canvas = out_canvas;
   a.tiles_per_frame = ceil_div(N, kTileM);
   a.total_tiles = (long long)B * a.tiles_per_frame;
-  const size_t smem = tc_smem_bytes(cell);
   if (out_global) B200BEV_CUDA_TRY(cudaMemsetAsync(out_global, 0, (size_t)B * 1024 * sizeof(float), st));
   if (out_canvas) B200BEV_CUDA_TRY(cudaMemsetAsync(out_canvas, 0, (size_t)B * n_cells * 1024 * sizeof(float), st));
   // CTA pairs (cta_group::2) when asked for and there are at least two tiles
   int cluster = tc_cluster_size();
   if (a.total_tiles < 2) cluster = 1;
   a.cluster = cluster;
+  const size_t smem = tc_smem_bytes(cell, cluster);
   // debug timeline: B200BEV_TC_TRACE=<file> dumps CTA 0's clock stamps after a (synchronous) launch
   if (const char* dbg = getenv("B200BEV_TC_DEBUG")) a.debug = atoi(dbg);
   const char* trace_path = getenv("B200BEV_TC_TRACE");
