@@ -18,6 +18,9 @@
 //
 // Tie order: torch.topk leaves it unspecified; this kernel defines it as ascending
 // flat index, which is what the oracle uses too.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200bev {
@@ -45,6 +48,7 @@ struct DecodeArgs {
   int32_t* count;
   unsigned long long* cand;  // workspace: (B, C, K) packed (key << 32 | ~index)
   int* done;                 // workspace: (B) arrival tickets, zero on entry and on exit
+  unsigned long long* dbg;   // debug only (B200BEV_DECODE_TRACE): clock stamps
 };
 
 __device__ __forceinline__ unsigned long long pack_entry(uint32_t key, uint32_t index) {
@@ -97,7 +101,8 @@ __device__ void load_plane_keys(const float* __restrict__ plane, int H, int W, u
 // Steps 2: top-K of keys[0..n) -> sel[0..K) sorted by (key desc, index asc); sel has P >= K slots
 // (P a power of two).  hist: 256 counters, wsum: 32 ints, scal: 4 ints.  All threads must call.
 __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long long* sel, int P,
-                           uint32_t* hist, int* wsum, int* scal) {
+                           uint32_t* hist, int* wsum, int* scal, unsigned long long* dbg = nullptr, int* dn = nullptr) {
+  auto stamp = [&]() { if (dbg && threadIdx.x == 0) dbg[(*dn)++] = clock64(); };
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = nthr >> 5;
   uint32_t prefix = 0, mask = 0;
@@ -113,9 +118,15 @@ __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long lon
         const uint32_t k = keys[i];
         if ((k & mask) == prefix) digit = (k >> shift) & 255u;
       }
-      // warp-aggregate: post-NMS most keys are the key of 0.0 and would serialise on one counter
-      const unsigned peers = __match_any_sync(FULL_MASK, digit);
-      if (digit < 256u && (peers & lanemask_lt()) == 0) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      if (pass == 0) {
+        // warp-aggregate: post-NMS most keys are the key of 0.0 and would serialise on one counter.  (Only in the
+        // first pass: later passes see a few matching keys among lanes that all differ, and MATCH.ANY costs ~600 clk
+        // on 32 distinct values — it was 3/4 of this function's time.)
+        const unsigned peers = __match_any_sync(FULL_MASK, digit);
+        if (digit < 256u && (peers & lanemask_lt()) == 0) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      } else if (digit < 256u) {
+        atomicAdd(&hist[digit], 1u);
+      }
     }
     __syncthreads();
     if (warp == 0) {
@@ -146,6 +157,7 @@ __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long lon
     mask |= 0xffu << shift;
     need = scal[1];
     __syncthreads();
+    stamp();
   }
   const uint32_t T = prefix;  // the K-th largest key
   const int need_eq = need;   // how many entries equal to T belong to the top K
@@ -159,9 +171,22 @@ __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long lon
       sel[s] = pack_entry(k, (uint32_t)i);
     }
   }
+  stamp();
   // entries equal to T, lowest index first
+  if (need_eq == 1) {
+    // the tie-free case: the one entry equal to T with the lowest index — a shared-memory minimum, one barrier,
+    // instead of walking the keys 256 at a time with two barriers per step
+    if (tid == 0) scal[5] = 0x7fffffff;
+    __syncthreads();
+    int best = 0x7fffffff;
+    for (int i = tid; i < n; i += nthr)
+      if (keys[i] == T && i < best) best = i;
+    if (best != 0x7fffffff) atomicMin(&scal[5], best);
+    __syncthreads();
+    if (tid == 0) sel[n_gt] = pack_entry(T, (uint32_t)scal[5]);
+  }
   int running = 0;
-  for (int base = 0; base < n && running < need_eq; base += nthr) {
+  for (int base = 0; need_eq > 1 && base < n && running < need_eq; base += nthr) {
     const int i = base + tid;
     const bool f = (i < n) && (keys[i] == T);
     const unsigned bal = __ballot_sync(FULL_MASK, f);
@@ -180,6 +205,21 @@ __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long lon
   }
   for (int r = K + tid; r < P; r += nthr) sel[r] = 0ull;
   __syncthreads();
+  stamp();
+  if (K <= nthr) {
+    // The common sizes: every entry counts the entries above it — K broadcast reads per thread and ONE barrier — and
+    // lands at its rank (the packed entries are all different, so the ranks are a permutation).  The bitonic
+    // network below needs 28 block-wide barriers for 128 entries (8,400 clk measured, this: ~1,500).
+    const unsigned long long mine = tid < K ? sel[tid] : 0ull;
+    int rank = 0;
+    if (tid < K)
+      for (int j = 0; j < K; ++j) rank += sel[j] > mine ? 1 : 0;
+    __syncthreads();
+    if (tid < K) sel[rank] = mine;
+    __syncthreads();
+    stamp();
+    return;
+  }
   // bitonic sort, descending
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -197,6 +237,7 @@ __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long lon
       __syncthreads();
     }
   }
+  stamp();
 }
 
 template <bool DO_NMS, bool DO_DECODE>
@@ -212,9 +253,13 @@ __global__ void __launch_bounds__(kDecodeThreads) centernet_topk_kernel(DecodeAr
   const int c = blockIdx.x, b = blockIdx.y;
   const int HW = a.H * a.W, K = a.K;
 
+  int dn = 0;
+  unsigned long long* dbg = (a.dbg && b == 0 && c == a.C - 1) ? a.dbg : nullptr;
+  if (dbg && tid == 0) dbg[dn++] = clock64();
   load_plane_keys<DO_NMS>(a.heat + ((size_t)b * a.C + c) * HW, a.H, a.W, keys);
   __syncthreads();
-  block_topk(keys, HW, K, sel, a.P, hist, wsum, scal);
+  if (dbg && tid == 0) dbg[dn++] = clock64();
+  block_topk(keys, HW, K, sel, a.P, hist, wsum, scal, dbg, &dn);
 
   unsigned long long* cand_b = a.cand + (size_t)b * a.C * K;
   for (int r = tid; r < K; r += blockDim.x) cand_b[(size_t)c * K + r] = sel[r];
@@ -231,7 +276,8 @@ __global__ void __launch_bounds__(kDecodeThreads) centernet_topk_kernel(DecodeAr
   for (int j = tid; j < n2; j += blockDim.x) keys[j] = (uint32_t)(__ldcg(cand_b + j) >> 32);
   if (tid == 0) scal[4] = 0;
   __syncthreads();
-  block_topk(keys, n2, K, sel, a.P, hist, wsum, scal);
+  if (a.dbg && b == 0 && tid == 0) { dbg = a.dbg + 16; dn = 0; dbg[dn++] = clock64(); } else dbg = nullptr;
+  block_topk(keys, n2, K, sel, a.P, hist, wsum, scal, dbg, &dn);
 
   int n_pass = 0;
   for (int r = tid; r < K; r += blockDim.x) {
@@ -275,6 +321,7 @@ __global__ void __launch_bounds__(kDecodeThreads) centernet_topk_kernel(DecodeAr
     if (tid == 0) a.count[b] = scal[4];
   }
   if (tid == 0) a.done[b] = 0;
+  if (dbg && tid == 0) dbg[dn++] = clock64();
 }
 
 // Stand-alone _nms (src/centernet_target.py:416-421): same warp patches, result written as floats.
@@ -336,7 +383,23 @@ int launch_topk(const DecodeArgs& a, cudaStream_t st) {
   auto kern = centernet_topk_kernel<DO_NMS, DO_DECODE>;
   if (smem > 48 * 1024) B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B200BEV_CUDA_TRY(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)a.B, st));
-  kern<<<dim3(a.C, a.B), kDecodeThreads, smem, st>>>(a);
+  DecodeArgs aa = a;
+  if (getenv("B200BEV_DECODE_TRACE")) {
+    B200BEV_CUDA_TRY(cudaMalloc(&aa.dbg, 32 * sizeof(unsigned long long)));
+    B200BEV_CUDA_TRY(cudaMemsetAsync(aa.dbg, 0, 32 * sizeof(unsigned long long), st));
+  }
+  kern<<<dim3(a.C, a.B), kDecodeThreads, smem, st>>>(aa);
+  if (aa.dbg) {
+    unsigned long long h[32];
+    B200BEV_CUDA_TRY(cudaStreamSynchronize(st));
+    B200BEV_CUDA_TRY(cudaMemcpy(h, aa.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "decode trace stage1 (class C-1 of sample 0), clk since start:");
+    for (int i = 1; i < 16 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
+    fprintf(stderr, "\n  stage 2 (merge CTA of sample 0), clk since its start:");
+    for (int i = 17; i < 32 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[16]);
+    fprintf(stderr, "  [stage-2 start is %lld clk after stage-1 start of that CTA]\n", (long long)(h[16] - h[0]));
+    cudaFree(aa.dbg);
+  }
   return launch_status();
 }
 
