@@ -51,6 +51,10 @@ PROTOTYPES = {
     "b200bev_centernet_topk": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
     "b200bev_centernet_decode": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f,
                                       _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "b200bev_centernet_decode_logits": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f,
+                                             _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "b200bev_dense_layer": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "b200bev_lidar_init": (_i, [_p, _i, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
 }
 
 _lock = threading.Lock()

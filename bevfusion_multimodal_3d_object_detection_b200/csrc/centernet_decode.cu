@@ -57,11 +57,21 @@ __device__ __forceinline__ unsigned long long pack_entry(uint32_t key, uint32_t 
 
 // Step 1: keys[y*W+x] = key(heat * keep) with keep = (3x3 max == heat), -inf padding
 // (F.max_pool2d(heat, 3, stride=1, padding=1), src/centernet_target.py:419-421).
-template <bool DO_NMS>
+//
+// SIGMOID: the plane holds the heat-map head's raw output and torch.sigmoid (src/fusion.py:870-871) is applied as the
+// values are loaded — 1/(1+exp(-x)) with the accurate expf and an IEEE divide, the expression ATen's CUDA sigmoid
+// evaluates, so the scores are the bits torch.sigmoid gives on the same device.  The peak test runs on the sigmoid
+// values, as in the reference: two logits that round to one float after the sigmoid form a plateau there too.
+__device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+template <bool DO_NMS, bool SIGMOID>
 __device__ void load_plane_keys(const float* __restrict__ plane, int H, int W, uint32_t* keys) {
   const int tid = threadIdx.x;
   if (!DO_NMS) {
-    for (int i = tid; i < H * W; i += blockDim.x) keys[i] = float_to_key(__ldg(plane + i));
+    for (int i = tid; i < H * W; i += blockDim.x) {
+      const float v = __ldg(plane + i);
+      keys[i] = float_to_key(SIGMOID ? sigmoid_f32(v) : v);
+    }
     return;
   }
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -75,7 +85,11 @@ __device__ void load_plane_keys(const float* __restrict__ plane, int H, int W, u
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
       const int y = y0 - 1 + r;
-      v[r] = (x_ok && y >= 0 && y < H) ? __ldg(plane + y * W + x) : -INFINITY;
+      v[r] = -INFINITY;
+      if (x_ok && y >= 0 && y < H) {
+        const float raw = __ldg(plane + y * W + x);
+        v[r] = SIGMOID ? sigmoid_f32(raw) : raw;
+      }
     }
     float hm[10];
 #pragma unroll
@@ -240,7 +254,7 @@ __device__ void block_topk(const uint32_t* keys, int n, int K, unsigned long lon
   stamp();
 }
 
-template <bool DO_NMS, bool DO_DECODE>
+template <bool DO_NMS, bool DO_DECODE, bool SIGMOID>
 __global__ void __launch_bounds__(kDecodeThreads) centernet_topk_kernel(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(kDecodeThreads) centernet_topk_kernel(DecodeAr
   int dn = 0;
   unsigned long long* dbg = (a.dbg && b == 0 && c == a.C - 1) ? a.dbg : nullptr;
   if (dbg && tid == 0) dbg[dn++] = clock64();
-  load_plane_keys<DO_NMS>(a.heat + ((size_t)b * a.C + c) * HW, a.H, a.W, keys);
+  load_plane_keys<DO_NMS, SIGMOID>(a.heat + ((size_t)b * a.C + c) * HW, a.H, a.W, keys);
   __syncthreads();
   if (dbg && tid == 0) dbg[dn++] = clock64();
   block_topk(keys, HW, K, sel, a.P, hist, wsum, scal, dbg, &dn);
@@ -377,10 +391,10 @@ size_t decode_smem_bytes(int C, int HW, int K, int P) {
   return (size_t)P * 8 + 256 * 4 + 32 * 4 + 8 * 4 + nkeys * 4;
 }
 
-template <bool DO_NMS, bool DO_DECODE>
+template <bool DO_NMS, bool DO_DECODE, bool SIGMOID = false>
 int launch_topk(const DecodeArgs& a, cudaStream_t st) {
   const size_t smem = decode_smem_bytes(a.C, a.H * a.W, a.K, a.P);
-  auto kern = centernet_topk_kernel<DO_NMS, DO_DECODE>;
+  auto kern = centernet_topk_kernel<DO_NMS, DO_DECODE, SIGMOID>;
   if (smem > 48 * 1024) B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B200BEV_CUDA_TRY(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)a.B, st));
   DecodeArgs aa = a;
@@ -452,12 +466,12 @@ extern "C" B200BEV_API int b200bev_centernet_topk(const float* scores, int B, in
   return launch_topk<false, false>(a, (cudaStream_t)stream);
 }
 
-extern "C" B200BEV_API int b200bev_centernet_decode(const float* heatmap, const float* offset, const float* size, const float* rot,
-                                        const float* vel, int B, int C, int H, int W, int K, float voxel_size,
-                                        float x_origin, float y_origin, float z_value, float score_thresh,
-                                        float* boxes, float* scores, int64_t* labels, float* velocities, int64_t* ys,
-                                        int64_t* xs, int64_t* ind, int32_t* count, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+namespace {
+int decode_entry(bool logits, const float* heatmap, const float* offset, const float* size, const float* rot,
+                 const float* vel, int B, int C, int H, int W, int K, float voxel_size, float x_origin, float y_origin,
+                 float z_value, float score_thresh, float* boxes, float* scores, int64_t* labels, float* velocities,
+                 int64_t* ys, int64_t* xs, int64_t* ind, int32_t* count, void* workspace, size_t workspace_bytes,
+                 void* stream) {
   if (!heatmap || !offset || !size || !rot || !vel || !boxes || !scores || !labels || !velocities || !count)
     return B200BEV_ERR_INVALID_ARGUMENT;
   const int rc = check_topk_shape(B, C, H, W, K, workspace_bytes, workspace);
@@ -470,5 +484,26 @@ extern "C" B200BEV_API int b200bev_centernet_decode(const float* heatmap, const 
   a.ys = ys; a.xs = xs; a.ind = ind; a.count = count;
   a.cand = reinterpret_cast<unsigned long long*>(workspace);
   a.done = reinterpret_cast<int*>(a.cand + (size_t)B * C * K);
-  return launch_topk<true, true>(a, (cudaStream_t)stream);
+  return logits ? launch_topk<true, true, true>(a, (cudaStream_t)stream) : launch_topk<true, true>(a, (cudaStream_t)stream);
+}
+}  // namespace
+
+extern "C" B200BEV_API int b200bev_centernet_decode(const float* heatmap, const float* offset, const float* size, const float* rot,
+                                        const float* vel, int B, int C, int H, int W, int K, float voxel_size,
+                                        float x_origin, float y_origin, float z_value, float score_thresh,
+                                        float* boxes, float* scores, int64_t* labels, float* velocities, int64_t* ys,
+                                        int64_t* xs, int64_t* ind, int32_t* count, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return decode_entry(false, heatmap, offset, size, rot, vel, B, C, H, W, K, voxel_size, x_origin, y_origin, z_value,
+                      score_thresh, boxes, scores, labels, velocities, ys, xs, ind, count, workspace, workspace_bytes, stream);
+}
+
+extern "C" B200BEV_API int b200bev_centernet_decode_logits(const float* heatmap_logits, const float* offset, const float* size,
+                                               const float* rot, const float* vel, int B, int C, int H, int W, int K,
+                                               float voxel_size, float x_origin, float y_origin, float z_value,
+                                               float score_thresh, float* boxes, float* scores, int64_t* labels,
+                                               float* velocities, int64_t* ys, int64_t* xs, int64_t* ind, int32_t* count,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_entry(true, heatmap_logits, offset, size, rot, vel, B, C, H, W, K, voxel_size, x_origin, y_origin, z_value,
+                      score_thresh, boxes, scores, labels, velocities, ys, xs, ind, count, workspace, workspace_bytes, stream);
 }

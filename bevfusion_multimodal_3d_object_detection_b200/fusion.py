@@ -37,6 +37,27 @@ def camera_branch(module: nn.Module, camera_features: torch.Tensor) -> torch.Ten
     return ops.bilinear_resize(module.camera_proj(cam), size)
 
 
+def lidar_branch(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tensor:
+    """src/fusion.py:258-262: lidar_init (two dense layers, the second a 164 MB weight) -> (B,128,s,s) ->
+    conv+BN+ReLU -> x2 bilinear upsample -> conv+BN+ReLU.  Eval mode on CUDA: the dense layers run on
+    `b200bev_lidar_init` and the upsample on `b200bev_bilinear_resize`; the two convolutions stay cuDNN."""
+    B = lidar_features.shape[0]
+    s = module.lidar_start_size
+    hidden = module.lidar_init[2].out_features // (s * s)
+    if module.training or not lidar_features.is_cuda:
+        return module.lidar_upsample(module.lidar_init(lidar_features).view(B, hidden, s, s))
+    l0, l2 = module.lidar_init[0], module.lidar_init[2]
+    x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s, s)
+    up = module.lidar_upsample
+    for i, layer in enumerate(up):
+        if isinstance(layer, nn.Upsample):
+            # scale_factor=2, align_corners=False: source coordinate (i+0.5)/2-0.5, what the size-based resize computes
+            x = ops.bilinear_resize(x, (int(x.shape[2] * layer.scale_factor), int(x.shape[3] * layer.scale_factor)))
+        else:
+            x = layer(x)
+    return x
+
+
 def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None, radar_features=None) -> torch.Tensor:
     """FlexibleBEVFusion.forward (src/fusion.py:209-297)."""
     parts = []
@@ -46,12 +67,14 @@ def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None,
         parts.append(camera_branch(module, camera_features))
     if module.use_lidar and lidar_features is not None:
         B = lidar_features.shape[0] if B is None else B
-        s = module.lidar_start_size
-        flat = module.lidar_init(lidar_features)                       # src/fusion.py:258
-        parts.append(module.lidar_upsample(flat.view(B, 128, s, s)))   # :259-262
+        parts.append(lidar_branch(module, lidar_features))
     if module.use_radar and radar_features is not None:
         B = radar_features.shape[0] if B is None else B
-        r = module.radar_proj(radar_features).view(B, module.bev_channels, 1, 1)
+        if module.training or not radar_features.is_cuda:
+            r = module.radar_proj(radar_features)
+        else:
+            r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)  # :274
+        r = r.view(B, module.bev_channels, 1, 1)
         parts.append(module.radar_refine(r.expand(B, module.bev_channels, module.bev_h, module.bev_w)))  # :274-281
     if not parts:
         raise ValueError("No modality features provided")              # :289

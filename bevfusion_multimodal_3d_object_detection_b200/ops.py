@@ -277,6 +277,43 @@ def camera_project(feats: torch.Tensor, intrinsics: torch.Tensor, ego2cam: torch
 
 
 # ------------------------------------------------------------------------------------------------
+# N2: dense layers around the canvas
+# ------------------------------------------------------------------------------------------------
+def dense_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """act(x @ weight.T + bias): nn.Linear (+ ReLU) on a small batch, e.g. radar_proj (src/fusion.py:170-173).
+    x (B,K), weight (O,K) in torch's nn.Linear layout, bias (O) -> (B,O)."""
+    x = _need_cuda(x, "input")
+    weight = _need_cuda(weight.detach(), "weight")
+    bias = None if bias is None else _need_cuda(bias.detach(), "bias")
+    if x.dim() != 2 or weight.dim() != 2 or weight.shape[1] != x.shape[1]:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and {tuple(weight.t().shape)})")
+    B, K = x.shape
+    O = int(weight.shape[0])
+    out = torch.empty((B, O), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().b200bev_dense_layer(_ptr(x), B, K, _ptr(weight), _ptr(bias), O, 1 if relu else 0, _ptr(out),
+                                                  _stream(x.device)))
+    return out
+
+
+def lidar_init(feats: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+               return_hidden: bool = False):
+    """Linear + ReLU + Linear of FlexibleBEVFusion.lidar_init (src/fusion.py:144-148): (B,K) -> (B,O)."""
+    feats = _need_cuda(feats, "lidar_features")
+    w1, b1, w2, b2 = (_need_cuda(t.detach(), n) for t, n in ((w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")))
+    B, K = feats.shape
+    hidden, O = int(w1.shape[0]), int(w2.shape[0])
+    if w1.shape[1] != K or w2.shape[1] != hidden:
+        raise RuntimeError(f"lidar_init: shapes do not chain: x {tuple(feats.shape)}, w1 {tuple(w1.shape)}, w2 {tuple(w2.shape)}")
+    hid = torch.empty((B, hidden), dtype=torch.float32, device=feats.device)
+    out = torch.empty((B, O), dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().b200bev_lidar_init(_ptr(feats), B, K, _ptr(w1), _ptr(b1), hidden, _ptr(w2), _ptr(b2), O,
+                                                 _ptr(hid), _ptr(out), _stream(feats.device)))
+    return (out, hid) if return_hidden else out
+
+
+# ------------------------------------------------------------------------------------------------
 # S3
 # ------------------------------------------------------------------------------------------------
 def centernet_nms(heat: torch.Tensor) -> torch.Tensor:
@@ -312,9 +349,10 @@ def centernet_topk(scores: torch.Tensor, K: int):
 
 def centernet_decode(heatmap: torch.Tensor, offset: torch.Tensor, size: torch.Tensor, rot: torch.Tensor,
                      vel: torch.Tensor, K: int, voxel: float, origin: Tuple[float, float] = (-51.2, -51.2),
-                     z_value: float = -1.0, score_thresh: float = 0.0):
+                     z_value: float = -1.0, score_thresh: float = 0.0, heat_is_logit: bool = False):
     """Fused NMS + top-K + gather + box assembly. Fixed-size device outputs:
-    dict(boxes (B,K,7), scores (B,K), labels (B,K) i64, velocities (B,K,2), ys, xs, ind (B,K) i64, count (B) i32)."""
+    dict(boxes (B,K,7), scores (B,K), labels (B,K) i64, velocities (B,K,2), ys, xs, ind (B,K) i64, count (B) i32).
+    heat_is_logit: `heatmap` is the head's raw output and torch.sigmoid (src/fusion.py:871) is applied inside the kernel."""
     heatmap = _need_cuda(heatmap, "heatmap")
     B, Cc, H, W = heatmap.shape
     maps = {"offset": (offset, 2), "size": (size, 3), "rot": (rot, 2), "vel": (vel, 2)}
@@ -337,7 +375,8 @@ def centernet_decode(heatmap: torch.Tensor, offset: torch.Tensor, size: torch.Te
         "count": torch.empty((B,), dtype=torch.int32, device=dev),
     }
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().b200bev_centernet_decode(
+        entry = _lib.lib().b200bev_centernet_decode_logits if heat_is_logit else _lib.lib().b200bev_centernet_decode
+        _lib.check(entry(
             _ptr(heatmap), _ptr(fixed["offset"]), _ptr(fixed["size"]), _ptr(fixed["rot"]), _ptr(fixed["vel"]),
             B, Cc, H, W, K, voxel, origin[0], origin[1], z_value, score_thresh,
             _ptr(o["boxes"]), _ptr(o["scores"]), _ptr(o["labels"]), _ptr(o["velocities"]),

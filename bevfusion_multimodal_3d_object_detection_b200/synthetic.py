@@ -141,6 +141,25 @@ def linear_weights(seed: int, c_in: int, c_out: int) -> Tuple[np.ndarray, np.nda
             g.uniform(-bound, bound, c_out).astype(np.float32))
 
 
+def global_features(seed: int, batch: int, channels: int) -> np.ndarray:
+    """Encoder outputs as the fusion module receives them: (B, C) f32, non-negative (they follow a ReLU and a max)."""
+    return np.abs(_rng(seed).standard_normal((batch, channels))).astype(np.float32)
+
+
+def head_weights(seed: int, in_channels: int, head_conv: int, classes: int) -> Dict[str, np.ndarray]:
+    """CenterNetHead parameters (src/fusion.py:822-854) by state_dict name, with weights large enough that the heat-map
+    logits spread (the reference's init, std 0.001, leaves every logit within 1e-3 of the -4.595 bias)."""
+    g = _rng(seed)
+    out = {}
+    for name, n_out in (("heatmap", classes), ("offset", 2), ("size", 3), ("rot", 2), ("vel", 2)):
+        out[f"{name}_head.0.weight"] = (g.standard_normal((head_conv, in_channels, 3, 3)) * 0.08).astype(np.float32)
+        out[f"{name}_head.0.bias"] = (g.standard_normal(head_conv) * 0.1).astype(np.float32)
+        out[f"{name}_head.2.weight"] = (g.standard_normal((n_out, head_conv, 1, 1)) * 0.3).astype(np.float32)
+        out[f"{name}_head.2.bias"] = (g.standard_normal(n_out) * 0.1).astype(np.float32)
+    out["heatmap_head.2.bias"] = out["heatmap_head.2.bias"] - np.float32(2.0)
+    return out
+
+
 def head_maps(seed: int, batch: int, classes: int = 10, H: int = 50, W: int = 50, peak_frac: float = 1.0):
     """CenterNet head outputs with pairwise-distinct heat-map values (tie-free top-K):
     heatmap is a random permutation of an evenly spaced grid in (0,1) per sample, so no two cells of a

@@ -181,6 +181,11 @@ B200BEV_API int b200bev_camera_project(const float* feats, int B, int n_cam, int
  *   ys/xs/ind (B,K) i64 (optional, may be NULL), count (B) i32 = #rows with score > score_thresh —
  *   rows [0,count) of sample b are the reference's output rows, in the same order.
  *   workspace: b200bev_centernet_workspace_bytes(B,C,K) bytes, 16-byte aligned.
+ * b200bev_centernet_decode_logits ("sigmoid fused into the NMS kernel"): the same launch fed with the
+ *   heat-map head's RAW output; replaces torch.sigmoid of CenterNetHead.forward, src/fusion.py:870-871, plus the
+ *   decode above.  The sigmoid is evaluated as the values are loaded (1/(1+expf(-x)), IEEE divide — the bits
+ *   torch.sigmoid gives on the device) and the peak test, both top-K stages and the threshold run on its result,
+ *   exactly as the reference orders them.  All other arguments as b200bev_centernet_decode.
  * ------------------------------------------------------------------------------------------- */
 B200BEV_API int b200bev_centernet_nms(const float* heat, int B, int C, int H, int W, float* out, void* stream);
 B200BEV_API size_t b200bev_centernet_workspace_bytes(int B, int C, int K);
@@ -196,6 +201,33 @@ B200BEV_API int b200bev_centernet_decode(const float* heatmap, const float* offs
                              float* boxes, float* scores, int64_t* labels, float* velocities,
                              int64_t* ys, int64_t* xs, int64_t* ind, int32_t* count,
                              void* workspace, size_t workspace_bytes, void* stream);
+B200BEV_API int b200bev_centernet_decode_logits(const float* heatmap_logits, const float* offset, const float* size,
+                                    const float* rot, const float* vel,
+                                    int B, int C, int H, int W, int K,
+                                    float voxel_size, float x_origin, float y_origin, float z_value,
+                                    float score_thresh,
+                                    float* boxes, float* scores, int64_t* labels, float* velocities,
+                                    int64_t* ys, int64_t* xs, int64_t* ind, int32_t* count,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * N2  dense layers on a small batch — the Linear stacks either side of the BEV canvas.
+ * b200bev_dense_layer: out = act(x W^T + bias) in fp32 FFMA (parity 1e-5).
+ *   Replaces: nn.Linear (+ nn.ReLU) of FlexibleBEVFusion.radar_proj, src/fusion.py:170-173 (applied :274), and each
+ *   layer of lidar_init.
+ *   x (B,K) f32; weight (O,K) f32 row-major — torch's own nn.Linear layout, no repacking; bias (O) or NULL;
+ *   relu != 0 applies max(.,0); out (B,O) f32.  Large layers (K % 128 == 0, O >= 1024) take the weight-streaming
+ *   kernel — each weight byte is read from HBM once per 32 batch rows — everything else one warp per output row.
+ * b200bev_lidar_init: Linear(K,hidden) + ReLU + Linear(hidden,O), FlexibleBEVFusion.lidar_init,
+ *   src/fusion.py:144-148 (applied :258; O = 128*25*25 = 80000, a 164 MB fp32 weight).
+ *   lidar_features (B,K); w1 (hidden,K), b1 (hidden); w2 (O,hidden), b2 (O); hidden_ws (B,hidden) workspace and
+ *   output (the activations between the two layers); out (B,O) — the caller views it as (B,128,25,25).
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API int b200bev_dense_layer(const float* x, int B, int K, const float* weight, const float* bias, int O,
+                        int relu, float* out, void* stream);
+B200BEV_API int b200bev_lidar_init(const float* lidar_features, int B, int K, const float* w1, const float* b1,
+                       int hidden, const float* w2, const float* b2, int O,
+                       float* hidden_ws, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -246,6 +246,29 @@ def camera_project(feats: np.ndarray, table: np.ndarray, bev_size) -> np.ndarray
 
 
 # ------------------------------------------------------------------------------------------------
+# N2 — dense layers around the canvas
+# ------------------------------------------------------------------------------------------------
+def dense_layer(x: np.ndarray, weight: np.ndarray, bias: Optional[np.ndarray] = None, relu: bool = False) -> np.ndarray:
+    """[pinned] nn.Linear (+ nn.ReLU): x @ W^T + b — FlexibleBEVFusion.radar_proj src/fusion.py:170-173 and each layer of
+    lidar_init src/fusion.py:144-148."""
+    y = np.asarray(x, dtype=F32) @ np.asarray(weight, dtype=F32).T
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=F32)
+    return np.maximum(y, F32(0.0)) if relu else y.astype(F32)
+
+
+def lidar_init(feats: np.ndarray, w1, b1, w2, b2) -> np.ndarray:
+    """[pinned] Linear + ReLU + Linear, src/fusion.py:144-148 (applied at :258)."""
+    return dense_layer(dense_layer(feats, w1, b1, relu=True), w2, b2)
+
+
+def sigmoid(x: np.ndarray) -> np.ndarray:
+    """[pinned] torch.sigmoid of the heat-map head, src/fusion.py:870-871, in fp32."""
+    x = np.asarray(x, dtype=F32)
+    return (F32(1.0) / (F32(1.0) + np.exp(-x, dtype=F32))).astype(F32)
+
+
+# ------------------------------------------------------------------------------------------------
 # S3 — CenterNet decode
 # ------------------------------------------------------------------------------------------------
 def nms(heat: np.ndarray) -> np.ndarray:

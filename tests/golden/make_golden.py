@@ -214,9 +214,67 @@ def lidar_prepare_cases():
     np.savez_compressed(OUT / "lidar_prepare.npz", **out)
 
 
+def glue_cases():
+    """the dense layers of FlexibleBEVFusion (lidar_init, radar_proj) and CenterNetHead's sigmoid in
+    front of the decode, all produced by the reference's own modules."""
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        fus = fusion.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=True, lidar_channels=1024,
+                                       radar_channels=256, bev_h=50, bev_w=50, bev_channels=256)
+    w1, b1 = syn.linear_weights(701, 1024, 512)
+    w2, b2 = syn.linear_weights(702, 512, 128 * 25 * 25)
+    wr, br = syn.linear_weights(703, 256, 256)
+    for lin, (w, b) in ((fus.lidar_init[0], (w1, b1)), (fus.lidar_init[2], (w2, b2)), (fus.radar_proj[0], (wr, br))):
+        lin.weight.copy_(torch.from_numpy(w))
+        lin.bias.copy_(torch.from_numpy(b))
+    fus.eval()
+    grabbed = {}
+    fus.lidar_init[1].register_forward_hook(lambda m, i, o: grabbed.update(hidden=o.clone()))
+    fus.lidar_init.register_forward_hook(lambda m, i, o: grabbed.update(lidar_init=o.clone()))
+    fus.radar_proj.register_forward_hook(lambda m, i, o: grabbed.update(radar_proj=o.clone()))
+    feats, radar = syn.global_features(704, 3, 1024), syn.global_features(705, 3, 256)
+    fus(lidar_features=torch.from_numpy(feats), radar_features=torch.from_numpy(radar))
+    out["dense_digest"] = syn.digest(w1, b1, w2, b2, wr, br, feats, radar)
+    out["lidar_hidden"] = grabbed["hidden"].numpy()
+    full = grabbed["lidar_init"].numpy()
+    np.testing.assert_allclose(orc.lidar_init(feats, w1, b1, w2, b2), full, rtol=0, atol=1e-5 * np.abs(full).max())
+    out["lidar_init_sub"] = full[:, ::16]                      # 5000 of 80000 columns keeps the fixture small
+    out["lidar_init_absmax"] = np.float32(np.abs(full).max())
+    out["radar_proj"] = grabbed["radar_proj"].numpy()
+
+    # CenterNetHead.forward (src/fusion.py:869-884) -> decode: the head's raw heat-map output next to what the
+    # reference decodes from its sigmoid
+    hw = syn.head_weights(711, 32, 16, 10)
+    with contextlib.redirect_stdout(io.StringIO()):
+        head = fusion.CenterNetHead(in_channels=32, num_classes=10, head_conv=16)
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in hw.items()})
+    head.eval()
+    head.heatmap_head.register_forward_hook(lambda m, i, o: grabbed.update(logits=o.clone()))
+    x = syn._rng(712).standard_normal((2, 32, 24, 40)).astype(np.float32)
+    pred = head(torch.from_numpy(x))
+    out["head_digest"] = syn.digest(x, *hw.values())
+    out["head_logits"] = grabbed["logits"].numpy()
+    assert torch.equal(torch.sigmoid(grabbed["logits"]), pred["heatmap"])
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        out[f"head_{k}"] = pred[k].numpy()
+    nms = centernet_target._nms(pred["heatmap"])
+    top = centernet_target._topk(nms, K=60)[0]
+    assert (top[:, :-1] > top[:, 1:]).all(), "ties among the winners: pick another seed"
+    thr = float(top[0, 30])                                   # about half of the winners of sample 0 pass
+    out["head_thresh"] = np.float32(thr)
+    for tag, t in (("all", 0.0), ("mid", thr)):
+        for b, d in enumerate(fusion_detection.decode_centernet_predictions(pred, score_thresh=t, max_detections=60)):
+            for k, v in d.items():
+                out[f"head_{tag}_b{b}_{k}"] = v.numpy()
+    np.savez_compressed(OUT / "bev_glue.npz", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases):
+    only = set(sys.argv[1:])
+    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases, glue_cases):
+        if only and fn.__name__ not in only:
+            continue
         fn()
         print("wrote", fn.__name__)
     for f in sorted(OUT.glob("*.npz")):

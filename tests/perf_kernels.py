@@ -106,12 +106,36 @@ def main():
         ):
             med, best = timeit(fn, reps=20)
             print(f"{name:34s} median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+    if args.what in ("dense", "all"):
+        g = torch.Generator(device=dev).manual_seed(2)
+        w1 = torch.randn((512, 1024), device=dev, generator=g) * 0.03
+        w2 = torch.randn((80000, 512), device=dev, generator=g) * 0.04
+        b1, b2 = torch.zeros(512, device=dev), torch.zeros(80000, device=dev)
+        for Bd in sorted({1, 8, 16, F}):
+            x = torch.rand((Bd, 1024), device=dev, generator=g)
+            hid = ops.dense_layer(x, w1, b1, relu=True)
+            med, best = timeit(lambda: ops.lidar_init(x, w1, b1, w2, b2), reps=20)
+            med2, best2 = timeit(lambda: ops.dense_layer(hid, w2, b2), reps=20)
+            by = 4.0 * (80000 * 512 + 80000 + Bd * (512 + 80000))
+            print(f"lidar_init batch {Bd:3d} (both layers) median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us | 512->80000 alone "
+                  f"median {med2 * 1e3:8.1f} us  best {best2 * 1e3:8.1f} us  {by / med2 / 1e6:8.1f} GB/s  "
+                  f"{2.0 * Bd * 512 * 80000 / med2 / 1e9:6.2f} TFLOP/s", flush=True)
+        ref = x @ w1.t()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        med3, _ = timeit(lambda: torch.addmm(b2, torch.relu(torch.addmm(b1, x, w1.t())), w2.t()), reps=20)
+        print(f"  (cuBLAS fp32, torch.addmm x2, batch {F}: median {med3 * 1e3:8.1f} us)", flush=True)
     if args.what in ("decode", "all"):
         maps = {k: to(v) for k, v in syn.head_maps(44, F, 10, G, G).items()}
         med, best = timeit(lambda: ops.centernet_decode(maps["heatmap"], maps["offset"], maps["size"], maps["rot"], maps["vel"],
                                                         100, 2.048), reps=20)
         by = F * (4.0 * 10 * G * G + 3600 + 6800)
         print(f"centernet_decode {F}x10x{G}x{G}       median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {by / med / 1e6:8.1f} GB/s", flush=True)
+        logits = torch.logit(maps["heatmap"].clamp(1e-6, 1 - 1e-6))
+        med, best = timeit(lambda: ops.centernet_decode(logits, maps["offset"], maps["size"], maps["rot"], maps["vel"],
+                                                        100, 2.048, heat_is_logit=True), reps=20)
+        med2, _ = timeit(lambda: ops.centernet_decode(torch.sigmoid(logits), maps["offset"], maps["size"], maps["rot"], maps["vel"],
+                                                      100, 2.048), reps=20)
+        print(f"  from logits (sigmoid fused)       median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us   torch.sigmoid + decode: {med2 * 1e3:8.1f} us", flush=True)
 
 
 if __name__ == "__main__":

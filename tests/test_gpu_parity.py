@@ -533,3 +533,64 @@ def test_random_shapes_bin_sort_prepare_decode(cuda, seed):
         assert cnt[b] == n
         np.testing.assert_array_equal(got["scores"][b, :n].cpu().numpy(), r["scores"])
         np.testing.assert_allclose(got["boxes"][b, :n].cpu().numpy(), r["boxes"], rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ N2: dense layers
+@pytest.mark.parametrize("B,K,O,relu,bias", [
+    (32, 512, 80000, False, True),      # lidar_init.2 at the bench batch: streaming kernel, 32-row batch tile
+    (3, 512, 80000, False, True),       # small batch: 8-row tile
+    (16, 512, 5000, True, True),        # 16-row tile, last CTA step ragged
+    (40, 256, 2048, True, False),       # two batch tiles, no bias
+    (5, 128, 1100, False, True),        # the smallest K the streaming kernel takes; rows not a multiple of 64
+    (32, 1024, 512, True, True),        # lidar_init.0: one warp per row
+    (7, 100, 33, False, True),          # any-shape form
+    (1, 256, 256, True, True),          # radar_proj at batch 1
+])
+def test_dense_layer_vs_oracle(cuda, B, K, O, relu, bias):
+    g = np.random.default_rng(B * 1000 + O)
+    x = np.abs(g.standard_normal((B, K))).astype(np.float32)
+    w, b = syn.linear_weights(B + K + O, K, O)
+    got = ops.dense_layer(dev_t(x, cuda), dev_t(w, cuda), dev_t(b, cuda) if bias else None, relu=relu)
+    ref = orc.dense_layer(x, w, b if bias else None, relu=relu)
+    assert tuple(got.shape) == (B, O)
+    assert max_rel(got.cpu().numpy(), ref) < FP32_TOL
+
+
+def test_lidar_init_vs_reference_golden(cuda, golden):
+    """Both layers in one call against what the reference's FlexibleBEVFusion.lidar_init produced."""
+    g = golden("bev_glue")
+    w1, b1 = syn.linear_weights(701, 1024, 512)
+    w2, b2 = syn.linear_weights(702, 512, 128 * 25 * 25)
+    feats = syn.global_features(704, 3, 1024)
+    out, hid = ops.lidar_init(dev_t(feats, cuda), dev_t(w1, cuda), dev_t(b1, cuda), dev_t(w2, cuda), dev_t(b2, cuda),
+                              return_hidden=True)
+    assert max_rel(hid.cpu().numpy(), g["lidar_hidden"]) < FP32_TOL
+    assert np.abs(out.cpu().numpy()[:, ::16] - g["lidar_init_sub"]).max() < FP32_TOL * float(g["lidar_init_absmax"])
+    wr, br = syn.linear_weights(703, 256, 256)
+    radar = syn.global_features(705, 3, 256)
+    rp = ops.dense_layer(dev_t(radar, cuda), dev_t(wr, cuda), dev_t(br, cuda), relu=True)
+    assert max_rel(rp.cpu().numpy(), g["radar_proj"]) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------ N1: sigmoid fused into the decode
+def test_decode_from_logits_vs_reference_head_golden(cuda, golden):
+    g = golden("bev_glue")
+    maps = {k: dev_t(g[f"head_{k}"], cuda) for k in ("offset", "size", "rot", "vel")}
+    logits = dev_t(g["head_logits"], cuda)
+    for tag, thr in (("all", 0.0), ("mid", float(g["head_thresh"]))):
+        fused = ops.centernet_decode(logits, maps["offset"], maps["size"], maps["rot"], maps["vel"], 60, 0.512,
+                                     score_thresh=thr, heat_is_logit=True)
+        # the same launch fed with torch.sigmoid of the same device: identical bits
+        two_step = ops.centernet_decode(torch.sigmoid(logits), maps["offset"], maps["size"], maps["rot"], maps["vel"], 60,
+                                        0.512, score_thresh=thr)
+        for k in ("scores", "boxes", "velocities", "ys", "xs", "ind", "count"):
+            assert torch.equal(fused[k], two_step[k]), k
+        # and the reference's own decode of its CPU sigmoid: same winners in the same order, scores to an ulp
+        for b in range(2):
+            n = int(fused["count"][b])
+            ref_scores = g[f"head_{tag}_b{b}_scores"]
+            assert abs(n - len(ref_scores)) <= (1 if tag == "mid" else 0)     # the threshold IS a score: an ulp decides it
+            n = min(n, len(ref_scores))
+            np.testing.assert_allclose(fused["scores"][b, :n].cpu().numpy(), ref_scores[:n], rtol=3e-7, atol=0)
+            np.testing.assert_allclose(fused["boxes"][b, :n].cpu().numpy(), g[f"head_{tag}_b{b}_boxes"][:n], rtol=0, atol=1e-5)
+            np.testing.assert_array_equal(fused["velocities"][b, :n].cpu().numpy(), g[f"head_{tag}_b{b}_velocities"][:n])

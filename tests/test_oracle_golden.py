@@ -243,3 +243,32 @@ def test_torch_port_decode_equals_reference(golden):
     for b, d in enumerate(dets):
         for k, v in d.items():
             np.testing.assert_array_equal(v.numpy(), g[f"ct_thr0.0_b{b}_{k}"])
+
+
+# ------------------------------------------------------------------------------------------------ N1 / N2
+def test_dense_layers_match_the_reference_fusion_module(golden):
+    """lidar_init (Linear+ReLU+Linear, 80000 outputs) and radar_proj of the reference's FlexibleBEVFusion."""
+    g = golden("bev_glue")
+    w1, b1 = syn.linear_weights(701, 1024, 512)
+    w2, b2 = syn.linear_weights(702, 512, 128 * 25 * 25)
+    wr, br = syn.linear_weights(703, 256, 256)
+    feats, radar = syn.global_features(704, 3, 1024), syn.global_features(705, 3, 256)
+    assert syn.digest(w1, b1, w2, b2, wr, br, feats, radar) == str(g["dense_digest"])
+    hidden = orc.dense_layer(feats, w1, b1, relu=True)
+    assert max_rel(hidden, g["lidar_hidden"]) < 1e-5
+    full = orc.lidar_init(feats, w1, b1, w2, b2)
+    assert full.shape == (3, 80000)
+    assert np.abs(full[:, ::16] - g["lidar_init_sub"]).max() < 1e-5 * float(g["lidar_init_absmax"])
+    assert max_rel(orc.dense_layer(radar, wr, br, relu=True), g["radar_proj"]) < 1e-5
+
+
+def test_sigmoid_then_decode_matches_the_reference_head(golden):
+    """CenterNetHead's raw heat-map output -> sigmoid -> decode, against what the reference decoded."""
+    g = golden("bev_glue")
+    heat = orc.sigmoid(g["head_logits"])
+    assert max_rel(heat, g["head_heatmap"]) < 1e-6
+    pred = {"heatmap": g["head_heatmap"], **{k: g[f"head_{k}"] for k in ("offset", "size", "rot", "vel")}}
+    for tag, thr in (("all", 0.0), ("mid", float(g["head_thresh"]))):
+        dets = orc.decode(pred, score_thresh=thr, max_detections=60, voxel_size_m=0.512)
+        _assert_dets(dets, g, f"head_{tag}", 2)
+    assert 0 < len(g["head_mid_b0_scores"]) < 60
