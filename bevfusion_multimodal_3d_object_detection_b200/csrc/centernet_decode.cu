@@ -85,11 +85,13 @@ __device__ void load_plane_keys(const float* __restrict__ plane, int H, int W, u
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
       const int y = y0 - 1 + r;
-      v[r] = -INFINITY;
-      if (x_ok && y >= 0 && y < H) {
-        const float raw = __ldg(plane + y * W + x);
-        v[r] = SIGMOID ? sigmoid_f32(raw) : raw;
-      }
+      v[r] = (x_ok && y >= 0 && y < H) ? __ldg(plane + y * W + x) : -INFINITY;
+    }
+    if (SIGMOID) {
+      // after all ten loads are in flight; sigmoid(-inf) = 1/(1+inf) = 0 would be a legal score, so the padding is
+      // put back explicitly
+#pragma unroll
+      for (int r = 0; r < 10; ++r) v[r] = (v[r] == -INFINITY) ? -INFINITY : sigmoid_f32(v[r]);
     }
     float hm[10];
 #pragma unroll

@@ -9,7 +9,7 @@
 // linear_stream_kernel<NB>: one CTA per SM, each owning a contiguous range of output rows (O/grid, so every CTA walks
 // the same number of 64-row steps).  The batch tile (TB = 4*NB rows of x, K floats each) stays in shared memory for the
 // whole kernel.  The 8 warps are 2 row groups x 4 K-quarters: a warp multiplies 32 weight rows x its quarter of K against
-// the whole batch tile, streaming its weights with its OWN cp.async ring (16-byte LDGSTS, 3 stages of 32 rows x 32 k,
+// the whole batch tile, streaming its weights with its OWN cp.async ring (16-byte LDGSTS, 3-5 stages of 32 rows x 32 k,
 // rows padded to 144 B so the eight row addresses of a 128-bit shared load fall in eight different bank groups) — no
 // block-wide barrier in the streaming loop, and the ring keeps running across step boundaries.  A thread holds a
 // 4 (rows) x NB (batch) register tile and reads both operands as float4 along k: 4 + NB shared loads per 16*NB FMAs.
@@ -26,7 +26,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kKC = 32;           // k floats per ring row
 constexpr int kRowF = kKC + 4;    // padded ring row (floats)
-constexpr int kStages = 3;
 constexpr int kStepRows = 64;     // output rows per CTA step: 2 groups of 32
 constexpr int kKSplit = 4;
 
@@ -41,7 +40,9 @@ struct LinArgs {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool real) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
   const int n = real ? 16 : 0;  // 0: nothing is read, the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+  // L2::256B: the 128-byte piece of a row this chunk needs arrives with its neighbour, which is the piece the next chunk
+  // of the same rows needs — DRAM sees 256-byte bursts instead of isolated 128-byte ones
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -49,14 +50,15 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int NB>
+// NB: batch rows per thread (tile of 4*NB rows); kStages: ring depth (kStages-1 chunks in flight per warp)
+template <int NB, int kStages>
 size_t stream_smem_bytes(int K) {
   const int TB = 4 * NB;
   return sizeof(float) * ((size_t)TB * (K + 4) + 8 * kStages * 32 * kRowF + 8 * TB * 33);
 }
 
-template <int NB>
-__global__ void __launch_bounds__(kThreads) linear_stream_kernel(LinArgs a) {
+template <int NB, int kStages>
+__global__ void __launch_bounds__(kThreads, 1) linear_stream_kernel(LinArgs a) {
   constexpr int TB = 4 * NB;
   extern __shared__ __align__(16) float smem[];
   const int K = a.K, xs_stride = K + 4;
@@ -120,22 +122,29 @@ __global__ void __launch_bounds__(kThreads) linear_stream_kernel(LinArgs a) {
       issue(q + kStages - 1);  // refills the slot consumed in the previous iteration
       const float* wt = my_ring + (size_t)(q % kStages) * 32 * kRowF + go * kRowF;
       const float* xt = xs + (size_t)gb * xs_stride + k_base + ch * kKC;
+      // operands of the next four k are fetched while the FMAs of these four run: with two warps per scheduler the
+      // shared-memory latency is not hidden by other warps
+      float4 wv[2][4], xv[2][NB];
+      auto fetch = [&](int set, int kk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[set][i] = *reinterpret_cast<const float4*>(wt + i * 8 * kRowF + kk);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) xv[set][j] = *reinterpret_cast<const float4*>(xt + (size_t)j * 4 * xs_stride + kk);
+      };
+      fetch(0, 0);
 #pragma unroll
       for (int kk = 0; kk < kKC; kk += 4) {
-        float4 wv[4], xv[NB];
+        const int cur = (kk >> 2) & 1;
+        if (kk + 4 < kKC) fetch(cur ^ 1, kk + 4);
+        // k component outermost: 4*NB independent FMAs between two that touch the same accumulator
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wv[i] = *reinterpret_cast<const float4*>(wt + i * 8 * kRowF + kk);
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) xv[j] = *reinterpret_cast<const float4*>(xt + (size_t)j * 4 * xs_stride + kk);
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < NB; ++j) {
-            acc[i][j] = fmaf(wv[i].x, xv[j].x, acc[i][j]);
-            acc[i][j] = fmaf(wv[i].y, xv[j].y, acc[i][j]);
-            acc[i][j] = fmaf(wv[i].z, xv[j].z, acc[i][j]);
-            acc[i][j] = fmaf(wv[i].w, xv[j].w, acc[i][j]);
-          }
+            for (int j = 0; j < NB; ++j)
+              acc[i][j] = fmaf(reinterpret_cast<const float*>(&wv[cur][i])[c], reinterpret_cast<const float*>(&xv[cur][j])[c],
+                               acc[i][j]);
       }
     }
 
@@ -200,10 +209,10 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(LinArgs a) {
   }
 }
 
-template <int NB>
+template <int NB, int S>
 int launch_stream(const LinArgs& a, cudaStream_t st) {
-  const size_t smem = stream_smem_bytes<NB>(a.K);
-  auto kern = linear_stream_kernel<NB>;
+  const size_t smem = stream_smem_bytes<NB, S>(a.K);
+  auto kern = linear_stream_kernel<NB, S>;
   B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int gx = sm_count();
   const int max_gx = ceil_div(a.O, kStepRows);
@@ -213,20 +222,24 @@ int launch_stream(const LinArgs& a, cudaStream_t st) {
   return launch_status();
 }
 
+constexpr size_t kSmemCap = 220 * 1024;
+
 }  // namespace
 
 int dense_layer(const float* x, int B, int K, const float* w, const float* bias, int O, int relu, float* out,
                 cudaStream_t st) {
   LinArgs a{x, w, bias, out, B, K, O, relu};
   const bool aligned = (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
-  // streaming form: K splits into four quarters of whole 32-float chunks, the batch tile fits next to the rings, and
-  // there are enough rows to give every SM several steps
-  if (aligned && K % (kKSplit * kKC) == 0 && O >= 16 * kStepRows && stream_smem_bytes<2>(K) <= 200 * 1024) {
-    if (B <= 8) return launch_stream<2>(a, st);
-    if (B <= 16 && stream_smem_bytes<4>(K) <= 200 * 1024) return launch_stream<4>(a, st);
-    if (stream_smem_bytes<8>(K) <= 220 * 1024) return launch_stream<8>(a, st);
-    if (stream_smem_bytes<4>(K) <= 200 * 1024) return launch_stream<4>(a, st);
-    return launch_stream<2>(a, st);
+  // streaming form: K splits into four quarters of whole 32-float chunks, there is more than one 64-row step of work,
+  // and a batch tile fits next to the rings (the widest tile that fits, the deepest ring next to it)
+  if (aligned && K % (kKSplit * kKC) == 0 && O >= 2 * kStepRows) {
+    if (B > 16 && stream_smem_bytes<8, 3>(K) <= kSmemCap) return launch_stream<8, 3>(a, st);
+    if (B > 8) {
+      if (stream_smem_bytes<4, 4>(K) <= kSmemCap) return launch_stream<4, 4>(a, st);
+      if (stream_smem_bytes<4, 3>(K) <= kSmemCap) return launch_stream<4, 3>(a, st);
+    }
+    if (stream_smem_bytes<2, 5>(K) <= kSmemCap) return launch_stream<2, 5>(a, st);
+    if (stream_smem_bytes<2, 3>(K) <= kSmemCap) return launch_stream<2, 3>(a, st);
   }
   long long blocks = ((long long)O + 7) / 8;
   const long long cap = (long long)sm_count() * 8;
