@@ -1,0 +1,352 @@
+// N1 — the convolutions between the hot-path kernels, as one implicit-GEMM tcgen05 kernel.
+//
+// Replaces, in eval mode and when the bf16 path is enabled (parity 1e-2): every Conv2d(k=3,pad=1 | k=1) + BatchNorm2d +
+// ReLU block of FlexibleBEVFusion — camera_proj src/fusion.py:126-133, lidar_upsample :151-166, radar_refine :176-183,
+// bev_fusion :199-207 — and the CenterNetHead convolutions src/fusion.py:822-854 (the five 3x3 convs as one 256->320
+// conv, the five 1x1 convs as one block-diagonal 320->19 conv).  BatchNorm is folded into weights and bias on the host.
+//
+// GEMM view: D[co][px] = sum over (tap, ci) W[co][tap][ci] * X[px + tap][ci].  The OUTPUT CHANNELS are the M = 128 rows of
+// the MMA (the 128 lanes of tensor memory) and the PIXELS its N = 256 columns, so an epilogue thread owns one output
+// channel and 32 consecutive pixels at a time — the NCHW fp32 layout the reference's next module expects is written
+// directly, 128 contiguous bytes per thread, bias + ReLU on the way out.  Both operands come from shared memory in the
+// K-major 128-byte-swizzled layout tests/cuda/umma_probe.cu pinned down:
+//   A = weights: pre-packed once per weight update (b200bev_conv_pack_bf16) into 16 KB stages [128 co][64 ci], ordered as
+//       the kernel consumes them ((co tile, tap, ci chunk)); one cp.async.bulk per stage.
+//   B = pixels:  the input lives channels-last in bf16 (b200bev_nchw_to_nhwc_bf16 writes it, straight into the channel
+//       slice of a concatenated input, so torch.cat disappears).  For a tap (dy,dx) row n of the stage is pixel
+//       (y+dy, x+dx) of output pixel n — 128 contiguous bytes of global memory, or zeros outside the image — moved with
+//       16-byte cp.async (zero-fill form) by all 256 threads straight to their swizzled place: im2col never exists in
+//       memory.
+// One persistent CTA per SM walks (pixel tile, co tile) pairs; ring of 4 stages (48 KB each), copies run two stages
+// ahead of the MMAs, a stage is released by tcgen05.commit.  fp32 accumulation in TMEM (256 columns).
+#include <cuda_bf16.h>
+
+#include "async_copy.cuh"
+#include "common.cuh"
+
+namespace b200bev {
+namespace {
+
+constexpr int kConvThreads = 256;
+constexpr int kTileCo = 128;   // M
+constexpr int kTilePx = 256;   // N
+constexpr int kKC = 64;        // bf16 k per stage (128-byte rows)
+constexpr int kStageA = kTileCo * kKC * 2;   // 16 KB
+constexpr int kStageB = kTilePx * kKC * 2;   // 32 KB
+constexpr int kStage = kStageA + kStageB;
+constexpr int kRing = 4;
+constexpr int kAhead = kRing - 2;            // copies issued this many stages ahead of the MMAs
+constexpr int kConvSmem = kRing * kStage + 1024 /*alignment slack*/ + 128 /*barriers*/;
+
+struct ConvArgs {
+  const __nv_bfloat16* x;     // (B, H, W, Cin) channels-last
+  const uint8_t* wimg;        // packed stages
+  const float* bias;          // (Cout) or null
+  float* out;                 // (B, Cout, H, W)
+  int B, H, W, Cin, Cout, taps, relu;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool real) {
+  const int n = real ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_to(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (the layout of both operands)
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, 128 x 256 x 16, bf16 -> f32
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#define CONV_TC_LD32(r, taddr)                                                                                             \
+  asm volatile(                                                                                                            \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"      \
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                           \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),        \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),             \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),            \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                          \
+      : "r"(taddr)                                                                                                         \
+      : "memory")
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-byte aligned tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRing * kStage);
+  uint64_t* full_a = bars;            // [kRing] weight stage landed (bulk copy, tx bytes)
+  uint64_t* empty = bars + kRing;     // [kRing] the MMAs that read the stage have completed
+  uint64_t* acc_full = bars + 2 * kRing;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_addr(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbarrier_init(&full_a[s], 1);
+      mbarrier_init(&empty[s], 1);
+    }
+    mbarrier_init(acc_full, 1);
+    mbarrier_init_fence();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  const int HW = a.H * a.W;
+  const long long n_px = (long long)a.B * HW;
+  const int n_px_tiles = (int)((n_px + kTilePx - 1) / kTilePx);
+  const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
+  const int ncc = a.Cin / kKC;
+  const int n_k = a.taps * ncc;
+  const int n_tiles = n_px_tiles * n_co_tiles;
+  // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTilePx >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
+
+  // this thread's part of a pixel stage: rows (tid>>3) + 32 j, 16-byte chunk tid&7 — the swizzled chunk is the same for
+  // all eight rows because they differ by multiples of 8
+  const int row0 = tid >> 3, chunk = tid & 7;
+  const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
+
+  uint32_t g = 0;        // stages issued so far (all tiles): ring slot and barrier phase
+  uint32_t n_done = 0;   // tiles finished: phase of acc_full
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_done) {
+    const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
+    const long long px0 = (long long)px_tile * kTilePx;
+    // the eight pixels this thread copies
+    int py[8], pxx[8];
+    long long poff[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long n = px0 + row0 + 32 * j;
+      if (n < n_px) {
+        const int p = (int)(n % HW);
+        py[j] = p / a.W;
+        pxx[j] = p - py[j] * a.W;
+        poff[j] = n * a.Cin + chunk * 8;
+      } else {
+        py[j] = -100000;   // fails every bounds test
+        pxx[j] = 0;
+        poff[j] = 0;
+      }
+    }
+    const uint8_t* wtile = a.wimg + (size_t)co_tile * n_k * kStageA;
+
+    for (int i = 0; i < n_k + kAhead; ++i) {
+      if (i < n_k) {
+        const uint32_t gp = g + i, slot = gp % kRing;
+        if (gp >= kRing) mbarrier_wait(&empty[slot], ((gp / kRing) - 1) & 1);
+        const int tap = i / ncc, cc = i - tap * ncc;
+        const int dy = a.taps == 9 ? tap / 3 - 1 : 0, dx = a.taps == 9 ? tap % 3 - 1 : 0;
+        const long long shift = ((long long)dy * a.W + dx) * a.Cin + cc * kKC;
+        const uint32_t bdst = smem_addr(ring + slot * kStage + kStageA) + dst_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int yy = py[j] + dy, xx = pxx[j] + dx;
+          const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+          cp_async16_zfill(bdst + j * 4096, a.x + (ok ? poff[j] + shift : 0), ok);
+        }
+        if (warp == 0 && elect_one()) {   // one lane of a converged warp: the copy's operands stay in uniform registers
+          mbarrier_expect_tx(&full_a[slot], kStageA);
+          bulk_copy_global_to_shared(ring + slot * kStage, wtile + (size_t)i * kStageA, kStageA, &full_a[slot]);
+        }
+      }
+      cp_async_commit_group();
+      const int c = i - kAhead;
+      if (c >= 0) {
+        cp_async_wait_group<kAhead>();      // this thread's copies of stage c have landed
+        fence_proxy_async_shared();         // ... and are visible to the tensor core's (asynchronous-proxy) reads
+        __syncthreads();
+        if (warp == 0 && elect_one()) {
+          const uint32_t gc = g + c, slot = gc % kRing;
+          mbarrier_wait(&full_a[slot], (gc / kRing) & 1);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_addr(ring + slot * kStage), b_addr = a_addr + kStageA;
+#pragma unroll
+          for (int s = 0; s < kKC / 16; ++s)
+            umma_ss(tmem, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc(b_addr + s * 32), idesc, !(c == 0 && s == 0));
+          tc_commit_to(&empty[slot]);
+          if (c == n_k - 1) tc_commit_to(acc_full);
+        }
+      }
+    }
+    g += n_k;
+
+    // epilogue: thread = one output channel (TMEM lane), warps 0-3 take pixel columns [0,128), warps 4-7 [128,256)
+    mbarrier_wait(acc_full, n_done & 1);
+    tc_fence_after_sync();
+    {
+      const int quad = warp & 3, half = warp >> 2;
+      const int co = co_tile * kTileCo + quad * 32 + lane;
+      const float bias = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[32];
+        const int col0 = half * 128 + q * 32;
+        CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const long long n0 = px0 + col0;
+        if (co < a.Cout && n0 < n_px) {
+          const int b = (int)(n0 / HW), p = (int)(n0 - (long long)b * HW);
+          float* dst = a.out + ((size_t)b * a.Cout + co) * HW + p;
+          if (p + 32 <= HW && (HW & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              v.x = __uint_as_float(r[j]) + bias;
+              v.y = __uint_as_float(r[j + 1]) + bias;
+              v.z = __uint_as_float(r[j + 2]) + bias;
+              v.w = __uint_as_float(r[j + 3]) + bias;
+              if (a.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(dst + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long n = n0 + j;
+              if (n < n_px) {
+                const int bb = (int)(n / HW), pp = (int)(n - (long long)bb * HW);
+                float v = __uint_as_float(r[j]) + bias;
+                if (a.relu) v = fmaxf(v, 0.f);
+                a.out[((size_t)bb * a.Cout + co) * HW + pp] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();   // every lane has read the accumulator before the next tile's first MMA overwrites it
+    tc_fence_after_sync();
+  }
+
+  cp_async_wait_group<0>();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
+// (Cout, Cin, taps) fp32 -> stages [co tile][tap][ci chunk] of [128 co][64 ci] bf16, 16-byte chunk c of row r at c ^ (r & 7)
+__global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, uint8_t* __restrict__ img,
+                                                        long long n_chunks) {
+  const int ncc = Cin / kKC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 7);
+    const int r = (int)((i >> 3) & 127);
+    const long long stage = i >> 10;
+    const int cc = (int)(stage % ncc);
+    const int tap = (int)((stage / ncc) % taps);
+    const int ct = (int)(stage / ((long long)ncc * taps));
+    const int co = ct * kTileCo + r;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ci = cc * kKC + c * 8 + e;
+      v[e] = __float2bfloat16_rn(co < Cout ? __ldg(w + ((size_t)co * Cin + ci) * taps + tap) : 0.f);
+    }
+    *reinterpret_cast<uint4*>(img + stage * kStageA + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// (B, C, H, W) fp32 -> channels [c_offset, c_offset + C) of (B, H, W, C_total) bf16.  Tile: 64 channels x 64 pixels.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int B, int C, int HW,
+                                                                __nv_bfloat16* __restrict__ out, int C_total, int c_offset) {
+  __shared__ float tile[64][65];
+  const int n_ct = ceil_div(C, 64), n_pt = ceil_div(HW, 64);
+  const long long n_tiles = (long long)B * n_ct * n_pt;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int pt = (int)(t % n_pt), ct = (int)((t / n_pt) % n_ct), b = (int)(t / ((long long)n_pt * n_ct));
+    const int c0 = ct * 64, p0 = pt * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+      const int c = i >> 6, p = i & 63;
+      tile[c][p] = (c0 + c < C && p0 + p < HW) ? __ldg(in + ((size_t)b * C + c0 + c) * HW + p0 + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int p = i >> 5, c2 = (i & 31) * 2;
+      if (p0 + p < HW && c0 + c2 < C) {
+        __nv_bfloat16* dst = out + ((size_t)b * HW + p0 + p) * C_total + c_offset + c0 + c2;
+        if (c0 + c2 + 1 < C) {
+          *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(tile[c2][p], tile[c2 + 1][p]);
+        } else {
+          *dst = __float2bfloat16_rn(tile[c2][p]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace b200bev
+
+using namespace b200bev;
+
+extern "C" B200BEV_API size_t b200bev_conv_pack_bytes(int Cout, int Cin, int taps) {
+  if (Cout <= 0 || Cin <= 0 || Cin % kKC != 0 || (taps != 1 && taps != 9)) return 0;
+  return (size_t)ceil_div(Cout, kTileCo) * taps * (Cin / kKC) * kStageA;
+}
+
+extern "C" B200BEV_API int b200bev_conv_pack_bf16(const float* weight, int Cout, int Cin, int taps, void* image, size_t image_bytes,
+                                      void* stream) {
+  const size_t need = b200bev_conv_pack_bytes(Cout, Cin, taps);
+  if (!weight || !image) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (need == 0) return B200BEV_ERR_UNSUPPORTED;
+  if (image_bytes < need || ((uintptr_t)image & 15)) return B200BEV_ERR_WORKSPACE;
+  const long long n_chunks = (long long)(need / 16);
+  long long blocks = (n_chunks + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  conv_pack_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(weight, Cout, Cin, taps, (uint8_t*)image, n_chunks);
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int C, int H, int W, void* out_nhwc, int C_total,
+                                         int c_offset, void* stream) {
+  if (!in || !out_nhwc || B <= 0 || C <= 0 || H <= 0 || W <= 0 || c_offset < 0 || c_offset + C > C_total)
+    return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((C_total & 1) || (c_offset & 1)) return B200BEV_ERR_UNSUPPORTED;   // paired bf16 stores
+  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, 64);
+  long long blocks = tiles < (long long)sm_count() * 8 ? tiles : (long long)sm_count() * 8;
+  nchw_to_nhwc_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__nv_bfloat16*)out_nhwc, C_total, c_offset);
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, int H, int W, int Cin, const void* weight_image,
+                                         const float* bias, int Cout, int taps, int relu, float* out_nchw, void* stream) {
+  if (!x_nhwc || !weight_image || !out_nchw || B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (Cin <= 0 || Cin % kKC != 0 || (taps != 1 && taps != 9)) return B200BEV_ERR_UNSUPPORTED;
+  if ((long long)B * H * W * Cin >= (1ll << 40)) return B200BEV_ERR_UNSUPPORTED;
+  if (((uintptr_t)x_nhwc | (uintptr_t)weight_image) & 15) return B200BEV_ERR_INVALID_ARGUMENT;
+  ConvArgs a{(const __nv_bfloat16*)x_nhwc, (const uint8_t*)weight_image, bias, out_nchw, B, H, W, Cin, Cout, taps, relu};
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  const long long tiles = (((long long)B * H * W + kTilePx - 1) / kTilePx) * ceil_div(Cout, kTileCo);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  conv_tc_kernel<<<grid, kConvThreads, kConvSmem, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}

@@ -8,7 +8,7 @@
 //
 // linear_stream_kernel<NB>: one CTA per SM, each owning a contiguous range of output rows (O/grid, so every CTA walks
 // the same number of 64-row steps).  The batch tile (TB = 4*NB rows of x, K floats each) stays in shared memory for the
-// whole kernel.  The 8 warps are 2 row groups x 4 K-quarters: a warp multiplies 32 weight rows x its quarter of K against
+// whole kernel.  The 8 warps are 2 row groups x 4 K-quarters: a warp multiplies 32 weight rows x its quarter of K (every fourth 32-float chunk) against
 // the whole batch tile, streaming its weights with its OWN cp.async ring (16-byte LDGSTS, 3-5 stages of 32 rows x 32 k,
 // rows padded to 144 B so the eight row addresses of a 128-bit shared load fall in eight different bank groups) — no
 // block-wide barrier in the streaming loop, and the ring keeps running across step boundaries.  A thread holds a
@@ -76,7 +76,6 @@ __global__ void __launch_bounds__(kThreads, 1) linear_stream_kernel(LinArgs a) {
   const int row_lo = (int)(O * blockIdx.x / gridDim.x), row_hi = (int)(O * (blockIdx.x + 1) / gridDim.x);
   const int n_steps = ceil_div(row_hi - row_lo, kStepRows);
   const int kq_len = K / kKSplit, nch = kq_len / kKC;
-  const int k_base = kq * kq_len;
   const int total = n_steps * nch;  // chunks this warp streams
 
   float* my_ring = ring + (size_t)warp * kStages * 32 * kRowF;
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_stream_kernel(LinArgs a) {
       const int step = q / nch, ch = q - step * nch;
       const int r0 = row_lo + step * kStepRows + og * 32;
       float* dst = my_ring + (size_t)(q % kStages) * 32 * kRowF;
-      const int k0 = k_base + ch * kKC;
+      const int k0 = (ch * kKSplit + kq) * kKC;   // the four K-split warps of a row group read four ADJACENT 128-byte pieces
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int p = lane + 32 * t, r = p >> 3, c = p & 7;
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_stream_kernel(LinArgs a) {
       __syncwarp();
       issue(q + kStages - 1);  // refills the slot consumed in the previous iteration
       const float* wt = my_ring + (size_t)(q % kStages) * 32 * kRowF + go * kRowF;
-      const float* xt = xs + (size_t)gb * xs_stride + k_base + ch * kKC;
+      const float* xt = xs + (size_t)gb * xs_stride + (ch * kKSplit + kq) * kKC;
       // operands of the next four k are fetched while the FMAs of these four run: with two warps per scheduler the
       // shared-memory latency is not hidden by other warps
       float4 wv[2][4], xv[2][NB];

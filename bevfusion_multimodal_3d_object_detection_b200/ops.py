@@ -314,6 +314,62 @@ def lidar_init(feats: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torc
 
 
 # ------------------------------------------------------------------------------------------------
+# N1: convolution blocks on tcgen05 (bf16, parity 1e-2)
+# ------------------------------------------------------------------------------------------------
+def fold_conv_bn(conv: torch.nn.Conv2d, bn: Optional[torch.nn.Module]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm2d folded into the convolution in float64 -> (weight (Cout,Cin,kh,kw), bias (Cout)) fp32."""
+    w, b = fold_batchnorm(conv.weight, conv.bias, bn)
+    return w.reshape(conv.weight.shape).float().contiguous(), b.float().contiguous()
+
+
+def conv_pack(weight: torch.Tensor) -> torch.Tensor:
+    """(Cout,Cin,kh,kw) fp32 on the device -> the swizzled bf16 stage image of b200bev_conv_bn_relu_bf16 (uint8 tensor)."""
+    weight = _need_cuda(weight, "weight")
+    Cout, Cin, kh, kw = weight.shape
+    taps = kh * kw
+    n = _lib.lib().b200bev_conv_pack_bytes(Cout, Cin, taps)
+    if n == 0:
+        raise _lib.B200BevError(_lib.ERR_UNSUPPORTED, f"conv {tuple(weight.shape)}: needs Cin % 64 == 0 and a 3x3 or 1x1 kernel")
+    img = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.lib().b200bev_conv_pack_bf16(_ptr(weight), Cout, Cin, taps, _ptr(img), n, _stream(weight.device)))
+    return img
+
+
+def nchw_to_nhwc_bf16(parts: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[(B,C_i,H,W) fp32] -> (B,H,W,sum C_i) bf16 channels-last: layout change, cast and torch.cat in one pass per part."""
+    parts = [_need_cuda(p, f"parts[{i}]") for i, p in enumerate(parts)]
+    B, _, H, W = parts[0].shape
+    c_total = sum(int(p.shape[1]) for p in parts)
+    out = torch.empty((B, H, W, c_total), dtype=torch.bfloat16, device=parts[0].device)
+    off = 0
+    with torch.cuda.device(out.device):
+        for p in parts:
+            if p.shape[0] != B or tuple(p.shape[2:]) != (H, W):
+                raise RuntimeError("Sizes of tensors must match except in dimension 1")      # what torch.cat says
+            _lib.check(_lib.lib().b200bev_nchw_to_nhwc_bf16(_ptr(p), B, int(p.shape[1]), H, W, _ptr(out), c_total, off,
+                                                            _stream(out.device)))
+            off += int(p.shape[1])
+    return out
+
+
+def conv_bn_relu_bf16(x_nhwc: torch.Tensor, image: torch.Tensor, bias: Optional[torch.Tensor], c_out: int, taps: int,
+                      relu: bool = True) -> torch.Tensor:
+    """(B,H,W,Cin) bf16 -> (B,Cout,H,W) fp32: 3x3 (padding 1) or 1x1 convolution + folded BatchNorm + ReLU on tcgen05."""
+    x_nhwc = _need_cuda(x_nhwc, "input", torch.bfloat16)
+    image = _need_cuda(image, "weight_image", torch.uint8)
+    bias = None if bias is None else _need_cuda(bias, "bias")
+    B, H, W, Cin = x_nhwc.shape
+    if image.numel() != _lib.lib().b200bev_conv_pack_bytes(c_out, Cin, taps):
+        raise ValueError("weight image does not belong to this (Cout, Cin, taps)")
+    out = torch.empty((B, c_out, H, W), dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().b200bev_conv_bn_relu_bf16(_ptr(x_nhwc), B, H, W, Cin, _ptr(image), _ptr(bias), c_out, taps,
+                                                        1 if relu else 0, _ptr(out), _stream(out.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # S3
 # ------------------------------------------------------------------------------------------------
 def centernet_nms(heat: torch.Tensor) -> torch.Tensor:

@@ -229,6 +229,29 @@ B200BEV_API int b200bev_lidar_init(const float* lidar_features, int B, int K, co
                        int hidden, const float* w2, const float* b2, int O,
                        float* hidden_ws, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * N1  the convolution blocks between the hot-path kernels, bf16 on tcgen05 tensor cores (parity 1e-2).
+ * b200bev_conv_bn_relu_bf16: Conv2d(k=3, padding=1 | k=1) [+ BatchNorm2d eval, folded by the caller] [+ ReLU] as one
+ *   implicit-GEMM launch.  Replaces the blocks of FlexibleBEVFusion — camera_proj src/fusion.py:126-133, lidar_upsample
+ *   :151-166, radar_refine :176-183, bev_fusion :199-207 — and CenterNetHead's convolutions src/fusion.py:822-854.
+ *   x_nhwc       (B,H,W,Cin) bf16 channels-last, Cin a multiple of 64 (b200bev_nchw_to_nhwc_bf16 makes it)
+ *   weight_image made by b200bev_conv_pack_bf16 from the folded (Cout,Cin,kh,kw) fp32 weight; taps = kh*kw = 9 or 1
+ *   bias         (Cout) f32 folded bias or NULL;  relu != 0 applies max(.,0)
+ *   out_nchw     (B,Cout,H,W) f32 — the layout the reference's next module takes
+ * b200bev_conv_pack_bf16: re-tiles a weight into the 16 KB swizzled stages the kernel streams (once per weight update);
+ *   b200bev_conv_pack_bytes gives the image size (0: unsupported shape).
+ * b200bev_nchw_to_nhwc_bf16: (B,C,H,W) f32 -> channels [c_offset, c_offset+C) of a (B,H,W,C_total) bf16 tensor; writing
+ *   the parts of a concatenated input into their slices replaces torch.cat of src/fusion.py:292.
+ * ------------------------------------------------------------------------------------------- */
+B200BEV_API size_t b200bev_conv_pack_bytes(int Cout, int Cin, int taps);
+B200BEV_API int b200bev_conv_pack_bf16(const float* weight, int Cout, int Cin, int taps,
+                           void* image, size_t image_bytes, void* stream);
+B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int C, int H, int W,
+                              void* out_nhwc, int C_total, int c_offset, void* stream);
+B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, int H, int W, int Cin,
+                              const void* weight_image, const float* bias, int Cout, int taps, int relu,
+                              float* out_nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,33 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = False
         med3, _ = timeit(lambda: torch.addmm(b2, torch.relu(torch.addmm(b1, x, w1.t())), w2.t()), reps=20)
         print(f"  (cuBLAS fp32, torch.addmm x2, batch {F}: median {med3 * 1e3:8.1f} us)", flush=True)
+    if args.what in ("conv", "all"):
+        g = torch.Generator(device=dev).manual_seed(3)
+        shapes = [("head 5x(256->64) as 256->320", 256, 320, 3, G, G), ("bev_fusion.0 768->512", 768, 512, 3, G, G),
+                  ("bev_fusion.3 512->256", 512, 256, 3, G, G), ("camera_proj.0 512->512 @57x100", 512, 512, 3, 57, 100),
+                  ("camera_proj.3 512->256 1x1 @57x100", 512, 256, 1, 57, 100), ("radar_refine 256->256", 256, 256, 3, G, G),
+                  ("lidar_upsample.4 128->256", 128, 256, 3, G, G)]
+        tot = {"tc": 0.0, "cudnn_bf16": 0.0, "cudnn_f32": 0.0, "flop": 0.0}
+        for name, cin, cout, k, H, W in shapes:
+            x = torch.randn((F, cin, H, W), device=dev, generator=g)
+            w = torch.randn((cout, cin, k, k), device=dev, generator=g) / (cin * k * k) ** 0.5
+            b = torch.randn(cout, device=dev, generator=g)
+            nhwc = ops.nchw_to_nhwc_bf16([x])
+            img = ops.conv_pack(w)
+            med, best = timeit(lambda: ops.conv_bn_relu_bf16(nhwc, img, b, cout, k * k), reps=10)
+            medl, _ = timeit(lambda: ops.nchw_to_nhwc_bf16([x]), reps=10)
+            xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            wb = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            bb = b.to(torch.bfloat16)
+            medc, _ = timeit(lambda: torch.relu_(torch.nn.functional.conv2d(xb, wb, bb, padding=k // 2)), reps=10)
+            torch.backends.cudnn.allow_tf32 = False
+            medf, _ = timeit(lambda: torch.relu_(torch.nn.functional.conv2d(x, w, b, padding=k // 2)), reps=5)
+            fl = 2.0 * F * H * W * cout * cin * k * k
+            tot["tc"] += med; tot["cudnn_bf16"] += medc; tot["cudnn_f32"] += medf; tot["flop"] += fl
+            print(f"conv {name:36s} tcgen05 {med * 1e3:8.1f} us ({fl / med / 1e9:7.1f} TFLOP/s)  layout pass {medl * 1e3:6.1f} us | "
+                  f"cuDNN bf16 NHWC {medc * 1e3:8.1f} us  cuDNN fp32 {medf * 1e3:8.1f} us", flush=True)
+        print(f"conv total ({F} frames): tcgen05 {tot['tc']:.3f} ms ({tot['flop'] / tot['tc'] / 1e9:.1f} TFLOP/s)  cuDNN bf16 "
+              f"{tot['cudnn_bf16']:.3f} ms  cuDNN fp32 {tot['cudnn_f32']:.3f} ms", flush=True)
     if args.what in ("decode", "all"):
         maps = {k: to(v) for k, v in syn.head_maps(44, F, 10, G, G).items()}
         med, best = timeit(lambda: ops.centernet_decode(maps["heatmap"], maps["offset"], maps["size"], maps["rot"], maps["vel"],

@@ -594,3 +594,36 @@ def test_decode_from_logits_vs_reference_head_golden(cuda, golden):
             np.testing.assert_allclose(fused["scores"][b, :n].cpu().numpy(), ref_scores[:n], rtol=3e-7, atol=0)
             np.testing.assert_allclose(fused["boxes"][b, :n].cpu().numpy(), g[f"head_{tag}_b{b}_boxes"][:n], rtol=0, atol=1e-5)
             np.testing.assert_array_equal(fused["velocities"][b, :n].cpu().numpy(), g[f"head_{tag}_b{b}_velocities"][:n])
+
+
+# ------------------------------------------------------------------------------------------------ N1: convolution blocks on tcgen05
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,relu", [
+    (2, 12, 20, 64, 64, 3, True),        # two pixel tiles, the second ragged
+    (3, 50, 50, 128, 320, 3, True),      # the batched head conv: partial channel tile, 32-pixel groups straddling frames
+    (2, 25, 25, 512, 256, 1, True),      # 1x1 (camera_proj's second block): HW = 625 is not a multiple of 4 -> scalar stores
+    (1, 7, 9, 64, 19, 1, False),         # tiny: one ragged tile, no ReLU (the head's second layer)
+    (4, 50, 50, 256, 256, 3, False),     # more tiles than one wave of the ring phases
+])
+def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
+    g = np.random.default_rng(Cin * 7 + Cout)
+    x = g.standard_normal((B, Cin, H, W)).astype(np.float32)
+    w = (g.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)
+    b = g.standard_normal(Cout).astype(np.float32)
+    xd, wd, bd = dev_t(x, cuda), dev_t(w, cuda), dev_t(b, cuda)
+    # the layout kernel: split the channels in two parts to exercise the concat form
+    half = Cin // 2
+    nhwc = ops.nchw_to_nhwc_bf16([xd[:, :half].contiguous(), xd[:, half:].contiguous()])
+    assert torch.equal(nhwc, xd.permute(0, 2, 3, 1).to(torch.bfloat16))
+    img = ops.conv_pack(wd)
+    got = ops.conv_bn_relu_bf16(nhwc, img, bd, Cout, k * k, relu=relu)
+    assert tuple(got.shape) == (B, Cout, H, W)
+    # (a) the same bf16-rounded operands in float64: only the accumulation order differs
+    xr = xd.to(torch.bfloat16).double()
+    wr = wd.to(torch.bfloat16).double()
+    ref = torch.nn.functional.conv2d(xr, wr, bd.double(), padding=k // 2)
+    ref = torch.relu(ref) if relu else ref
+    assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    # (b) the fp32 convolution the reference runs: the bf16 tolerance of north_star
+    ref32 = torch.nn.functional.conv2d(xd.double(), wd.double(), bd.double(), padding=k // 2)
+    ref32 = torch.relu(ref32) if relu else ref32
+    assert max_rel(got.cpu().numpy(), ref32.cpu().numpy()) < BF16_TOL
