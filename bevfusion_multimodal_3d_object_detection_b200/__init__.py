@@ -10,11 +10,11 @@ from . import _lib  # noqa: F401
 from .centernet_decode import (_nms, _topk, decode_centernet_predictions,  # noqa: F401
                                decode_centernet_predictions_fusion_detection)
 from .encoders import MultiRadarEncoder, PointNetLiDAREncoder, RadarEncoder, load_config  # noqa: F401
-from .fusion import FlexibleBEVFusion  # noqa: F401
+from .fusion import CenterNetHead, FlexibleBEVFusion  # noqa: F401
 from .patch import patch, unpatch  # noqa: F401
 
 __all__ = [
-    "PointNetLiDAREncoder", "RadarEncoder", "MultiRadarEncoder", "FlexibleBEVFusion",
+    "PointNetLiDAREncoder", "RadarEncoder", "MultiRadarEncoder", "FlexibleBEVFusion", "CenterNetHead",
     "decode_centernet_predictions", "decode_centernet_predictions_fusion_detection", "_nms", "_topk",
     "load_config", "patch", "unpatch",
 ]

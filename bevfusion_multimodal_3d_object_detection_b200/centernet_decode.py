@@ -38,9 +38,11 @@ def decode_centernet_predictions(predictions: Dict[str, torch.Tensor], score_thr
                                  voxel_size: float = CENTERNET_TARGET_VOXEL) -> List[Dict[str, torch.Tensor]]:
     """List (one dict per sample) of boxes (n,7) [x,y,z,w,l,h,yaw], scores (n,), labels (n,) int64,
     velocities (n,2); n <= max_detections is the number of winners with score > score_thresh."""
-    out = ops.centernet_decode(predictions["heatmap"], predictions["offset"], predictions["size"],
+    # the mirror head also hands over its raw heat-map output: the sigmoid then runs inside the decode launch
+    logits = predictions.get("heatmap_logits")
+    out = ops.centernet_decode(predictions["heatmap"] if logits is None else logits, predictions["offset"], predictions["size"],
                                predictions["rot"], predictions["vel"], max_detections, voxel_size,
-                               PC_ORIGIN, GROUND_Z, score_thresh)
+                               PC_ORIGIN, GROUND_Z, score_thresh, heat_is_logit=logits is not None)
     counts = out["count"].tolist()                      # the one host sync of the call
     detections = []
     for b, n in enumerate(counts):

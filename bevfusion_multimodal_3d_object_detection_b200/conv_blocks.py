@@ -1,0 +1,141 @@
+"""Host side of SURVEY 8f N1: the Conv2d + BatchNorm2d + ReLU stacks of the reference's fusion module and detection
+head on the tcgen05 convolution kernel (`b200bev_conv_bn_relu_bf16`).
+
+The kernel computes in bf16 with fp32 accumulation (parity 1e-2 of max|ref|, north_star's bf16 bound), so this path is
+opt-in: `module.b200_precision = "bf16"` or `B200BEV_PRECISION=bf16`; the default stays the reference's own fp32
+cuDNN convolutions between the kernels (parity 1e-5).  Eval mode only — BatchNorm is folded with its running
+statistics.  Folded and packed weights are a cache keyed on the parameters' version counters, rebuilt after
+`load_state_dict` or an optimizer step (SURVEY 8b "Ownership / state").
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .encoders import _state_key, default_precision
+
+HEADS = ("heatmap", "offset", "size", "rot", "vel")       # CenterNetHead's sub-modules, src/fusion.py:822-854
+
+
+def wants_bf16(module: nn.Module) -> bool:
+    return (getattr(module, "b200_precision", None) or default_precision()) == "bf16"
+
+
+def _conv_ok(conv: nn.Conv2d) -> bool:
+    k = conv.kernel_size
+    return (k in ((3, 3), (1, 1)) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.padding == (k[0] // 2, k[1] // 2) and conv.in_channels % 64 == 0 and conv.padding_mode == "zeros")
+
+
+def supported(seq: nn.Sequential) -> bool:
+    """True when every layer of the stack is a Conv2d the kernel takes, a BatchNorm2d, a ReLU or a bilinear Upsample."""
+    for layer in seq:
+        if isinstance(layer, nn.Conv2d):
+            if not _conv_ok(layer):
+                return False
+        elif isinstance(layer, nn.Upsample):
+            if layer.mode != "bilinear" or layer.align_corners:
+                return False
+        elif not isinstance(layer, (nn.BatchNorm2d, nn.ReLU)):
+            return False
+    return True
+
+
+def _plan(seq: nn.Sequential, device: torch.device) -> List[Dict]:
+    key = _state_key(seq, device)
+    cache = seq.__dict__.get("_b200bev_conv_cache")
+    if cache is not None and cache["key"] == key:
+        return cache["steps"]
+    layers = list(seq)
+    steps: List[Dict] = []
+    i = 0
+    while i < len(layers):
+        layer = layers[i]
+        if isinstance(layer, nn.Conv2d):
+            bn = layers[i + 1] if i + 1 < len(layers) and isinstance(layers[i + 1], nn.BatchNorm2d) else None
+            j = i + (2 if bn is not None else 1)
+            relu = j < len(layers) and isinstance(layers[j], nn.ReLU)
+            w, b = ops.fold_conv_bn(layer, bn)
+            steps.append({"kind": "conv", "image": ops.conv_pack(w.to(device)), "bias": b.to(device),
+                          "c_out": layer.out_channels, "taps": layer.kernel_size[0] * layer.kernel_size[1], "relu": relu})
+            i = j + (1 if relu else 0)
+        elif isinstance(layer, nn.Upsample):
+            steps.append({"kind": "upsample", "scale": layer.scale_factor})
+            i += 1
+        else:
+            raise RuntimeError(f"conv_blocks: unexpected layer {type(layer).__name__} (check supported() first)")
+    seq.__dict__["_b200bev_conv_cache"] = {"key": key, "steps": steps}
+    return steps
+
+
+def run(seq: nn.Sequential, parts: Sequence[torch.Tensor]) -> torch.Tensor:
+    """`seq(torch.cat(parts, dim=1))` for a conv/BN/ReLU(/Upsample) stack: (B,C_i,H,W) fp32 parts -> (B,C_out,H',W') fp32."""
+    parts = list(parts)
+    for step in _plan(seq, parts[0].device):
+        if step["kind"] == "conv":
+            nhwc = ops.nchw_to_nhwc_bf16(parts)          # layout + cast + concat in one pass per part
+            parts = [ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
+        else:
+            x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+            s = step["scale"]
+            sy, sx = (s, s) if not isinstance(s, (tuple, list)) else s
+            parts = [ops.bilinear_resize(x, (int(x.shape[2] * sy), int(x.shape[3] * sx)))]
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# CenterNetHead: five 3x3 convs as one, five 1x1 convs as one block-diagonal conv, sigmoid left to the decode kernel
+# ------------------------------------------------------------------------------------------------
+def head_supported(head: nn.Module) -> bool:
+    try:
+        subs = [getattr(head, f"{n}_head") for n in HEADS]
+    except AttributeError:
+        return False
+    hidden = sum(s[0].out_channels for s in subs)
+    return all(len(s) == 3 and _conv_ok(s[0]) and s[2].kernel_size == (1, 1) for s in subs) and hidden % 64 == 0
+
+
+def _head_plan(head: nn.Module, device: torch.device) -> Dict:
+    key = _state_key(head, device)
+    cache = head.__dict__.get("_b200bev_conv_cache")
+    if cache is not None and cache["key"] == key:
+        return cache
+    subs = [getattr(head, f"{n}_head") for n in HEADS]
+    w1 = torch.cat([s[0].weight.detach() for s in subs], dim=0).float().to(device).contiguous()   # (5*hc, Cin, 3, 3)
+    b1 = torch.cat([s[0].bias.detach() for s in subs], dim=0).float().to(device).contiguous()
+    hidden = int(w1.shape[0])
+    outs = [s[2].out_channels for s in subs]
+    w2 = torch.zeros((sum(outs), hidden, 1, 1), dtype=torch.float32, device=device)
+    r = c = 0
+    for s, n in zip(subs, outs):
+        hc = s[0].out_channels
+        w2[r:r + n, c:c + hc] = s[2].weight.detach().float().to(device)
+        r += n
+        c += hc
+    b2 = torch.cat([s[2].bias.detach() for s in subs], dim=0).float().to(device).contiguous()
+    cache = {"key": key, "img1": ops.conv_pack(w1), "b1": b1, "hidden": hidden, "img2": ops.conv_pack(w2), "b2": b2, "outs": outs}
+    head.__dict__["_b200bev_conv_cache"] = cache
+    return cache
+
+
+def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """CenterNetHead.forward (src/fusion.py:869-884).  Eval mode with the bf16 path enabled: two tcgen05 launches for the
+    ten convolutions; the dict also carries `heatmap_logits`, which `decode_centernet_predictions` feeds to the decode
+    kernel so that the sigmoid is not a separate pass there."""
+    if head.training or not x.is_cuda or not wants_bf16(head) or not head_supported(head) or x.shape[1] % 64 != 0:
+        pred = {n: getattr(head, f"{n}_head")(x) for n in HEADS}
+        pred["heatmap"] = torch.sigmoid(pred["heatmap"])
+        return pred
+    p = _head_plan(head, x.device)
+    hid = ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), p["img1"], p["b1"], p["hidden"], 9, relu=True)
+    both = ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([hid]), p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
+    pred, c = {}, 0
+    for n, k in zip(HEADS, p["outs"]):
+        pred[n] = both[:, c:c + k].contiguous()
+        c += k
+    pred["heatmap_logits"] = pred["heatmap"]
+    pred["heatmap"] = torch.sigmoid(pred["heatmap_logits"])
+    return pred

@@ -13,13 +13,14 @@ describes: calibrated projection of the BEV cell centres and a one-pass gather o
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import conv_blocks, ops
 from .encoders import load_config
 
 
@@ -34,7 +35,16 @@ def camera_branch(module: nn.Module, camera_features: torch.Tensor) -> torch.Ten
         cam = camera_features.mean(dim=1) if camera_features.dim() == 5 else camera_features
         return F.interpolate(module.camera_proj(cam), size=size, mode="bilinear", align_corners=False)
     cam = ops.camera_mean(camera_features) if camera_features.dim() == 5 else camera_features
-    return ops.bilinear_resize(module.camera_proj(cam), size)
+    return ops.bilinear_resize(_stack(module, module.camera_proj, [cam]), size)
+
+
+def _stack(module: nn.Module, seq: nn.Sequential, parts) -> torch.Tensor:
+    """A conv/BN/ReLU stack of the fusion module in eval mode: the tcgen05 convolution kernel when the bf16 path is
+    enabled on the module (parity 1e-2), else the reference's own fp32 cuDNN layers (parity 1e-5)."""
+    if conv_blocks.wants_bf16(module) and parts[0].is_cuda and conv_blocks.supported(seq) \
+            and sum(int(p.shape[1]) for p in parts) % 64 == 0:
+        return conv_blocks.run(seq, parts)
+    return seq(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
 
 
 def lidar_branch(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tensor:
@@ -49,6 +59,8 @@ def lidar_branch(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tenso
     l0, l2 = module.lidar_init[0], module.lidar_init[2]
     x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s, s)
     up = module.lidar_upsample
+    if conv_blocks.wants_bf16(module) and conv_blocks.supported(up) and hidden % 64 == 0:
+        return conv_blocks.run(up, [x])
     for i, layer in enumerate(up):
         if isinstance(layer, nn.Upsample):
             # scale_factor=2, align_corners=False: source coordinate (i+0.5)/2-0.5, what the size-based resize computes
@@ -75,10 +87,13 @@ def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None,
         else:
             r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)  # :274
         r = r.view(B, module.bev_channels, 1, 1)
-        parts.append(module.radar_refine(r.expand(B, module.bev_channels, module.bev_h, module.bev_w)))  # :274-281
+        r = r.expand(B, module.bev_channels, module.bev_h, module.bev_w)
+        parts.append(module.radar_refine(r) if module.training else _stack(module, module.radar_refine, [r]))  # :274-281
     if not parts:
         raise ValueError("No modality features provided")              # :289
-    return module.bev_fusion(torch.cat(parts, dim=1))                  # :292-295
+    if module.training:
+        return module.bev_fusion(torch.cat(parts, dim=1))              # :292-295
+    return _stack(module, module.bev_fusion, parts)                    # the concat happens inside the layout kernel
 
 
 class FlexibleBEVFusion(nn.Module):
@@ -144,3 +159,32 @@ class FlexibleBEVFusion(nn.Module):
     def get_config_str(self) -> str:
         names = [n for n, on in (("camera", self.use_camera), ("lidar", self.use_lidar), ("radar", self.use_radar)) if on]
         return "+".join(names)
+
+
+class CenterNetHead(nn.Module):
+    """Constructor contract, sub-module and state_dict names of src/fusion.py:788-867; forward :869-884."""
+
+    def __init__(self, in_channels: Optional[int] = None, num_classes: Optional[int] = None, head_conv: Optional[int] = None,
+                 config: Optional[Dict] = None, config_path: Optional[str] = None):
+        super().__init__()
+        if config is not None or config_path is not None:
+            if config is None:
+                config = load_config(config_path)
+            cfg = config.get("model", {}).get("centernet_head", {})
+            in_channels = cfg.get("in_channels", 256) if in_channels is None else in_channels
+            num_classes = config.get("dataset", {}).get("num_classes", 10) if num_classes is None else num_classes
+            head_conv = cfg.get("head_conv", 64) if head_conv is None else head_conv
+        in_channels = 256 if in_channels is None else in_channels
+        self.num_classes = 10 if num_classes is None else num_classes
+        head_conv = 64 if head_conv is None else head_conv
+        for name, n_out in zip(conv_blocks.HEADS, (self.num_classes, 2, 3, 2, 2)):
+            setattr(self, f"{name}_head", nn.Sequential(nn.Conv2d(in_channels, head_conv, 3, padding=1, bias=True),
+                                                        nn.ReLU(inplace=True), nn.Conv2d(head_conv, n_out, 1, bias=True)))
+        for m in self.modules():                                  # src/fusion.py:856-867
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, std=0.001)
+                nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.heatmap_head[-1].bias, -math.log((1 - 0.01) / 0.01))
+
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return conv_blocks.head_forward(self, x)

@@ -12,6 +12,7 @@ name from their own src/ directory:
     encoders.PointNetLiDAREncoder.forward     (src/encoders.py:271)
     encoders.MultiRadarEncoder.forward        (src/encoders.py:628)
     fusion.FlexibleBEVFusion.forward          (src/fusion.py:209)
+    fusion.CenterNetHead.forward              (src/fusion.py:869)
     centernet_target.{_nms,_topk,decode_centernet_predictions}    (src/centernet_target.py:326-452)
     fusion_detection.{_nms,_topk,decode_centernet_predictions}    (src/fusion_detection.py:695-820)
 
@@ -32,7 +33,7 @@ import importlib
 import sys
 from typing import Dict, List, Tuple
 
-from . import _lib, centernet_decode, encoders, fusion
+from . import _lib, centernet_decode, conv_blocks, encoders, fusion
 
 _saved: List[Tuple[object, str, object]] = []
 
@@ -72,6 +73,9 @@ def patch(precision: str = None) -> Dict[str, List[str]]:
               lambda self, camera_features=None, lidar_features=None, radar_features=None:
               fusion.fusion_forward(self, camera_features, lidar_features, radar_features))
         done["fusion"] = ["FlexibleBEVFusion.forward"]
+        if hasattr(fus_mod, "CenterNetHead"):
+            _swap(fus_mod.CenterNetHead, "forward", lambda self, x: conv_blocks.head_forward(self, x))
+            done["fusion"].append("CenterNetHead.forward")
     variants = {"centernet_target": centernet_decode.CENTERNET_TARGET_VOXEL,
                 "fusion_detection": centernet_decode.FUSION_DETECTION_VOXEL}
     for mod_name, voxel in variants.items():

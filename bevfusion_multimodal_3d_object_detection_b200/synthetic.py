@@ -146,7 +146,7 @@ def global_features(seed: int, batch: int, channels: int) -> np.ndarray:
     return np.abs(_rng(seed).standard_normal((batch, channels))).astype(np.float32)
 
 
-def head_weights(seed: int, in_channels: int, head_conv: int, classes: int) -> Dict[str, np.ndarray]:
+def head_weights(seed: int, in_channels: int, head_conv: int, classes: int, out_scale: float = 1.0) -> Dict[str, np.ndarray]:
     """CenterNetHead parameters (src/fusion.py:822-854) by state_dict name, with weights large enough that the heat-map
     logits spread (the reference's init, std 0.001, leaves every logit within 1e-3 of the -4.595 bias)."""
     g = _rng(seed)
@@ -154,9 +154,31 @@ def head_weights(seed: int, in_channels: int, head_conv: int, classes: int) -> D
     for name, n_out in (("heatmap", classes), ("offset", 2), ("size", 3), ("rot", 2), ("vel", 2)):
         out[f"{name}_head.0.weight"] = (g.standard_normal((head_conv, in_channels, 3, 3)) * 0.08).astype(np.float32)
         out[f"{name}_head.0.bias"] = (g.standard_normal(head_conv) * 0.1).astype(np.float32)
-        out[f"{name}_head.2.weight"] = (g.standard_normal((n_out, head_conv, 1, 1)) * 0.3).astype(np.float32)
+        out[f"{name}_head.2.weight"] = (g.standard_normal((n_out, head_conv, 1, 1)) * (0.3 * out_scale)).astype(np.float32)
         out[f"{name}_head.2.bias"] = (g.standard_normal(n_out) * 0.1).astype(np.float32)
     out["heatmap_head.2.bias"] = out["heatmap_head.2.bias"] - np.float32(2.0)
+    return out
+
+
+def fill_state_dict(seed: int, shapes: Dict[str, Tuple[int, ...]]) -> Dict[str, np.ndarray]:
+    """Seeded values for every float entry of a state_dict, by name and shape: conv / linear weights N(0, 1/fan_in),
+    BatchNorm weight U(0.5,1.5), running_var U(0.5,2), everything else 1-D N(0, 0.2^2) — statistics away from the
+    identity, the same on every machine (torch's own initialisers depend on construction order)."""
+    g = _rng(seed)
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        if name.endswith("num_batches_tracked"):
+            continue
+        if len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            out[name] = (g.standard_normal(shape) / np.sqrt(fan_in)).astype(np.float32)
+        elif name.endswith("running_var"):
+            out[name] = g.uniform(0.5, 2.0, shape).astype(np.float32)
+        elif name.endswith("weight"):
+            out[name] = g.uniform(0.5, 1.5, shape).astype(np.float32)
+        else:
+            out[name] = (g.standard_normal(shape) * 0.2).astype(np.float32)
     return out
 
 

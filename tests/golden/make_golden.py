@@ -266,6 +266,17 @@ def glue_cases():
         for b, d in enumerate(fusion_detection.decode_centernet_predictions(pred, score_thresh=t, max_detections=60)):
             for k, v in d.items():
                 out[f"head_{tag}_b{b}_{k}"] = v.numpy()
+    # the convolution stacks of the fusion module with channel counts the tcgen05 kernel takes (multiples of 64):
+    # camera_proj (3x3 + 1x1), F.interpolate, bev_fusion (3x3, 3x3), src/fusion.py:229-248,292-295
+    with contextlib.redirect_stdout(io.StringIO()):
+        cf = fusion.FlexibleBEVFusion(use_camera=True, use_lidar=False, use_radar=False, camera_channels=64,
+                                      bev_h=12, bev_w=20, bev_channels=64)
+    sd = syn.fill_state_dict(731, {k: tuple(v.shape) for k, v in cf.state_dict().items()})
+    cf.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    cf.eval()
+    cam = syn.camera_features(732, 2, n_cam=6, channels=64, h=9, w=14)
+    out["stack_digest"] = syn.digest(cam, *[sd[k] for k in sorted(sd)])
+    out["stack_out"] = cf(camera_features=torch.from_numpy(cam)).numpy()
     np.savez_compressed(OUT / "bev_glue.npz", **out)
 
 

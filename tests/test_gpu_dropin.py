@@ -220,3 +220,83 @@ def test_encode_fuse_head_decode_chain_on_device(cuda):
     for d, r in zip(dets, ref):
         np.testing.assert_array_equal(d["scores"].cpu().numpy(), r["scores"])
         np.testing.assert_allclose(d["boxes"].cpu().numpy(), r["boxes"], rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f N1 / N2
+def _conv_fusion(cuda):
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=False, use_radar=False, camera_channels=64, bev_h=12, bev_w=20,
+                                    bev_channels=64)
+    sd = syn.fill_state_dict(731, {k: tuple(v.shape) for k, v in fus.state_dict().items()})
+    fus.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    return fus.eval().to(cuda)
+
+
+def test_fusion_conv_stacks_vs_reference_golden_fp32_and_tcgen05(cuda, golden):
+    """camera_proj + resize + bev_fusion of the reference's module: the default path (kernels + fp32 cuDNN convs, 1e-5)
+    and the opt-in bf16 path (every convolution on the tcgen05 kernel, 1e-2) against the reference's own output."""
+    g = golden("bev_glue")
+    fus = _conv_fusion(cuda)
+    cam = torch.from_numpy(syn.camera_features(732, 2, n_cam=6, channels=64, h=9, w=14)).to(cuda)
+    with torch.no_grad():
+        out32 = fus(camera_features=cam)
+        assert max_rel(out32.cpu().numpy(), g["stack_out"]) < 5 * FP32_TOL        # four conv layers deep
+        fus.b200_precision = "bf16"
+        out16 = fus(camera_features=cam)
+        assert "_b200bev_conv_cache" in fus.bev_fusion.__dict__                   # the tcgen05 path did run
+        assert out16.dtype == torch.float32 and tuple(out16.shape) == (2, 64, 12, 20)
+        assert max_rel(out16.cpu().numpy(), g["stack_out"]) < BF16_TOL
+        # weight updates invalidate the packed images
+        fus.bev_fusion[3].weight.mul_(2.0)
+        assert not torch.allclose(fus(camera_features=cam), out16)
+
+
+def test_all_three_branches_on_the_tcgen05_convs(cuda):
+    """camera + lidar (lidar_init kernel, upsample kernel) + radar (dense kernel, broadcast) + concat-free bev_fusion."""
+    torch.manual_seed(3)
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=64, lidar_channels=128,
+                                    radar_channels=64, bev_h=50, bev_w=50, bev_channels=64)
+    for mod in fus.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+    fus = fus.eval().to(cuda)
+    cam = torch.from_numpy(syn.camera_features(733, 2, n_cam=6, channels=64, h=28, w=50)).to(cuda)
+    lidar = torch.rand(2, 128, device=cuda)
+    radar = torch.rand(2, 64, device=cuda)
+    with torch.no_grad():
+        ref = fus(camera_features=cam, lidar_features=lidar, radar_features=radar)      # fp32 convolutions
+        fus.b200_precision = "bf16"
+        got = fus(camera_features=cam, lidar_features=lidar, radar_features=radar)
+    assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < BF16_TOL
+
+
+def test_centernet_head_mirror_vs_reference_golden_and_fused_path(cuda, golden):
+    g = golden("bev_glue")
+    # (1) the reference's own head (32 -> 16 channels: below the tensor-core kernel's granularity -> torch layers)
+    head = b200bev.CenterNetHead(in_channels=32, num_classes=10, head_conv=16)
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in syn.head_weights(711, 32, 16, 10).items()})
+    head = head.eval().to(cuda)
+    x = torch.from_numpy(syn._rng(712).standard_normal((2, 32, 24, 40)).astype(np.float32)).to(cuda)
+    with torch.no_grad():
+        pred = head(x)
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        assert max_rel(pred[k].cpu().numpy(), g[f"head_{k}"]) < FP32_TOL, k
+    # (2) 64 -> 5 x 64 channels with the bf16 path on: two tcgen05 launches, sigmoid inside the decode launch
+    big = b200bev.CenterNetHead(in_channels=64, num_classes=10, head_conv=64)
+    # second-layer weights scaled so that the logits spread over a few units, as a trained head's do: the bf16 bound is
+    # relative to max|ref| and the sigmoid pins that at <= 1 while the logit error grows with the logit range
+    big.load_state_dict({k: torch.from_numpy(v) for k, v in syn.head_weights(713, 64, 64, 10, out_scale=0.3).items()})
+    big = big.eval().to(cuda)
+    xb = torch.from_numpy(syn._rng(714).standard_normal((3, 64, 50, 50)).astype(np.float32)).to(cuda)
+    with torch.no_grad():
+        ref = big(xb)
+        big.b200_precision = "bf16"
+        got = big(xb)
+    assert "heatmap_logits" in got and "heatmap_logits" not in ref
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        assert got[k].is_contiguous() and max_rel(got[k].cpu().numpy(), ref[k].cpu().numpy()) < BF16_TOL, k
+    dets = b200bev.decode_centernet_predictions(got, score_thresh=0.0, max_detections=50)
+    plain = {k: v for k, v in got.items() if k != "heatmap_logits"}
+    want = b200bev.decode_centernet_predictions(plain, score_thresh=0.0, max_detections=50)
+    for d, w in zip(dets, want):
+        assert torch.equal(d["scores"], w["scores"]) and torch.equal(d["boxes"], w["boxes"])
