@@ -21,6 +21,8 @@
 // ahead of the MMAs, a stage is released by tcgen05.commit.  fp32 accumulation in TMEM (256 columns).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "async_copy.cuh"
 #include "common.cuh"
 
@@ -36,7 +38,7 @@ constexpr int kStageB = kTilePx * kKC * 2;   // 32 KB
 constexpr int kStage = kStageA + kStageB;
 constexpr int kRing = 4;
 constexpr int kAhead = kRing - 2;            // copies issued this many stages ahead of the MMAs
-constexpr int kConvSmem = kRing * kStage + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr int kConvSmem = kRing * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct ConvArgs {
   const __nv_bfloat16* x;     // (B, H, W, Cin) channels-last
@@ -252,6 +254,211 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(ConvArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
+// ---- warp-specialised form (default) -----------------------------------------------------------------------------------
+// The kernel above runs its producers, the MMA issue and the epilogue in one instruction stream: every stage pays the
+// chain "MMA(c-2) done -> copies issued -> wait -> fence -> block barrier -> MMA(c) issued" (~800 clk against 512 clk of
+// tensor work), the pipeline drains at every tile boundary and the accumulator is read out while the tensor pipe idles
+// (conv 768->512: 57 % of the sustained bf16 peak; the five-head conv: 37 %).  Here the three jobs are three groups of
+// warps that meet only at mbarriers:
+//   warps 0-7   producers: im2col pixel rows by cp.async, the weight stage by one bulk copy; they run ahead over tile
+//               boundaries, held back only by the ring (`empty`, released by tcgen05.commit)
+//   warp 12     MMA issuer: waits for a stage's rows (`full_b`, one arrival per producer warp) and weights (`full_a`),
+//               issues four 128x256x16 MMAs, commits the stage; the accumulator alternates between two 256-column
+//               halves of tensor memory
+//   warps 8-11  epilogue: one TMEM lane quadrant each; tile t is read out, biased, clamped and stored while the MMAs
+//               of tile t+1 run into the other half (`acc_full` / `acc_empty`)
+constexpr int kWsThreads = 416;
+constexpr int kLag = 2;   // a producer waits for its own copies of stage c two stages after issuing them
+
+__global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRing * kStage);
+  uint64_t* full_a = bars;
+  uint64_t* full_b = bars + kRing;
+  uint64_t* empty = bars + 2 * kRing;
+  uint64_t* acc_full = bars + 3 * kRing;       // [2]
+  uint64_t* acc_empty = bars + 3 * kRing + 2;  // [2]
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbarrier_init(&full_a[s], 1);
+      mbarrier_init(&full_b[s], 8);
+      mbarrier_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbarrier_init(&acc_full[s], 1);
+      mbarrier_init(&acc_empty[s], 4);
+    }
+    mbarrier_init_fence();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  const int HW = a.H * a.W;
+  const long long n_px = (long long)a.B * HW;
+  const int n_px_tiles = (int)((n_px + kTilePx - 1) / kTilePx);
+  const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
+  const int ncc = a.Cin / kKC;
+  const int n_k = a.taps * ncc;
+  const int n_tiles = n_px_tiles * n_co_tiles;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * n_k;   // stages this CTA streams
+
+  if (warp < 8) {
+    // ---- producers ----
+    const int row0 = tid >> 3, chunk = tid & 7;
+    const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
+    int py[8], pxx[8];
+    long long poff[8];
+    int tile = blockIdx.x, i = 0;   // the stage being produced: k-stage i of `tile`
+    const uint8_t* wtile = nullptr;
+    for (int it = 0; it < total + kLag; ++it) {
+      if (it < total) {
+        if (i == 0) {
+          const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
+          const long long px0 = (long long)px_tile * kTilePx;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long n = px0 + row0 + 32 * j;
+            if (n < n_px) {
+              const int p = (int)(n % HW);
+              py[j] = p / a.W;
+              pxx[j] = p - py[j] * a.W;
+              poff[j] = n * a.Cin + chunk * 8;
+            } else {
+              py[j] = -100000;
+              pxx[j] = 0;
+              poff[j] = 0;
+            }
+          }
+          wtile = a.wimg + (size_t)co_tile * n_k * kStageA;
+        }
+        const uint32_t slot = (uint32_t)it % kRing;
+        if (it >= kRing) mbarrier_wait(&empty[slot], (((uint32_t)it / kRing) - 1) & 1);
+        const int tap = i / ncc, cc = i - tap * ncc;
+        const int dy = a.taps == 9 ? tap / 3 - 1 : 0, dx = a.taps == 9 ? tap % 3 - 1 : 0;
+        const long long shift = ((long long)dy * a.W + dx) * a.Cin + cc * kKC;
+        const uint32_t bdst = smem_addr(ring + slot * kStage + kStageA) + dst_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int yy = py[j] + dy, xx = pxx[j] + dx;
+          const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+          cp_async16_zfill(bdst + j * 4096, a.x + (ok ? poff[j] + shift : 0), ok);
+        }
+        if (warp == 0 && elect_one()) {
+          mbarrier_expect_tx(&full_a[slot], kStageA);
+          bulk_copy_global_to_shared(ring + slot * kStage, wtile + (size_t)i * kStageA, kStageA, &full_a[slot]);
+        }
+        if (++i == n_k) {
+          i = 0;
+          tile += gridDim.x;
+        }
+      }
+      cp_async_commit_group();
+      const int c = it - kLag;
+      if (c >= 0) {
+        cp_async_wait_group<kLag>();    // this thread's rows of stage c have landed
+        fence_proxy_async_shared();     // ... and are ordered before the tensor core's asynchronous-proxy reads
+        __syncwarp();
+        if (lane == 0) mbarrier_arrive(&full_b[(uint32_t)c % kRing]);
+      }
+    }
+  } else if (warp == 12) {
+    // ---- MMA issuer ----
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTilePx >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
+    int i = 0, tile_seq = 0;
+    for (int c = 0; c < total; ++c) {
+      const uint32_t slot = (uint32_t)c % kRing, use = (uint32_t)c / kRing;
+      const uint32_t buf = tile_seq & 1;
+      if (i == 0 && tile_seq >= 2) mbarrier_wait(&acc_empty[buf], ((tile_seq >> 1) - 1) & 1);
+      mbarrier_wait(&full_b[slot], use & 1);
+      mbarrier_wait(&full_a[slot], use & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_addr(ring + slot * kStage), b_addr = a_addr + kStageA;
+        const uint32_t d = tmem + buf * kTilePx;
+#pragma unroll
+        for (int s = 0; s < kKC / 16; ++s)
+          umma_ss(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc(b_addr + s * 32), idesc, !(i == 0 && s == 0));
+        tc_commit_to(&empty[slot]);
+        if (i == n_k - 1) tc_commit_to(&acc_full[buf]);
+      }
+      __syncwarp();
+      if (++i == n_k) {
+        i = 0;
+        ++tile_seq;
+      }
+    }
+  } else {
+    // ---- epilogue: warp 8+q owns TMEM lanes [32q, 32q+32) = output channels co_tile*128 + 32q + lane ----
+    const int quad = warp & 3;
+    int tile = blockIdx.x;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
+      const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
+      const long long px0 = (long long)px_tile * kTilePx;
+      const uint32_t buf = tile_seq & 1;
+      const int co = co_tile * kTileCo + quad * 32 + lane;
+      const float bias = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+      mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int q = 0; q < kTilePx / 32; ++q) {
+        uint32_t r[32];
+        const int col0 = q * 32;
+        CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const long long n0 = px0 + col0;
+        if (co < a.Cout && n0 < n_px) {
+          const int b = (int)(n0 / HW), p = (int)(n0 - (long long)b * HW);
+          float* dst = a.out + ((size_t)b * a.Cout + co) * HW + p;
+          if (p + 32 <= HW && (HW & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v;
+              v.x = __uint_as_float(r[j]) + bias;
+              v.y = __uint_as_float(r[j + 1]) + bias;
+              v.z = __uint_as_float(r[j + 2]) + bias;
+              v.w = __uint_as_float(r[j + 3]) + bias;
+              if (a.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(dst + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long n = n0 + j;
+              if (n < n_px) {
+                const int bb = (int)(n / HW), pp = (int)(n - (long long)bb * HW);
+                float v = __uint_as_float(r[j]) + bias;
+                if (a.relu) v = fmaxf(v, 0.f);
+                a.out[((size_t)bb * a.Cout + co) * HW + pp] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();   // the tensor-memory loads above are complete (wait::ld) before the half is handed back
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
+    }
+  }
+
+  cp_async_wait_group<0>();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 // (Cout, Cin, taps) fp32 -> stages [co tile][tap][ci chunk] of [128 co][64 ci] bf16, 16-byte chunk c of row r at c ^ (r & 7)
 __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, uint8_t* __restrict__ img,
                                                         long long n_chunks) {
@@ -344,9 +551,15 @@ extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, 
   if ((long long)B * H * W * Cin >= (1ll << 40)) return B200BEV_ERR_UNSUPPORTED;
   if (((uintptr_t)x_nhwc | (uintptr_t)weight_image) & 15) return B200BEV_ERR_INVALID_ARGUMENT;
   ConvArgs a{(const __nv_bfloat16*)x_nhwc, (const uint8_t*)weight_image, bias, out_nchw, B, H, W, Cin, Cout, taps, relu};
-  B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
   const long long tiles = (((long long)B * H * W + kTilePx - 1) / kTilePx) * ceil_div(Cout, kTileCo);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  conv_tc_kernel<<<grid, kConvThreads, kConvSmem, (cudaStream_t)stream>>>(a);
+  const char* impl = getenv("B200BEV_CONV_IMPL");
+  if (impl && impl[0] == 's') {   // "single": the one-instruction-stream kernel, kept for A/B timing
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+    conv_tc_kernel<<<grid, kConvThreads, kConvSmem, (cudaStream_t)stream>>>(a);
+    return launch_status();
+  }
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  conv_tc_ws_kernel<<<grid, kWsThreads, kConvSmem, (cudaStream_t)stream>>>(a);
   return launch_status();
 }
