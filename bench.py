@@ -412,6 +412,75 @@ def run_b200_arm(args):
     except Exception as e:      # never let the side measurement break the bench line
         prep = {"error": str(e)[:200]}
 
+    # ---- the kernels either side of the path (dense layers, conv blocks), timed on their own ----
+    glue = None
+    if not args.no_alt:
+        try:
+            def med_ms(fn, reps=5):
+                fn()
+                ts = []
+                for _ in range(reps):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                    ts.append(e0.elapsed_time(e1))
+                return statistics.median(ts)
+
+            gg = torch.Generator(device=dev).manual_seed(seed + 7)
+            w1 = torch.randn((512, 1024), device=dev, generator=gg) * 0.03
+            w2 = torch.randn((128 * 25 * 25, 512), device=dev, generator=gg) * 0.04
+            b1, b2 = torch.zeros(512, device=dev), torch.zeros(128 * 25 * 25, device=dev)
+            gfeat = torch.rand((F, 1024), device=dev, generator=gg)
+            li_ms = med_ms(lambda: ops.lidar_init(gfeat, w1, b1, w2, b2))
+            li_bytes = 4.0 * (w1.numel() + w2.numel() + b1.numel() + b2.numel() + F * (1024 + 2 * 512 + 80000))
+            torch.backends.cuda.matmul.allow_tf32 = False
+            li_cublas = med_ms(lambda: torch.addmm(b2, torch.relu(torch.addmm(b1, gfeat, w1.t())), w2.t()))
+            del w2
+            shapes = [("head 5x(256->64) as 256->320", 256, 320, 3, BEV_H, BEV_W), ("bev_fusion.0 768->512", 768, 512, 3, BEV_H, BEV_W),
+                      ("bev_fusion.3 512->256", 512, 256, 3, BEV_H, BEV_W), ("camera_proj.0 512->512", 512, 512, 3, FEAT_H, FEAT_W),
+                      ("camera_proj.3 512->256 1x1", 512, 256, 1, FEAT_H, FEAT_W), ("radar_refine.0 256->256", 256, 256, 3, BEV_H, BEV_W),
+                      ("radar_refine.3 256->256", 256, 256, 3, BEV_H, BEV_W), ("lidar_upsample.4 128->256", 128, 256, 3, BEV_H, BEV_W)]
+            convs, tot = [], {"tc": 0.0, "layout": 0.0, "cudnn_bf16": 0.0, "cudnn_f32": 0.0, "flop": 0.0}
+            torch.backends.cudnn.allow_tf32 = False
+            for name, cin, cout, k, H, W in shapes:
+                x = torch.randn((F, cin, H, W), device=dev, generator=gg)
+                w = torch.randn((cout, cin, k, k), device=dev, generator=gg) / (cin * k * k) ** 0.5
+                b = torch.randn(cout, device=dev, generator=gg)
+                nhwc, img = ops.nchw_to_nhwc_bf16([x]), ops.conv_pack(w)
+                t_tc = med_ms(lambda: ops.conv_bn_relu_bf16(nhwc, img, b, cout, k * k))
+                t_lay = med_ms(lambda: ops.nchw_to_nhwc_bf16([x]))
+                xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                wb, bb = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), b.to(torch.bfloat16)
+                t_c16 = med_ms(lambda: torch.relu_(torch.nn.functional.conv2d(xb, wb, bb, padding=k // 2)))
+                t_c32 = med_ms(lambda: torch.relu_(torch.nn.functional.conv2d(x, w, b, padding=k // 2)), reps=3)
+                fl = 2.0 * F * H * W * cout * cin * k * k
+                convs.append({"block": name, "ms": round(t_tc, 4), "tflops": round(fl / t_tc / 1e9, 1), "layout_ms": round(t_lay, 4),
+                              "cudnn_bf16_nhwc_ms": round(t_c16, 4), "cudnn_fp32_ms": round(t_c32, 4)})
+                for kk, v in (("tc", t_tc), ("layout", t_lay), ("cudnn_bf16", t_c16), ("cudnn_f32", t_c32), ("flop", fl)):
+                    tot[kk] += v
+                del x, nhwc, xb
+            logits = torch.logit(maps["heatmap"].clamp(1e-6, 1 - 1e-6))
+            dl_ms = med_ms(lambda: ops.centernet_decode(logits, maps["offset"], maps["size"], maps["rot"], maps["vel"], TOPK, 2.048,
+                                                        heat_is_logit=True))
+            tfl = tot["flop"] / tot["tc"] / 1e9
+            glue = {
+                "note": "SURVEY 8f N1/N2 kernels, not part of the timed step; every block of FlexibleBEVFusion and CenterNetHead "
+                        f"at {F} frames",
+                "lidar_init": {"ms": round(li_ms, 4), "bound": "hbm", "achieved": round(li_bytes / li_ms / 1e6, 1),
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(li_bytes / li_ms / 1e6 / peaks["hbm_gbs"], 4),
+                               "dtype": "f32", "cublas_fp32_ms": round(li_cublas, 4)},
+                "conv_blocks": {"ms": round(tot["tc"], 4), "bound": "tensor", "achieved": round(tfl, 1), "peak": peaks["bf16_tflops_sustained"],
+                                "unit": "TFLOP/s", "frac": round(tfl / peaks["bf16_tflops_sustained"], 4), "dtype": "bf16",
+                                "layout_passes_ms": round(tot["layout"], 4), "cudnn_bf16_nhwc_ms": round(tot["cudnn_bf16"], 4),
+                                "cudnn_fp32_ms": round(tot["cudnn_f32"], 4), "blocks": convs},
+                "decode_from_logits_ms": round(dl_ms, 4),
+            }
+        except Exception as e:
+            glue = {"error": str(e)[:300]}
+
     # ---- the fp32-parity path of the dominant stage, for the record (outside the timed region) ----
     alt = None
     if dtype == "bf16" and not args.no_alt:
@@ -496,7 +565,7 @@ def run_b200_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": workload_config(args, F), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": sum(launches_per_step.values()) * args.steps, "clocks": clock_summary, "kernels": kernels,
-            "lidar_prepare": prep, "fp32_path": alt,
+            "lidar_prepare": prep, "fp32_path": alt, "glue_next": glue,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(ConvArgs a) {
 //   warps 8-11  epilogue: one TMEM lane quadrant each; tile t is read out, biased, clamped and stored while the MMAs
 //               of tile t+1 run into the other half (`acc_full` / `acc_empty`)
 constexpr int kWsThreads = 416;
-constexpr int kLag = 2;   // a producer waits for its own copies of stage c two stages after issuing them
+constexpr int kLag = 3;   // a producer hands stage c over (waits for its own copies of it) three stages after issuing them
 
 __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -322,6 +322,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
     int tile = blockIdx.x, i = 0;   // the stage being produced: k-stage i of `tile`
     const uint8_t* wtile = nullptr;
     for (int it = 0; it < total + kLag; ++it) {
+      // first hand over the oldest stage in flight (nothing below may delay the MMAs: the ring wait of the new stage is
+      // a wait for an MMA to FINISH, and put in front of this arrival it serialised the tensor pipe — 2.9 ms vs 2.3)
+      const int c = it - kLag;
+      if (c >= 0) {
+        cp_async_wait_group<kLag - 1>();   // this thread's rows of stage c have landed (groups it-kLag+1 .. it-1 may be pending)
+        fence_proxy_async_shared();        // ... and are ordered before the tensor core's asynchronous-proxy reads
+        __syncwarp();
+        if (lane == 0) mbarrier_arrive(&full_b[(uint32_t)c % kRing]);
+      }
       if (it < total) {
         if (i == 0) {
           const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
@@ -364,13 +373,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         }
       }
       cp_async_commit_group();
-      const int c = it - kLag;
-      if (c >= 0) {
-        cp_async_wait_group<kLag>();    // this thread's rows of stage c have landed
-        fence_proxy_async_shared();     // ... and are ordered before the tensor core's asynchronous-proxy reads
-        __syncwarp();
-        if (lane == 0) mbarrier_arrive(&full_b[(uint32_t)c % kRing]);
-      }
     }
   } else if (warp == 12) {
     // ---- MMA issuer ----

@@ -81,6 +81,21 @@ def main():
     if want("decode"):
         maps = {k: to(v) for k, v in syn.head_maps(44, F, 10, G, G).items()}
         run(lambda: ops.centernet_decode(maps["heatmap"], maps["offset"], maps["size"], maps["rot"], maps["vel"], 100, 2.048))
+    if want("dense"):
+        g = torch.Generator(device=dev).manual_seed(2)
+        w1 = torch.randn((512, 1024), device=dev, generator=g) * 0.03
+        w2 = torch.randn((80000, 512), device=dev, generator=g) * 0.04
+        b1, b2 = torch.zeros(512, device=dev), torch.zeros(80000, device=dev)
+        x = torch.rand((F, 1024), device=dev, generator=g)
+        run(lambda: ops.lidar_init(x, w1, b1, w2, b2))
+    if want("conv"):
+        g = torch.Generator(device=dev).manual_seed(3)
+        for cin, cout, k, H, W in ((768, 512, 3, G, G), (256, 320, 3, G, G), (512, 256, 1, 57, 100)):
+            x = torch.randn((F, cin, H, W), device=dev, generator=g)
+            w = torch.randn((cout, cin, k, k), device=dev, generator=g) / (cin * k * k) ** 0.5
+            b = torch.randn(cout, device=dev, generator=g)
+            img = ops.conv_pack(w)
+            run(lambda: ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), img, b, cout, k * k))
     print("prof_stages done", flush=True)
 
 
