@@ -461,6 +461,255 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// ---- 3x3 form with the pixel rows shared by the nine taps (default for 3x3 when an image row fits) ---------------------
+// In the kernels above every tap re-reads its 256 pixel rows from L2: 48 KB per 512 clk of tensor work, 96 B/clk per SM,
+// and with ~2,000 clk from "slot free" to "MMA issued" the four-slot ring cannot keep that in flight (ncu: tensor pipe
+// active 49 % on the 768->512 block).  A 3x3 tap is the SAME pixels displaced by (dy, dx).  Here a tile is R whole image
+// rows of one frame, laid out in shared memory with ONE zero pixel between consecutive image rows and a halo row above
+// and below:   padded index L(y, x) = (y - y0 + 1) (W + 1) + x + 1,   x = -1 is the shared pad pixel.
+// Output column n = ry (W + 1) + x  (x = W is a dummy column) then needs, for tap (dy, dx), padded row
+// n + (1 + dy)(W + 1) + (1 + dx): one block of N + 2 (W + 1) + 2 rows per 64 input channels serves all nine taps, each tap
+// being the same shared-memory block entered `off` rows later (the 128-byte swizzle is a function of the shared-memory
+// address, so a row-displaced descriptor reads every row with the phase it was written with).  Zero padding of the
+// convolution comes from the pad pixels and from halo rows outside the frame, zero-filled by the copy.  Pixel traffic
+// drops ninefold (41 B/clk per SM with the weights), and the copies of a block have nine taps of MMAs to hide behind.
+//   warps 0-7 pixel blocks (cp.async, two buffers) | warp 13 weight stages (bulk copies, ring of 4) | warp 12 MMA issue
+//   | warps 8-11 epilogue (accumulator double-buffered in tensor memory), all meeting at mbarriers only.
+constexpr int kHaloThreads = 448;
+constexpr int kHaloMaxRows = 448;                       // 56 KB per pixel block
+constexpr int kHaloBlock = kHaloMaxRows * 128;
+constexpr int kHaloEpi = 4 * 32 * 33 * 4;                // per epilogue warp: a 32 x 32 transposing tile
+constexpr int kHaloSmem = 2 * kHaloBlock + kRing * kStageA + kHaloEpi + 1024 + 256;
+constexpr int kHaloRowsPerThread = kHaloMaxRows / 32;   // 14
+
+struct HaloGeom {
+  int R;       // image rows per tile
+  int N;       // MMA columns: R (W + 1) rounded up to 16
+  int Q;       // rows of a pixel block
+  int tiles_per_frame;
+};
+
+__host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g) {
+  const int R = kTilePx / (W + 1);
+  if (R < 1) return false;
+  const int rows = R < H ? R : H;
+  const int N = (rows * (W + 1) + 15) & ~15;
+  const int Q = N + 2 * (W + 1) + 2;
+  if (N > kTilePx || Q > kHaloMaxRows) return false;
+  g->R = rows;
+  g->N = N;
+  g->Q = Q;
+  g->tiles_per_frame = (H + rows - 1) / rows;
+  return true;
+}
+
+__device__ __forceinline__ uint64_t kmajor_sw128_desc_at(uint32_t saddr, int base_offset_mode) {
+  uint64_t d = kmajor_sw128_desc(saddr);
+  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvArgs a, HaloGeom geo, int base_offset_mode) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* blocks = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // [2][kHaloBlock]
+  uint8_t* wring = blocks + 2 * kHaloBlock;                                          // [kRing][kStageA]
+  float* epi = reinterpret_cast<float*>(wring + kRing * kStageA);                    // [4][32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + kRing * kStageA + kHaloEpi);
+  uint64_t* full_a = bars;                     // [kRing]
+  uint64_t* empty_a = bars + kRing;            // [kRing]
+  uint64_t* full_blk = bars + 2 * kRing;       // [2]
+  uint64_t* empty_blk = bars + 2 * kRing + 2;  // [2]
+  uint64_t* acc_full = bars + 2 * kRing + 4;   // [2]
+  uint64_t* acc_empty = bars + 2 * kRing + 6;  // [2]
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbarrier_init(&full_a[s], 1);
+      mbarrier_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbarrier_init(&full_blk[s], 8);
+      mbarrier_init(&empty_blk[s], 1);
+      mbarrier_init(&acc_full[s], 1);
+      mbarrier_init(&acc_empty[s], 4);
+    }
+    mbarrier_init_fence();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  const int W1 = a.W + 1, HW = a.H * a.W;
+  const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
+  const int ncc = a.Cin / kKC;
+  const int n_tiles = a.B * geo.tiles_per_frame * n_co_tiles;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // tile -> (co tile, frame, first image row): the co tiles of one pixel tile are neighbours in the grid (shared pixels in L2)
+  auto tile_coords = [&](int tile, int& co_tile, int& b, int& y0) {
+    co_tile = tile % n_co_tiles;
+    const int pt = tile / n_co_tiles;
+    b = pt / geo.tiles_per_frame;
+    y0 = (pt - b * geo.tiles_per_frame) * geo.R;
+  };
+
+  if (warp < 8) {
+    // ---- pixel blocks: one per (tile, 64-channel chunk) ----
+    const int row0 = tid >> 3, chunk = tid & 7;
+    const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
+    const int n_blocks = my_tiles * ncc;
+    int tile = blockIdx.x, cc = 0;
+    long long goff[kHaloRowsPerThread];   // element offset of this thread's piece of padded row q = row0 + 32 j, or -1: zeros
+    for (int bi = 0; bi <= n_blocks; ++bi) {
+      if (bi >= 1) {
+        cp_async_wait_group<0>();      // block bi-1 has landed (this thread's part)
+        fence_proxy_async_shared();
+        __syncwarp();
+        if (lane == 0) mbarrier_arrive(&full_blk[(bi - 1) & 1]);
+      }
+      if (bi < n_blocks) {
+        if (cc == 0) {
+          int co_tile, b, y0;
+          tile_coords(tile, co_tile, b, y0);
+#pragma unroll
+          for (int j = 0; j < kHaloRowsPerThread; ++j) {
+            const int q = row0 + 32 * j;
+            const int ry = q / W1 - 1, x = q - (ry + 1) * W1 - 1;
+            const int y = y0 + ry;
+            goff[j] = (q < geo.Q && x >= 0 && y >= 0 && y < a.H) ? (((long long)b * a.H + y) * a.W + x) * a.Cin + chunk * 8 : -1;
+          }
+        }
+        const int buf = bi & 1;
+        if (bi >= 2) mbarrier_wait(&empty_blk[buf], ((bi >> 1) - 1) & 1);
+        const uint32_t bdst = smem_addr(blocks + buf * kHaloBlock) + dst_off;
+#pragma unroll
+        for (int j = 0; j < kHaloRowsPerThread; ++j) {
+          if (row0 + 32 * j < geo.Q) {
+            const bool ok = goff[j] >= 0;
+            cp_async16_zfill(bdst + j * 4096, a.x + (ok ? goff[j] + cc * kKC : 0), ok);
+          }
+        }
+        cp_async_commit_group();
+        if (++cc == ncc) {
+          cc = 0;
+          tile += gridDim.x;
+        }
+      }
+    }
+  } else if (warp == 13) {
+    // ---- weight stages: (tile, chunk, tap) in the order the MMAs use them ----
+    const int total = my_tiles * ncc * 9;
+    int tile = blockIdx.x, cc = 0, tap = 0;
+    int co_tile, b, y0;
+    tile_coords(tile, co_tile, b, y0);
+    for (int g = 0; g < total; ++g) {
+      const uint32_t slot = (uint32_t)g % kRing;
+      if (g >= kRing) mbarrier_wait(&empty_a[slot], (((uint32_t)g / kRing) - 1) & 1);
+      if (elect_one()) {
+        mbarrier_expect_tx(&full_a[slot], kStageA);
+        bulk_copy_global_to_shared(wring + slot * kStageA, a.wimg + ((size_t)co_tile * 9 * ncc + (size_t)tap * ncc + cc) * kStageA,
+                                   kStageA, &full_a[slot]);
+      }
+      __syncwarp();
+      if (++tap == 9) {
+        tap = 0;
+        if (++cc == ncc) {
+          cc = 0;
+          tile += gridDim.x;
+          tile_coords(tile, co_tile, b, y0);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ---- MMA issuer ----
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(geo.N >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
+    int g = 0, bi = 0;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
+      const uint32_t buf = tile_seq & 1;
+      if (tile_seq >= 2) mbarrier_wait(&acc_empty[buf], ((tile_seq >> 1) - 1) & 1);
+      const uint32_t d = tmem + buf * kTilePx;
+      for (int cc = 0; cc < ncc; ++cc, ++bi) {
+        mbarrier_wait(&full_blk[bi & 1], (bi >> 1) & 1);
+        const uint32_t blk = smem_addr(blocks + (bi & 1) * kHaloBlock);
+        for (int tap = 0; tap < 9; ++tap, ++g) {
+          const uint32_t slot = (uint32_t)g % kRing;
+          mbarrier_wait(&full_a[slot], ((uint32_t)g / kRing) & 1);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_addr(wring + slot * kStageA);
+            const uint32_t b_addr = blk + (uint32_t)((tap / 3) * W1 + tap % 3) * 128;   // (1+dy)(W+1) + (1+dx) rows in
+#pragma unroll
+            for (int s = 0; s < kKC / 16; ++s)
+              umma_ss(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc_at(b_addr + s * 32, base_offset_mode), idesc,
+                      !(cc == 0 && tap == 0 && s == 0));
+            tc_commit_to(&empty_a[slot]);
+            if (tap == 8) tc_commit_to(&empty_blk[bi & 1]);
+            if (tap == 8 && cc == ncc - 1) tc_commit_to(&acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: warp 8+q owns TMEM lanes [32q, 32q+32) = 32 output channels ----
+    // A TMEM load gives a lane ONE channel and 32 columns; stored like that, a warp's store instruction touches 32
+    // channel planes with 4 bytes each (32 partial sectors: the stores, not the MMAs, set the pace of the small blocks).
+    // Each warp turns its 32 x 32 piece through a private shared-memory tile instead: then a lane is one PIXEL, and a
+    // store instruction writes up to 128 contiguous bytes of one channel plane.
+    const int quad = warp & 3;
+    float* tp = epi + quad * 32 * 33;
+    int tile = blockIdx.x;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
+      int co_tile, b, y0;
+      tile_coords(tile, co_tile, b, y0);
+      const uint32_t buf = tile_seq & 1;
+      const int co0 = co_tile * kTileCo + quad * 32;
+      const float bias = (a.bias && co0 + lane < a.Cout) ? __ldg(a.bias + co0 + lane) : 0.f;
+      const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;   // channels of this warp that exist (may be <= 0)
+      float* oplane = a.out + ((size_t)b * a.Cout + co0) * HW;
+      mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int col0 = 0; col0 < geo.N; col0 += 32) {
+        uint32_t r[32];
+        CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]) + bias;
+          if (a.relu) v = fmaxf(v, 0.f);
+          tp[lane * 33 + j] = v;
+        }
+        __syncwarp();
+        // this lane's pixel: column n = col0 + lane
+        const int n = col0 + lane;
+        const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
+        const bool px_ok = x < a.W && ry < geo.R && y < a.H;
+        float* dst = oplane + (px_ok ? y * a.W + x : 0);
+        for (int c = 0; c < n_ch; ++c) {
+          const float v = tp[c * 33 + lane];
+          if (px_ok) dst[(size_t)c * HW] = v;
+        }
+        __syncwarp();
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
+    }
+  }
+
+  cp_async_wait_group<0>();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 // (Cout, Cin, taps) fp32 -> stages [co tile][tap][ci chunk] of [128 co][64 ci] bf16, 16-byte chunk c of row r at c ^ (r & 7)
 __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, uint8_t* __restrict__ img,
                                                         long long n_chunks) {
@@ -559,6 +808,16 @@ extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, 
   if (impl && impl[0] == 's') {   // "single": the one-instruction-stream kernel, kept for A/B timing
     B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
     conv_tc_kernel<<<grid, kConvThreads, kConvSmem, (cudaStream_t)stream>>>(a);
+    return launch_status();
+  }
+  HaloGeom geo;
+  const bool want_halo = !(impl && impl[0] == 'w');   // "ws": the per-tap warp-specialised kernel for 3x3 too
+  if (taps == 9 && want_halo && halo_geometry(H, W, &geo)) {
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
+    const long long htiles = (long long)B * geo.tiles_per_frame * ceil_div(Cout, kTileCo);
+    const int hgrid = (int)(htiles < sm_count() ? htiles : sm_count());
+    const char* bo = getenv("B200BEV_CONV_BASE_OFFSET");
+    conv3x3_tc_halo_kernel<<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, bo ? atoi(bo) : 0);
     return launch_status();
   }
   B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
