@@ -462,6 +462,32 @@ def run_b200_arm(args):
                 for kk, v in (("tc", t_tc), ("layout", t_lay), ("cudnn_bf16", t_c16), ("cudnn_f32", t_c32), ("flop", fl)):
                     tot[kk] += v
                 del x, nhwc, xb
+            # the whole inference chain through the module interface the reference's pipelines call (mirror classes,
+            # random-init weights of the base.yaml sizes): encoders -> FlexibleBEVFusion -> CenterNetHead -> decode
+            import bevfusion_multimodal_3d_object_detection_b200 as b200bev
+            torch.manual_seed(7)
+            enc_l = b200bev.PointNetLiDAREncoder(input_channels=4, feat_dim=1024).eval().to(dev)
+            enc_r = b200bev.MultiRadarEncoder(input_channels=7, feat_dim=256, num_radars=5, fusion_method="concat").eval().to(dev)
+            fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=FEAT_C,
+                                            bev_h=BEV_H, bev_w=BEV_W, bev_channels=256).eval().to(dev)
+            head = b200bev.CenterNetHead(in_channels=256, num_classes=N_CLASSES, head_conv=64).eval().to(dev)
+
+            def chain():
+                with torch.no_grad():
+                    bev = fus(camera_features=feats, lidar_features=enc_l(lidar), radar_features=enc_r(radars))
+                    return decode_centernet_predictions(head(bev), score_thresh=0.0, max_detections=TOPK)
+
+            chain_ms = {}
+            for prec in ("f32", "bf16"):
+                for m in (enc_l, fus, head):
+                    m.b200_precision = prec
+                chain_ms[prec] = med_ms(chain, reps=3)
+            modules = {"note": "mirror modules in eval mode, camera features + points + radar -> decoded boxes, host sync of the decode "
+                               "counts included; f32 = kernels + the reference's own fp32 cuDNN convolutions (parity 1e-5), bf16 = "
+                               "tcgen05 MLP and convolution kernels (parity 1e-2)",
+                       "f32_ms": round(chain_ms["f32"], 3), "f32_frames_per_s": round(F / chain_ms["f32"] * 1e3, 1),
+                       "bf16_ms": round(chain_ms["bf16"], 3), "bf16_frames_per_s": round(F / chain_ms["bf16"] * 1e3, 1)}
+            del enc_l, enc_r, fus, head
             logits = torch.logit(maps["heatmap"].clamp(1e-6, 1 - 1e-6))
             dl_ms = med_ms(lambda: ops.centernet_decode(logits, maps["offset"], maps["size"], maps["rot"], maps["vel"], TOPK, 2.048,
                                                         heat_is_logit=True))
@@ -477,6 +503,7 @@ def run_b200_arm(args):
                                 "layout_passes_ms": round(tot["layout"], 4), "cudnn_bf16_nhwc_ms": round(tot["cudnn_bf16"], 4),
                                 "cudnn_fp32_ms": round(tot["cudnn_f32"], 4), "blocks": convs},
                 "decode_from_logits_ms": round(dl_ms, 4),
+                "module_chain": modules,
             }
         except Exception as e:
             glue = {"error": str(e)[:300]}

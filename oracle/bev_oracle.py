@@ -262,6 +262,29 @@ def lidar_init(feats: np.ndarray, w1, b1, w2, b2) -> np.ndarray:
     return dense_layer(dense_layer(feats, w1, b1, relu=True), w2, b2)
 
 
+def conv_bn_relu(x: np.ndarray, weight: np.ndarray, bias: Optional[np.ndarray], bn: Optional[Dict[str, np.ndarray]] = None,
+                 relu: bool = True) -> np.ndarray:
+    """[pinned] nn.Conv2d(k=3, padding=1 | k=1) -> nn.BatchNorm2d (eval) -> nn.ReLU, the block every stack of
+    FlexibleBEVFusion is made of (camera_proj src/fusion.py:126-133, bev_fusion :199-207) and CenterNetHead's layers
+    (:822-854).  x (B,C,H,W), weight (O,C,k,k); bn = dict(weight, bias, running_mean, running_var) or None."""
+    x = np.asarray(x, dtype=F32)
+    B, C, H, W = x.shape
+    O, _, k, _ = weight.shape
+    pad = k // 2
+    xp = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    y = np.zeros((B, O, H, W), dtype=F32)
+    for ky in range(k):
+        for kx in range(k):
+            y += np.einsum("oc,bchw->bohw", weight[:, :, ky, kx].astype(F32), xp[:, :, ky:ky + H, kx:kx + W], optimize=True).astype(F32)
+    if bias is not None:
+        y = y + bias.astype(F32)[None, :, None, None]
+    if bn is not None:
+        inv = F32(1.0) / np.sqrt(bn["running_var"].astype(F32) + BN_EPS)
+        y = (y - bn["running_mean"].astype(F32)[None, :, None, None]) * (inv * bn["weight"].astype(F32))[None, :, None, None] \
+            + bn["bias"].astype(F32)[None, :, None, None]
+    return np.maximum(y, F32(0.0)) if relu else y.astype(F32)
+
+
 def sigmoid(x: np.ndarray) -> np.ndarray:
     """[pinned] torch.sigmoid of the heat-map head, src/fusion.py:870-871, in fp32."""
     x = np.asarray(x, dtype=F32)

@@ -272,3 +272,30 @@ def test_sigmoid_then_decode_matches_the_reference_head(golden):
         dets = orc.decode(pred, score_thresh=thr, max_detections=60, voxel_size_m=0.512)
         _assert_dets(dets, g, f"head_{tag}", 2)
     assert 0 < len(g["head_mid_b0_scores"]) < 60
+
+
+def test_conv_stacks_match_the_reference_fusion_module(golden):
+    """camera mean -> camera_proj (3x3 + 1x1 blocks) -> bilinear resize -> bev_fusion (two 3x3 blocks), restated block by
+    block, against the output of the reference's FlexibleBEVFusion with the same state_dict."""
+    g = golden("bev_glue")
+    shapes = {}
+    for name, (ci, co, k) in {"camera_proj.0": (64, 512, 3), "camera_proj.3": (512, 64, 1), "bev_fusion.0": (64, 128, 3),
+                              "bev_fusion.3": (128, 64, 3)}.items():
+        seq, idx = name.split(".")
+        shapes[f"{name}.weight"], shapes[f"{name}.bias"] = (co, ci, k, k), (co,)
+        for stat in ("weight", "bias", "running_mean", "running_var"):
+            shapes[f"{seq}.{int(idx) + 1}.{stat}"] = (co,)
+        shapes[f"{seq}.{int(idx) + 1}.num_batches_tracked"] = ()
+    sd = syn.fill_state_dict(731, shapes)
+    cam = syn.camera_features(732, 2, n_cam=6, channels=64, h=9, w=14)
+    assert syn.digest(cam, *[sd[k] for k in sorted(sd)]) == str(g["stack_digest"])
+
+    def block(x, name, relu=True):
+        seq, idx = name.split(".")
+        bn = {s: sd[f"{seq}.{int(idx) + 1}.{s}"] for s in ("weight", "bias", "running_mean", "running_var")}
+        return orc.conv_bn_relu(x, sd[f"{name}.weight"], sd[f"{name}.bias"], bn, relu)
+
+    x = block(block(orc.camera_mean(cam), "camera_proj.0"), "camera_proj.3")
+    x = orc.bilinear_resize(x, (12, 20))
+    x = block(block(x, "bev_fusion.0"), "bev_fusion.3")
+    assert max_rel(x, g["stack_out"]) < 5e-5      # four fp32 convolutions deep, different summation order
