@@ -72,12 +72,25 @@ def _plan(seq: nn.Sequential, device: torch.device) -> List[Dict]:
 
 
 def run(seq: nn.Sequential, parts: Sequence[torch.Tensor]) -> torch.Tensor:
-    """`seq(torch.cat(parts, dim=1))` for a conv/BN/ReLU(/Upsample) stack: (B,C_i,H,W) fp32 parts -> (B,C_out,H',W') fp32."""
+    """`seq(torch.cat(parts, dim=1))` for a conv/BN/ReLU(/Upsample) stack: (B,C_i,H,W) fp32 parts -> (B,C_out,H',W') fp32.
+    Between two convolutions the activations stay channels-last bf16 (written by the first launch's epilogue)."""
     parts = list(parts)
-    for step in _plan(seq, parts[0].device):
+    steps = _plan(seq, parts[0].device)
+    nhwc = None                                          # activations already in the next conv's input layout
+    for k, step in enumerate(steps):
         if step["kind"] == "conv":
-            nhwc = ops.nchw_to_nhwc_bf16(parts)          # layout + cast + concat in one pass per part
-            parts = [ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
+            if nhwc is None:
+                nhwc = ops.nchw_to_nhwc_bf16(parts)      # layout + cast + concat in one pass per part
+            chained = k + 1 < len(steps) and steps[k + 1]["kind"] == "conv"
+            if chained:
+                B, H, W, _ = nhwc.shape
+                nxt = torch.empty((B, H, W, step["c_out"]), dtype=torch.bfloat16, device=nhwc.device)
+                ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"],
+                                      out_nhwc=nxt, want_nchw=False)
+                nhwc, parts = nxt, []
+            else:
+                parts = [ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
+                nhwc = None
         else:
             x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
             s = step["scale"]
@@ -130,8 +143,10 @@ def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         pred["heatmap"] = torch.sigmoid(pred["heatmap"])
         return pred
     p = _head_plan(head, x.device)
-    hid = ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), p["img1"], p["b1"], p["hidden"], 9, relu=True)
-    both = ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([hid]), p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
+    B, _, H, W = x.shape
+    hid = torch.empty((B, H, W, p["hidden"]), dtype=torch.bfloat16, device=x.device)      # stays channels-last bf16
+    ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), p["img1"], p["b1"], p["hidden"], 9, relu=True, out_nhwc=hid, want_nchw=False)
+    both = ops.conv_bn_relu_bf16(hid, p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
     pred, c = {}, 0
     for n, k in zip(HEADS, p["outs"]):
         pred[n] = both[:, c:c + k].contiguous()

@@ -44,8 +44,10 @@ struct ConvArgs {
   const __nv_bfloat16* x;     // (B, H, W, Cin) channels-last
   const uint8_t* wimg;        // packed stages
   const float* bias;          // (Cout) or null
-  float* out;                 // (B, Cout, H, W)
+  float* out;                 // (B, Cout, H, W) fp32, or null
   int B, H, W, Cin, Cout, taps, relu;
+  __nv_bfloat16* out_nhwc;    // (B, H, W, out_ct) bf16 channels-last, channels [out_coff, out_coff + Cout), or null:
+  int out_ct, out_coff;       // the input layout of the next convolution, written without a separate layout pass
 };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool real) {
@@ -212,7 +214,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(ConvArgs a) {
         CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const long long n0 = px0 + col0;
-        if (co < a.Cout && n0 < n_px) {
+        if (a.out_nhwc && co < a.Cout) {
+          // a lane is a channel: for one pixel the warp writes 32 consecutive bf16 channels (64 contiguous bytes)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + j < n_px) {
+              float v = __uint_as_float(r[j]) + bias;
+              if (a.relu) v = fmaxf(v, 0.f);
+              a.out_nhwc[(size_t)(n0 + j) * a.out_ct + a.out_coff + co] = __float2bfloat16_rn(v);
+            }
+          }
+        }
+        if (a.out && co < a.Cout && n0 < n_px) {
           const int b = (int)(n0 / HW), p = (int)(n0 - (long long)b * HW);
           float* dst = a.out + ((size_t)b * a.Cout + co) * HW + p;
           if (p + 32 <= HW && (HW & 3) == 0) {
@@ -419,7 +432,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const long long n0 = px0 + col0;
-        if (co < a.Cout && n0 < n_px) {
+        if (a.out_nhwc && co < a.Cout) {
+          // a lane is a channel: for one pixel the warp writes 32 consecutive bf16 channels (64 contiguous bytes)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + j < n_px) {
+              float v = __uint_as_float(r[j]) + bias;
+              if (a.relu) v = fmaxf(v, 0.f);
+              a.out_nhwc[(size_t)(n0 + j) * a.out_ct + a.out_coff + co] = __float2bfloat16_rn(v);
+            }
+          }
+        }
+        if (a.out && co < a.Cout && n0 < n_px) {
           const int b = (int)(n0 / HW), p = (int)(n0 - (long long)b * HW);
           float* dst = a.out + ((size_t)b * a.Cout + co) * HW + p;
           if (p + 32 <= HW && (HW & 3) == 0) {
@@ -503,13 +527,16 @@ __host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g) {
   return true;
 }
 
+// Descriptor of a block entered a whole number of 128-byte rows after its 1024-byte-aligned base.  Measured on B200
+// (the 3x3 parity tests run with both settings): the swizzle is applied to the absolute shared-memory address, so the
+// descriptor's "matrix base offset" field stays 0; setting it to (address >> 7) & 7 gives wrong results.
 __device__ __forceinline__ uint64_t kmajor_sw128_desc_at(uint32_t saddr, int base_offset_mode) {
   uint64_t d = kmajor_sw128_desc(saddr);
   if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
   return d;
 }
 
-__global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvArgs a, HaloGeom geo, int base_offset_mode) {
+__global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvArgs a, HaloGeom geo, int base_offset_mode /* 0: see kmajor_sw128_desc_at */) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* blocks = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // [2][kHaloBlock]
   uint8_t* wring = blocks + 2 * kHaloBlock;                                          // [kRing][kStageA]
@@ -684,7 +711,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         for (int j = 0; j < 32; ++j) {
           float v = __uint_as_float(r[j]) + bias;
           if (a.relu) v = fmaxf(v, 0.f);
+          r[j] = __float_as_uint(v);
           tp[lane * 33 + j] = v;
+        }
+        if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
+          int ry = col0 / W1, x = col0 - ry * W1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (lane < n_ch && x < a.W && ry < geo.R && y0 + ry < a.H)   // lane = channel: 64 contiguous bytes per pixel
+              a.out_nhwc[(((size_t)b * a.H + y0 + ry) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
+                  __float2bfloat16_rn(__uint_as_float(r[j]));
+            if (++x == W1) {
+              x = 0;
+              ++ry;
+            }
+          }
         }
         __syncwarp();
         // this lane's pixel: column n = col0 + lane
@@ -692,9 +733,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
         const bool px_ok = x < a.W && ry < geo.R && y < a.H;
         float* dst = oplane + (px_ok ? y * a.W + x : 0);
-        for (int c = 0; c < n_ch; ++c) {
-          const float v = tp[c * 33 + lane];
-          if (px_ok) dst[(size_t)c * HW] = v;
+        if (a.out) {
+          for (int c = 0; c < n_ch; ++c) {
+            const float v = tp[c * 33 + lane];
+            if (px_ok) dst[(size_t)c * HW] = v;
+          }
         }
         __syncwarp();
       }
@@ -795,13 +838,16 @@ extern "C" B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int
   return launch_status();
 }
 
-extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, int H, int W, int Cin, const void* weight_image,
-                                         const float* bias, int Cout, int taps, int relu, float* out_nchw, void* stream) {
-  if (!x_nhwc || !weight_image || !out_nchw || B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+namespace {
+int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* weight_image, const float* bias, int Cout, int taps,
+                int relu, float* out_nchw, void* out_nhwc, int out_ct, int out_coff, void* stream) {
+  if (!x_nhwc || !weight_image || (!out_nchw && !out_nhwc) || B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
   if (Cin <= 0 || Cin % kKC != 0 || (taps != 1 && taps != 9)) return B200BEV_ERR_UNSUPPORTED;
   if ((long long)B * H * W * Cin >= (1ll << 40)) return B200BEV_ERR_UNSUPPORTED;
   if (((uintptr_t)x_nhwc | (uintptr_t)weight_image) & 15) return B200BEV_ERR_INVALID_ARGUMENT;
-  ConvArgs a{(const __nv_bfloat16*)x_nhwc, (const uint8_t*)weight_image, bias, out_nchw, B, H, W, Cin, Cout, taps, relu};
+  if (out_nhwc && (out_coff < 0 || out_coff + Cout > out_ct)) return B200BEV_ERR_INVALID_ARGUMENT;
+  ConvArgs a{(const __nv_bfloat16*)x_nhwc, (const uint8_t*)weight_image, bias, out_nchw, B, H, W, Cin, Cout, taps, relu,
+             (__nv_bfloat16*)out_nhwc, out_ct, out_coff};
   const long long tiles = (((long long)B * H * W + kTilePx - 1) / kTilePx) * ceil_div(Cout, kTileCo);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const char* impl = getenv("B200BEV_CONV_IMPL");
@@ -816,11 +862,24 @@ extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, 
     B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
     const long long htiles = (long long)B * geo.tiles_per_frame * ceil_div(Cout, kTileCo);
     const int hgrid = (int)(htiles < sm_count() ? htiles : sm_count());
-    const char* bo = getenv("B200BEV_CONV_BASE_OFFSET");
-    conv3x3_tc_halo_kernel<<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, bo ? atoi(bo) : 0);
+    conv3x3_tc_halo_kernel<<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, 0);
     return launch_status();
   }
   B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
   conv_tc_ws_kernel<<<grid, kWsThreads, kConvSmem, (cudaStream_t)stream>>>(a);
   return launch_status();
+}
+}  // namespace
+
+extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, int H, int W, int Cin, const void* weight_image,
+                                         const float* bias, int Cout, int taps, int relu, float* out_nchw, void* stream) {
+  if (!out_nchw) return B200BEV_ERR_INVALID_ARGUMENT;
+  return launch_conv(x_nhwc, B, H, W, Cin, weight_image, bias, Cout, taps, relu, out_nchw, nullptr, 0, 0, stream);
+}
+
+extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16_nhwc(const void* x_nhwc, int B, int H, int W, int Cin, const void* weight_image,
+                                              const float* bias, int Cout, int taps, int relu, void* out_nhwc, int out_c_total,
+                                              int out_c_offset, float* out_nchw, void* stream) {
+  if (!out_nhwc) return B200BEV_ERR_INVALID_ARGUMENT;
+  return launch_conv(x_nhwc, B, H, W, Cin, weight_image, bias, Cout, taps, relu, out_nchw, out_nhwc, out_c_total, out_c_offset, stream);
 }

@@ -354,19 +354,29 @@ def nchw_to_nhwc_bf16(parts: Sequence[torch.Tensor]) -> torch.Tensor:
 
 
 def conv_bn_relu_bf16(x_nhwc: torch.Tensor, image: torch.Tensor, bias: Optional[torch.Tensor], c_out: int, taps: int,
-                      relu: bool = True) -> torch.Tensor:
-    """(B,H,W,Cin) bf16 -> (B,Cout,H,W) fp32: 3x3 (padding 1) or 1x1 convolution + folded BatchNorm + ReLU on tcgen05."""
+                      relu: bool = True, out_nhwc: Optional[torch.Tensor] = None, c_offset: int = 0, want_nchw: bool = True):
+    """(B,H,W,Cin) bf16 -> (B,Cout,H,W) fp32: 3x3 (padding 1) or 1x1 convolution + folded BatchNorm + ReLU on tcgen05.
+    out_nhwc: a (B,H,W,C_total) bf16 tensor whose channels [c_offset, c_offset+Cout) also receive the result — the input
+    layout of the next convolution; with want_nchw=False only that is written and it is what the call returns."""
     x_nhwc = _need_cuda(x_nhwc, "input", torch.bfloat16)
     image = _need_cuda(image, "weight_image", torch.uint8)
     bias = None if bias is None else _need_cuda(bias, "bias")
     B, H, W, Cin = x_nhwc.shape
     if image.numel() != _lib.lib().b200bev_conv_pack_bytes(c_out, Cin, taps):
         raise ValueError("weight image does not belong to this (Cout, Cin, taps)")
-    out = torch.empty((B, c_out, H, W), dtype=torch.float32, device=x_nhwc.device)
-    with torch.cuda.device(out.device):
-        _lib.check(_lib.lib().b200bev_conv_bn_relu_bf16(_ptr(x_nhwc), B, H, W, Cin, _ptr(image), _ptr(bias), c_out, taps,
-                                                        1 if relu else 0, _ptr(out), _stream(out.device)))
-    return out
+    dev = x_nhwc.device
+    out = torch.empty((B, c_out, H, W), dtype=torch.float32, device=dev) if want_nchw or out_nhwc is None else None
+    with torch.cuda.device(dev):
+        if out_nhwc is None:
+            _lib.check(_lib.lib().b200bev_conv_bn_relu_bf16(_ptr(x_nhwc), B, H, W, Cin, _ptr(image), _ptr(bias), c_out, taps,
+                                                            1 if relu else 0, _ptr(out), _stream(dev)))
+            return out
+        if out_nhwc.dtype != torch.bfloat16 or not out_nhwc.is_contiguous() or tuple(out_nhwc.shape[:3]) != (B, H, W):
+            raise ValueError(f"out_nhwc must be a contiguous (B,H,W,C) bf16 tensor matching {(B, H, W)}")
+        _lib.check(_lib.lib().b200bev_conv_bn_relu_bf16_nhwc(_ptr(x_nhwc), B, H, W, Cin, _ptr(image), _ptr(bias), c_out, taps,
+                                                             1 if relu else 0, _ptr(out_nhwc), int(out_nhwc.shape[3]), c_offset,
+                                                             _ptr(out), _stream(dev)))
+    return out if out is not None else out_nhwc
 
 
 # ------------------------------------------------------------------------------------------------

@@ -251,6 +251,14 @@ B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int C, int H, 
 B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, int H, int W, int Cin,
                               const void* weight_image, const float* bias, int Cout, int taps, int relu,
                               float* out_nchw, void* stream);
+/* Same launch writing the result as the NEXT convolution's input: channels [out_c_offset, out_c_offset + Cout) of a
+ * (B,H,W,out_c_total) bf16 channels-last tensor (a conv -> conv chain, or a branch writing its slice of the concatenated
+ * bev_fusion input, src/fusion.py:292) — no fp32 round trip and no layout pass in between.  out_nchw may be given as
+ * well (both are written) or NULL. */
+B200BEV_API int b200bev_conv_bn_relu_bf16_nhwc(const void* x_nhwc, int B, int H, int W, int Cin,
+                                   const void* weight_image, const float* bias, int Cout, int taps, int relu,
+                                   void* out_nhwc, int out_c_total, int out_c_offset,
+                                   float* out_nchw, void* stream);
 
 #ifdef __cplusplus
 }

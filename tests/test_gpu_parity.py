@@ -623,6 +623,14 @@ def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
     ref = torch.nn.functional.conv2d(xr, wr, bd.double(), padding=k // 2)
     ref = torch.relu(ref) if relu else ref
     assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    # the channels-last bf16 output (the next convolution's input), written into a slice of a wider tensor
+    wide = torch.full((B, H, W, Cout + 6), 7.0, dtype=torch.bfloat16, device=cuda)
+    both = ops.conv_bn_relu_bf16(nhwc, img, bd, Cout, k * k, relu=relu, out_nhwc=wide, c_offset=4)
+    assert torch.equal(both, got)
+    assert torch.equal(wide[..., 4:4 + Cout], got.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert bool((wide[..., :4] == 7).all()) and bool((wide[..., 4 + Cout:] == 7).all())
+    only = ops.conv_bn_relu_bf16(nhwc, img, bd, Cout, k * k, relu=relu, out_nhwc=torch.empty_like(wide), c_offset=0, want_nchw=False)
+    assert only.dtype == torch.bfloat16 and torch.equal(only[..., :Cout], wide[..., 4:4 + Cout])
     # (b) the fp32 convolution the reference runs: the bf16 tolerance of north_star
     ref32 = torch.nn.functional.conv2d(xd.double(), wd.double(), bd.double(), padding=k // 2)
     ref32 = torch.relu(ref32) if relu else ref32
