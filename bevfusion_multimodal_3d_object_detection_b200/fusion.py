@@ -54,7 +54,7 @@ def lidar_branch(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tenso
     B = lidar_features.shape[0]
     s = module.lidar_start_size
     hidden = module.lidar_init[2].out_features // (s * s)
-    if module.training or not lidar_features.is_cuda:
+    if module.training:
         return module.lidar_upsample(module.lidar_init(lidar_features).view(B, hidden, s, s))
     l0, l2 = module.lidar_init[0], module.lidar_init[2]
     x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s, s)
@@ -82,7 +82,7 @@ def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None,
         parts.append(lidar_branch(module, lidar_features))
     if module.use_radar and radar_features is not None:
         B = radar_features.shape[0] if B is None else B
-        if module.training or not radar_features.is_cuda:
+        if module.training:
             r = module.radar_proj(radar_features)
         else:
             r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)  # :274
@@ -134,7 +134,11 @@ class FlexibleBEVFusion(nn.Module):
         if self.use_camera:
             self.camera_proj = nn.Sequential(*_conv_bn_relu(camera_channels, 512, 3), *_conv_bn_relu(512, c, 1))
         if self.use_lidar:
-            self.lidar_start_size = 25   # hard-coded in the reference too (src/fusion.py:141)
+            # The reference hard-codes 25 (src/fusion.py:141): its lidar BEV is always 50x50 and torch.cat raises for any
+            # other grid.  Same value — and the same state_dict shapes — at 50x50; half the grid otherwise, so
+            # that the 2x-resolution configuration (BASELINE configs[4], 100x100) runs with the lidar branch.
+            square_even = self.bev_h == self.bev_w and self.bev_h % 2 == 0
+            self.lidar_start_size = self.bev_h // 2 if square_even else 25
             self.lidar_init = nn.Sequential(nn.Linear(lidar_channels, 512), nn.ReLU(inplace=True),
                                             nn.Linear(512, 128 * self.lidar_start_size ** 2))
             self.lidar_upsample = nn.Sequential(

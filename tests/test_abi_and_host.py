@@ -275,3 +275,46 @@ def test_calibration_plumbing_round_trip():
     assert tuple(Kb.shape) == (2, 6, 3, 3) and tuple(Eb.shape) == (2, 6, 3, 4)
     with pytest.raises(ValueError):
         dataset.calibration_from_info(info, frame="world")
+
+
+def test_centernet_head_mirror_state_dict_and_default_path(golden):
+    """The head mirror keeps the reference's sub-module / state_dict names (src/fusion.py:822-854) and, with the bf16
+    path off, runs the reference's own layers: its CPU output equals what the reference's CenterNetHead produced."""
+    import bevfusion_multimodal_3d_object_detection_b200 as b200bev
+    from bevfusion_multimodal_3d_object_detection_b200 import conv_blocks
+
+    g = golden("bev_glue")
+    head = b200bev.CenterNetHead(in_channels=32, num_classes=10, head_conv=16)
+    want = {f"{n}_head.{i}.{p}" for n in conv_blocks.HEADS for i in (0, 2) for p in ("weight", "bias")}
+    assert set(head.state_dict()) == want
+    assert abs(float(head.heatmap_head[2].bias.detach()[0]) + 4.59512) < 1e-4                  # prior 0.01, src/fusion.py:865-867
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in syn.head_weights(711, 32, 16, 10).items()})
+    x = torch.from_numpy(syn._rng(712).standard_normal((2, 32, 24, 40)).astype(np.float32))
+    with torch.no_grad():
+        pred = head.eval()(x)
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        np.testing.assert_allclose(pred[k].numpy(), g[f"head_{k}"], rtol=0, atol=1e-6 * float(np.abs(g[f"head_{k}"]).max()) + 1e-7)
+    assert "heatmap_logits" not in pred
+    # what the tcgen05 path accepts: Cin a multiple of 64, 3x3/pad 1 or 1x1, hidden width a multiple of 64
+    assert not conv_blocks.head_supported(head)
+    assert conv_blocks.head_supported(b200bev.CenterNetHead(in_channels=256, num_classes=10, head_conv=64))
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=512, bev_h=50, bev_w=50)
+    assert all(conv_blocks.supported(s) for s in (fus.camera_proj, fus.lidar_upsample, fus.radar_refine, fus.bev_fusion))
+    odd = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=False, use_radar=False, camera_channels=16, bev_h=8, bev_w=8,
+                                    bev_channels=8)
+    assert not conv_blocks.supported(odd.camera_proj)
+    with pytest.raises(RuntimeError):                                                 # eval + CPU: no fallback for the kernels
+        fus.eval()(lidar_features=torch.zeros(1, 1024))
+
+
+def test_lidar_start_size_follows_the_grid():
+    """25 at the reference's 50x50 grid (same state_dict shapes), half the grid for other even square grids
+    — the reference itself raises in torch.cat there (src/fusion.py:141,292)."""
+    f50 = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=False, bev_h=50, bev_w=50, bev_channels=8)
+    assert f50.lidar_start_size == 25 and f50.lidar_init[2].out_features == 128 * 25 * 25
+    f20 = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=False, lidar_channels=32, bev_h=20, bev_w=20,
+                                    bev_channels=8)
+    assert f20.lidar_start_size == 10
+    f20.train()
+    out = f20(lidar_features=torch.randn(2, 32))
+    assert tuple(out.shape) == (2, 8, 20, 20)
