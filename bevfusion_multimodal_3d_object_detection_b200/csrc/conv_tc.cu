@@ -38,7 +38,8 @@ constexpr int kStageB = kTilePx * kKC * 2;   // 32 KB
 constexpr int kStage = kStageA + kStageB;
 constexpr int kRing = 4;
 constexpr int kAhead = kRing - 2;            // copies issued this many stages ahead of the MMAs
-constexpr int kConvSmem = kRing * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kEpiTile = 4 * 32 * 33 * 4;   // per epilogue warp: a 32 x 32 transposing tile
+constexpr int kConvSmem = kRing * kStage + kEpiTile + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct ConvArgs {
   const __nv_bfloat16* x;     // (B, H, W, Cin) channels-last
@@ -286,7 +287,8 @@ constexpr int kLag = 3;   // a producer hands stage c over (waits for its own co
 __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRing * kStage);
+  float* epi = reinterpret_cast<float*>(ring + kRing * kStage);   // [4][32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRing * kStage + kEpiTile);
   uint64_t* full_a = bars;
   uint64_t* full_b = bars + kRing;
   uint64_t* empty = bars + 2 * kRing;
@@ -414,15 +416,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
       }
     }
   } else {
-    // ---- epilogue: warp 8+q owns TMEM lanes [32q, 32q+32) = output channels co_tile*128 + 32q + lane ----
+    // ---- epilogue: warp 8+q owns TMEM lanes [32q, 32q+32) = 32 output channels; each 32 x 32 piece is turned through a
+    // private shared-memory tile so that a store instruction writes contiguous pixels of ONE channel plane (see the 3x3
+    // kernel below) ----
     const int quad = warp & 3;
+    float* tp = epi + quad * 32 * 33;
     int tile = blockIdx.x;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
       const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
       const long long px0 = (long long)px_tile * kTilePx;
       const uint32_t buf = tile_seq & 1;
-      const int co = co_tile * kTileCo + quad * 32 + lane;
+      const int co0 = co_tile * kTileCo + quad * 32;
+      const int co = co0 + lane;
       const float bias = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+      const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;
       mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
       tc_fence_after_sync();
 #pragma unroll 1
@@ -432,46 +439,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const long long n0 = px0 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]) + bias;
+          if (a.relu) v = fmaxf(v, 0.f);
+          r[j] = __float_as_uint(v);
+          tp[lane * 33 + j] = v;
+        }
         if (a.out_nhwc && co < a.Cout) {
           // a lane is a channel: for one pixel the warp writes 32 consecutive bf16 channels (64 contiguous bytes)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n0 + j < n_px) {
-              float v = __uint_as_float(r[j]) + bias;
-              if (a.relu) v = fmaxf(v, 0.f);
-              a.out_nhwc[(size_t)(n0 + j) * a.out_ct + a.out_coff + co] = __float2bfloat16_rn(v);
-            }
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < n_px) a.out_nhwc[(size_t)(n0 + j) * a.out_ct + a.out_coff + co] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        }
+        __syncwarp();
+        if (a.out) {
+          const long long n = n0 + lane;   // this lane's pixel
+          const bool px_ok = n < n_px;
+          const int b = px_ok ? (int)(n / HW) : 0, p = px_ok ? (int)(n - (long long)b * HW) : 0;
+          float* dst = a.out + ((size_t)b * a.Cout + co0) * HW + p;
+          for (int c = 0; c < n_ch; ++c) {
+            const float v = tp[c * 33 + lane];
+            if (px_ok) dst[(size_t)c * HW] = v;
           }
         }
-        if (a.out && co < a.Cout && n0 < n_px) {
-          const int b = (int)(n0 / HW), p = (int)(n0 - (long long)b * HW);
-          float* dst = a.out + ((size_t)b * a.Cout + co) * HW + p;
-          if (p + 32 <= HW && (HW & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = __uint_as_float(r[j]) + bias;
-              v.y = __uint_as_float(r[j + 1]) + bias;
-              v.z = __uint_as_float(r[j + 2]) + bias;
-              v.w = __uint_as_float(r[j + 3]) + bias;
-              if (a.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(dst + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long n = n0 + j;
-              if (n < n_px) {
-                const int bb = (int)(n / HW), pp = (int)(n - (long long)bb * HW);
-                float v = __uint_as_float(r[j]) + bias;
-                if (a.relu) v = fmaxf(v, 0.f);
-                a.out[((size_t)bb * a.Cout + co) * HW + pp] = v;
-              }
-            }
-          }
-        }
+        __syncwarp();
       }
       tc_fence_before_sync();   // the tensor-memory loads above are complete (wait::ld) before the half is handed back
       __syncwarp();
@@ -775,32 +767,33 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
   }
 }
 
-// (B, C, H, W) fp32 -> channels [c_offset, c_offset + C) of (B, H, W, C_total) bf16.  Tile: 64 channels x 64 pixels.
+// (B, C, H, W) fp32 -> channels [c_offset, c_offset + C) of (B, H, W, C_total) bf16.  A thread owns one pixel and 8
+// consecutive channels: eight loads, each 128 contiguous bytes per warp (a lane is a pixel of one channel plane), one
+// 16-byte store; the eight warps of a block cover the 64 channels of the same 32 pixels, so every 128-byte line of the
+// output is completed by one block within a few hundred cycles.  No shared memory, 8 independent loads per thread.
 __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int B, int C, int HW,
                                                                 __nv_bfloat16* __restrict__ out, int C_total, int c_offset) {
-  __shared__ float tile[64][65];
-  const int n_ct = ceil_div(C, 64), n_pt = ceil_div(HW, 64);
-  const long long n_tiles = (long long)B * n_ct * n_pt;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int pt = (int)(t % n_pt), ct = (int)((t / n_pt) % n_ct), b = (int)(t / ((long long)n_pt * n_ct));
-    const int c0 = ct * 64, p0 = pt * 64;
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-      const int c = i >> 6, p = i & 63;
-      tile[c][p] = (c0 + c < C && p0 + p < HW) ? __ldg(in + ((size_t)b * C + c0 + c) * HW + p0 + p) : 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 32);
+  const long long n_items = (long long)B * n_cg * n_pg;   // block items: 64 channels x 32 pixels
+  const bool vec_out = (C_total & 7) == 0 && (c_offset & 7) == 0 && ((uintptr_t)out & 15) == 0;
+  for (long long t = blockIdx.x; t < n_items; t += gridDim.x) {
+    const int pg = (int)(t % n_pg), cg = (int)((t / n_pg) % n_cg), b = (int)(t / ((long long)n_pg * n_cg));
+    const int p = pg * 32 + lane, c0 = cg * 64 + warp * 8;
+    if (p >= HW || c0 >= C) continue;
+    const float* src = in + ((size_t)b * C + c0) * HW + p;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (c0 + e < C) ? __ldg(src + (size_t)e * HW) : 0.f;
+    __nv_bfloat16* dst = out + ((size_t)b * HW + p) * C_total + c_offset + c0;
+    if (vec_out && c0 + 8 <= C) {
+      __align__(16) __nv_bfloat162 w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
+    } else {
+      for (int e = 0; e < 8 && c0 + e < C; ++e) dst[e] = __float2bfloat16_rn(v[e]);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-      const int p = i >> 5, c2 = (i & 31) * 2;
-      if (p0 + p < HW && c0 + c2 < C) {
-        __nv_bfloat16* dst = out + ((size_t)b * HW + p0 + p) * C_total + c_offset + c0 + c2;
-        if (c0 + c2 + 1 < C) {
-          *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(tile[c2][p], tile[c2 + 1][p]);
-        } else {
-          *dst = __float2bfloat16_rn(tile[c2][p]);
-        }
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -831,9 +824,8 @@ extern "C" B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int
                                          int c_offset, void* stream) {
   if (!in || !out_nhwc || B <= 0 || C <= 0 || H <= 0 || W <= 0 || c_offset < 0 || c_offset + C > C_total)
     return B200BEV_ERR_INVALID_ARGUMENT;
-  if ((C_total & 1) || (c_offset & 1)) return B200BEV_ERR_UNSUPPORTED;   // paired bf16 stores
-  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, 64);
-  long long blocks = tiles < (long long)sm_count() * 8 ? tiles : (long long)sm_count() * 8;
+  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, 32);
+  long long blocks = tiles < (long long)sm_count() * 16 ? tiles : (long long)sm_count() * 16;
   nchw_to_nhwc_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__nv_bfloat16*)out_nhwc, C_total, c_offset);
   return launch_status();
 }
