@@ -421,6 +421,7 @@ def run_b200_arm(args):
                 ts = []
                 for _ in range(reps):
                     flush.zero_()
+                    flush.view(torch.int64).sum()   # leave L2 cold AND clean: the dirty lines of the flush are not this kernel's
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     fn()

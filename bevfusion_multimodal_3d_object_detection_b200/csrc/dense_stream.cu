@@ -18,6 +18,8 @@
 //
 // linear_rows_kernel: the any-shape form (one warp per output row, weights read once, x from L2) — used for the small
 // layers (lidar_init.0: 2 MB of weights; radar_proj: 256 KB) and whenever the streaming kernel's shape rules fail.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200bev {
@@ -175,6 +177,149 @@ __global__ void __launch_bounds__(kThreads, 1) linear_stream_kernel(LinArgs a) {
   cp_async_wait<0>();
 }
 
+// ---- row-streaming form (default for batch <= 16) -------------------------------------------------------------------------
+// What the streaming kernel above taught (profiles/r01_ncu_dense.txt, tests/cuda/stream_read.cu): with 8 warps per SM a
+// B200 reads HBM at 3.4-3.6 TB/s whatever is in flight per warp (deeper rings, bulk copies, contiguous 32 KB runs all gave
+// the same 51 us for this 164 MB weight); 16 warps reach 4.9-5.2 TB/s, 32 warps 5.6.  So this form runs 16 warps per SM
+// and makes room for them by keeping the batch tile in REGISTERS: a lane keeps its K-slice of every batch row
+// (KPL * BT <= 64 floats), the only shared-memory traffic is one 128-bit load per 4*BT FMAs, and a row is shared by
+// KS = K / (32 * KPL) warps whose partial sums meet in shared memory once per chunk round.  The weights arrive as whole
+// row slices through per-warp cp.async rings (4 slots of 2 KB); chunk round q of CTA x covers rows
+// [(q * grid + x) * STEP, +STEP), so the grid reads one contiguous window at a time, like a grid-stride copy.  The K-sum
+// over the 32 lanes is a transposing butterfly (BT-1 shuffles leave lane b with batch row b's sum).
+constexpr int kRsWarps = 16;
+constexpr int kRsThreads = kRsWarps * 32;
+constexpr int kRsSlots = 4;
+constexpr int kRsChunkBytes = 2048;
+
+template <int HALF>
+__device__ __forceinline__ void add_butterfly_level(float* v, int lane) {
+  const bool up = (lane & HALF) != 0;
+#pragma unroll
+  for (int j = 0; j < HALF; ++j) {
+    const float send = up ? v[j] : v[j + HALF];
+    const float keep = up ? v[j + HALF] : v[j];
+    v[j] = keep + __shfl_xor_sync(FULL_MASK, send, HALF);
+  }
+}
+// v[0..BT) per lane -> v[0] = sum over all 32 lanes of v[lane & (BT-1)]
+template <int BT>
+__device__ __forceinline__ float warp_sum_transposed(float* v, int lane) {
+  if constexpr (BT >= 16) add_butterfly_level<8>(v, lane);
+  if constexpr (BT >= 8) add_butterfly_level<4>(v, lane);
+  add_butterfly_level<2>(v, lane);
+  add_butterfly_level<1>(v, lane);
+  float s = v[0];
+#pragma unroll
+  for (int m = BT; m < 32; m <<= 1) s += __shfl_xor_sync(FULL_MASK, s, m);
+  return s;
+}
+
+template <int BT, int KPL, int KS>   // batch tile; K floats per lane; warps per row: K = 32 * KPL * KS
+__global__ void __launch_bounds__(kRsThreads, 1) linear_rowstream_kernel(LinArgs a) {
+  constexpr int RL = kRsWarps / KS;                 // rows the CTA works on side by side
+  constexpr int SLICE = 32 * KPL;                   // floats of a row one warp handles
+  constexpr int RPC = kRsChunkBytes / (SLICE * 4);  // rows per chunk
+  constexpr int STEP = RL * RPC;                    // rows the CTA consumes per chunk round
+  extern __shared__ __align__(16) float smem[];
+  float* ring = smem;                                              // [warps][kRsSlots][RPC][SLICE]
+  float* red = ring + kRsWarps * kRsSlots * (kRsChunkBytes / 4);   // [2][RL][RPC][KS][BT] partial sums
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ks = warp % KS, rl = warp / KS;
+  const int K = a.K, b0 = blockIdx.y * BT;
+  const int row_hi = a.O;
+  const int total_steps = ceil_div(a.O, STEP);
+  const int n_chunks = total_steps > (int)blockIdx.x ? (total_steps - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int kw0 = ks * SLICE;
+  auto step_row = [&](int q) { return (q * (int)gridDim.x + (int)blockIdx.x) * STEP; };
+
+  float* my_ring = ring + (size_t)warp * kRsSlots * (kRsChunkBytes / 4);
+  auto issue = [&](int q) {
+    if (q < n_chunks) {
+      const int r0 = step_row(q) + rl * RPC;
+      float* dst = my_ring + (size_t)(q % kRsSlots) * (kRsChunkBytes / 4);
+#pragma unroll
+      for (int t = 0; t < kRsChunkBytes / 512; ++t) {
+        const int p = lane + 32 * t;                  // 16-byte piece of the chunk
+        const int r = p / (SLICE / 4), c = p - r * (SLICE / 4);
+        const int row = r0 + r;
+        const bool real = row < row_hi;
+        cp_async16(dst + p * 4, a.w + (size_t)(real ? row : 0) * K + kw0 + c * 4, real);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s2 = 0; s2 < kRsSlots - 1; ++s2) issue(s2);
+
+  // this lane's slice of the batch tile: float4 f of the slice is k = kw0 + (f * 32 + lane) * 4
+  float xr[BT][KPL];
+#pragma unroll
+  for (int b = 0; b < BT; ++b)
+#pragma unroll
+    for (int f = 0; f < KPL / 4; ++f) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + b < a.B) v = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(b0 + b) * K + kw0) + f * 32 + lane);
+      xr[b][4 * f] = v.x; xr[b][4 * f + 1] = v.y; xr[b][4 * f + 2] = v.z; xr[b][4 * f + 3] = v.w;
+    }
+
+  for (int q = 0; q < n_chunks; ++q) {
+    cp_async_wait<kRsSlots - 2>();
+    __syncwarp();
+    issue(q + kRsSlots - 1);
+    const float* wt = my_ring + (size_t)(q % kRsSlots) * (kRsChunkBytes / 4);
+    float* my_red = red + (size_t)(((q & 1) * RL + rl) * RPC) * KS * BT;
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) {
+      float acc[BT];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+#pragma unroll
+      for (int f = 0; f < KPL / 4; ++f) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + r * SLICE + (f * 32 + lane) * 4);
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          acc[b] = fmaf(w4.x, xr[b][4 * f], acc[b]);
+          acc[b] = fmaf(w4.y, xr[b][4 * f + 1], acc[b]);
+          acc[b] = fmaf(w4.z, xr[b][4 * f + 2], acc[b]);
+          acc[b] = fmaf(w4.w, xr[b][4 * f + 3], acc[b]);
+        }
+      }
+      const float s = warp_sum_transposed<BT>(acc, lane);   // lane l holds batch row l & (BT-1)
+      if (lane < BT) my_red[(r * KS + ks) * BT + lane] = s;
+    }
+    __syncthreads();   // the partial sums of every row of this chunk round are in shared memory (red is double-buffered)
+    for (int i = tid; i < STEP * BT; i += kRsThreads) {
+      const int rr = i % STEP, b = i / STEP;      // consecutive threads: consecutive output rows of one batch row
+      const int row = step_row(q) + rr;
+      if (row < row_hi && b0 + b < a.B) {
+        const float* pr = red + (size_t)((q & 1) * RL * RPC + rr) * KS * BT + b;
+        float v = 0.f;
+#pragma unroll
+        for (int k2 = 0; k2 < KS; ++k2) v += pr[k2 * BT];
+        v += a.bias ? __ldg(a.bias + row) : 0.f;
+        if (a.relu) v = fmaxf(v, 0.f);
+        a.out[(size_t)(b0 + b) * a.O + row] = v;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int BT, int KPL, int KS>
+int launch_rowstream(const LinArgs& a, cudaStream_t st) {
+  constexpr int RL = kRsWarps / KS, RPC = kRsChunkBytes / (32 * KPL * 4);
+  const size_t smem = (size_t)kRsWarps * kRsSlots * kRsChunkBytes + sizeof(float) * 2 * RL * RPC * KS * BT;
+  auto kern = linear_rowstream_kernel<BT, KPL, KS>;
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int gx = sm_count();
+  const int max_gx = ceil_div(a.O, RL * RPC);
+  if (gx > max_gx) gx = max_gx;
+  kern<<<dim3(gx, ceil_div(a.B, BT)), kRsThreads, smem, st>>>(a);
+  return launch_status();
+}
+
 // any shape: warp per output row, 8 batch rows per pass
 __global__ void __launch_bounds__(256) linear_rows_kernel(LinArgs a) {
   const int lane = threadIdx.x & 31;
@@ -229,6 +374,14 @@ int dense_layer(const float* x, int B, int K, const float* w, const float* bias,
                 cudaStream_t st) {
   LinArgs a{x, w, bias, out, B, K, O, relu};
   const bool aligned = (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
+  // row-streaming form (16 warps per SM, batch tile in registers): batch <= 8, K = 128 .. 512.  (A 16-row tile runs too —
+  // linear_rowstream_kernel<16, 4, 4> — but its shuffles and FMAs take 74 us on the 164 MB layer where the kernel below
+  // takes 65.)
+  if (aligned && O >= 256 && B <= 8 && !getenv("B200BEV_DENSE_OLD")) {
+    if (K == 512) return launch_rowstream<8, 8, 2>(a, st);
+    if (K == 256) return launch_rowstream<8, 8, 1>(a, st);
+    if (K == 128) return launch_rowstream<8, 4, 1>(a, st);
+  }
   // streaming form: K splits into four quarters of whole 32-float chunks, there is more than one 64-row step of work,
   // and a batch tile fits next to the rings (the widest tile that fits, the deepest ring next to it)
   if (aligned && K % (kKSplit * kKC) == 0 && O >= 2 * kStepRows) {
