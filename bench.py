@@ -437,6 +437,9 @@ def run_b200_arm(args):
             gfeat = torch.rand((F, 1024), device=dev, generator=gg)
             li_ms = med_ms(lambda: ops.lidar_init(gfeat, w1, b1, w2, b2))
             li_bytes = 4.0 * (w1.numel() + w2.numel() + b1.numel() + b2.numel() + F * (1024 + 2 * 512 + 80000))
+            hid8 = torch.rand((8, 512), device=dev, generator=gg)
+            l2_ms = med_ms(lambda: ops.dense_layer(hid8, w2, b2))                      # the 164 MB layer alone, HBM-bound
+            l2_bytes = 4.0 * (w2.numel() + b2.numel() + 8 * (512 + 80000))
             torch.backends.cuda.matmul.allow_tf32 = False
             li_cublas = med_ms(lambda: torch.addmm(b2, torch.relu(torch.addmm(b1, gfeat, w1.t())), w2.t()))
             del w2
@@ -498,7 +501,9 @@ def run_b200_arm(args):
                         f"at {F} frames",
                 "lidar_init": {"ms": round(li_ms, 4), "bound": "hbm", "achieved": round(li_bytes / li_ms / 1e6, 1),
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(li_bytes / li_ms / 1e6 / peaks["hbm_gbs"], 4),
-                               "dtype": "f32", "cublas_fp32_ms": round(li_cublas, 4)},
+                               "dtype": "f32", "cublas_fp32_ms": round(li_cublas, 4),
+                               "layer2_batch8": {"ms": round(l2_ms, 4), "achieved": round(l2_bytes / l2_ms / 1e6, 1), "unit": "GB/s",
+                                                 "frac": round(l2_bytes / l2_ms / 1e6 / peaks["hbm_gbs"], 4)}},
                 "conv_blocks": {"ms": round(tot["tc"], 4), "bound": "tensor", "achieved": round(tfl, 1), "peak": peaks["bf16_tflops_sustained"],
                                 "unit": "TFLOP/s", "frac": round(tfl / peaks["bf16_tflops_sustained"], 4), "dtype": "bf16",
                                 "layout_passes_ms": round(tot["layout"], 4), "cudnn_bf16_nhwc_ms": round(tot["cudnn_bf16"], 4),
