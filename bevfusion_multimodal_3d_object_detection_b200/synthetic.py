@@ -204,6 +204,29 @@ def head_maps(seed: int, batch: int, classes: int = 10, H: int = 50, W: int = 50
     }
 
 
+def ground_truth_near(seed: int, detections: Sequence[Dict[str, np.ndarray]], n_from_pred: int = 12, n_random: int = 6):
+    """Ground-truth dicts for a metrics check: the first `n_from_pred` detected boxes of each sample, displaced by up to
+    ~1.5 m and resized a little, plus random boxes; mostly class 0 (the only label the reference's decode emits,
+    SURVEY Q1), a few other classes and two invalid (-1) rows."""
+    g = _rng(seed)
+    out = []
+    for d in detections:
+        # rounded to the millimetre: the ground truth must not depend on the last bits of whoever decoded (atan2 differs by
+        # an ulp between numpy, torch-CPU and the device)
+        base = np.round(np.asarray(d["boxes"], dtype=np.float64)[:n_from_pred], 3).astype(np.float32)
+        base[:, :2] += g.uniform(-1.1, 1.1, (len(base), 2)).astype(np.float32)
+        base[:, 3:6] *= g.uniform(0.8, 1.25, (len(base), 3)).astype(np.float32)
+        base[:, 6] += g.uniform(-0.4, 0.4, len(base)).astype(np.float32)
+        rnd = np.concatenate([g.uniform(-50, 50, (n_random, 2)), np.full((n_random, 1), -1.0), g.uniform(0.5, 5, (n_random, 3)),
+                              g.uniform(-3.1, 3.1, (n_random, 1))], axis=1).astype(np.float32)
+        boxes = np.concatenate([base, rnd])
+        labels = np.zeros(len(boxes), dtype=np.int64)
+        labels[-n_random:-n_random + 2] = (3, 5)
+        labels[-2:] = -1
+        out.append({"boxes": boxes, "labels": labels})
+    return out
+
+
 def camera_rig(img_w: float = 1600.0, img_h: float = 900.0) -> Tuple[np.ndarray, np.ndarray]:
     """Six pinhole cameras, nuScenes-like: intrinsics (6,3,3) and ego->camera [R|t] (6,3,4), f32.
     Ego frame: x forward, y left, z up (the lidar-frame convention of src/data_converter.py:237-247);

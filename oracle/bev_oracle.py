@@ -356,3 +356,77 @@ def decode(pred: Dict[str, np.ndarray], score_thresh: float = 0.3, max_detection
         boxes = np.stack([wx, wy, wz, size[:, 0], size[:, 1], size[:, 2], yaw], axis=1).astype(F32)  # :400-404
         out.append({"boxes": boxes, "scores": scores[b][m], "labels": classes[b][m], "velocities": vel})
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 — the consumer of the decode outputs: mAP / NDS
+# ------------------------------------------------------------------------------------------------
+CLASS_NAMES = ("car", "truck", "bus", "trailer", "construction_vehicle", "pedestrian", "motorcycle", "bicycle",
+               "traffic_cone", "barrier")
+
+
+def _greedy_assign(dist: np.ndarray, scores: np.ndarray, threshold: float) -> List[Tuple[int, int]]:
+    """Predictions in descending score order each take the nearest still-free ground-truth box if it is within
+    `threshold` metres (centre distance) — the matching rule of src/utils_v2.py:14-37 and :52-71.  Returns
+    [(rank in score order, prediction index, gt index or -1)]."""
+    order = np.argsort(-scores)
+    free = np.ones(dist.shape[1], dtype=bool)
+    out = []
+    for rank, p in enumerate(order):
+        g = -1
+        if free.any():
+            d = np.where(free, dist[p], np.inf)
+            best = int(np.argmin(d))
+            if d[best] <= threshold:
+                g = best
+                free[best] = False
+        out.append((rank, int(p), g))
+    return out
+
+
+def compute_metrics(predictions: Sequence[Dict[str, np.ndarray]], ground_truths: Sequence[Dict[str, np.ndarray]],
+                    threshold: float = 2.0) -> Dict:
+    """[pinned] utils_v2.compute_metrics, src/utils_v2.py:94-205: per sample and class an 11-point interpolated AP over the
+    greedy centre-distance matching (:42-88), mean over samples then classes = mAP; translation / scale / orientation
+    errors of the matched pairs; NDS = mean(5 mAP, 1 - min(mATE/4, 1), 1 - min(mASE, 1), 1 - min(mAOE/pi, 1)).
+    Inputs are the shim's per-sample dicts (boxes (n,7), scores, labels) as numpy arrays."""
+    n_cls = len(CLASS_NAMES)
+    aps = [[] for _ in range(n_cls)]
+    ate, ase, aoe = [], [], []
+    for pred, gt in zip(predictions, ground_truths):
+        pb, ps, pl = (np.asarray(pred[k]) for k in ("boxes", "scores", "labels"))
+        gb, gl = np.asarray(gt["boxes"]), np.asarray(gt["labels"])
+        keep = gl >= 0
+        gb, gl = gb[keep], gl[keep]
+        if len(gb) == 0 and len(pb) == 0:
+            continue
+        for c in range(n_cls):
+            cp, cs, cg = pb[pl == c], ps[pl == c], gb[gl == c]
+            if len(cp) == 0 and len(cg) == 0:
+                continue
+            if len(cp) == 0 or len(cg) == 0:
+                aps[c].append(0.0)
+                continue
+            dist = np.sqrt(((cp[:, None, :2] - cg[None, :, :2]) ** 2).sum(axis=2))
+            assign = _greedy_assign(dist, cs, threshold)
+            hit = np.array([1.0 if g >= 0 else 0.0 for _, _, g in assign])
+            tp, fp = np.cumsum(hit), np.cumsum(1.0 - hit)
+            recall, precision = tp / len(cg), tp / (tp + fp + 1e-10)
+            ap = 0.0
+            for t in np.linspace(0, 1, 11):
+                ok = precision[recall >= t]
+                ap += (ok.max() if len(ok) else 0) / 11.0
+            aps[c].append(ap)
+            for _, p, g in assign:
+                if g < 0:
+                    continue
+                a, b = cp[p], cg[g]
+                ate.append(np.linalg.norm(a[:2] - b[:2]))
+                ase.append(np.mean(np.abs(a[3:6] - b[3:6]) / (b[3:6] + 1e-6)))
+                d = a[6] - b[6]
+                aoe.append(abs(np.arctan2(np.sin(d), np.cos(d))))
+    class_ap = [float(np.mean(v)) if v else 0.0 for v in aps]
+    m_ap = float(np.mean(class_ap))
+    m_ate, m_ase, m_aoe = (float(np.mean(v)) if v else 1.0 for v in (ate, ase, aoe))
+    nds = float(np.mean([5 * m_ap, 1 - min(m_ate / 4.0, 1.0), 1 - min(m_ase, 1.0), 1 - min(m_aoe / np.pi, 1.0)]))
+    return {"mAP": m_ap, "NDS": nds, "AP_per_class": dict(zip(CLASS_NAMES, class_ap))}

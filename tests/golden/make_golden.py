@@ -280,10 +280,27 @@ def glue_cases():
     np.savez_compressed(OUT / "bev_glue.npz", **out)
 
 
+def metrics_cases():
+    """N4: the reference's compute_metrics (src/utils_v2.py:94-205) on the reference's own decode outputs."""
+    import utils_v2  # noqa: E402  (reference)
+
+    maps = syn.head_maps(501, 3)
+    dets = fusion_detection.decode_centernet_predictions({k: torch.from_numpy(v) for k, v in maps.items()},
+                                                        score_thresh=0.3, max_detections=100)
+    gts = syn.ground_truth_near(801, [{k: v.numpy() for k, v in d.items()} for d in dets])
+    m_t = utils_v2.compute_metrics(dets, gts)                                             # torch tensors, as the shim returns
+    m_n = utils_v2.compute_metrics([{k: v.numpy() for k, v in d.items()} for d in dets], gts)
+    assert m_t == m_n and m_t["mAP"] > 0
+    out = {"mAP": np.float64(m_t["mAP"]), "NDS": np.float64(m_t["NDS"]),
+           "AP_per_class": np.array([m_t["AP_per_class"][c] for c in orc.CLASS_NAMES], dtype=np.float64),
+           "gt_digest": np.array(syn.digest(*[a for g in gts for a in g.values()]))}
+    np.savez_compressed(OUT / "metrics.npz", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = set(sys.argv[1:])
-    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases, glue_cases):
+    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases, glue_cases, metrics_cases):
         if only and fn.__name__ not in only:
             continue
         fn()

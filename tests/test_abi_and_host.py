@@ -318,3 +318,24 @@ def test_lidar_start_size_follows_the_grid():
     f20.train()
     out = f20(lidar_features=torch.randn(2, 32))
     assert tuple(out.shape) == (2, 8, 20, 20)
+
+
+def test_reference_metrics_consumer_accepts_the_shim_format():
+    """With the reference checkout present (build container only): utils_v2.compute_metrics takes the list-of-dicts the
+    shim's decode returns — torch tensors with the reference's dtypes — and agrees with the numpy restatement."""
+    ref_src = Path("/root/reference/src")
+    if not (ref_src / "utils_v2.py").exists():
+        pytest.skip("reference checkout not present (GPU box)")
+    sys.path.insert(0, str(ref_src))
+    try:
+        import utils_v2
+    finally:
+        sys.path.remove(str(ref_src))
+    from oracle import bev_oracle as orc
+
+    dets = orc.decode(syn.head_maps(501, 3), score_thresh=0.3, max_detections=100, voxel_size_m=0.512)
+    gts = syn.ground_truth_near(801, dets)
+    shim_format = [{k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in d.items()} for d in dets]
+    assert shim_format[0]["labels"].dtype == torch.int64 and shim_format[0]["boxes"].dtype == torch.float32
+    got, want = utils_v2.compute_metrics(shim_format, gts), orc.compute_metrics(dets, gts)
+    assert abs(got["mAP"] - want["mAP"]) < 1e-12 and abs(got["NDS"] - want["NDS"]) < 1e-6

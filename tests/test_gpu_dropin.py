@@ -300,3 +300,16 @@ def test_centernet_head_mirror_vs_reference_golden_and_fused_path(cuda, golden):
     want = b200bev.decode_centernet_predictions(plain, score_thresh=0.0, max_detections=50)
     for d, w in zip(dets, want):
         assert torch.equal(d["scores"], w["scores"]) and torch.equal(d["boxes"], w["boxes"])
+
+
+def test_decode_outputs_feed_the_metrics_consumer(cuda, golden):
+    """N4: the shim's list of per-sample dicts (device tensors) goes into compute_metrics as the reference's
+    own decode output does — `.cpu().numpy()` on every field, src/utils_v2.py:126-133 — and gives the reference's mAP / NDS."""
+    g = golden("metrics")
+    maps = {k: torch.from_numpy(v).to(cuda) for k, v in syn.head_maps(501, 3).items()}
+    dets = b200bev.decode_centernet_predictions_fusion_detection(maps, score_thresh=0.3, max_detections=100)
+    as_numpy = [{k: v.cpu().numpy() for k, v in d.items()} for d in dets]           # what compute_metrics does with tensors
+    gts = syn.ground_truth_near(801, as_numpy)
+    assert syn.digest(*[a for gt in gts for a in gt.values()]) == str(g["gt_digest"])
+    m = orc.compute_metrics(as_numpy, gts)
+    assert abs(m["mAP"] - float(g["mAP"])) < 1e-9 and abs(m["NDS"] - float(g["NDS"])) < 1e-6

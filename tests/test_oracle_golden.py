@@ -299,3 +299,15 @@ def test_conv_stacks_match_the_reference_fusion_module(golden):
     x = orc.bilinear_resize(x, (12, 20))
     x = block(block(x, "bev_fusion.0"), "bev_fusion.3")
     assert max_rel(x, g["stack_out"]) < 5e-5      # four fp32 convolutions deep, different summation order
+
+
+def test_metrics_consumer_restatement_matches_the_reference(golden):
+    """N4: mAP / NDS of the reference's compute_metrics on its own decode outputs, restated in numpy."""
+    g = golden("metrics")
+    dets = orc.decode(syn.head_maps(501, 3), score_thresh=0.3, max_detections=100, voxel_size_m=0.512)
+    gts = syn.ground_truth_near(801, dets)
+    assert syn.digest(*[a for gt in gts for a in gt.values()]) == str(g["gt_digest"])
+    m = orc.compute_metrics(dets, gts)
+    assert abs(m["mAP"] - float(g["mAP"])) < 1e-12 and abs(m["NDS"] - float(g["NDS"])) < 1e-6
+    np.testing.assert_allclose([m["AP_per_class"][c] for c in orc.CLASS_NAMES], g["AP_per_class"], rtol=0, atol=1e-12)
+    assert 0.0 < m["mAP"] < 1.0 and m["AP_per_class"]["car"] > 0.1
