@@ -414,7 +414,7 @@ def run_b200_arm(args):
 
     # ---- the kernels either side of the path (dense layers, conv blocks), timed on their own ----
     glue = None
-    if not args.no_alt:
+    if not args.no_alt and world == 1:      # single-GPU side measurement; the scaling runs keep to the contract's timed region
         try:
             def med_ms(fn, reps=5):
                 fn()

@@ -767,32 +767,44 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
   }
 }
 
-// (B, C, H, W) fp32 -> channels [c_offset, c_offset + C) of (B, H, W, C_total) bf16.  A thread owns one pixel and 8
-// consecutive channels: eight loads, each 128 contiguous bytes per warp (a lane is a pixel of one channel plane), one
+// (B, C, H, W) fp32 -> channels [c_offset, c_offset + C) of (B, H, W, C_total) bf16.  A thread owns one pixel (or four
+// consecutive ones) and 8 consecutive channels: eight loads, each 128 (512) contiguous bytes per warp (a lane is a pixel of one channel plane), one
 // 16-byte store; the eight warps of a block cover the 64 channels of the same 32 pixels, so every 128-byte line of the
 // output is completed by one block within a few hundred cycles.  No shared memory, 8 independent loads per thread.
+template <int PX>   // pixels per thread: 4 (128-bit loads along the plane; needs HW % 4 == 0) or 1
 __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int B, int C, int HW,
                                                                 __nv_bfloat16* __restrict__ out, int C_total, int c_offset) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 32);
-  const long long n_items = (long long)B * n_cg * n_pg;   // block items: 64 channels x 32 pixels
+  const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 32 * PX);
+  const long long n_items = (long long)B * n_cg * n_pg;   // block items: 64 channels x 32*PX pixels
   const bool vec_out = (C_total & 7) == 0 && (c_offset & 7) == 0 && ((uintptr_t)out & 15) == 0;
   for (long long t = blockIdx.x; t < n_items; t += gridDim.x) {
     const int pg = (int)(t % n_pg), cg = (int)((t / n_pg) % n_cg), b = (int)(t / ((long long)n_pg * n_cg));
-    const int p = pg * 32 + lane, c0 = cg * 64 + warp * 8;
+    const int p = (pg * 32 + lane) * PX, c0 = cg * 64 + warp * 8;
     if (p >= HW || c0 >= C) continue;
     const float* src = in + ((size_t)b * C + c0) * HW + p;
-    float v[8];
+    float v[8][PX];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (c0 + e < C) ? __ldg(src + (size_t)e * HW) : 0.f;
-    __nv_bfloat16* dst = out + ((size_t)b * HW + p) * C_total + c_offset + c0;
-    if (vec_out && c0 + 8 <= C) {
-      __align__(16) __nv_bfloat162 w[4];
+    for (int e = 0; e < 8; ++e) {
+      if (PX == 4) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + e < C) q = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)e * HW));
+        v[e][0] = q.x; v[e][PX > 1 ? 1 : 0] = q.y; v[e][PX > 2 ? 2 : 0] = q.z; v[e][PX > 3 ? 3 : 0] = q.w;
+      } else {
+        v[e][0] = (c0 + e < C) ? __ldg(src + (size_t)e * HW) : 0.f;
+      }
+    }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
-    } else {
-      for (int e = 0; e < 8 && c0 + e < C; ++e) dst[e] = __float2bfloat16_rn(v[e]);
+    for (int i = 0; i < PX; ++i) {
+      __nv_bfloat16* dst = out + ((size_t)b * HW + p + i) * C_total + c_offset + c0;
+      if (vec_out && c0 + 8 <= C) {
+        __align__(16) __nv_bfloat162 w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = __floats2bfloat162_rn(v[2 * e][i], v[2 * e + 1][i]);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
+      } else {
+        for (int e = 0; e < 8 && c0 + e < C; ++e) dst[e] = __float2bfloat16_rn(v[e][i]);
+      }
     }
   }
 }
@@ -824,9 +836,13 @@ extern "C" B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int
                                          int c_offset, void* stream) {
   if (!in || !out_nhwc || B <= 0 || C <= 0 || H <= 0 || W <= 0 || c_offset < 0 || c_offset + C > C_total)
     return B200BEV_ERR_INVALID_ARGUMENT;
-  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, 32);
+  const bool quad = ((H * W) & 3) == 0 && ((uintptr_t)in & 15) == 0;   // four pixels per thread, 128-bit loads
+  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, quad ? 128 : 32);
   long long blocks = tiles < (long long)sm_count() * 16 ? tiles : (long long)sm_count() * 16;
-  nchw_to_nhwc_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__nv_bfloat16*)out_nhwc, C_total, c_offset);
+  if (quad)
+    nchw_to_nhwc_bf16_kernel<4><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__nv_bfloat16*)out_nhwc, C_total, c_offset);
+  else
+    nchw_to_nhwc_bf16_kernel<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__nv_bfloat16*)out_nhwc, C_total, c_offset);
   return launch_status();
 }
 
