@@ -491,6 +491,34 @@ def run_b200_arm(args):
                                "tcgen05 MLP and convolution kernels (parity 1e-2)",
                        "f32_ms": round(chain_ms["f32"], 3), "f32_frames_per_s": round(F / chain_ms["f32"] * 1e3, 1),
                        "bf16_ms": round(chain_ms["bf16"], 3), "bf16_frames_per_s": round(F / chain_ms["bf16"] * 1e3, 1)}
+            # the same chain captured once in a CUDA graph (fixed-size decode outputs, the counts read back after the
+            # replay): ~45 launches and their allocator calls become one graph launch
+            try:
+                def chain_device():
+                    with torch.no_grad():
+                        pred = head(fus(camera_features=feats, lidar_features=enc_l(lidar), radar_features=enc_r(radars)))
+                        return ops.centernet_decode(pred["heatmap_logits"], pred["offset"], pred["size"], pred["rot"], pred["vel"],
+                                                    TOPK, 2.048, score_thresh=0.0, heat_is_logit=True)
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        chain_device()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    g_out = chain_device()
+                eager_out = chain_device()
+                graph.replay()
+                torch.cuda.synchronize(dev)
+                same = bool(torch.equal(g_out["scores"], eager_out["scores"]) and torch.equal(g_out["count"], eager_out["count"]))
+                modules["bf16_graph_ms"] = round(med_ms(lambda: (graph.replay(), g_out["count"].tolist()), reps=5), 3)
+                modules["bf16_graph_frames_per_s"] = round(F / modules["bf16_graph_ms"] * 1e3, 1)
+                modules["graph_equals_eager"] = same
+                del graph, g_out
+            except Exception as e:
+                modules["graph_error"] = str(e)[:200]
             del enc_l, enc_r, fus, head
             logits = torch.logit(maps["heatmap"].clamp(1e-6, 1 - 1e-6))
             dl_ms = med_ms(lambda: ops.centernet_decode(logits, maps["offset"], maps["size"], maps["rot"], maps["vel"], TOPK, 2.048,
