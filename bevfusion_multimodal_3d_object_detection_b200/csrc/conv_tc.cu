@@ -17,8 +17,9 @@
 //       (y+dy, x+dx) of output pixel n — 128 contiguous bytes of global memory, or zeros outside the image — moved with
 //       16-byte cp.async (zero-fill form) by all 256 threads straight to their swizzled place: im2col never exists in
 //       memory.
-// One persistent CTA per SM walks (pixel tile, co tile) pairs; ring of 4 stages (48 KB each), copies run two stages
-// ahead of the MMAs, a stage is released by tcgen05.commit.  fp32 accumulation in TMEM (256 columns).
+// One persistent CTA per SM walks (pixel tile, co tile) pairs; warp-specialised (producers / MMA issuer / epilogue meet at
+// mbarriers only), stages released by tcgen05.commit, fp32 accumulation double-buffered in TMEM (2 x 256 columns).  Two
+// kernels: the 3x3 form in which the nine taps share the pixel rows in shared memory, and the per-tap form (1x1, wide images).
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -29,7 +30,6 @@
 namespace b200bev {
 namespace {
 
-constexpr int kConvThreads = 256;
 constexpr int kTileCo = 128;   // M
 constexpr int kTilePx = 256;   // N
 constexpr int kKC = 64;        // bf16 k per stage (128-byte rows)
@@ -37,7 +37,6 @@ constexpr int kStageA = kTileCo * kKC * 2;   // 16 KB
 constexpr int kStageB = kTilePx * kKC * 2;   // 32 KB
 constexpr int kStage = kStageA + kStageB;
 constexpr int kRing = 4;
-constexpr int kAhead = kRing - 2;            // copies issued this many stages ahead of the MMAs
 constexpr int kEpiTile = 4 * 32 * 33 * 4;   // per epilogue warp: a 32 x 32 transposing tile
 constexpr int kConvSmem = kRing * kStage + kEpiTile + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -95,185 +94,13 @@ __device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bde
       : "r"(taddr)                                                                                                         \
       : "memory")
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(ConvArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-byte aligned tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRing * kStage);
-  uint64_t* full_a = bars;            // [kRing] weight stage landed (bulk copy, tx bytes)
-  uint64_t* empty = bars + kRing;     // [kRing] the MMAs that read the stage have completed
-  uint64_t* acc_full = bars + 2 * kRing;
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_addr(&tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (tid == 0) {
-    for (int s = 0; s < kRing; ++s) {
-      mbarrier_init(&full_a[s], 1);
-      mbarrier_init(&empty[s], 1);
-    }
-    mbarrier_init(acc_full, 1);
-    mbarrier_init_fence();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-
-  const int HW = a.H * a.W;
-  const long long n_px = (long long)a.B * HW;
-  const int n_px_tiles = (int)((n_px + kTilePx - 1) / kTilePx);
-  const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
-  const int ncc = a.Cin / kKC;
-  const int n_k = a.taps * ncc;
-  const int n_tiles = n_px_tiles * n_co_tiles;
-  // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTilePx >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
-
-  // this thread's part of a pixel stage: rows (tid>>3) + 32 j, 16-byte chunk tid&7 — the swizzled chunk is the same for
-  // all eight rows because they differ by multiples of 8
-  const int row0 = tid >> 3, chunk = tid & 7;
-  const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
-
-  uint32_t g = 0;        // stages issued so far (all tiles): ring slot and barrier phase
-  uint32_t n_done = 0;   // tiles finished: phase of acc_full
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_done) {
-    const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
-    const long long px0 = (long long)px_tile * kTilePx;
-    // the eight pixels this thread copies
-    int py[8], pxx[8];
-    long long poff[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long long n = px0 + row0 + 32 * j;
-      if (n < n_px) {
-        const int p = (int)(n % HW);
-        py[j] = p / a.W;
-        pxx[j] = p - py[j] * a.W;
-        poff[j] = n * a.Cin + chunk * 8;
-      } else {
-        py[j] = -100000;   // fails every bounds test
-        pxx[j] = 0;
-        poff[j] = 0;
-      }
-    }
-    const uint8_t* wtile = a.wimg + (size_t)co_tile * n_k * kStageA;
-
-    for (int i = 0; i < n_k + kAhead; ++i) {
-      if (i < n_k) {
-        const uint32_t gp = g + i, slot = gp % kRing;
-        if (gp >= kRing) mbarrier_wait(&empty[slot], ((gp / kRing) - 1) & 1);
-        const int tap = i / ncc, cc = i - tap * ncc;
-        const int dy = a.taps == 9 ? tap / 3 - 1 : 0, dx = a.taps == 9 ? tap % 3 - 1 : 0;
-        const long long shift = ((long long)dy * a.W + dx) * a.Cin + cc * kKC;
-        const uint32_t bdst = smem_addr(ring + slot * kStage + kStageA) + dst_off;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int yy = py[j] + dy, xx = pxx[j] + dx;
-          const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
-          cp_async16_zfill(bdst + j * 4096, a.x + (ok ? poff[j] + shift : 0), ok);
-        }
-        if (warp == 0 && elect_one()) {   // one lane of a converged warp: the copy's operands stay in uniform registers
-          mbarrier_expect_tx(&full_a[slot], kStageA);
-          bulk_copy_global_to_shared(ring + slot * kStage, wtile + (size_t)i * kStageA, kStageA, &full_a[slot]);
-        }
-      }
-      cp_async_commit_group();
-      const int c = i - kAhead;
-      if (c >= 0) {
-        cp_async_wait_group<kAhead>();      // this thread's copies of stage c have landed
-        fence_proxy_async_shared();         // ... and are visible to the tensor core's (asynchronous-proxy) reads
-        __syncthreads();
-        if (warp == 0 && elect_one()) {
-          const uint32_t gc = g + c, slot = gc % kRing;
-          mbarrier_wait(&full_a[slot], (gc / kRing) & 1);
-          tc_fence_after_sync();
-          const uint32_t a_addr = smem_addr(ring + slot * kStage), b_addr = a_addr + kStageA;
-#pragma unroll
-          for (int s = 0; s < kKC / 16; ++s)
-            umma_ss(tmem, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc(b_addr + s * 32), idesc, !(c == 0 && s == 0));
-          tc_commit_to(&empty[slot]);
-          if (c == n_k - 1) tc_commit_to(acc_full);
-        }
-      }
-    }
-    g += n_k;
-
-    // epilogue: thread = one output channel (TMEM lane), warps 0-3 take pixel columns [0,128), warps 4-7 [128,256)
-    mbarrier_wait(acc_full, n_done & 1);
-    tc_fence_after_sync();
-    {
-      const int quad = warp & 3, half = warp >> 2;
-      const int co = co_tile * kTileCo + quad * 32 + lane;
-      const float bias = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        uint32_t r[32];
-        const int col0 = half * 128 + q * 32;
-        CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const long long n0 = px0 + col0;
-        if (a.out_nhwc && co < a.Cout) {
-          // a lane is a channel: for one pixel the warp writes 32 consecutive bf16 channels (64 contiguous bytes)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n0 + j < n_px) {
-              float v = __uint_as_float(r[j]) + bias;
-              if (a.relu) v = fmaxf(v, 0.f);
-              a.out_nhwc[(size_t)(n0 + j) * a.out_ct + a.out_coff + co] = __float2bfloat16_rn(v);
-            }
-          }
-        }
-        if (a.out && co < a.Cout && n0 < n_px) {
-          const int b = (int)(n0 / HW), p = (int)(n0 - (long long)b * HW);
-          float* dst = a.out + ((size_t)b * a.Cout + co) * HW + p;
-          if (p + 32 <= HW && (HW & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = __uint_as_float(r[j]) + bias;
-              v.y = __uint_as_float(r[j + 1]) + bias;
-              v.z = __uint_as_float(r[j + 2]) + bias;
-              v.w = __uint_as_float(r[j + 3]) + bias;
-              if (a.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(dst + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long n = n0 + j;
-              if (n < n_px) {
-                const int bb = (int)(n / HW), pp = (int)(n - (long long)bb * HW);
-                float v = __uint_as_float(r[j]) + bias;
-                if (a.relu) v = fmaxf(v, 0.f);
-                a.out[((size_t)bb * a.Cout + co) * HW + pp] = v;
-              }
-            }
-          }
-        }
-      }
-    }
-    tc_fence_before_sync();
-    __syncthreads();   // every lane has read the accumulator before the next tile's first MMA overwrites it
-    tc_fence_after_sync();
-  }
-
-  cp_async_wait_group<0>();
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
-}
-
-// ---- warp-specialised form (default) -----------------------------------------------------------------------------------
-// The kernel above runs its producers, the MMA issue and the epilogue in one instruction stream: every stage pays the
-// chain "MMA(c-2) done -> copies issued -> wait -> fence -> block barrier -> MMA(c) issued" (~800 clk against 512 clk of
-// tensor work), the pipeline drains at every tile boundary and the accumulator is read out while the tensor pipe idles
-// (conv 768->512: 57 % of the sustained bf16 peak; the five-head conv: 37 %).  Here the three jobs are three groups of
-// warps that meet only at mbarriers:
+// ---- per-tap form: 1x1 convolutions, and 3x3 when an image row does not fit a tile ----------------------------------------
+// 256 flat pixels per tile, one 48 KB stage (weight stage + the tap's pixel rows) per (tap, 64-channel chunk) in a ring of
+// four.  (The first version ran producers, MMA issue and epilogue in ONE instruction stream: every stage paid the chain
+// "MMA(c-2) done -> copies issued -> wait -> fence -> block barrier -> MMA(c) issued", ~800 clk against 512 clk of tensor
+// work, the pipeline drained at every tile boundary and the accumulator was read out while the tensor pipe idled —
+// 57 % of the sustained bf16 peak on 768->512, 37 % on the five-head conv.)  Three groups of warps that meet only at
+// mbarriers:
 //   warps 0-7   producers: im2col pixel rows by cp.async, the weight stage by one bulk copy; they run ahead over tile
 //               boundaries, held back only by the ring (`empty`, released by tcgen05.commit)
 //   warp 12     MMA issuer: waits for a stage's rows (`full_b`, one arrival per producer warp) and weights (`full_a`),
@@ -859,13 +686,8 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
   const long long tiles = (((long long)B * H * W + kTilePx - 1) / kTilePx) * ceil_div(Cout, kTileCo);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const char* impl = getenv("B200BEV_CONV_IMPL");
-  if (impl && impl[0] == 's') {   // "single": the one-instruction-stream kernel, kept for A/B timing
-    B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
-    conv_tc_kernel<<<grid, kConvThreads, kConvSmem, (cudaStream_t)stream>>>(a);
-    return launch_status();
-  }
   HaloGeom geo;
-  const bool want_halo = !(impl && impl[0] == 'w');   // "ws": the per-tap warp-specialised kernel for 3x3 too
+  const bool want_halo = !(impl && impl[0] == 'p');   // "per-tap": the per-tap kernel for 3x3 too (A/B timing)
   if (taps == 9 && want_halo && halo_geometry(H, W, &geo)) {
     B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
     const long long htiles = (long long)B * geo.tiles_per_frame * ceil_div(Cout, kTileCo);
