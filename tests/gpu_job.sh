@@ -16,6 +16,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-alt > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?" >> gpurun_out/rc.txt
 ncu --set full --clock-control none -o gpurun_out/prof_stages -f python tests/prof_stages.py --reps 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" >> gpurun_out/rc.txt
 python tools/ncu_summary.py gpurun_out/prof_stages.ncu-rep gpurun_out/prof_stages_summary.csv >> gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none -k regex:"linear_rowstream|conv3x3_tc_halo|conv_tc_ws|nchw_to_nhwc" -o gpurun_out/prof_next -f python tests/prof_stages.py --reps 1 --frames 8 --only dense,conv > gpurun_out/ncu_next.log 2>&1; python tools/ncu_summary.py gpurun_out/prof_next.ncu-rep gpurun_out/prof_next_summary.csv >> gpurun_out/ncu_next.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pointnet_mlp_tc -o gpurun_out/prof_tc_cell -f python tests/prof_stages.py --reps 1 --only mlp_tc_cell > gpurun_out/ncu_tc.log 2>&1; echo "ncu tc rc=$?" >> gpurun_out/rc.txt
 fi
 for f in $(ls -S gpurun_out/*.ncu-rep 2>/dev/null); do
