@@ -71,22 +71,29 @@ def _plan(seq: nn.Sequential, device: torch.device) -> List[Dict]:
     return steps
 
 
-def run(seq: nn.Sequential, parts: Sequence[torch.Tensor]) -> torch.Tensor:
+def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc: Optional[torch.Tensor] = None,
+        out_nhwc: Optional[torch.Tensor] = None, c_offset: int = 0) -> Optional[torch.Tensor]:
     """`seq(torch.cat(parts, dim=1))` for a conv/BN/ReLU(/Upsample) stack: (B,C_i,H,W) fp32 parts -> (B,C_out,H',W') fp32.
-    Between two convolutions the activations stay channels-last bf16 (written by the first launch's epilogue)."""
-    parts = list(parts)
-    steps = _plan(seq, parts[0].device)
-    nhwc = None                                          # activations already in the next conv's input layout
+    Between two convolutions the activations stay channels-last bf16 (written by the first launch's epilogue).
+    nhwc: the input already as a (B,H,W,C) bf16 tensor (instead of `parts`).  out_nhwc / c_offset: the stack's last
+    convolution writes channels [c_offset, ...) of this channels-last bf16 tensor — the concatenated input of the next
+    stack — and nothing else; returns None."""
+    parts = list(parts) if parts is not None else []
+    device = nhwc.device if nhwc is not None else parts[0].device
+    steps = _plan(seq, device)
+    if out_nhwc is not None and steps[-1]["kind"] != "conv":
+        raise ValueError("out_nhwc needs a stack that ends in a convolution block")
     for k, step in enumerate(steps):
         if step["kind"] == "conv":
             if nhwc is None:
                 nhwc = ops.nchw_to_nhwc_bf16(parts)      # layout + cast + concat in one pass per part
-            chained = k + 1 < len(steps) and steps[k + 1]["kind"] == "conv"
-            if chained:
+            last = k + 1 == len(steps)
+            chained = not last and steps[k + 1]["kind"] == "conv"
+            if chained or (last and out_nhwc is not None):
                 B, H, W, _ = nhwc.shape
-                nxt = torch.empty((B, H, W, step["c_out"]), dtype=torch.bfloat16, device=nhwc.device)
+                nxt, off = (out_nhwc, c_offset) if last else (torch.empty((B, H, W, step["c_out"]), dtype=torch.bfloat16, device=device), 0)
                 ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"],
-                                      out_nhwc=nxt, want_nchw=False)
+                                      out_nhwc=nxt, c_offset=off, want_nchw=False)
                 nhwc, parts = nxt, []
             else:
                 parts = [ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
@@ -96,6 +103,8 @@ def run(seq: nn.Sequential, parts: Sequence[torch.Tensor]) -> torch.Tensor:
             s = step["scale"]
             sy, sx = (s, s) if not isinstance(s, (tuple, list)) else s
             parts = [ops.bilinear_resize(x, (int(x.shape[2] * sy), int(x.shape[3] * sx)))]
+    if out_nhwc is not None:
+        return None
     return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
 
 

@@ -636,6 +636,49 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
   }
 }
 
+// camera_features.mean(dim=1) (src/fusion.py:233-234) written straight as the channels-last bf16 input of camera_proj's
+// first convolution: (B, n_cam, C, HW) fp32 -> channels [c_offset, c_offset + C) of (B, HW, C_total) bf16.  Same thread
+// shape as the layout kernel (four pixels x eight channels, 128-bit loads along the plane), same arithmetic as
+// camera_mean_vec4_kernel (sum in camera order, IEEE divide), so the result is the bf16 rounding of that kernel's output.
+__global__ void __launch_bounds__(256) camera_mean_nhwc_bf16_kernel(const float* __restrict__ in, int B, int n_cam, int C, int HW,
+                                                                    __nv_bfloat16* __restrict__ out, int C_total, int c_offset) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 128);
+  const long long n_items = (long long)B * n_cg * n_pg;
+  const float denom = (float)n_cam;
+  for (long long t = blockIdx.x; t < n_items; t += gridDim.x) {
+    const int pg = (int)(t % n_pg), cg = (int)((t / n_pg) % n_cg), b = (int)(t / ((long long)n_pg * n_cg));
+    const int p = (pg * 32 + lane) * 4, c0 = cg * 64 + warp * 8;
+    if (p >= HW || c0 >= C) continue;
+    float v[8][4];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + e < C) {
+        const float* src = in + (((size_t)b * n_cam) * C + c0 + e) * HW + p;
+        s4 = ld_stream_f4(reinterpret_cast<const float4*>(src));
+        for (int cam = 1; cam < n_cam; ++cam) {
+          const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)cam * C * HW));
+          s4.x = __fadd_rn(s4.x, q.x); s4.y = __fadd_rn(s4.y, q.y); s4.z = __fadd_rn(s4.z, q.z); s4.w = __fadd_rn(s4.w, q.w);
+        }
+      }
+      v[e][0] = __fdiv_rn(s4.x, denom); v[e][1] = __fdiv_rn(s4.y, denom); v[e][2] = __fdiv_rn(s4.z, denom); v[e][3] = __fdiv_rn(s4.w, denom);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16* dst = out + ((size_t)b * HW + p + i) * C_total + c_offset + c0;
+      if (c0 + 8 <= C) {
+        __align__(16) __nv_bfloat162 w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = __floats2bfloat162_rn(v[2 * e][i], v[2 * e + 1][i]);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
+      } else {
+        for (int e = 0; e < 8 && c0 + e < C; ++e) dst[e] = __float2bfloat16_rn(v[e][i]);
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace b200bev
 
@@ -656,6 +699,19 @@ extern "C" B200BEV_API int b200bev_conv_pack_bf16(const float* weight, int Cout,
   long long blocks = (n_chunks + 255) / 256;
   if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
   conv_pack_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(weight, Cout, Cin, taps, (uint8_t*)image, n_chunks);
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_camera_mean_nhwc_bf16(const float* feats, int B, int n_cam, int C, int H, int W, void* out_nhwc,
+                                             int C_total, int c_offset, void* stream) {
+  if (!feats || !out_nhwc || B <= 0 || n_cam <= 0 || C <= 0 || H <= 0 || W <= 0 || c_offset < 0 || c_offset + C > C_total)
+    return B200BEV_ERR_INVALID_ARGUMENT;
+  // 128-bit loads along the plane and 128-bit stores of 8 channels
+  if (((H * W) & 3) || ((uintptr_t)feats & 15) || (C_total & 7) || (c_offset & 7) || ((uintptr_t)out_nhwc & 15)) return B200BEV_ERR_UNSUPPORTED;
+  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, 128);
+  long long blocks = tiles < (long long)sm_count() * 16 ? tiles : (long long)sm_count() * 16;
+  camera_mean_nhwc_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(feats, B, n_cam, C, H * W, (__nv_bfloat16*)out_nhwc, C_total,
+                                                                           c_offset);
   return launch_status();
 }
 

@@ -70,8 +70,57 @@ def lidar_branch(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tenso
     return x
 
 
+def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_features) -> Optional[torch.Tensor]:
+    """The whole eval-mode forward with the bf16 path on: every convolution on the tcgen05 kernel, and no
+    tensor between two kernels in any layout but the one its consumer reads — the camera mean leaves its kernel as
+    camera_proj's channels-last bf16 input, the lidar and radar stacks write their slices of bev_fusion's concatenated
+    input from their last convolution's epilogue (torch.cat of src/fusion.py:292 never happens).  Returns None when a
+    stack has a shape the kernel does not take; the caller then runs the layer-by-layer path."""
+    c = module.bev_channels
+    use = [module.use_camera and camera_features is not None, module.use_lidar and lidar_features is not None,
+           module.use_radar and radar_features is not None]
+    stacks = [module.camera_proj if use[0] else None, module.lidar_upsample if use[1] else None,
+              module.radar_refine if use[2] else None, module.bev_fusion]
+    if not any(use) or c % 64 != 0 or not all(conv_blocks.supported(s) for s in stacks if s is not None):
+        return None
+    first = next(t for t, u in zip((camera_features, lidar_features, radar_features), use) if u)
+    if not first.is_cuda:
+        return None
+    if use[0] and camera_features.shape[-3] % 64 != 0:
+        return None
+    B, H, W = first.shape[0], module.bev_h, module.bev_w
+    cat = torch.empty((B, H, W, c * sum(use)), dtype=torch.bfloat16, device=first.device)
+    off = 0
+    if use[0]:
+        hw = camera_features.shape[-2] * camera_features.shape[-1]
+        if camera_features.dim() == 5 and hw % 4 == 0:
+            x = conv_blocks.run(module.camera_proj, nhwc=ops.camera_mean_nhwc_bf16(camera_features))
+        else:
+            cam = ops.camera_mean(camera_features) if camera_features.dim() == 5 else camera_features
+            x = conv_blocks.run(module.camera_proj, [cam])
+        ops.nchw_to_nhwc_bf16([ops.bilinear_resize(x, (H, W))], out=cat, c_offset=off)      # src/fusion.py:242-247
+        off += c
+    if use[1]:
+        s0 = module.lidar_start_size
+        hidden = module.lidar_init[2].out_features // (s0 * s0)
+        if hidden % 64 != 0:
+            return None
+        l0, l2 = module.lidar_init[0], module.lidar_init[2]
+        x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s0, s0)
+        conv_blocks.run(module.lidar_upsample, [x], out_nhwc=cat, c_offset=off)              # :258-262
+        off += c
+    if use[2]:
+        r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)
+        conv_blocks.run(module.radar_refine, [r.view(B, c, 1, 1).expand(B, c, H, W)], out_nhwc=cat, c_offset=off)   # :274-281
+    return conv_blocks.run(module.bev_fusion, nhwc=cat)                                      # :292-295
+
+
 def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None, radar_features=None) -> torch.Tensor:
     """FlexibleBEVFusion.forward (src/fusion.py:209-297)."""
+    if not module.training and conv_blocks.wants_bf16(module):
+        out = _fused_bf16_path(module, camera_features, lidar_features, radar_features)
+        if out is not None:
+            return out
     parts = []
     B = None
     if module.use_camera and camera_features is not None:

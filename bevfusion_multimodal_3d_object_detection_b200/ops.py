@@ -336,13 +336,19 @@ def conv_pack(weight: torch.Tensor) -> torch.Tensor:
     return img
 
 
-def nchw_to_nhwc_bf16(parts: Sequence[torch.Tensor]) -> torch.Tensor:
-    """[(B,C_i,H,W) fp32] -> (B,H,W,sum C_i) bf16 channels-last: layout change, cast and torch.cat in one pass per part."""
+def nchw_to_nhwc_bf16(parts: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None, c_offset: int = 0) -> torch.Tensor:
+    """[(B,C_i,H,W) fp32] -> (B,H,W,sum C_i) bf16 channels-last: layout change, cast and torch.cat in one pass per part.
+    `out`: an existing (B,H,W,C_total) bf16 tensor; the parts go to its channels from `c_offset` on."""
     parts = [_need_cuda(p, f"parts[{i}]") for i, p in enumerate(parts)]
     B, _, H, W = parts[0].shape
-    c_total = sum(int(p.shape[1]) for p in parts)
-    out = torch.empty((B, H, W, c_total), dtype=torch.bfloat16, device=parts[0].device)
-    off = 0
+    c_sum = sum(int(p.shape[1]) for p in parts)
+    if out is None:
+        out = torch.empty((B, H, W, c_sum), dtype=torch.bfloat16, device=parts[0].device)
+        c_offset = 0
+    elif out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape[:3]) != (B, H, W) or c_offset + c_sum > out.shape[3]:
+        raise ValueError(f"out must be a contiguous (B,H,W,C) bf16 tensor with room for {c_sum} channels at offset {c_offset}")
+    c_total = int(out.shape[3])
+    off = c_offset
     with torch.cuda.device(out.device):
         for p in parts:
             if p.shape[0] != B or tuple(p.shape[2:]) != (H, W):
@@ -350,6 +356,19 @@ def nchw_to_nhwc_bf16(parts: Sequence[torch.Tensor]) -> torch.Tensor:
             _lib.check(_lib.lib().b200bev_nchw_to_nhwc_bf16(_ptr(p), B, int(p.shape[1]), H, W, _ptr(out), c_total, off,
                                                             _stream(out.device)))
             off += int(p.shape[1])
+    return out
+
+
+def camera_mean_nhwc_bf16(feats: torch.Tensor) -> torch.Tensor:
+    """(B,n_cam,C,h,w) fp32 -> (B,h,w,C) bf16: camera_features.mean(dim=1) (src/fusion.py:234) delivered as the
+    channels-last input of camera_proj's first convolution."""
+    feats = _need_cuda(feats, "camera_features")
+    if feats.dim() != 5:
+        raise ValueError("camera_features must be (B, n_cam, C, h, w)")
+    B, n_cam, Cc, h, w = feats.shape
+    out = torch.empty((B, h, w, Cc), dtype=torch.bfloat16, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().b200bev_camera_mean_nhwc_bf16(_ptr(feats), B, n_cam, Cc, h, w, _ptr(out), Cc, 0, _stream(feats.device)))
     return out
 
 

@@ -242,8 +242,13 @@ B200BEV_API int b200bev_lidar_init(const float* lidar_features, int B, int K, co
  *   b200bev_conv_pack_bytes gives the image size (0: unsupported shape).
  * b200bev_nchw_to_nhwc_bf16: (B,C,H,W) f32 -> channels [c_offset, c_offset+C) of a (B,H,W,C_total) bf16 tensor; writing
  *   the parts of a concatenated input into their slices replaces torch.cat of src/fusion.py:292.
+ * b200bev_camera_mean_nhwc_bf16: camera_features.mean(dim=1) (src/fusion.py:233-234) fused with that layout step:
+ *   feats (B,n_cam,C,H,W) f32 -> channels [c_offset, c_offset+C) of (B,H,W,C_total) bf16 = the bf16 rounding of
+ *   b200bev_camera_mean's result (same summation order, IEEE divide).  Needs H*W % 4 == 0 and C_total, c_offset % 8 == 0.
  * ------------------------------------------------------------------------------------------- */
 B200BEV_API size_t b200bev_conv_pack_bytes(int Cout, int Cin, int taps);
+B200BEV_API int b200bev_camera_mean_nhwc_bf16(const float* feats, int B, int n_cam, int C, int H, int W,
+                                  void* out_nhwc, int C_total, int c_offset, void* stream);
 B200BEV_API int b200bev_conv_pack_bf16(const float* weight, int Cout, int Cin, int taps,
                            void* image, size_t image_bytes, void* stream);
 B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int C, int H, int W,

@@ -76,6 +76,21 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.b200bev_centernet_topk(one, 1, 2, 6, 7, 5, one, one, one, one, one, one, 8, null) == _lib.ERR_WORKSPACE
     assert lib.b200bev_camera_project(one, 2, 6, 8, 4, 4, one, one, 3, 1600, 900, 0, 0, 1, 1, 0, 5, 5, one, null, null) \
         == _lib.ERR_INVALID_ARGUMENT                     # T must be 1 or B
+    # SURVEY 8f entry points: dense layers and convolution blocks
+    assert lib.b200bev_dense_layer(null, 1, 4, one, null, 4, 0, one, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_dense_layer(one, 0, 4, one, null, 4, 0, one, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_lidar_init(one, 1, 4, one, one, 4, one, one, 4, null, one, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_conv_pack_bytes(320, 256, 9) == 3 * 9 * 4 * 16384          # 3 channel tiles x 9 taps x 4 chunks of 16 KB
+    assert lib.b200bev_conv_pack_bytes(19, 320, 1) == 5 * 16384
+    assert lib.b200bev_conv_pack_bytes(64, 48, 9) == 0 and lib.b200bev_conv_pack_bytes(64, 64, 25) == 0
+    assert lib.b200bev_conv_pack_bf16(one, 64, 48, 9, one, 1 << 20, null) == _lib.ERR_UNSUPPORTED
+    assert lib.b200bev_conv_pack_bf16(one, 64, 64, 9, one, 16, null) == _lib.ERR_WORKSPACE
+    assert lib.b200bev_conv_bn_relu_bf16(one, 1, 4, 4, 48, one, null, 8, 9, 1, one, null) == _lib.ERR_UNSUPPORTED
+    assert lib.b200bev_conv_bn_relu_bf16(one, 1, 4, 4, 64, one, null, 8, 9, 1, null, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_conv_bn_relu_bf16_nhwc(one, 1, 4, 4, 64, one, null, 8, 1, 1, one, 12, 8, null, null) == _lib.ERR_INVALID_ARGUMENT  # slice past C_total
+    assert lib.b200bev_nchw_to_nhwc_bf16(one, 1, 8, 4, 4, one, 12, 8, null) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.b200bev_centernet_decode_logits(null, one, one, one, one, 1, 1, 4, 4, 2, 1.0, 0, 0, 0, 0, one, one, one, one, null, null,
+                                               null, one, one, 64, null) == _lib.ERR_INVALID_ARGUMENT
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

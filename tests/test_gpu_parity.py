@@ -606,6 +606,8 @@ def test_decode_from_logits_vs_reference_head_golden(cuda, golden):
     (2, 57, 100, 64, 64, 3, True),       # camera_proj's image: two image rows per tile (N = 208), last tile one row
     (1, 3, 300, 64, 32, 3, True),        # an image row wider than a tile: the per-tap kernel takes the 3x3 too
     (5, 5, 6, 64, 130, 3, True),         # whole frames smaller than a tile; a 2-channel last channel tile
+    (3, 1, 1, 64, 1, 3, False),          # one pixel, one output channel: every tap but the centre is padding
+    (1, 1, 7, 128, 5, 1, True),          # a single image row through the 1x1 form
 ])
 def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
     g = np.random.default_rng(Cin * 7 + Cout)
@@ -638,3 +640,18 @@ def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
     ref32 = torch.nn.functional.conv2d(xd.double(), wd.double(), bd.double(), padding=k // 2)
     ref32 = torch.relu(ref32) if relu else ref32
     assert max_rel(got.cpu().numpy(), ref32.cpu().numpy()) < BF16_TOL
+
+
+def test_camera_mean_channels_last_bf16_is_the_rounded_mean(cuda):
+    """The fused mean + layout kernel gives exactly bf16(camera_mean): same summation order, IEEE divide."""
+    for B, C, h, w in ((2, 64, 8, 14), (1, 72, 6, 10), (3, 512, 8, 8)):
+        feats = dev_t(syn.camera_features(77 + C, B, n_cam=6, channels=C, h=h, w=w), cuda)
+        got = ops.camera_mean_nhwc_bf16(feats)
+        want = ops.camera_mean(feats).permute(0, 2, 3, 1).to(torch.bfloat16)
+        assert tuple(got.shape) == (B, h, w, C) and torch.equal(got, want)
+    with pytest.raises(_lib.B200BevError):
+        ops.camera_mean_nhwc_bf16(dev_t(syn.camera_features(5, 1, n_cam=2, channels=64, h=3, w=5), cuda))   # H*W % 4 != 0
+    wide = torch.zeros((2, 4, 4, 24), dtype=torch.bfloat16, device=cuda)
+    x = torch.rand((2, 8, 4, 4), device=cuda)
+    ops.nchw_to_nhwc_bf16([x], out=wide, c_offset=8)
+    assert torch.equal(wide[..., 8:16], x.permute(0, 2, 3, 1).to(torch.bfloat16)) and float(wide[..., :8].abs().max()) == 0.0
