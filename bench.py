@@ -499,24 +499,16 @@ def run_b200_arm(args):
                         pred = head(fus(camera_features=feats, lidar_features=enc_l(lidar), radar_features=enc_r(radars)))
                         return ops.centernet_decode(pred["heatmap_logits"], pred["offset"], pred["size"], pred["rot"], pred["vel"],
                                                     TOPK, 2.048, score_thresh=0.0, heat_is_logit=True)
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    for _ in range(2):
-                        chain_device()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                torch.cuda.synchronize(dev)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    g_out = chain_device()
+                graphed = runtime.GraphedStep(chain_device, dev)
+                g_out = graphed.outputs
                 eager_out = chain_device()
-                graph.replay()
+                graphed.replay()
                 torch.cuda.synchronize(dev)
                 same = bool(torch.equal(g_out["scores"], eager_out["scores"]) and torch.equal(g_out["count"], eager_out["count"]))
-                modules["bf16_graph_ms"] = round(med_ms(lambda: (graph.replay(), g_out["count"].tolist()), reps=5), 3)
+                modules["bf16_graph_ms"] = round(med_ms(lambda: (graphed.replay(), g_out["count"].tolist()), reps=5), 3)
                 modules["bf16_graph_frames_per_s"] = round(F / modules["bf16_graph_ms"] * 1e3, 1)
                 modules["graph_equals_eager"] = same
-                del graph, g_out
+                del graphed, g_out
             except Exception as e:
                 modules["graph_error"] = str(e)[:200]
             del enc_l, enc_r, fus, head

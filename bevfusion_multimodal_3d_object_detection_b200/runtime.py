@@ -117,3 +117,33 @@ class FramePipeline:
             step({k: v[: e - b] for k, v in slot.dev.items()}, b, e)
             slot.free.record(compute)
         compute.wait_stream(self.copy_stream)
+
+
+class GraphedStep:
+    """A fixed-shape device step captured once in a CUDA graph and replayed.
+
+    `fn()` must read its inputs from tensors that stay allocated (copy new data INTO them between replays) and must
+    not synchronise with the host: every kernel of this package qualifies (they only enqueue on the current stream; the
+    list-of-dicts form of `decode_centernet_predictions` does not — it reads the counts back — so a step ends with
+    `ops.centernet_decode`, whose outputs have fixed shapes).  Weight caches (folded / packed parameters) are built by the
+    warm-up calls, outside the capture.  The tensors `fn` returned during capture are the step's outputs: a replay
+    overwrites them in place.
+    """
+
+    def __init__(self, fn: Callable[[], object], device: torch.device, warmup: int = 2):
+        self.device = device
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.outputs = fn()
+
+    def replay(self):
+        """Enqueues the whole step on the current stream; returns the (static) output tensors."""
+        self.graph.replay()
+        return self.outputs

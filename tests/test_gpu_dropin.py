@@ -313,3 +313,35 @@ def test_decode_outputs_feed_the_metrics_consumer(cuda, golden):
     assert syn.digest(*[a for gt in gts for a in gt.values()]) == str(g["gt_digest"])
     m = orc.compute_metrics(as_numpy, gts)
     assert abs(m["mAP"] - float(g["mAP"])) < 1e-9 and abs(m["NDS"] - float(g["NDS"])) < 1e-6
+
+
+def test_graphed_step_replays_the_chain_bit_for_bit(cuda):
+    """runtime.GraphedStep: fusion -> head -> fixed-size decode captured in one CUDA graph; new inputs are copied into
+    the captured tensors, a replay gives what the eager calls give."""
+    from bevfusion_multimodal_3d_object_detection_b200 import ops, runtime
+
+    torch.manual_seed(9)
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=64, lidar_channels=128,
+                                    radar_channels=64, bev_h=50, bev_w=50, bev_channels=64).eval().to(cuda)
+    head = b200bev.CenterNetHead(in_channels=64, num_classes=10, head_conv=64)
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in syn.head_weights(713, 64, 64, 10, out_scale=0.3).items()})
+    head = head.eval().to(cuda)
+    fus.b200_precision = head.b200_precision = "bf16"
+    cam = torch.from_numpy(syn.camera_features(733, 2, n_cam=6, channels=64, h=28, w=50)).to(cuda)
+    lidar, radar = torch.rand(2, 128, device=cuda), torch.rand(2, 64, device=cuda)
+
+    def step():
+        pred = head(fus(camera_features=cam, lidar_features=lidar, radar_features=radar))
+        return ops.centernet_decode(pred["heatmap_logits"], pred["offset"], pred["size"], pred["rot"], pred["vel"], 40, 2.048,
+                                    heat_is_logit=True)
+
+    graphed = runtime.GraphedStep(step, cuda)
+    for seed in (1, 2):
+        cam.copy_(torch.from_numpy(syn.camera_features(740 + seed, 2, n_cam=6, channels=64, h=28, w=50)).to(cuda))
+        lidar.copy_(torch.rand(2, 128, device=cuda))
+        with torch.no_grad():
+            eager = {k: v.clone() for k, v in step().items()}
+        out = graphed.replay()
+        torch.cuda.synchronize()
+        for k in ("scores", "boxes", "velocities", "ys", "xs", "count"):
+            assert torch.equal(out[k], eager[k]), k
