@@ -88,6 +88,8 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         return None
     if use[0] and camera_features.shape[-3] % 64 != 0:
         return None
+    if use[1] and (module.lidar_init[2].out_features // module.lidar_start_size ** 2) % 64 != 0:
+        return None
     B, H, W = first.shape[0], module.bev_h, module.bev_w
     cat = torch.empty((B, H, W, c * sum(use)), dtype=torch.bfloat16, device=first.device)
     off = 0
@@ -103,8 +105,6 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
     if use[1]:
         s0 = module.lidar_start_size
         hidden = module.lidar_init[2].out_features // (s0 * s0)
-        if hidden % 64 != 0:
-            return None
         l0, l2 = module.lidar_init[0], module.lidar_init[2]
         x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s0, s0)
         conv_blocks.run(module.lidar_upsample, [x], out_nhwc=cat, c_offset=off)              # :258-262
