@@ -1,0 +1,174 @@
+"""Executable model of the synchronisation protocol of conv3x3_tc_halo_kernel (csrc/conv_tc.cu) — test infrastructure.
+
+Agents, as in the kernel: 8 pixel-producer warps (cp.async into one of two pixel blocks, one `full_blk` arrival per
+warp), the weight warp (bulk copies into a ring of `ring` stages, `full_a` by transaction bytes), the MMA issuer (waits
+`acc_empty` at a tile's first MMA, `full_blk` per 64-channel chunk, `full_a` per tap; its commits release `empty_a`,
+`empty_blk`, `acc_full` when the tensor pipe retires the MMAs) and 4 epilogue warps (read one accumulator half, arrive on
+`acc_empty`).  Waiters only see a phase PARITY, so the model replays the loops under random schedules with asynchronous
+completions (copies land at arbitrary times, the pipe retires MMA groups in issue order at arbitrary times) and reports
+deadlocks and hazards: a slot refilled while MMAs that read it are in flight, an MMA issued on a slot whose data has
+not landed, an accumulator half overwritten before every epilogue warp has read it or read before its MMAs retired.
+It mirrors the kernel's loops one to one: change both together.
+"""
+from __future__ import annotations
+
+import random
+from collections import deque
+
+N_PRODUCERS = 8
+N_EPILOGUE = 4
+TAPS = 9
+
+
+class Bar:
+    def __init__(self, count: int = 1):
+        self.bit, self.count, self.pending = 0, count, 0
+
+    def done(self, parity: int) -> bool:       # mbarrier.try_wait.parity
+        return self.bit != parity
+
+    def arrive(self):
+        self.pending += 1
+        if self.pending == self.count:
+            self.pending, self.bit = 0, self.bit ^ 1
+
+
+def make_bars(ring: int):
+    return {"full_a": [Bar() for _ in range(ring)], "empty_a": [Bar() for _ in range(ring)],
+            "full_blk": [Bar(N_PRODUCERS) for _ in range(2)], "empty_blk": [Bar() for _ in range(2)],
+            "acc_full": [Bar() for _ in range(2)], "acc_empty": [Bar(N_EPILOGUE) for _ in range(2)]}
+
+
+def pixel_producer(w, n_tiles, ncc, bars, st):
+    n_blocks = n_tiles * ncc
+    for bi in range(n_blocks + 1):
+        if bi >= 1:
+            yield ("landed", ("blk", w, bi - 1))                       # cp.async.wait_group 0
+            bars["full_blk"][(bi - 1) & 1].arrive()
+            yield ("step",)
+        if bi < n_blocks:
+            buf = bi & 1
+            if bi >= 2:
+                yield ("wait", bars["empty_blk"][buf], ((bi >> 1) - 1) & 1)
+            if st["blk_reading"][buf]:
+                st["hazard"] = f"pixel block {buf} refilled (block {bi}) while MMAs still read it"
+            st["inflight"].append(("blk", w, bi))                      # cp.async issued
+            yield ("step",)
+
+
+def weight_producer(n_tiles, ncc, ring, bars, st):
+    for g in range(n_tiles * ncc * TAPS):
+        slot = g % ring
+        if g >= ring:
+            yield ("wait", bars["empty_a"][slot], ((g // ring) - 1) & 1)
+        if st["a_reading"][slot]:
+            st["hazard"] = f"weight slot {slot} refilled (stage {g}) while MMAs still read it"
+        st["inflight"].append(("a", slot, g))                          # expect_tx + bulk copy
+        yield ("step",)
+
+
+def issuer(n_tiles, ncc, ring, bars, st):
+    g = bi = 0
+    for t in range(n_tiles):
+        buf = t & 1
+        if t >= 2:
+            yield ("wait", bars["acc_empty"][buf], ((t >> 1) - 1) & 1)
+        for cc in range(ncc):
+            yield ("wait", bars["full_blk"][bi & 1], (bi >> 1) & 1)
+            if st["blk_data"][bi & 1] != bi:
+                st["hazard"] = f"MMAs of block {bi} issued on pixel data of block {st['blk_data'][bi & 1]}"
+            for tap in range(TAPS):
+                slot = g % ring
+                yield ("wait", bars["full_a"][slot], (g // ring) & 1)
+                if st["a_data"][slot] != g:
+                    st["hazard"] = f"MMAs of stage {g} issued on weights of stage {st['a_data'][slot]}"
+                commits = [("empty_a", slot)]
+                if tap == TAPS - 1:
+                    commits.append(("empty_blk", bi & 1))
+                    if cc == ncc - 1:
+                        commits.append(("acc_full", buf))
+                st["a_reading"][slot] += 1
+                st["blk_reading"][bi & 1] += 1
+                st["pipe"].append({"slot": slot, "blk": bi & 1, "commits": commits, "tile": t, "buf": buf,
+                                   "first": cc == 0 and tap == 0})
+                g += 1
+                yield ("step",)
+            bi += 1
+
+
+def epilogue(q, n_tiles, bars, st):
+    for t in range(n_tiles):
+        buf = t & 1
+        yield ("wait", bars["acc_full"][buf], (t >> 1) & 1)
+        if st["acc_tile"][buf] != t:
+            st["hazard"] = f"epilogue warp {q} read accumulator {buf} for tile {t} but it holds {st['acc_tile'][buf]}"
+        yield ("step",)                                                # tcgen05.ld + stores
+        st["acc_unread"][buf] -= 1
+        bars["acc_empty"][buf].arrive()
+        yield ("step",)
+
+
+def run(n_tiles: int, ncc: int, seed: int, ring: int = 4, bars=None, max_steps: int = 400_000, slow=(), slow_factor: int = 40) -> str:
+    """slow: agent kinds ('epilogue', 'producer', 'weights', 'issuer', 'copy', 'retire') scheduled `slow_factor` times less often."""
+    rng = random.Random(seed)
+    bars = bars or make_bars(ring)
+    st = {"inflight": [], "pipe": deque(), "hazard": None, "a_reading": [0] * ring, "blk_reading": [0, 0],
+          "a_data": [None] * ring, "blk_data": [None, None], "blk_landed": {}, "acc_tile": [None, None], "acc_unread": [0, 0],
+          "landed": set()}
+    agents = [pixel_producer(w, n_tiles, ncc, bars, st) for w in range(N_PRODUCERS)]
+    agents += [weight_producer(n_tiles, ncc, ring, bars, st), issuer(n_tiles, ncc, ring, bars, st)]
+    agents += [epilogue(q, n_tiles, bars, st) for q in range(N_EPILOGUE)]
+    kinds = ["producer"] * N_PRODUCERS + ["weights", "issuer"] + ["epilogue"] * N_EPILOGUE
+    pending = [None] * len(agents)
+    alive = set(range(len(agents)))
+    for _ in range(max_steps):
+        if st["hazard"]:
+            return "hazard: " + st["hazard"]
+        if not alive and not st["inflight"] and not st["pipe"]:
+            return "ok"
+        moves = []
+        for i in alive:
+            p = pending[i]
+            if p is None or p[0] == "step" or (p[0] == "wait" and p[1].done(p[2])) or (p[0] == "landed" and p[1] in st["landed"]):
+                moves.append(("agent", i))
+        if st["inflight"]:
+            moves.append(("copy", None))
+        if st["pipe"]:
+            moves.append(("retire", None))
+        if not moves:
+            stuck = {i: pending[i] and (pending[i][0], pending[i][2] if pending[i][0] == "wait" else pending[i][1]) for i in alive}
+            return f"deadlock: {stuck}"
+        weights = [1 if (kinds[i] if k == "agent" else k) in slow else slow_factor for k, i in moves]
+        kind, i = rng.choices(moves, weights=weights)[0]
+        if kind == "agent":
+            try:
+                pending[i] = next(agents[i])
+            except StopIteration:
+                alive.discard(i)
+        elif kind == "copy":                                           # one copy lands (any order)
+            c = st["inflight"].pop(rng.randrange(len(st["inflight"])))
+            if c[0] == "a":
+                _, slot, g = c
+                st["a_data"][slot] = g
+                bars["full_a"][slot].arrive()
+            else:
+                _, w, bi = c
+                st["landed"].add(c)
+                got = st["blk_landed"].setdefault(bi, 0) + 1
+                st["blk_landed"][bi] = got
+                if got == N_PRODUCERS:
+                    st["blk_data"][bi & 1] = bi
+        else:                                                          # the pipe retires the oldest MMA group
+            m = st["pipe"].popleft()
+            if m["first"]:                                             # accumulate = 0: the half is overwritten from here on
+                if st["acc_unread"][m["buf"]]:
+                    st["hazard"] = f"accumulator {m['buf']} overwritten by tile {m['tile']} before every epilogue warp read it"
+                st["acc_tile"][m["buf"]] = None
+            st["a_reading"][m["slot"]] -= 1
+            st["blk_reading"][m["blk"]] -= 1
+            for name, idx in m["commits"]:
+                if name == "acc_full":
+                    st["acc_tile"][m["buf"]] = m["tile"]
+                    st["acc_unread"][m["buf"]] = N_EPILOGUE
+                bars[name][idx].arrive()
+    return "timeout"

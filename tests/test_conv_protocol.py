@@ -1,0 +1,37 @@
+"""The mbarrier protocol of the 3x3 tcgen05 convolution kernel, replayed on the CPU (tests/conv_protocol_model.py): no
+schedule of the pixel producers, the weight warp, the MMA issuer, the epilogue warps, the copies and the tensor pipe may
+deadlock, refill a slot that MMAs still read, issue on data that has not landed, or hand an accumulator half over early."""
+import pytest
+
+from tests import conv_protocol_model as model
+
+
+@pytest.mark.parametrize("n_tiles,ncc", [(1, 1), (1, 4), (2, 2), (3, 2), (5, 1), (4, 12)])
+def test_conv_protocol_has_no_deadlock_or_hazard(n_tiles, ncc):
+    for seed in range(8):
+        assert model.run(n_tiles, ncc, seed) == "ok", f"seed {seed}"
+    # adversarial schedules: one kind of agent (or the copies, or the tensor pipe) forty times slower than the rest
+    for seed, slow in enumerate(("epilogue", "producer", "weights", "issuer", "copy", "retire")):
+        assert model.run(n_tiles, ncc, 100 + seed, slow=(slow,)) == "ok", f"slow {slow}"
+
+
+def test_model_catches_a_missing_accumulator_handshake():
+    """Without the acc_empty wait the third tile's first MMA overwrites a half the epilogue has not read."""
+    outcomes = set()
+    for seed in range(20):
+        bars = model.make_bars(4)
+        for b in bars["acc_empty"]:
+            b.done = lambda parity: True
+        outcomes.add(model.run(4, 1, seed, bars=bars, slow=("epilogue",)))
+    assert any(o.startswith("hazard: accumulator") or o.startswith("hazard: epilogue") for o in outcomes), outcomes
+
+
+def test_model_catches_a_ring_refilled_too_early():
+    """If the weight warp did not wait for `empty_a`, a stage would be overwritten under the MMAs that read it."""
+    outcomes = set()
+    for seed in range(20):
+        bars = model.make_bars(4)
+        for b in bars["empty_a"]:
+            b.done = lambda parity: True
+        outcomes.add(model.run(2, 2, seed, bars=bars, slow=("retire",)))
+    assert any(o.startswith("hazard") or o.startswith("deadlock") for o in outcomes), outcomes
