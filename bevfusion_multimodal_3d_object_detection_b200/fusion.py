@@ -7,8 +7,10 @@ same forward signature and exceptions.  The hot-path piece — src/fusion.py:229
     mean over the 6 cameras  ->  [camera_proj convs, cuDNN]  ->  bilinear resize to (bev_h, bev_w)
 
 and in eval mode on CUDA the first and the last step are `b200bev_camera_mean` and
-`b200bev_bilinear_resize`.  The convolutions between and after them are the reference's own glue
- and stay torch/cuDNN.  `project_cameras()` is the geometric form north_star
+`b200bev_bilinear_resize`; the dense layers (`lidar_init`, `radar_proj`) run on `b200bev_lidar_init` /
+`b200bev_dense_layer`.  The convolution blocks between them are the reference's own fp32 cuDNN layers by
+default (parity 1e-5) and the tcgen05 convolution kernel when `b200_precision = "bf16"` (parity 1e-2; `conv_blocks.py`,
+`_fused_bf16_path` below).  `project_cameras()` is the geometric form north_star
 describes: calibrated projection of the BEV cell centres and a one-pass gather of all cameras.
 """
 from __future__ import annotations
