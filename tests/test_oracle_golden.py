@@ -311,3 +311,27 @@ def test_metrics_consumer_restatement_matches_the_reference(golden):
     assert abs(m["mAP"] - float(g["mAP"])) < 1e-12 and abs(m["NDS"] - float(g["NDS"])) < 1e-6
     np.testing.assert_allclose([m["AP_per_class"][c] for c in orc.CLASS_NAMES], g["AP_per_class"], rtol=0, atol=1e-12)
     assert 0.0 < m["mAP"] < 1.0 and m["AP_per_class"]["car"] > 0.1
+
+
+@pytest.mark.parametrize("B,C,O,H,W,k", [(2, 5, 7, 6, 9, 3), (1, 8, 3, 1, 1, 3), (3, 4, 4, 5, 2, 1)])
+def test_conv_and_dense_restatements_against_aten(B, C, O, H, W, k):
+    """The numpy conv block and dense layer against the ATen ops the reference calls (conv2d, batch_norm in eval mode,
+    relu, linear), on shapes with edges everywhere."""
+    g = np.random.default_rng(B * 100 + C)
+    x = g.standard_normal((B, C, H, W)).astype(np.float32)
+    w = g.standard_normal((O, C, k, k)).astype(np.float32)
+    b = g.standard_normal(O).astype(np.float32)
+    bn = {"weight": g.uniform(0.5, 1.5, O).astype(np.float32), "bias": g.standard_normal(O).astype(np.float32),
+          "running_mean": g.standard_normal(O).astype(np.float32), "running_var": g.uniform(0.5, 2.0, O).astype(np.float32)}
+    t = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), padding=k // 2)
+    t = torch.nn.functional.batch_norm(t, torch.from_numpy(bn["running_mean"]), torch.from_numpy(bn["running_var"]),
+                                       torch.from_numpy(bn["weight"]), torch.from_numpy(bn["bias"]), training=False, eps=1e-5)
+    assert max_rel(orc.conv_bn_relu(x, w, b, bn, relu=True), torch.relu(t).numpy()) < 1e-5
+    assert max_rel(orc.conv_bn_relu(x, w, b, None, relu=False),
+                   torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), padding=k // 2).numpy()) < 1e-5
+    xf = x.reshape(B, -1)
+    wl = g.standard_normal((11, xf.shape[1])).astype(np.float32)
+    bl = g.standard_normal(11).astype(np.float32)
+    lin = torch.nn.functional.linear(torch.from_numpy(xf), torch.from_numpy(wl), torch.from_numpy(bl))
+    assert max_rel(orc.dense_layer(xf, wl, bl, relu=True), torch.relu(lin).numpy()) < 1e-5
+    assert max_rel(orc.sigmoid(xf), torch.sigmoid(torch.from_numpy(xf)).numpy()) < 1e-6
