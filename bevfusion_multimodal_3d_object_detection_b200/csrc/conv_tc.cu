@@ -640,29 +640,55 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __r
 // first convolution: (B, n_cam, C, HW) fp32 -> channels [c_offset, c_offset + C) of (B, HW, C_total) bf16.  Same thread
 // shape as the layout kernel (four pixels x eight channels, 128-bit loads along the plane), same arithmetic as
 // camera_mean_vec4_kernel (sum in camera order, IEEE divide), so the result is the bf16 rounding of that kernel's output.
+template <int NCAM>   // cameras known at compile time (6: the nuScenes rig): all loads of two channels in flight; 0: any number
 __global__ void __launch_bounds__(256) camera_mean_nhwc_bf16_kernel(const float* __restrict__ in, int B, int n_cam, int C, int HW,
                                                                     __nv_bfloat16* __restrict__ out, int C_total, int c_offset) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 128);
   const long long n_items = (long long)B * n_cg * n_pg;
   const float denom = (float)n_cam;
+  const size_t cam_stride = (size_t)C * HW;
   for (long long t = blockIdx.x; t < n_items; t += gridDim.x) {
     const int pg = (int)(t % n_pg), cg = (int)((t / n_pg) % n_cg), b = (int)(t / ((long long)n_pg * n_cg));
     const int p = (pg * 32 + lane) * 4, c0 = cg * 64 + warp * 8;
     if (p >= HW || c0 >= C) continue;
     float v[8][4];
+    const float* base = in + (((size_t)b * n_cam) * C + c0) * HW + p;
+    if (NCAM > 0 && c0 + 8 <= C) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + e < C) {
-        const float* src = in + (((size_t)b * n_cam) * C + c0 + e) * HW + p;
-        s4 = ld_stream_f4(reinterpret_cast<const float4*>(src));
-        for (int cam = 1; cam < n_cam; ++cam) {
-          const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)cam * C * HW));
-          s4.x = __fadd_rn(s4.x, q.x); s4.y = __fadd_rn(s4.y, q.y); s4.z = __fadd_rn(s4.z, q.z); s4.w = __fadd_rn(s4.w, q.w);
+      for (int e = 0; e < 8; e += 2) {
+        float4 q[2][NCAM > 0 ? NCAM : 1];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int cam = 0; cam < NCAM; ++cam)
+            q[h][cam] = ld_stream_f4(reinterpret_cast<const float4*>(base + (size_t)(e + h) * HW + cam * cam_stride));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 s4 = q[h][0];
+#pragma unroll
+          for (int cam = 1; cam < NCAM; ++cam) {
+            s4.x = __fadd_rn(s4.x, q[h][cam].x); s4.y = __fadd_rn(s4.y, q[h][cam].y);
+            s4.z = __fadd_rn(s4.z, q[h][cam].z); s4.w = __fadd_rn(s4.w, q[h][cam].w);
+          }
+          v[e + h][0] = __fdiv_rn(s4.x, denom); v[e + h][1] = __fdiv_rn(s4.y, denom);
+          v[e + h][2] = __fdiv_rn(s4.z, denom); v[e + h][3] = __fdiv_rn(s4.w, denom);
         }
       }
-      v[e][0] = __fdiv_rn(s4.x, denom); v[e][1] = __fdiv_rn(s4.y, denom); v[e][2] = __fdiv_rn(s4.z, denom); v[e][3] = __fdiv_rn(s4.w, denom);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + e < C) {
+          const float* src = base + (size_t)e * HW;
+          s4 = ld_stream_f4(reinterpret_cast<const float4*>(src));
+          for (int cam = 1; cam < n_cam; ++cam) {
+            const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(src + cam * cam_stride));
+            s4.x = __fadd_rn(s4.x, q.x); s4.y = __fadd_rn(s4.y, q.y); s4.z = __fadd_rn(s4.z, q.z); s4.w = __fadd_rn(s4.w, q.w);
+          }
+        }
+        v[e][0] = __fdiv_rn(s4.x, denom); v[e][1] = __fdiv_rn(s4.y, denom); v[e][2] = __fdiv_rn(s4.z, denom); v[e][3] = __fdiv_rn(s4.w, denom);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -710,8 +736,12 @@ extern "C" B200BEV_API int b200bev_camera_mean_nhwc_bf16(const float* feats, int
   if (((H * W) & 3) || ((uintptr_t)feats & 15) || (C_total & 7) || (c_offset & 7) || ((uintptr_t)out_nhwc & 15)) return B200BEV_ERR_UNSUPPORTED;
   const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, 128);
   long long blocks = tiles < (long long)sm_count() * 16 ? tiles : (long long)sm_count() * 16;
-  camera_mean_nhwc_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(feats, B, n_cam, C, H * W, (__nv_bfloat16*)out_nhwc, C_total,
-                                                                           c_offset);
+  if (n_cam == 6)
+    camera_mean_nhwc_bf16_kernel<6><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(feats, B, n_cam, C, H * W, (__nv_bfloat16*)out_nhwc,
+                                                                                C_total, c_offset);
+  else
+    camera_mean_nhwc_bf16_kernel<0><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(feats, B, n_cam, C, H * W, (__nv_bfloat16*)out_nhwc,
+                                                                                C_total, c_offset);
   return launch_status();
 }
 

@@ -18,4 +18,17 @@ for _ in range(2):
     flush.zero_()
     b = ops.nchw_to_nhwc_bf16([x])
 torch.cuda.synchronize()
+for name, fn in (("camera_mean_nhwc_bf16", lambda: ops.camera_mean_nhwc_bf16(feats)), ("camera_mean", lambda: ops.camera_mean(feats)),
+                 ("nchw_to_nhwc_bf16 768x50x50", lambda: ops.nchw_to_nhwc_bf16([x]))):
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        flush.view(torch.int64).sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print(f"{name:32s} median {sorted(ts)[2] * 1e3:8.1f} us")
 print(float(a.float().abs().max()), float(b.float().abs().max()))

@@ -644,8 +644,8 @@ def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
 
 def test_camera_mean_channels_last_bf16_is_the_rounded_mean(cuda):
     """The fused mean + layout kernel gives exactly bf16(camera_mean): same summation order, IEEE divide."""
-    for B, C, h, w in ((2, 64, 8, 14), (1, 72, 6, 10), (3, 512, 8, 8)):
-        feats = dev_t(syn.camera_features(77 + C, B, n_cam=6, channels=C, h=h, w=w), cuda)
+    for B, C, h, w, n_cam in ((2, 64, 8, 14, 6), (1, 72, 6, 10, 6), (3, 512, 8, 8, 6), (2, 64, 4, 6, 3)):
+        feats = dev_t(syn.camera_features(77 + C, B, n_cam=n_cam, channels=C, h=h, w=w), cuda)
         got = ops.camera_mean_nhwc_bf16(feats)
         want = ops.camera_mean(feats).permute(0, 2, 3, 1).to(torch.bfloat16)
         assert tuple(got.shape) == (B, h, w, C) and torch.equal(got, want)
