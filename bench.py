@@ -497,7 +497,7 @@ def run_b200_arm(args):
                 def chain_device():
                     with torch.no_grad():
                         pred = head(fus(camera_features=feats, lidar_features=enc_l(lidar), radar_features=enc_r(radars)))
-                        return ops.centernet_decode(pred["heatmap_logits"], pred["offset"], pred["size"], pred["rot"], pred["vel"],
+                        return ops.centernet_decode(conv_blocks.logits_of(pred["heatmap"]), pred["offset"], pred["size"], pred["rot"], pred["vel"],
                                                     TOPK, 2.048, score_thresh=0.0, heat_is_logit=True)
                 graphed = runtime.GraphedStep(chain_device, dev)
                 g_out = graphed.outputs

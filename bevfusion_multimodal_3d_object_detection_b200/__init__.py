@@ -11,10 +11,12 @@ from .centernet_decode import (_nms, _topk, decode_centernet_predictions,  # noq
                                decode_centernet_predictions_fusion_detection)
 from .encoders import MultiRadarEncoder, PointNetLiDAREncoder, RadarEncoder, load_config  # noqa: F401
 from .fusion import CenterNetHead, FlexibleBEVFusion  # noqa: F401
+from .detector import BEVDetectorChain  # noqa: F401
+from .weight_cache import invalidate_cache  # noqa: F401
 from .patch import patch, unpatch  # noqa: F401
 
 __all__ = [
     "PointNetLiDAREncoder", "RadarEncoder", "MultiRadarEncoder", "FlexibleBEVFusion", "CenterNetHead",
     "decode_centernet_predictions", "decode_centernet_predictions_fusion_detection", "_nms", "_topk",
-    "load_config", "patch", "unpatch",
+    "load_config", "patch", "unpatch", "BEVDetectorChain", "invalidate_cache",
 ]

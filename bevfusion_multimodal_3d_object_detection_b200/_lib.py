@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "_native" / "libb200bev.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK = 0
 ERR_INVALID_ARGUMENT = 1
 ERR_UNSUPPORTED = 2
@@ -24,6 +24,7 @@ ERR_CUDA = 1000
 F32 = 0
 BF16_TENSOR = 1
 RADAR_FUSION = {"concat": 0, "max": 1, "mean": 2}
+PROJECT_IMPL = {"auto": 0, "staged": 1, "gather": 2}
 
 _p = C.c_void_p
 _i = C.c_int
@@ -45,7 +46,7 @@ PROTOTYPES = {
                                   _i, _p, _p, _p, _p, _p]),
     "b200bev_camera_mean": (_i, [_p, _i, _i, C.c_int64, _p, _p]),
     "b200bev_bilinear_resize": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
-    "b200bev_camera_project": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _p, _p, _p]),
+    "b200bev_camera_project": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _p, _p, _i, _p]),
     "b200bev_centernet_nms": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "b200bev_centernet_workspace_bytes": (_z, [_i, _i, _i]),
     "b200bev_centernet_topk": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),

@@ -43,8 +43,9 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
-def _fingerprint() -> str:
+def _fingerprint(extra: str = "") -> str:
     h = hashlib.sha256()
+    h.update(extra.encode())
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200bev.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
@@ -54,13 +55,15 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def is_current() -> bool:
-    return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _fingerprint()
+def is_current(debug_env: bool = False) -> bool:
+    return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _fingerprint("debug-env" if debug_env else "")
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every csrc/*.cu for sm_100a and link libb200bev.so. Returns the library path."""
-    if not force and is_current():
+def build(force: bool = False, verbose: bool = False, debug_env: bool = False) -> Path:
+    """Compile every csrc/*.cu for sm_100a and link libb200bev.so. Returns the library path.
+    debug_env: -DB200BEV_DEBUG_ENV, the build in which the experiment / trace environment switches exist
+    (csrc/common.cuh: debug_env); tools/tc_timeline.py and tests/trace_tc.py need it.  The release build has none."""
+    if not force and is_current(debug_env):
         return LIB
     OUT_DIR.mkdir(exist_ok=True)
     nvcc = _nvcc()
@@ -68,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in sources():
         obj = OUT_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DB200BEV_DEBUG_ENV"] if debug_env else []), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -89,7 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print(" ".join(link), flush=True)
     subprocess.run(link, check=True)
-    STAMP.write_text(_fingerprint() + "\n")
+    STAMP.write_text(_fingerprint("debug-env" if debug_env else "") + "\n")
     return LIB
 
 
@@ -97,8 +100,9 @@ def main() -> None:
     ap = argparse.ArgumentParser(description=__doc__)
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--debug-env", action="store_true", help="build with the experiment / trace environment switches")
     args = ap.parse_args()
-    print(build(force=args.force, verbose=args.verbose))
+    print(build(force=args.force, verbose=args.verbose, debug_env=args.debug_env))
 
 
 if __name__ == "__main__":

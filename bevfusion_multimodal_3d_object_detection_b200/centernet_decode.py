@@ -13,7 +13,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from . import ops
+from . import conv_blocks, ops
 
 CENTERNET_TARGET_VOXEL = 2.048    # src/centernet_target.py:389
 FUSION_DETECTION_VOXEL = 0.512    # src/fusion_detection.py:757
@@ -38,8 +38,10 @@ def decode_centernet_predictions(predictions: Dict[str, torch.Tensor], score_thr
                                  voxel_size: float = CENTERNET_TARGET_VOXEL) -> List[Dict[str, torch.Tensor]]:
     """List (one dict per sample) of boxes (n,7) [x,y,z,w,l,h,yaw], scores (n,), labels (n,) int64,
     velocities (n,2); n <= max_detections is the number of winners with score > score_thresh."""
-    # the mirror head also hands over its raw heat-map output: the sigmoid then runs inside the decode launch
-    logits = predictions.get("heatmap_logits")
+    # The bf16 head notes its raw output on the heat-map tensor it returns: if `predictions['heatmap']` still IS that
+    # tensor, untouched, the sigmoid runs inside the decode launch (bit-identical to torch.sigmoid + decode on the
+    # device).  Any other tensor under 'heatmap' is decoded as it is, as the reference does (src/centernet_target.py:345).
+    logits = conv_blocks.logits_of(predictions["heatmap"])
     out = ops.centernet_decode(predictions["heatmap"] if logits is None else logits, predictions["offset"], predictions["size"],
                                predictions["rot"], predictions["vel"], max_detections, voxel_size,
                                PC_ORIGIN, GROUND_Z, score_thresh, heat_is_logit=logits is not None)

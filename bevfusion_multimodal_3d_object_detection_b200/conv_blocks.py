@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import ops
 from .encoders import _state_key, default_precision
+from .weight_cache import mark_dirty, wants_autograd
 
 HEADS = ("heatmap", "offset", "size", "rot", "vel")       # CenterNetHead's sub-modules, src/fusion.py:822-854
 
@@ -145,9 +146,12 @@ def _head_plan(head: nn.Module, device: torch.device) -> Dict:
 
 def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
     """CenterNetHead.forward (src/fusion.py:869-884).  Eval mode with the bf16 path enabled: two tcgen05 launches for the
-    ten convolutions; the dict also carries `heatmap_logits`, which `decode_centernet_predictions` feeds to the decode
-    kernel so that the sigmoid is not a separate pass there."""
-    if head.training or not x.is_cuda or not wants_bf16(head) or not head_supported(head) or x.shape[1] % 64 != 0:
+    ten convolutions; the returned heat map remembers the raw output it is the sigmoid of (`attach_logits`), which
+    `decode_centernet_predictions` feeds to the decode kernel so that the sigmoid is not a separate pass there."""
+    if head.training:
+        mark_dirty(head)
+    if head.training or not x.is_cuda or not wants_bf16(head) or not head_supported(head) or x.shape[1] % 64 != 0 \
+            or wants_autograd(head, x):
         pred = {n: getattr(head, f"{n}_head")(x) for n in HEADS}
         pred["heatmap"] = torch.sigmoid(pred["heatmap"])
         return pred
@@ -160,6 +164,34 @@ def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
     for n, k in zip(HEADS, p["outs"]):
         pred[n] = both[:, c:c + k].contiguous()
         c += k
-    pred["heatmap_logits"] = pred["heatmap"]
-    pred["heatmap"] = torch.sigmoid(pred["heatmap_logits"])
+    logits = pred["heatmap"]
+    pred["heatmap"] = attach_logits(torch.sigmoid(logits), logits)
     return pred
+
+
+_LOGITS_ATTR = "_b200bev_logits"
+
+
+def attach_logits(heatmap: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+    """Remembers, ON the heat-map tensor the head returns, the raw output it is the sigmoid of.  The dict keeps exactly
+    the reference's five keys (src/fusion.py:877-883); a caller that replaces or edits `predictions['heatmap']`
+    (flip-TTA averaging, masking, temperature scaling) hands the decode a tensor without the note, or with a newer
+    version counter, and the decode then uses that tensor as it is — as the reference would."""
+    try:
+        setattr(heatmap, _LOGITS_ATTR, (logits, heatmap._version))
+    except RuntimeError:       # inference tensors carry no version counter: no shortcut for them
+        pass
+    return heatmap
+
+
+def logits_of(heatmap: torch.Tensor) -> Optional[torch.Tensor]:
+    """The head's raw heat-map output if `heatmap` is still, bit for bit, the sigmoid the head computed from it; else None."""
+    note = getattr(heatmap, _LOGITS_ATTR, None)
+    if note is None:
+        return None
+    logits, version = note
+    try:
+        same = heatmap._version == version
+    except RuntimeError:
+        same = False
+    return logits if same and logits.shape == heatmap.shape and logits.device == heatmap.device else None

@@ -440,7 +440,7 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
   cfg.numAttrs = 1;
 
   // ranked form: the widest per-warp histogram that fits shared memory (and 16-bit counts)
-  const char* force = getenv("B200BEV_BINSORT");
+  const char* force = debug_env("B200BEV_BINSORT");
   const bool legacy = force && force[0] == 'l';
   if (!legacy) {
     const size_t kLimit = 220 * 1024;
@@ -458,7 +458,7 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
       if (a.cache_cells) smem += cache;
       else if ((long long)W * H >= 0xffff) break;   // cell ids would not fit the packed form: legacy kernel
       RankedArgs ra{a, NW, sub, nullptr};
-      if (getenv("B200BEV_BINSORT_TRACE")) B200BEV_CUDA_TRY(cudaMalloc(&ra.dbg, 16 * sizeof(unsigned long long)));
+      if (debug_env("B200BEV_BINSORT_TRACE")) B200BEV_CUDA_TRY(cudaMalloc(&ra.dbg, 16 * sizeof(unsigned long long)));
       if (smem > 48 * 1024)
         B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cfg.dynamicSmemBytes = smem;

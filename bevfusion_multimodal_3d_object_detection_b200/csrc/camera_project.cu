@@ -471,9 +471,6 @@ __global__ void __launch_bounds__(kStagedThreads, 1) camera_project_staged_kerne
   }
 }
 
-// "gather" | "staged" | nullptr: B200BEV_PROJECT_IMPL forces one implementation (tests, experiments)
-const char* forced_impl() { return getenv("B200BEV_PROJECT_IMPL"); }
-
 }  // namespace
 }  // namespace b200bev
 
@@ -482,10 +479,11 @@ using namespace b200bev;
 extern "C" B200BEV_API int b200bev_camera_project(const float* feats, int B, int n_cam, int C, int h, int w, const float* intrinsics,
                                       const float* ego2cam, int T, float img_w, float img_h, float x_min, float y_min,
                                       float voxel_x, float voxel_y, float z_plane, int W, int H, float* out,
-                                      float* uv_valid, void* stream) {
+                                      float* uv_valid, int impl, void* stream) {
   if (!feats || !intrinsics || !ego2cam || !out || B <= 0 || n_cam <= 0 || C <= 0 || h <= 0 || w <= 0 || W <= 0 || H <= 0)
     return B200BEV_ERR_INVALID_ARGUMENT;
   if (T != 1 && T != B) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (impl < B200BEV_PROJECT_AUTO || impl > B200BEV_PROJECT_GATHER) return B200BEV_ERR_INVALID_ARGUMENT;
   if (!(img_w > 0.0f) || !(img_h > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
   if (n_cam > kMaxCams || B > 65535) return B200BEV_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
@@ -515,7 +513,7 @@ extern "C" B200BEV_API int b200bev_camera_project(const float* feats, int B, int
     tab_cap = (int)((want + 15) / 16 * 16);
     ring_bytes = kMaxSmemOptin - kCtrlBytes - tab_cap * kEntryBytes;
     int cg_max = 4;
-    if (const char* e = getenv("B200BEV_PROJECT_CG")) {   // experiments: 1, 2 or 4
+    if (const char* e = debug_env("B200BEV_PROJECT_CG")) {   // experiments: 1, 2 or 4
       const int v = atoi(e);
       if (v == 1 || v == 2 || v == 4) cg_max = v;
     }
@@ -524,10 +522,8 @@ extern "C" B200BEV_API int b200bev_camera_project(const float* feats, int B, int
       if ((long long)cg * plane * (long long)sizeof(float) <= ring_bytes && scratch <= ring_bytes) { CG = cg; break; }
     if (CG == 0) staged = false;
   }
-  if (const char* f = forced_impl()) {
-    if (f[0] == 'g') staged = false;
-    else if (f[0] == 's' && !staged) return B200BEV_ERR_UNSUPPORTED;
-  }
+  if (impl == B200BEV_PROJECT_GATHER) staged = false;
+  else if (impl == B200BEV_PROJECT_STAGED && !staged) return B200BEV_ERR_UNSUPPORTED;
   if (staged) {
     const long long items = (long long)n_parts * B * ceil_div(C, CG);
     const int grid = (int)std::min<long long>(items, sm_count());

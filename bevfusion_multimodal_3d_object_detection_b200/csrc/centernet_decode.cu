@@ -400,7 +400,7 @@ int launch_topk(const DecodeArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024) B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B200BEV_CUDA_TRY(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)a.B, st));
   DecodeArgs aa = a;
-  if (getenv("B200BEV_DECODE_TRACE")) {
+  if (debug_env("B200BEV_DECODE_TRACE")) {
     B200BEV_CUDA_TRY(cudaMalloc(&aa.dbg, 32 * sizeof(unsigned long long)));
     B200BEV_CUDA_TRY(cudaMemsetAsync(aa.dbg, 0, 32 * sizeof(unsigned long long), st));
   }

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "b200bev.h"
 
 #ifndef __CUDA_ARCH_LIST__
@@ -24,6 +26,16 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? B200BEV_OK : B
   } while (0)
 
 inline int launch_status() { return cuda_status(cudaGetLastError()); }
+
+// Experiment and trace switches (B200BEV_TC_TRACE, B200BEV_DECODE_TRACE, B200BEV_CONV_IMPL, ...) exist only in a library
+// built with -DB200BEV_DEBUG_ENV (`python -m bevfusion_multimodal_3d_object_detection_b200.build --debug-env`).  In the
+// release library this is a constant null: no getenv on a launch path, and the trace branches — which allocate and
+// synchronise, i.e. cannot run under CUDA-graph capture — are compiled out.
+#ifdef B200BEV_DEBUG_ENV
+inline const char* debug_env(const char* name) { return getenv(name); }
+#else
+inline const char* debug_env(const char*) { return nullptr; }
+#endif
 
 // SM count of the current device, cached per thread (re-entrant: no shared mutable global).
 inline int sm_count() {

@@ -771,7 +771,7 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
              (__nv_bfloat16*)out_nhwc, out_ct, out_coff};
   const long long tiles = (((long long)B * H * W + kTilePx - 1) / kTilePx) * ceil_div(Cout, kTileCo);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  const char* impl = getenv("B200BEV_CONV_IMPL");
+  const char* impl = debug_env("B200BEV_CONV_IMPL");
   HaloGeom geo;
   const bool want_halo = !(impl && impl[0] == 'p');   // "per-tap": the per-tap kernel for 3x3 too (A/B timing)
   if (taps == 9 && want_halo && halo_geometry(H, W, &geo)) {

@@ -377,7 +377,7 @@ int dense_layer(const float* x, int B, int K, const float* w, const float* bias,
   // row-streaming form (16 warps per SM, batch tile in registers): batch <= 8, K = 128 .. 512.  (A 16-row tile runs too —
   // linear_rowstream_kernel<16, 4, 4> — but its shuffles and FMAs take 74 us on the 164 MB layer where the kernel below
   // takes 65.)
-  if (aligned && O >= 256 && B <= 8 && !getenv("B200BEV_DENSE_OLD")) {
+  if (aligned && O >= 256 && B <= 8 && !debug_env("B200BEV_DENSE_OLD")) {
     if (K == 512) return launch_rowstream<8, 8, 2>(a, st);
     if (K == 256) return launch_rowstream<8, 8, 1>(a, st);
     if (K == 128) return launch_rowstream<8, 4, 1>(a, st);

@@ -964,7 +964,7 @@ bool tc_dims_supported(const int32_t* dims, int n_layers) {
 // stream drives both SMs, each CTA keeps half of every weight stage, so the shared-memory traffic of the B operand
 // and of the weight stream, and the MMA instructions issued per tile, are halved.  B200BEV_TC_CLUSTER=1|2 overrides.
 int tc_cluster_size() {
-  const char* e = getenv("B200BEV_TC_CLUSTER");
+  const char* e = debug_env("B200BEV_TC_CLUSTER");
   if (e) {
     const int v = atoi(e);
     if (v == 1 || v == 2) return v;
@@ -1004,8 +1004,8 @@ int pointnet_encode_tc(const float* points, int B, int N, int C, const float* pa
   a.cluster = cluster;
   const size_t smem = tc_smem_bytes(cell, cluster);
   // debug timeline: B200BEV_TC_TRACE=<file> dumps CTA 0's clock stamps after a (synchronous) launch
-  if (const char* dbg = getenv("B200BEV_TC_DEBUG")) a.debug = atoi(dbg);
-  const char* trace_path = getenv("B200BEV_TC_TRACE");
+  if (const char* dbg = debug_env("B200BEV_TC_DEBUG")) a.debug = atoi(dbg);
+  const char* trace_path = debug_env("B200BEV_TC_TRACE");
   unsigned long long* d_trace = nullptr;
   if (trace_path) {
     B200BEV_CUDA_TRY(cudaMalloc(&d_trace, kTraceLen * sizeof(unsigned long long)));

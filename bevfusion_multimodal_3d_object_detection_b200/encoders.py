@@ -25,6 +25,7 @@ import torch.nn.functional as F
 import yaml
 
 from . import _lib, ops
+from .weight_cache import invalidate_cache, mark_dirty, state_token, wants_autograd  # noqa: F401
 
 PRECISIONS = {"f32": _lib.F32, "fp32": _lib.F32, "bf16": _lib.BF16_TENSOR}
 
@@ -55,15 +56,14 @@ def _mlp_stages(module: nn.Module) -> List[Tuple[nn.Conv1d, nn.Module]]:
 
 
 def _state_key(module: nn.Module, device: torch.device):
-    key = [str(device)]
-    for t in list(module.parameters()) + list(module.buffers()):
-        key.append((t.data_ptr(), t._version, str(t.device)))
-    return tuple(key)
+    """Cache key of a module's packed weights (weight_cache.state_token: hooks + version counters, no per-call walk)."""
+    return state_token(module, device)
 
 
 def packed_params(module: nn.Module, device: torch.device, want_bf16: bool = False):
     """(blob, dims, tc_blob|None) for a PointNet-style module; rebuilt only when a parameter or a
-    BatchNorm statistic changed (tensor version counters) — e.g. after load_state_dict."""
+    BatchNorm statistic changed (load_state_dict hook, training-mode forward, tensor version counters; see
+    weight_cache.py — `invalidate_cache(module)` after writes through `.data`)."""
     key = _state_key(module, device)
     cache = module.__dict__.get("_b200bev_cache")
     if cache is None or cache["key"] != key:
@@ -105,8 +105,12 @@ def _precision_of(module: nn.Module) -> int:
 
 def lidar_forward(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """PointNetLiDAREncoder.forward (src/encoders.py:271-306)."""
-    if module.training or getattr(module, "return_point_features", False):
-        # training graph, or the per-point output nothing in the pipelines enables (src/encoders.py:239)
+    if module.training:
+        mark_dirty(module)                                   # an optimizer step follows: rebuild at the next eval forward
+    if module.training or getattr(module, "return_point_features", False) \
+            or (x.is_cuda and wants_autograd(module, x)):
+        # training graph; the per-point output nothing in the pipelines enables (src/encoders.py:239); or an eval-mode
+        # call that autograd records (the kernels return tensors without a grad_fn)
         xb = _as_bnc(x, module.input_channels).transpose(1, 2)
         feat = _torch_mlp(module, xb)
         glob = torch.max(feat, 2)[0]
@@ -142,6 +146,8 @@ def multi_radar_forward(module: nn.Module, radar_list: Sequence[torch.Tensor]) -
         raise ValueError(f"Unknown fusion method: {module.fusion_method}")
     enc = module.radar_encoder
     if module.training:
+        mark_dirty(enc)
+    if module.training or (len(radar_list) > 0 and radar_list[0].is_cuda and wants_autograd(module, list(radar_list))):
         feats = torch.stack([torch.max(_torch_mlp(enc, _as_bnc(r, enc.input_channels).transpose(1, 2)), 2)[0]
                              for r in radar_list], dim=1)
         if module.fusion_method == "concat":
@@ -217,6 +223,8 @@ class RadarEncoder(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training:
+            mark_dirty(self)
+        if self.training or (x.is_cuda and wants_autograd(self, x)):
             return torch.max(_torch_mlp(self, _as_bnc(x, self.input_channels).transpose(1, 2)), 2)[0]
         pts = _as_bnc(x, self.input_channels)
         blob, dims, _ = packed_params(self, pts.device)

@@ -24,16 +24,27 @@ import torch.nn.functional as F
 
 from . import conv_blocks, ops
 from .encoders import load_config
+from .weight_cache import mark_dirty, wants_autograd
 
 
 def _conv_bn_relu(c_in: int, c_out: int, k: int) -> List[nn.Module]:
     return [nn.Conv2d(c_in, c_out, k, padding=k // 2), nn.BatchNorm2d(c_out), nn.ReLU(inplace=True)]
 
 
-def camera_branch(module: nn.Module, camera_features: torch.Tensor) -> torch.Tensor:
+def lidar_start_size(module: nn.Module) -> int:
+    """Side of the square map `lidar_init` produces.  The reference keeps it in a local (`start_size = 25`,
+    src/fusion.py:141), so on the reference's own class it is recovered from the layer shapes."""
+    s = getattr(module, "lidar_start_size", None)
+    if s is None:
+        hidden = module.lidar_upsample[0].in_channels
+        s = math.isqrt(module.lidar_init[2].out_features // hidden)
+    return int(s)
+
+
+def camera_branch(module: nn.Module, camera_features: torch.Tensor, torch_graph: bool = False) -> torch.Tensor:
     """src/fusion.py:233-247 with the mean and the resize on the b200bev kernels (eval, CUDA)."""
     size = (module.bev_h, module.bev_w)
-    if module.training:
+    if torch_graph:
         cam = camera_features.mean(dim=1) if camera_features.dim() == 5 else camera_features
         return F.interpolate(module.camera_proj(cam), size=size, mode="bilinear", align_corners=False)
     cam = ops.camera_mean(camera_features) if camera_features.dim() == 5 else camera_features
@@ -49,14 +60,14 @@ def _stack(module: nn.Module, seq: nn.Sequential, parts) -> torch.Tensor:
     return seq(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
 
 
-def lidar_branch(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tensor:
+def lidar_branch(module: nn.Module, lidar_features: torch.Tensor, torch_graph: bool = False) -> torch.Tensor:
     """src/fusion.py:258-262: lidar_init (two dense layers, the second a 164 MB weight) -> (B,128,s,s) ->
     conv+BN+ReLU -> x2 bilinear upsample -> conv+BN+ReLU.  Eval mode on CUDA: the dense layers run on
     `b200bev_lidar_init` and the upsample on `b200bev_bilinear_resize`; the two convolutions stay cuDNN."""
     B = lidar_features.shape[0]
-    s = module.lidar_start_size
+    s = lidar_start_size(module)
     hidden = module.lidar_init[2].out_features // (s * s)
-    if module.training:
+    if torch_graph:
         return module.lidar_upsample(module.lidar_init(lidar_features).view(B, hidden, s, s))
     l0, l2 = module.lidar_init[0], module.lidar_init[2]
     x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s, s)
@@ -90,7 +101,7 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         return None
     if use[0] and camera_features.shape[-3] % 64 != 0:
         return None
-    if use[1] and (module.lidar_init[2].out_features // module.lidar_start_size ** 2) % 64 != 0:
+    if use[1] and (module.lidar_init[2].out_features // lidar_start_size(module) ** 2) % 64 != 0:
         return None
     B, H, W = first.shape[0], module.bev_h, module.bev_w
     cat = torch.empty((B, H, W, c * sum(use)), dtype=torch.bfloat16, device=first.device)
@@ -105,7 +116,7 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         ops.nchw_to_nhwc_bf16([ops.bilinear_resize(x, (H, W))], out=cat, c_offset=off)      # src/fusion.py:242-247
         off += c
     if use[1]:
-        s0 = module.lidar_start_size
+        s0 = lidar_start_size(module)
         hidden = module.lidar_init[2].out_features // (s0 * s0)
         l0, l2 = module.lidar_init[0], module.lidar_init[2]
         x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s0, s0)
@@ -117,9 +128,22 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
     return conv_blocks.run(module.bev_fusion, nhwc=cat)                                      # :292-295
 
 
+def _torch_graph_wanted(module: nn.Module, *feats) -> bool:
+    """Training mode (BatchNorm batch statistics + autograd), or an eval-mode call on CUDA that autograd
+    records: both run the module's own torch layers on the input's device.  Eval mode on a CPU tensor still raises in
+    the kernels' front end — there is no CPU fallback."""
+    if module.training:
+        for sub in module.children():
+            mark_dirty(sub)
+        return True
+    live = [f for f in feats if f is not None]
+    return bool(live) and live[0].is_cuda and wants_autograd(module, *live)
+
+
 def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None, radar_features=None) -> torch.Tensor:
     """FlexibleBEVFusion.forward (src/fusion.py:209-297)."""
-    if not module.training and conv_blocks.wants_bf16(module):
+    torch_graph = _torch_graph_wanted(module, camera_features, lidar_features, radar_features)
+    if not torch_graph and conv_blocks.wants_bf16(module):
         out = _fused_bf16_path(module, camera_features, lidar_features, radar_features)
         if out is not None:
             return out
@@ -127,22 +151,22 @@ def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None,
     B = None
     if module.use_camera and camera_features is not None:
         B = camera_features.shape[0]
-        parts.append(camera_branch(module, camera_features))
+        parts.append(camera_branch(module, camera_features, torch_graph))
     if module.use_lidar and lidar_features is not None:
         B = lidar_features.shape[0] if B is None else B
-        parts.append(lidar_branch(module, lidar_features))
+        parts.append(lidar_branch(module, lidar_features, torch_graph))
     if module.use_radar and radar_features is not None:
         B = radar_features.shape[0] if B is None else B
-        if module.training:
+        if torch_graph:
             r = module.radar_proj(radar_features)
         else:
             r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)  # :274
         r = r.view(B, module.bev_channels, 1, 1)
         r = r.expand(B, module.bev_channels, module.bev_h, module.bev_w)
-        parts.append(module.radar_refine(r) if module.training else _stack(module, module.radar_refine, [r]))  # :274-281
+        parts.append(module.radar_refine(r) if torch_graph else _stack(module, module.radar_refine, [r]))  # :274-281
     if not parts:
         raise ValueError("No modality features provided")              # :289
-    if module.training:
+    if torch_graph:
         return module.bev_fusion(torch.cat(parts, dim=1))              # :292-295
     return _stack(module, module.bev_fusion, parts)                    # the concat happens inside the layout kernel
 
@@ -155,7 +179,7 @@ class FlexibleBEVFusion(nn.Module):
                  lidar_channels: Optional[int] = None, radar_channels: Optional[int] = None,
                  bev_h: Optional[int] = None, bev_w: Optional[int] = None, bev_channels: Optional[int] = None,
                  pc_range: Optional[List[float]] = None, config: Optional[Dict] = None,
-                 config_path: Optional[str] = None):
+                 config_path: Optional[str] = None, lidar_start_size: Optional[int] = None):
         super().__init__()
         pick = lambda explicit, fallback: fallback if explicit is None else explicit
         if config is not None or config_path is not None:
@@ -186,10 +210,10 @@ class FlexibleBEVFusion(nn.Module):
             self.camera_proj = nn.Sequential(*_conv_bn_relu(camera_channels, 512, 3), *_conv_bn_relu(512, c, 1))
         if self.use_lidar:
             # The reference hard-codes 25 (src/fusion.py:141): its lidar BEV is always 50x50 and torch.cat raises for any
-            # other grid.  Same value — and the same state_dict shapes — at 50x50; half the grid otherwise, so
-            # that the 2x-resolution configuration (BASELINE configs[4], 100x100) runs with the lidar branch.
-            square_even = self.bev_h == self.bev_w and self.bev_h % 2 == 0
-            self.lidar_start_size = self.bev_h // 2 if square_even else 25
+            # other grid.  25 is the default here too, so the state_dict shapes are the reference's for every
+            # grid.  `lidar_start_size=` is this package's explicit extension: e.g. 50 lets the
+            # 2x-resolution configuration (BASELINE configs[4], 100x100) run with the lidar branch.
+            self.lidar_start_size = 25 if lidar_start_size is None else int(lidar_start_size)
             self.lidar_init = nn.Sequential(nn.Linear(lidar_channels, 512), nn.ReLU(inplace=True),
                                             nn.Linear(512, 128 * self.lidar_start_size ** 2))
             self.lidar_upsample = nn.Sequential(

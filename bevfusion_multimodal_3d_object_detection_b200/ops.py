@@ -248,9 +248,12 @@ def bilinear_resize(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
 def camera_project(feats: torch.Tensor, intrinsics: torch.Tensor, ego2cam: torch.Tensor,
                    img_size: Tuple[float, float], bev_size: Tuple[int, int],
                    pc_range: Sequence[float] = DEFAULT_PC_RANGE, z_plane: float = 0.0,
-                   return_table: bool = False):
+                   return_table: bool = False, impl: str = "auto"):
     """Geometric camera->BEV gather. feats (B,n_cam,C,h,w); intrinsics (T,n_cam,3,3); ego2cam (T,n_cam,3,4);
-    img_size = (img_w, img_h) in pixels; bev_size = (H, W). Returns (B,C,H,W) [, table (T,H*W,n_cam,3)]."""
+    img_size = (img_w, img_h) in pixels; bev_size = (H, W). Returns (B,C,H,W) [, table (T,H*W,n_cam,3)].
+    impl: "auto", or "staged" / "gather" to name one of the two kernels (same bits; used by the parity tests)."""
+    if impl not in _lib.PROJECT_IMPL:
+        raise ValueError(f"impl must be one of {sorted(_lib.PROJECT_IMPL)}")
     feats = _need_cuda(feats, "camera_features")
     intrinsics = _need_cuda(intrinsics, "intrinsics")
     ego2cam = _need_cuda(ego2cam, "ego2cam")
@@ -272,7 +275,7 @@ def camera_project(feats: torch.Tensor, intrinsics: torch.Tensor, ego2cam: torch
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b200bev_camera_project(
             _ptr(feats), B, n_cam, Cc, h, w, _ptr(intrinsics), _ptr(ego2cam), T, float(img_size[0]), float(img_size[1]),
-            pc_range[0], pc_range[1], vx, vy, z_plane, W, H, _ptr(out), _ptr(table), _stream(dev)))
+            pc_range[0], pc_range[1], vx, vy, z_plane, W, H, _ptr(out), _ptr(table), _lib.PROJECT_IMPL[impl], _stream(dev)))
     return (out, table) if return_table else out
 
 

@@ -53,28 +53,42 @@ def _module(name: str):
 
 
 def patch(precision: str = None) -> Dict[str, List[str]]:
-    """Installs the kernels behind the reference's names. Returns {module: [patched names]}."""
+    """Installs the kernels behind the reference's names. Returns {module: [patched names]}.
+
+    precision: None (each module's own `b200_precision` attribute, else `B200BEV_PRECISION`, else "f32"), "f32" or
+    "bf16".  A value given here is written to `b200_precision` of EVERY patched module the first time its forward runs —
+    LiDAR encoder, radar encoder, fusion module and detection head alike — unless the module already carries its own
+    setting, so `patch("bf16")` moves the MLP and all convolution blocks together and `patch("f32")` wins over the
+    environment variable."""
     _lib.lib()  # fail now if the CUDA extension is missing
+    if precision is not None and precision not in encoders.PRECISIONS:
+        raise ValueError(f"unknown precision {precision!r}; choose one of {sorted(encoders.PRECISIONS)}")
     if _saved:
         return {}
+
+    def with_precision(fn):
+        """The reference's method signature in front of `fn(self, ...)`, stamping the patch-wide precision on first use."""
+        @functools.wraps(fn)
+        def forward(self, *args, **kwargs):
+            if precision is not None and getattr(self, "b200_precision", None) is None:
+                self.b200_precision = precision
+            return fn(self, *args, **kwargs)
+        return forward
+
     done: Dict[str, List[str]] = {}
     enc_mod, fus_mod = _module("encoders"), _module("fusion")
     if enc_mod is not None and hasattr(enc_mod, "PointNetLiDAREncoder") and enc_mod is not encoders:
-        def lidar_fwd(self, x):
-            if precision is not None and getattr(self, "b200_precision", None) is None:
-                self.b200_precision = precision
-            return encoders.lidar_forward(self, x)
-
-        _swap(enc_mod.PointNetLiDAREncoder, "forward", lidar_fwd)
-        _swap(enc_mod.MultiRadarEncoder, "forward", lambda self, radar_list: encoders.multi_radar_forward(self, radar_list))
+        _swap(enc_mod.PointNetLiDAREncoder, "forward", with_precision(lambda self, x: encoders.lidar_forward(self, x)))
+        _swap(enc_mod.MultiRadarEncoder, "forward",
+              with_precision(lambda self, radar_list: encoders.multi_radar_forward(self, radar_list)))
         done["encoders"] = ["PointNetLiDAREncoder.forward", "MultiRadarEncoder.forward"]
     if fus_mod is not None and hasattr(fus_mod, "FlexibleBEVFusion") and fus_mod is not fusion:
         _swap(fus_mod.FlexibleBEVFusion, "forward",
-              lambda self, camera_features=None, lidar_features=None, radar_features=None:
-              fusion.fusion_forward(self, camera_features, lidar_features, radar_features))
+              with_precision(lambda self, camera_features=None, lidar_features=None, radar_features=None:
+                             fusion.fusion_forward(self, camera_features, lidar_features, radar_features)))
         done["fusion"] = ["FlexibleBEVFusion.forward"]
         if hasattr(fus_mod, "CenterNetHead"):
-            _swap(fus_mod.CenterNetHead, "forward", lambda self, x: conv_blocks.head_forward(self, x))
+            _swap(fus_mod.CenterNetHead, "forward", with_precision(lambda self, x: conv_blocks.head_forward(self, x)))
             done["fusion"].append("CenterNetHead.forward")
     variants = {"centernet_target": centernet_decode.CENTERNET_TARGET_VOXEL,
                 "fusion_detection": centernet_decode.FUSION_DETECTION_VOXEL}

@@ -182,6 +182,21 @@ def fill_state_dict(seed: int, shapes: Dict[str, Tuple[int, ...]]) -> Dict[str, 
     return out
 
 
+DETECTOR_PREFIXES = ("lidar_encoder.", "radar_encoder.", "fusion.", "det_head.")
+
+
+def detector_state(seed: int, shapes: Dict[str, Tuple[int, ...]], head_in: int = 256, head_conv: int = 64, classes: int = 10):
+    """Seeded parameters of the whole inference chain by the reference's state_dict names (`lidar_encoder.*`,
+    `radar_encoder.*`, `fusion.*`, `det_head.*`; `shapes` = name -> shape, e.g. from the modules' own state_dict()):
+    fill_state_dict for the encoders and the fusion module, head_weights (logits that spread) for `det_head.*`."""
+    body = {k: v for k, v in shapes.items() if not k.startswith("det_head.")}
+    out = fill_state_dict(seed, body)
+    if any(k.startswith("det_head.") for k in shapes):
+        for k, v in head_weights(seed + 1, head_in, head_conv, classes, out_scale=0.3).items():
+            out["det_head." + k] = v
+    return out
+
+
 def head_maps(seed: int, batch: int, classes: int = 10, H: int = 50, W: int = 50, peak_frac: float = 1.0):
     """CenterNet head outputs with pairwise-distinct heat-map values (tie-free top-K):
     heatmap is a random permutation of an evenly spaced grid in (0,1) per sample, so no two cells of a
@@ -246,3 +261,15 @@ def camera_rig(img_w: float = 1600.0, img_h: float = 900.0) -> Tuple[np.ndarray,
         Ks.append(K)
         Es.append(np.concatenate([R, t[:, None]], axis=1))
     return np.stack(Ks).astype(np.float32), np.stack(Es).astype(np.float32)
+
+
+# The whole-chain case of tests/golden/detector_chain.npz (made by tests/golden/make_golden.py: chain_cases)
+CHAIN_SEED, CHAIN_FRAMES, CHAIN_POINTS = 901, 2, 3000
+
+
+def chain_inputs(seed: int = CHAIN_SEED, frames: int = CHAIN_FRAMES, points: int = CHAIN_POINTS, feat_hw=(28, 50)):
+    """(lidar (F,N,4), 5 radars (F,125,7), camera features (F,6,512,h,w)) of the whole-chain case."""
+    lidar = lidar_batch(seed + 10, frames, n_valid=points - 40, n_total=points)
+    radars = radar_batch(seed + 11, frames)
+    cam = camera_features(seed + 12, frames, n_cam=6, channels=512, h=feat_hw[0], w=feat_hw[1])
+    return lidar, radars, cam

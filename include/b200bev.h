@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200BEV_ABI_VERSION 1
+#define B200BEV_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define B200BEV_API __attribute__((visibility("default")))
@@ -156,7 +156,12 @@ B200BEV_API int b200bev_radar_encode(const float* const* radar_points, const int
  *   img_w/img_h  pixel size the intrinsics refer to (1600x900)
  *   out        (B,C,H,W) f32
  *   uv_valid   optional (T,H*W,n_cam,3) f32 debug/table output: feature-map u, v and valid(0/1)
+ *   impl       B200BEV_PROJECT_AUTO, or one of the two kernels by name (they give the same bits; the
+ *              parity tests run both): _STAGED returns B200BEV_ERR_UNSUPPORTED where bands do not fit
  * ------------------------------------------------------------------------------------------- */
+#define B200BEV_PROJECT_AUTO 0
+#define B200BEV_PROJECT_STAGED 1
+#define B200BEV_PROJECT_GATHER 2
 B200BEV_API int b200bev_camera_mean(const float* feats, int B, int n_cam, int64_t inner, float* out, void* stream);
 B200BEV_API int b200bev_bilinear_resize(const float* in, int B, int C, int h, int w,
                             float* out, int H, int W, void* stream);
@@ -164,7 +169,7 @@ B200BEV_API int b200bev_camera_project(const float* feats, int B, int n_cam, int
                            const float* intrinsics, const float* ego2cam, int T,
                            float img_w, float img_h,
                            float x_min, float y_min, float voxel_x, float voxel_y, float z_plane,
-                           int W, int H, float* out, float* uv_valid, void* stream);
+                           int W, int H, float* out, float* uv_valid, int impl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * S3  CenterNet peak extraction and box decode.

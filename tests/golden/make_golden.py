@@ -297,10 +297,54 @@ def metrics_cases():
     np.savez_compressed(OUT / "metrics.npz", **out)
 
 
+def chain_cases():
+    """The reference's whole inference pass behind the camera backbone — PointNetLiDAREncoder, MultiRadarEncoder,
+    FlexibleBEVFusion, CenterNetHead as FlexibleMultiModal3DDetector.forward chains them (src/fusion.py:1113-1137) — and
+    eval.py's decode (src/eval.py:58-62), at the base.yaml sizes, with one seeded state_dict under the reference's names.
+    This is what the drop-in route must reproduce end to end and what bench.py's step runs."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        mods = {"lidar_encoder.": encoders.PointNetLiDAREncoder(input_channels=4, feat_dim=1024, use_bn=True),
+                "radar_encoder.": encoders.MultiRadarEncoder(input_channels=7, feat_dim=256, num_radars=5, fusion_method="concat"),
+                "fusion.": fusion.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=512,
+                                                    lidar_channels=1024, radar_channels=256, bev_h=50, bev_w=50, bev_channels=256),
+                "det_head.": fusion.CenterNetHead(in_channels=256, num_classes=10, head_conv=64)}
+    shapes = {pre + k: tuple(v.shape) for pre, m in mods.items() for k, v in m.state_dict().items()}
+    sd = syn.detector_state(syn.CHAIN_SEED, shapes)
+    for pre, m in mods.items():
+        m.load_state_dict({k[len(pre):]: torch.from_numpy(v) for k, v in sd.items() if k.startswith(pre)}, strict=False)
+        m.eval()
+    lidar, radars, cam = syn.chain_inputs()
+    out = {"state_digest": syn.digest(*[sd[k] for k in sorted(sd)]), "input_digest": syn.digest(lidar, *radars, cam),
+           "shape_names": np.array(sorted(shapes))}
+    for k in sorted(shapes):
+        out["shape__" + k] = np.array(shapes[k], dtype=np.int64)
+    lf = mods["lidar_encoder."](torch.from_numpy(lidar))
+    rf = mods["radar_encoder."]([torch.from_numpy(r) for r in radars])
+    bev = mods["fusion."](camera_features=torch.from_numpy(cam), lidar_features=lf, radar_features=rf)
+    pred = mods["det_head."](bev)
+    out["lidar_feat"], out["radar_feat"] = lf.numpy(), rf.numpy()
+    out["bev_sub"] = bev[:, ::8].numpy()
+    out["bev_absmax"] = np.float32(bev.abs().max())
+    for k, v in pred.items():
+        out["pred_" + k] = v.numpy()
+    top = fusion_detection._topk(fusion_detection._nms(pred["heatmap"]), K=100)[0]
+    assert (top[:, :-1] > top[:, 1:]).all(), "ties among the winners: pick another seed"
+    dets = fusion_detection.decode_centernet_predictions(pred, score_thresh=0.0, max_detections=100)
+    for b, d in enumerate(dets):
+        for k, v in d.items():
+            out[f"det_b{b}_{k}"] = v.numpy()
+    # the torch port bench.py's reference arm times must be this, op for op
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    pbev, ppred, pdets = torch_port.detector_chain(tsd, torch.from_numpy(cam), torch.from_numpy(lidar),
+                                                   [torch.from_numpy(r) for r in radars])
+    assert torch.allclose(pbev, bev, rtol=0, atol=1e-6 * float(bev.abs().max())), "port differs from the reference"
+    np.savez_compressed(OUT / "detector_chain.npz", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = set(sys.argv[1:])
-    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases, glue_cases, metrics_cases):
+    for fn in (lidar_cases, radar_cases, camera_cases, decode_cases, lidar_prepare_cases, glue_cases, metrics_cases, chain_cases):
         if only and fn.__name__ not in only:
             continue
         fn()

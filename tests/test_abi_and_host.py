@@ -74,7 +74,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert ws >= 2 * 43 * 8 + 4
     assert lib.b200bev_centernet_topk(one, 1, 2, 6, 7, 43, one, one, one, one, one, one, ws, null) == _lib.ERR_K_OUT_OF_RANGE
     assert lib.b200bev_centernet_topk(one, 1, 2, 6, 7, 5, one, one, one, one, one, one, 8, null) == _lib.ERR_WORKSPACE
-    assert lib.b200bev_camera_project(one, 2, 6, 8, 4, 4, one, one, 3, 1600, 900, 0, 0, 1, 1, 0, 5, 5, one, null, null) \
+    assert lib.b200bev_camera_project(one, 2, 6, 8, 4, 4, one, one, 3, 1600, 900, 0, 0, 1, 1, 0, 5, 5, one, null, 0, null) \
         == _lib.ERR_INVALID_ARGUMENT                     # T must be 1 or B
     # SURVEY 8f entry points: dense layers and convolution blocks
     assert lib.b200bev_dense_layer(null, 1, 4, one, null, 4, 0, one, null) == _lib.ERR_INVALID_ARGUMENT
@@ -322,14 +322,18 @@ def test_centernet_head_mirror_state_dict_and_default_path(golden):
         fus.eval()(lidar_features=torch.zeros(1, 1024))
 
 
-def test_lidar_start_size_follows_the_grid():
-    """25 at the reference's 50x50 grid (same state_dict shapes), half the grid for other even square grids
-    — the reference itself raises in torch.cat there (src/fusion.py:141,292)."""
-    f50 = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=False, bev_h=50, bev_w=50, bev_channels=8)
-    assert f50.lidar_start_size == 25 and f50.lidar_init[2].out_features == 128 * 25 * 25
+def test_lidar_start_size_is_the_references_25_unless_asked():
+    """The reference hard-codes 25 (src/fusion.py:141): the mirror keeps it for every grid so that the state_dict shapes
+    match; `lidar_start_size=` is the explicit extension that lets other grids run with the lidar branch (the reference
+    itself raises in torch.cat there, src/fusion.py:292)."""
+    for hw in (50, 200):
+        f = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=False, bev_h=hw, bev_w=hw, bev_channels=8)
+        assert f.lidar_start_size == 25 and tuple(f.lidar_init[2].weight.shape) == (128 * 25 * 25, 512)
     f20 = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=False, lidar_channels=32, bev_h=20, bev_w=20,
-                                    bev_channels=8)
-    assert f20.lidar_start_size == 10
+                                    bev_channels=8, lidar_start_size=10)
+    assert fusion.lidar_start_size(f20) == 10
+    del f20.lidar_start_size                       # the reference's class has no such attribute: recovered from the shapes
+    assert fusion.lidar_start_size(f20) == 10
     f20.train()
     out = f20(lidar_features=torch.randn(2, 32))
     assert tuple(out.shape) == (2, 8, 20, 20)

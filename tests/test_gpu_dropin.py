@@ -292,14 +292,22 @@ def test_centernet_head_mirror_vs_reference_golden_and_fused_path(cuda, golden):
         ref = big(xb)
         big.b200_precision = "bf16"
         got = big(xb)
-    assert "heatmap_logits" in got and "heatmap_logits" not in ref
+    from bevfusion_multimodal_3d_object_detection_b200 import conv_blocks
+    assert set(got) == set(ref) == {"heatmap", "offset", "size", "rot", "vel"}          # the reference's five keys, nothing else
+    assert conv_blocks.logits_of(got["heatmap"]) is not None and conv_blocks.logits_of(ref["heatmap"]) is None
     for k in ("heatmap", "offset", "size", "rot", "vel"):
         assert got[k].is_contiguous() and max_rel(got[k].cpu().numpy(), ref[k].cpu().numpy()) < BF16_TOL, k
     dets = b200bev.decode_centernet_predictions(got, score_thresh=0.0, max_detections=50)
-    plain = {k: v for k, v in got.items() if k != "heatmap_logits"}
+    plain = {**got, "heatmap": got["heatmap"].clone()}                                  # a new tensor: no note, sigmoid already applied
     want = b200bev.decode_centernet_predictions(plain, score_thresh=0.0, max_detections=50)
     for d, w in zip(dets, want):
         assert torch.equal(d["scores"], w["scores"]) and torch.equal(d["boxes"], w["boxes"])
+    # a caller that edits the heat map in place (masking, temperature, flip-TTA averaging) is decoded on what it left there
+    got["heatmap"].mul_(0.5)
+    assert conv_blocks.logits_of(got["heatmap"]) is None
+    halved = b200bev.decode_centernet_predictions(got, score_thresh=0.0, max_detections=50)
+    for d, w in zip(halved, want):
+        assert torch.equal(d["scores"], w["scores"] * 0.5)
 
 
 def test_decode_outputs_feed_the_metrics_consumer(cuda, golden):
@@ -318,7 +326,7 @@ def test_decode_outputs_feed_the_metrics_consumer(cuda, golden):
 def test_graphed_step_replays_the_chain_bit_for_bit(cuda):
     """runtime.GraphedStep: fusion -> head -> fixed-size decode captured in one CUDA graph; new inputs are copied into
     the captured tensors, a replay gives what the eager calls give."""
-    from bevfusion_multimodal_3d_object_detection_b200 import ops, runtime
+    from bevfusion_multimodal_3d_object_detection_b200 import conv_blocks, ops, runtime
 
     torch.manual_seed(9)
     fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=64, lidar_channels=128,
@@ -332,7 +340,7 @@ def test_graphed_step_replays_the_chain_bit_for_bit(cuda):
 
     def step():
         pred = head(fus(camera_features=cam, lidar_features=lidar, radar_features=radar))
-        return ops.centernet_decode(pred["heatmap_logits"], pred["offset"], pred["size"], pred["rot"], pred["vel"], 40, 2.048,
+        return ops.centernet_decode(conv_blocks.logits_of(pred["heatmap"]), pred["offset"], pred["size"], pred["rot"], pred["vel"], 40, 2.048,
                                     heat_is_logit=True)
 
     graphed = runtime.GraphedStep(step, cuda)
@@ -345,3 +353,94 @@ def test_graphed_step_replays_the_chain_bit_for_bit(cuda):
         torch.cuda.synchronize()
         for k in ("scores", "boxes", "velocities", "ys", "xs", "count"):
             assert torch.equal(out[k], eager[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ the whole chain
+def _chain(cuda, precision):
+    chain = b200bev.BEVDetectorChain(precision=precision)
+    sd = syn.detector_state(syn.CHAIN_SEED, chain.state_shapes())
+    chain.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return chain.eval().to(cuda)
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_detector_chain_reproduces_the_reference_end_to_end(cuda, golden, precision, tol):
+    """Encoders -> FlexibleBEVFusion -> CenterNetHead -> decode on the kernels, with the reference's state_dict names,
+    against what the REFERENCE's own modules produced for the same state and inputs (tests/golden/detector_chain.npz,
+    src/fusion.py:1113-1137 + src/eval.py:58-62)."""
+    g = golden("detector_chain")
+    chain = _chain(cuda, precision)
+    lidar, radars, cam = syn.chain_inputs()
+    assert syn.digest(lidar, *radars, cam) == str(g["input_digest"])
+    args = (torch.from_numpy(cam).to(cuda), torch.from_numpy(lidar).to(cuda), [torch.from_numpy(r).to(cuda) for r in radars])
+    with torch.no_grad():
+        lf = chain.lidar_encoder(args[1])
+        rf = chain.radar_encoder(args[2])
+        bev = chain.fusion(camera_features=args[0], lidar_features=lf, radar_features=rf)
+        pred = chain(*args)
+        dets = chain.detect(*args, score_thresh=0.0, max_detections=100)
+        fixed = chain.detect_fixed(*args, score_thresh=0.0, max_detections=100)
+    assert max_rel(lf.cpu().numpy(), g["lidar_feat"]) < tol
+    assert max_rel(rf.cpu().numpy(), g["radar_feat"]) < FP32_TOL                # the radar MLP is fp32 in both settings
+    # five / seven layers deep: the bound is on max|ref| of each tensor (SURVEY §7)
+    deep = 4 * tol if precision == "f32" else 2 * tol
+    assert max_rel(bev[:, ::8].cpu().numpy(), g["bev_sub"]) < deep
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        assert max_rel(pred[k].cpu().numpy(), g["pred_" + k]) < deep, k
+    assert fixed["count"].tolist() == [len(d["scores"]) for d in dets]
+    if precision == "f32":
+        for b, d in enumerate(dets):
+            n = len(g[f"det_b{b}_scores"])
+            assert len(d["scores"]) == n
+            np.testing.assert_allclose(d["scores"].cpu().numpy(), g[f"det_b{b}_scores"], rtol=0, atol=2e-5)
+            # same winners in the same order wherever the reference's neighbouring scores are further apart than the tolerance
+            gap = np.abs(np.diff(g[f"det_b{b}_scores"]))
+            stable = np.concatenate([[True], gap[:-1] > 1e-4]) & np.concatenate([gap > 1e-4, [True]])
+            np.testing.assert_allclose(d["boxes"].cpu().numpy()[stable], g[f"det_b{b}_boxes"][stable], rtol=0, atol=2e-3)
+            assert d["labels"].dtype == torch.int64 and not bool(d["labels"].any())          # SURVEY Q1
+
+
+def test_eval_mode_under_autograd_stays_differentiable(cuda):
+    """Eval mode with autograd recording (frozen-backbone fine-tuning, saliency): the kernels return tensors without a
+    grad_fn, so such calls take the modules' torch graph on the GPU — as the reference's eval-mode modules behave — and
+    the same call under no_grad runs the kernels and agrees."""
+    chain = b200bev.BEVDetectorChain(camera_channels=64, bev_channels=64)
+    sd = syn.detector_state(77, chain.state_shapes(), head_in=64)
+    chain.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    chain = chain.eval().to(cuda)
+    lidar, radars, _ = syn.chain_inputs(frames=1, points=700)
+    cam = torch.from_numpy(syn.camera_features(5, 1, channels=64, h=12, w=20)).to(cuda)
+    pts = torch.from_numpy(lidar).to(cuda).requires_grad_(True)
+    rad = [torch.from_numpy(r).to(cuda) for r in radars]
+    pred = chain(cam, pts, rad)                                  # grad mode is on, parameters and `pts` require grad
+    assert pred["heatmap"].requires_grad
+    pred["heatmap"].sum().backward()
+    assert pts.grad is not None and float(pts.grad.abs().sum()) > 0
+    assert chain.fusion.bev_fusion[0].weight.grad is not None
+    with torch.no_grad():
+        fast = chain(cam, pts, rad)
+    assert not fast["heatmap"].requires_grad
+    for k in pred:
+        assert max_rel(fast[k].cpu().numpy(), pred[k].detach().cpu().numpy()) < 4 * FP32_TOL, k
+    # parameters frozen and inputs without grad: nothing to differentiate -> kernels even with grad mode on
+    for p in chain.parameters():
+        p.requires_grad_(False)
+    b200bev.invalidate_cache(chain)
+    frozen = chain(cam, pts.detach(), rad)
+    assert not frozen["heatmap"].requires_grad and torch.equal(frozen["heatmap"], fast["heatmap"])
+
+
+def test_cache_invalidation_after_data_writes(cuda):
+    """`.data` writes do not bump a tensor's version counter: `invalidate_cache` is the documented call after them."""
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    enc = load_mlp(b200bev.PointNetLiDAREncoder(input_channels=4), layers).to(cuda)
+    pts = torch.from_numpy(syn.lidar_batch(205, 1, n_valid=500, n_total=512)).to(cuda)
+    with torch.no_grad():
+        a = enc(pts)
+        enc.bn5.bias.data.add_(0.75)                            # invisible to the version counter
+        b200bev.invalidate_cache(enc)
+        b = enc(pts)
+        assert bool((b >= a).all()) and float((b - a).max()) > 0.7     # the maxima moved up by the bias shift (0.75, before the ReLU)
+        with torch.no_grad():
+            enc.bn5.bias.add_(-0.75)                            # an ordinary in-place op IS seen
+        assert torch.allclose(enc(pts), a, atol=1e-5)

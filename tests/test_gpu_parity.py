@@ -253,9 +253,8 @@ def test_camera_mean_odd_sizes(cuda):
 
 
 @pytest.fixture(params=["staged", "gather"])
-def project_impl(request, monkeypatch):
+def project_impl(request):
     """Both camera_project kernels (TMA-staged bands / plain global gather) must give the same bits."""
-    monkeypatch.setenv("B200BEV_PROJECT_IMPL", request.param)
     return request.param
 
 
@@ -264,7 +263,7 @@ def test_camera_projection(cuda, golden, project_impl):
     K, E = syn.camera_rig()
     feats = syn.camera_features(402, 1, n_cam=6, channels=8, h=57, w=100)
     canvas, table = ops.camera_project(dev_t(feats, cuda), dev_t(K, cuda), dev_t(E, cuda), (1600.0, 900.0), (50, 50),
-                                       return_table=True)
+                                       return_table=True, impl=project_impl)
     np.testing.assert_array_equal(table[0].cpu().numpy(), g["project_table"])   # (u, v, valid) bit-exact
     assert max_rel(canvas[0].cpu().numpy(), g["project_canvas_grid_sample"]) < FP32_TOL
     assert max_rel(canvas[0].cpu().numpy(), orc.camera_project(feats[0], g["project_table"], (50, 50))) < 1e-6
@@ -277,14 +276,14 @@ def test_camera_projection_per_sample_rigs_and_big_grid(cuda, project_impl):
     Ks, Es = np.stack([K, K]), np.stack([E, E2])
     feats = syn.camera_features(403, 2, n_cam=6, channels=5, h=28, w=50)
     canvas, table = ops.camera_project(dev_t(feats, cuda), dev_t(Ks, cuda), dev_t(Es, cuda), (1600.0, 900.0), (100, 100),
-                                       return_table=True)
+                                       return_table=True, impl=project_impl)
     for b in range(2):
         t = orc.project_cells(Ks[b], Es[b], (1600.0, 900.0), (28, 50), (100, 100), syn.PC_RANGE)
         np.testing.assert_array_equal(table[b].cpu().numpy(), t)
         assert max_rel(canvas[b].cpu().numpy(), orc.camera_project(feats[b], t, (100, 100))) < 1e-6
 
 
-def test_camera_projection_staged_equals_gather_full_size(cuda, monkeypatch):
+def test_camera_projection_staged_equals_gather_full_size(cuda):
     """BASELINE-size features (6x512x57x100, 3 frames, ragged channel tail): the staged kernel and the
     gather kernel agree bit for bit, and a blind camera / an all-blind rig give zeros, not garbage."""
     K, E = syn.camera_rig()
@@ -293,9 +292,8 @@ def test_camera_projection_staged_equals_gather_full_size(cuda, monkeypatch):
     Kd, Ed = dev_t(K, cuda), dev_t(E, cuda)
     outs = {}
     for impl in ("staged", "gather"):
-        monkeypatch.setenv("B200BEV_PROJECT_IMPL", impl)
-        outs[impl] = ops.camera_project(feats, Kd, Ed, (1600.0, 900.0), (50, 50))
-        outs[impl + "_big"] = ops.camera_project(feats[:1, :, :37].contiguous(), Kd, Ed, (1600.0, 900.0), (100, 100))
+        outs[impl] = ops.camera_project(feats, Kd, Ed, (1600.0, 900.0), (50, 50), impl=impl)
+        outs[impl + "_big"] = ops.camera_project(feats[:1, :, :37].contiguous(), Kd, Ed, (1600.0, 900.0), (100, 100), impl=impl)
     assert torch.equal(outs["staged"], outs["gather"])
     assert torch.equal(outs["staged_big"], outs["gather_big"])
     assert float(outs["staged"].abs().max()) > 0
@@ -307,13 +305,12 @@ def test_camera_projection_staged_equals_gather_full_size(cuda, monkeypatch):
     for rig in (E_sky, E_far):
         res = {}
         for impl in ("staged", "gather"):
-            monkeypatch.setenv("B200BEV_PROJECT_IMPL", impl)
-            res[impl] = ops.camera_project(feats[:2, :, :9].contiguous(), Kd, dev_t(rig, cuda), (1600.0, 900.0), (50, 50))
+            res[impl] = ops.camera_project(feats[:2, :, :9].contiguous(), Kd, dev_t(rig, cuda), (1600.0, 900.0), (50, 50), impl=impl)
         assert torch.equal(res["staged"], res["gather"])
     assert float(res["staged"].abs().max()) == 0.0
 
 
-def test_camera_projection_overlapping_cameras(cuda, monkeypatch):
+def test_camera_projection_overlapping_cameras(cuda):
     """Means over 3 and 6 cameras (not powers of two: the IEEE-division branch) and a rig whose cameras all
     see most of the grid, which overflows the staged kernel's shared-memory table and takes its
     gather-from-global segment path.  All against the oracle, and staged == gather bit for bit."""
@@ -331,8 +328,7 @@ def test_camera_projection_overlapping_cameras(cuda, monkeypatch):
         assert int(table[:, :, 2].sum(axis=1).max()) == min_overlap
         res = {}
         for impl in ("staged", "gather"):
-            monkeypatch.setenv("B200BEV_PROJECT_IMPL", impl)
-            res[impl] = ops.camera_project(d, dev_t(K, cuda), dev_t(rig, cuda), (1600.0, 900.0), bev)
+            res[impl] = ops.camera_project(d, dev_t(K, cuda), dev_t(rig, cuda), (1600.0, 900.0), bev, impl=impl)
         assert torch.equal(res["staged"], res["gather"])
         for b in range(2):
             assert max_rel(res["staged"][b].cpu().numpy(), orc.camera_project(feats[b], table, bev)) < 1e-6
@@ -483,11 +479,59 @@ def test_tensor_core_cell_canvas(cuda, B, N, W):
     empty_cells = (off[:, 1:] - off[:, :-1]) == 0
     assert not bool(canvas[empty_cells].any())                  # untouched cells stay exactly zero
     ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, W)
-    ref = orc.pointnet_cell_max(pts[0], layers, ref_cell[0], W * W)
-    assert max_rel(canvas[0].cpu().numpy(), ref) < BF16_TOL
+    for b in range(B):                                          # every batch element against the numpy oracle
+        ref = orc.pointnet_cell_max(pts[b], layers, ref_cell[b], W * W)
+        assert max_rel(canvas[b].cpu().numpy(), ref) < BF16_TOL, b
     only = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.BF16_TENSOR, tc_params=tc,
                                want_global=False)
     assert torch.equal(only, canvas)                            # deterministic, with or without the global output
+
+
+def _oracle_cells(pts_b, layers, cell_b, cells):
+    """Oracle canvas rows of the chosen cells only: the MLP runs on the points that fall into them."""
+    keep = np.isin(cell_b, cells)
+    remap = np.searchsorted(cells, cell_b[keep]).astype(np.int32)
+    return orc.pointnet_cell_max(pts_b[keep], layers, remap, len(cells))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "f32"])
+def test_cell_canvas_at_the_stress_shape(cuda, precision):
+    """BASELINE configs[4] shapes: 4 frames x 300,000 points (10 sweeps), 100x100 grid.  bin_sort takes its "ranks in the
+    upper half of the cell word" path here and the cell-mode MLP kernels consume its output.  Every frame is checked:
+    against the numpy oracle on sampled cells (dense centre cells, sparse rim cells, the cell of the zero-padding rows),
+    and — the bf16 kernel — against the fp32 kernel on ALL cells."""
+    B, N, W = 4, 300000, 100
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, tc = _tc(cuda, layers)
+    pts = syn.lidar_batch(1300, B, n_valid=N - 2000, n_total=N)          # 2,000 zero rows: they land in one cell (SURVEY Q5)
+    pts[:, 11::97, 1] = -80.0                                            # out-of-grid points: global max only
+    d = dev_t(pts, cuda)
+    cell, perm, off = ops.bin_sort(d, W, W)
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, W)
+    np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
+    g32, c32 = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W)
+    if precision == "bf16":
+        glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.BF16_TENSOR, tc_params=tc)
+        tol = BF16_TOL
+        assert float((canvas - c32).abs().max()) < tol * float(c32.max())
+        assert float((glob - g32).abs().max()) < tol * float(g32.max())
+    else:
+        glob, canvas, tol = g32, c32, FP32_TOL
+    counts = (off[:, 1:] - off[:, :-1]).cpu().numpy()
+    assert int(counts.max()) > 1000 and int(off[:, -1].max()) < N        # a cell far over 255 points; some points out of grid
+    rng = np.random.default_rng(77)
+    for b in range(B):
+        assert not bool(canvas[b][torch.from_numpy(counts[b] == 0).to(cuda)].any())       # empty cells stay exactly zero
+        occupied = np.flatnonzero(counts[b])
+        order = occupied[np.argsort(counts[b][occupied])]
+        cells = np.unique(np.concatenate([order[:8], order[-6:], rng.choice(occupied, 24, replace=False),
+                                          [int(ref_cell[b, N - 1])]]))   # sparsest, densest, random, the zero-row cell
+        ref = _oracle_cells(pts[b], layers, ref_cell[b], cells)
+        got = canvas[b][torch.from_numpy(cells).to(cuda)].cpu().numpy()
+        scale = float(c32[b].max())
+        assert float(np.abs(got - ref).max()) < tol * scale, b
+    ref_g = np.stack([orc.pointnet_global(pts[b:b + 1, ::37], layers)[0] for b in range(B)])   # a lower bound of the maxima
+    assert bool((glob.cpu().numpy() >= ref_g * (1 - 2 * tol) - tol).all())
 
 
 # ------------------------------------------------------------------------------------------------ randomised shapes

@@ -335,3 +335,35 @@ def test_conv_and_dense_restatements_against_aten(B, C, O, H, W, k):
     lin = torch.nn.functional.linear(torch.from_numpy(xf), torch.from_numpy(wl), torch.from_numpy(bl))
     assert max_rel(orc.dense_layer(xf, wl, bl, relu=True), torch.relu(lin).numpy()) < 1e-5
     assert max_rel(orc.sigmoid(xf), torch.sigmoid(torch.from_numpy(xf)).numpy()) < 1e-6
+
+
+def test_detector_chain_port_and_mirror_names_vs_reference_golden(golden):
+    """The whole inference pass behind the camera backbone (src/fusion.py:1113-1137 + src/eval.py:58-62): the torch port
+    the reference arm times reproduces what the reference's own modules produced, and the mirror chain has the
+    reference's state_dict names and shapes for those sub-modules."""
+    import bevfusion_multimodal_3d_object_detection_b200 as b200bev
+
+    g = golden("detector_chain")
+    chain = b200bev.BEVDetectorChain()
+    shapes = chain.state_shapes()
+    assert sorted(shapes) == [str(n) for n in g["shape_names"]]
+    for k, shp in shapes.items():
+        assert tuple(int(v) for v in g["shape__" + k]) == shp, k
+    sd = syn.detector_state(syn.CHAIN_SEED, shapes)
+    assert syn.digest(*[sd[k] for k in sorted(sd)]) == str(g["state_digest"])
+    lidar, radars, cam = syn.chain_inputs()
+    assert syn.digest(lidar, *radars, cam) == str(g["input_digest"])
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    bev, pred, dets = torch_port.detector_chain(tsd, torch.from_numpy(cam), torch.from_numpy(lidar), [torch.from_numpy(r) for r in radars])
+    assert max_rel(bev[:, ::8].numpy(), g["bev_sub"]) < 1e-5
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        assert max_rel(pred[k].numpy(), g["pred_" + k]) < 1e-5, k
+    for b, d in enumerate(dets):
+        assert d["scores"].shape == g[f"det_b{b}_scores"].shape
+        np.testing.assert_allclose(d["scores"].numpy(), g[f"det_b{b}_scores"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(d["boxes"].numpy(), g[f"det_b{b}_boxes"], rtol=0, atol=1e-4)
+    # training mode of the mirror chain is the plain torch graph (CPU is fine there): loads the same state and runs
+    chain.load_state_dict(tsd)
+    chain.train()
+    out = chain(torch.from_numpy(cam[:1, :, :, :8, :10]), torch.from_numpy(lidar[:1, :64]), [torch.from_numpy(r[:1]) for r in radars])
+    assert set(out) == {"heatmap", "offset", "size", "rot", "vel"} and tuple(out["heatmap"].shape) == (1, 10, 50, 50)
