@@ -42,6 +42,10 @@ PROTOTYPES = {
     "b200bev_pointnet_encode": (_i, [_p, _i, _i, _i, _p, C.POINTER(C.c_int32), _i, _p, _p, _i, _i, _p, _p, _p, _p]),
     "b200bev_pointnet_pack_bf16_bytes": (_z, [C.POINTER(C.c_int32), _i]),
     "b200bev_pointnet_pack_bf16": (_i, [_p, C.POINTER(C.c_int32), _i, _p, _z, _p]),
+    "b200bev_pointnet_pack_split_bytes": (_z, [C.POINTER(C.c_int32), _i]),
+    "b200bev_pointnet_pack_split": (_i, [_p, C.POINTER(C.c_int32), _i, _p, _z, _p]),
+    "b200bev_pointnet_split_workspace_bytes": (_z, [_i, _i]),
+    "b200bev_pointnet_encode_split": (_i, [_p, _i, _i, _i, C.POINTER(C.c_int32), _i, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "b200bev_radar_encode": (_i, [C.POINTER(_p), C.POINTER(C.c_int32), _i, _i, _i, _p, C.POINTER(C.c_int32), _i,
                                   _i, _p, _p, _p, _p, _p]),
     "b200bev_camera_mean": (_i, [_p, _i, _i, C.c_int64, _p, _p]),
@@ -100,6 +104,49 @@ def lib() -> C.CDLL:
             raise ImportError(f"libb200bev ABI version {got}, binding expects {ABI_VERSION}")
         _handle = h
     return _handle
+
+
+# ---- optional call accounting (bench.py: `gpu_launches`) -------------------------------------------------------------
+# Kernels one call of an entry point launches (memsets not counted); entries absent here launch one, entries mapped to 0 none.
+KERNELS_PER_CALL = {
+    "b200bev_abi_version": 0, "b200bev_error_string": 0, "b200bev_device_info": 0, "b200bev_lidar_prepare_workspace_bytes": 0,
+    "b200bev_pointnet_pack_bf16_bytes": 0, "b200bev_centernet_workspace_bytes": 0, "b200bev_conv_pack_bytes": 0,
+    "b200bev_pointnet_pack_split_bytes": 0, "b200bev_pointnet_split_workspace_bytes": 0,
+    "b200bev_radar_encode": 2, "b200bev_lidar_init": 2, "b200bev_lidar_prepare": 1,
+    "b200bev_pointnet_encode_split": 5,       # per pass: layer 1 + four GEMM launches (one pass up to ~1M points)
+    "b200bev_pointnet_pack_split": 2,
+}
+_call_counts = None
+
+
+def enable_call_counting() -> None:
+    """Wraps every entry point of the loaded library in a counter (reset_call_counts / kernel_launches)."""
+    global _call_counts
+    if _call_counts is not None:
+        return
+    h = lib()
+    _call_counts = {}
+    for name in PROTOTYPES:
+        fn = getattr(h, name)
+
+        def counted(*args, _fn=fn, _name=name):
+            _call_counts[_name] = _call_counts.get(_name, 0) + 1
+            return _fn(*args)
+
+        setattr(h, name, counted)
+
+
+def reset_call_counts() -> None:
+    if _call_counts is not None:
+        _call_counts.clear()
+
+
+def kernel_launches() -> int:
+    """Kernels launched by the entry-point calls since the last reset (KERNELS_PER_CALL per call; the fp32-accuracy
+    tensor-core MLP reports its own count through `pointnet_split_launches`)."""
+    if _call_counts is None:
+        return 0
+    return sum(n * KERNELS_PER_CALL.get(name, 1) for name, n in _call_counts.items())
 
 
 def check(status: int) -> None:

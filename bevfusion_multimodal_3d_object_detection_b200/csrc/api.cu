@@ -9,6 +9,9 @@ int pointnet_encode_f32(const float* points, int B, int N, int C, const float* p
 int pointnet_encode_tc(const float* points, int B, int N, int C, const float* params, const int32_t* dims,
                        int n_layers, const int32_t* perm, const int32_t* offsets, int n_cells, const void* tc_params,
                        float* out_global, float* out_canvas, cudaStream_t st);
+int pointnet_encode_split(const float* points, int B, int N, int C, const int32_t* dims, int n_layers, const int32_t* perm,
+                          const int32_t* offsets, int n_cells, const void* image, float* out_global, float* out_canvas,
+                          void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace b200bev
 
 using namespace b200bev;
@@ -65,4 +68,16 @@ extern "C" B200BEV_API int b200bev_pointnet_encode(const float* points, int B, i
                               out_canvas, st);
   }
   return B200BEV_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" B200BEV_API int b200bev_pointnet_encode_split(const float* points, int B, int N, int C, const int32_t* dims, int n_layers,
+                                             const int32_t* perm, const int32_t* offsets, int n_cells, const void* image,
+                                             float* out_global, float* out_canvas, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+  if (!points || !dims || !image || !workspace || B <= 0 || C <= 0 || N <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (!out_global && !out_canvas) return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((perm == nullptr) != (offsets == nullptr)) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (out_canvas && (!perm || n_cells <= 0)) return B200BEV_ERR_INVALID_ARGUMENT;
+  return pointnet_encode_split(points, B, N, C, dims, n_layers, perm, offsets, n_cells, image, out_global, out_canvas, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
 }

@@ -60,10 +60,15 @@ def _state_key(module: nn.Module, device: torch.device):
     return state_token(module, device)
 
 
-def packed_params(module: nn.Module, device: torch.device, want_bf16: bool = False):
+def packed_params(module: nn.Module, device: torch.device, want_bf16: bool = False, precision: Optional[int] = None):
     """(blob, dims, tc_blob|None) for a PointNet-style module; rebuilt only when a parameter or a
     BatchNorm statistic changed (load_state_dict hook, training-mode forward, tensor version counters; see
-    weight_cache.py — `invalidate_cache(module)` after writes through `.data`)."""
+    weight_cache.py — `invalidate_cache(module)` after writes through `.data`).
+    tc_blob is the tensor-core weight image of the asked precision: the bf16 stage image for BF16_TENSOR, the split-fp16
+    image of the fp32-accuracy tensor-core path for F32 (None when the layer widths are not the ones that path takes —
+    the FFMA kernel then runs)."""
+    if precision is None:
+        precision = _lib.BF16_TENSOR if want_bf16 else None
     key = _state_key(module, device)
     cache = module.__dict__.get("_b200bev_cache")
     if cache is None or cache["key"] != key:
@@ -73,11 +78,16 @@ def packed_params(module: nn.Module, device: torch.device, want_bf16: bool = Fal
             ws.append(w)
             bs.append(b)
         blob, dims = ops.pack_mlp_params(ws, bs, device)
-        cache = {"key": key, "blob": blob, "dims": dims, "tc": None}
+        cache = {"key": key, "blob": blob, "dims": dims, "tc": {}}
         module.__dict__["_b200bev_cache"] = cache
-    if want_bf16 and cache["tc"] is None:
-        cache["tc"] = ops.pack_mlp_params_bf16(cache["blob"], cache["dims"])
-    return cache["blob"], cache["dims"], cache["tc"]
+    if precision is None:
+        return cache["blob"], cache["dims"], None
+    if precision not in cache["tc"]:
+        if precision == _lib.BF16_TENSOR:
+            cache["tc"][precision] = ops.pack_mlp_params_bf16(cache["blob"], cache["dims"])
+        else:
+            cache["tc"][precision] = ops.pack_mlp_params_split(cache["blob"], cache["dims"])     # None if unsupported widths
+    return cache["blob"], cache["dims"], cache["tc"][precision]
 
 
 def _as_bnc(x: torch.Tensor, channels: int) -> torch.Tensor:
@@ -120,7 +130,7 @@ def lidar_forward(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
         return glob
     pts = _as_bnc(x, module.input_channels)
     prec = _precision_of(module)
-    blob, dims, tc = packed_params(module, pts.device, want_bf16=(prec == _lib.BF16_TENSOR))
+    blob, dims, tc = packed_params(module, pts.device, precision=prec)
     return ops.pointnet_encode(pts, blob, dims, precision=prec, tc_params=tc)
 
 
@@ -134,7 +144,7 @@ def lidar_cell_canvas(module: nn.Module, x: torch.Tensor, bev_size: Tuple[int, i
     H, W = int(bev_size[0]), int(bev_size[1])
     _, perm, offsets = ops.bin_sort(pts, W, H, pc_range)
     prec = _precision_of(module)
-    blob, dims, tc = packed_params(module, pts.device, want_bf16=(prec == _lib.BF16_TENSOR))
+    blob, dims, tc = packed_params(module, pts.device, precision=prec)
     canvas = ops.pointnet_encode(pts, blob, dims, perm=perm, offsets=offsets, n_cells=H * W, precision=prec,
                                  tc_params=tc, want_global=False)
     return canvas.view(pts.shape[0], H, W, dims[-1]).permute(0, 3, 1, 2)

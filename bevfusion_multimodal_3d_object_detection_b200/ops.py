@@ -149,13 +149,29 @@ def pack_mlp_params_bf16(params: torch.Tensor, dims: Sequence[int]) -> torch.Ten
     return out
 
 
+def pack_mlp_params_split(params: torch.Tensor, dims: Sequence[int]) -> Optional[torch.Tensor]:
+    """Weight image of the fp32-accuracy tensor-core MLP (split fp16 operands, b200bev_pointnet_pack_split), or None when
+    the layer widths are not the C-64-128-256-512-1024 that kernel takes (the FFMA kernel then runs)."""
+    params = _need_cuda(params, "params")
+    d = _i32(dims)
+    n_bytes = _lib.lib().b200bev_pointnet_pack_split_bytes(d, len(dims) - 1)
+    if n_bytes == 0:
+        return None
+    out = torch.empty(n_bytes, dtype=torch.uint8, device=params.device)
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.lib().b200bev_pointnet_pack_split(_ptr(params), d, len(dims) - 1, _ptr(out), n_bytes, _stream(params.device)))
+    return out
+
+
 def pointnet_encode(points: torch.Tensor, params: torch.Tensor, dims: Sequence[int],
                     perm: Optional[torch.Tensor] = None, offsets: Optional[torch.Tensor] = None,
                     n_cells: int = 0, precision: int = _lib.F32, tc_params: Optional[torch.Tensor] = None,
                     want_global: bool = True, want_canvas: Optional[bool] = None):
     """Fused shared-MLP + max.  Returns the global maxima (B, C_out) and/or the per-cell canvas
     (B, n_cells, C_out): one tensor if one was asked for, the pair (global, canvas) if both.
-    The canvas needs perm/offsets from bin_sort; by default it is produced whenever they are given."""
+    The canvas needs perm/offsets from bin_sort; by default it is produced whenever they are given.
+    precision / tc_params: F32 + None -> FFMA kernel (any layer widths); F32 + the image of pack_mlp_params_split -> the
+    same fp32 accuracy on the tensor cores; BF16_TENSOR + the image of pack_mlp_params_bf16 -> bf16 tcgen05 (1e-2)."""
     points = _need_cuda(points, "points")
     params = _need_cuda(params, "params")
     if points.dim() != 3:
@@ -176,6 +192,17 @@ def pointnet_encode(points: torch.Tensor, params: torch.Tensor, dims: Sequence[i
         offsets = _need_cuda(offsets, "offsets", torch.int32)
     glob = torch.empty((B, c_out), dtype=torch.float32, device=dev) if want_global else None
     canvas = torch.empty((B, n_cells, c_out), dtype=torch.float32, device=dev) if want_canvas else None
+    if precision == _lib.F32 and tc_params is not None:
+        # fp32 accuracy on the tensor cores: the split-fp16 image of pack_mlp_params_split was handed in
+        tc_params = _need_cuda(tc_params, "tc_params", torch.uint8)
+        ws = torch.empty(_lib.lib().b200bev_pointnet_split_workspace_bytes(B, N), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().b200bev_pointnet_encode_split(
+                _ptr(points), B, N, Cc, _i32(dims), len(dims) - 1, _ptr(perm), _ptr(offsets), n_cells, _ptr(tc_params),
+                _ptr(glob), _ptr(canvas), _ptr(ws), ws.numel(), _stream(dev)))
+        if want_global and want_canvas:
+            return glob, canvas
+        return glob if want_global else canvas
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b200bev_pointnet_encode(
             _ptr(points), B, N, Cc, _ptr(params), _i32(dims), len(dims) - 1, _ptr(perm), _ptr(offsets), n_cells,

@@ -8,7 +8,9 @@ time and, if a caller wants one list, for gathering the per-frame detection coun
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
+from pathlib import Path
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -61,6 +63,56 @@ def gather_counts(local_counts: Sequence[int], device: Optional[torch.device] = 
     return out
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int) -> Optional[int]:
+    """NUMA node of a CUDA device, from its PCI address in sysfs (None when the platform does not say)."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int((Path("/sys/bus/pci/devices") / bus / "numa_node").read_text().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(local_rank: int, local_world: int = 1) -> Dict[str, object]:
+    """Pins this process (and so its pinned-memory allocations, by first touch) to CPUs next to its GPU.
+
+    One process per GPU feeds its device from pinned host memory; on a multi-socket host a rank whose buffers sit on
+    the other socket pays the inter-socket link on every copy, and ranks left on "all CPUs" migrate and share cores.
+    The CPUs of the GPU's NUMA node (all CPUs when sysfs gives no node) are divided evenly among the ranks that
+    share that node.  Call before allocating pinned buffers.  Returns what was done, for the bench record."""
+    info: Dict[str, object] = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        node = gpu_numa_node(local_rank)
+        info["numa_node"] = node
+        all_cpus = sorted(os.sched_getaffinity(0))
+        cpus = all_cpus
+        sharers, my_pos = local_world, local_rank
+        if node is not None:
+            node_cpus = set(_parse_cpulist((Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text()))
+            cpus = [c for c in all_cpus if c in node_cpus] or all_cpus
+            same = [r for r in range(local_world) if gpu_numa_node(r) == node]
+            sharers, my_pos = max(1, len(same)), (same.index(local_rank) if local_rank in same else 0)
+        per = max(1, len(cpus) // sharers)
+        mine = cpus[my_pos * per:(my_pos + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(len(mine), 4)))
+        info.update(cpus=f"{mine[0]}-{mine[-1]} ({len(mine)} of {len(all_cpus)})", bound=True, ranks_on_node=sharers)
+    except Exception as e:      # affinity is an optimisation, never a reason to fail
+        info["error"] = str(e)[:120]
+    return info
+
+
 @dataclass
 class _Slot:
     dev: Dict[str, torch.Tensor]
@@ -92,6 +144,61 @@ class FramePipeline:
             for _ in range(2)
         ]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in host_inputs.values())
+        self.graphs: List[GraphedStep] = []
+
+    def _bounds(self) -> List[Tuple[int, int]]:
+        return [(b, min(b + self.chunk, self.n_frames)) for b in range(0, self.n_frames, self.chunk)]
+
+    def _upload(self, i: int, bounds) -> None:
+        b, e = bounds[i]
+        slot = self.slots[i & 1]
+        with torch.cuda.stream(self.copy_stream):
+            if i >= 2:
+                self.copy_stream.wait_event(slot.free)
+            for k, t in self.host.items():
+                slot.dev[k][: e - b].copy_(t[b:e], non_blocking=True)
+            slot.ready.record(self.copy_stream)
+
+    def capture(self, step: Callable[[Dict[str, torch.Tensor], int, int], object]) -> None:
+        """Captures `step(slot_inputs, 0, chunk)` once per slot in a CUDA graph (the slot tensors keep their addresses, so
+        a replay computes on whatever the last upload put there).  Needs n_frames % chunk == 0.  `step` must not touch
+        frame-indexed tensors outside the slot (every chunk replays the same graph)."""
+        if self.n_frames % self.chunk:
+            raise ValueError("capture needs whole chunks")
+        self.graphs = [GraphedStep(lambda s=slot: step(s.dev, 0, self.chunk), self.device) for slot in self.slots]
+
+    def run_captured(self, after: Callable[[object, int, int], None]) -> None:
+        """One pass over all frames: upload chunk i+1 while the graph of chunk i runs; `after(outputs, begin, end)` is
+        called on the compute stream after each replay (enqueue the device->host copies of the results there)."""
+        compute = torch.cuda.current_stream(self.device)
+        bounds = self._bounds()
+        self.copy_stream.wait_stream(compute)
+        self._upload(0, bounds)
+        for i, (b, e) in enumerate(bounds):
+            if i + 1 < len(bounds):
+                self._upload(i + 1, bounds)
+            slot = self.slots[i & 1]
+            compute.wait_event(slot.ready)
+            after(self.graphs[i & 1].replay(), b, e)
+            slot.free.record(compute)
+        compute.wait_stream(self.copy_stream)
+
+    def h2d_only_ms(self, reps: int = 3) -> float:
+        """Milliseconds of one pass of the uploads alone (no kernels): what the host side allows this pipeline."""
+        bounds = self._bounds()
+        best = float("inf")
+        for _ in range(max(1, reps)):
+            torch.cuda.synchronize(self.device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(self.copy_stream):
+                e0.record(self.copy_stream)
+                for i, (b, e) in enumerate(bounds):
+                    for k, t in self.host.items():
+                        self.slots[i & 1].dev[k][: e - b].copy_(t[b:e], non_blocking=True)
+                e1.record(self.copy_stream)
+            torch.cuda.synchronize(self.device)
+            best = min(best, e0.elapsed_time(e1))
+        return best
 
     def run(self, step: Callable[[Dict[str, torch.Tensor], int, int], None]) -> None:
         compute = torch.cuda.current_stream(self.device)

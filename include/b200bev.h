@@ -125,6 +125,26 @@ B200BEV_API size_t b200bev_pointnet_pack_bf16_bytes(const int32_t* dims, int n_l
 B200BEV_API int b200bev_pointnet_pack_bf16(const float* params, const int32_t* dims, int n_layers,
                                void* tc_params, size_t tc_bytes, void* stream);
 
+/* fp32-accuracy tensor-core path of S1b (csrc/pointnet_mlp_split.cu): every fp32 product of the shared MLP as three fp16
+ * tcgen05 products with fp32 accumulation, operands scaled by exact powers of two (weights per output channel at pack
+ * time, activations per layer from the layer's own maximum, reduced on the device).  Same arithmetic contract as
+ * b200bev_pointnet_encode with B200BEV_F32 — PointNetLiDAREncoder.forward, src/encoders.py:289-298, parity 1e-5 of
+ * max|ref| — for the layer widths C-64-128-256-512-1024 only (pack_split_bytes returns 0 otherwise; use the FFMA kernel).
+ *   image      made by b200bev_pointnet_pack_split from the same fp32 `params` blob; call once per weight update
+ *   workspace  device scratch, >= b200bev_pointnet_split_workspace_bytes(1, N) (one frame per pass); with
+ *              b200bev_pointnet_split_workspace_bytes(B, N) the batch runs in as few passes as ~1M points allow.
+ *              Holds the fp32 activations between the five layer launches; 256-byte aligned.
+ * Outputs and perm/offsets/n_cells as in b200bev_pointnet_encode. */
+B200BEV_API size_t b200bev_pointnet_pack_split_bytes(const int32_t* dims, int n_layers);
+B200BEV_API int b200bev_pointnet_pack_split(const float* params, const int32_t* dims, int n_layers,
+                                void* image, size_t image_bytes, void* stream);
+B200BEV_API size_t b200bev_pointnet_split_workspace_bytes(int B, int N);
+B200BEV_API int b200bev_pointnet_encode_split(const float* points, int B, int N, int C,
+                                  const int32_t* dims, int n_layers,
+                                  const int32_t* perm, const int32_t* offsets, int n_cells,
+                                  const void* image, float* out_global, float* out_canvas,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * S1c  multi-radar encoder: shared MLP + max per radar, then fusion.
  * Replaces: MultiRadarEncoder.forward, src/encoders.py:628-661.

@@ -221,11 +221,11 @@ def detector_chain(sd: Dict[str, torch.Tensor], camera_features=None, lidar_poin
 
 
 @torch.no_grad()
-def cell_canvas(points: torch.Tensor, layers, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
+def cell_canvas(points: torch.Tensor, layers, cell: torch.Tensor, n_cells: int, with_global: bool = False):
     """north_star S1 on the CPU: per-point features (what the reference exposes with return_point_features=True,
     src/encoders.py:300-304) scatter-max'ed into the (B, n_cells, C) canvas; one frame at a time (the per-point
     tensor of a frame is 143 MB at 35,000 x 1024)."""
-    out = []
+    out, glob = [], []
     for b in range(points.shape[0]):
         x = points[b:b + 1].transpose(1, 2)
         for lay in layers:
@@ -233,10 +233,11 @@ def cell_canvas(points: torch.Tensor, layers, cell: torch.Tensor, n_cells: int) 
             if "bn_var" in lay:
                 x = F.batch_norm(x, lay["bn_mean"], lay["bn_var"], lay["bn_weight"], lay["bn_bias"], training=False, eps=1e-5)
             x = F.relu(x)
+        glob.append(torch.max(x, 2)[0][0])                                # src/encoders.py:298 — the reference's output
         feat = x[0].t()                                                   # (N, C)
         ok = cell[b] >= 0
         canvas = torch.zeros((n_cells, feat.shape[1]), dtype=feat.dtype)
         idx = cell[b][ok].long().unsqueeze(1).expand(-1, feat.shape[1])
         canvas.scatter_reduce_(0, idx, feat[ok], reduce="amax", include_self=True)   # features are >= 0 (ReLU): zeros = empty
         out.append(canvas)
-    return torch.stack(out)
+    return (torch.stack(out), torch.stack(glob)) if with_global else torch.stack(out)

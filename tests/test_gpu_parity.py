@@ -487,6 +487,109 @@ def test_tensor_core_cell_canvas(cuda, B, N, W):
     assert torch.equal(only, canvas)                            # deterministic, with or without the global output
 
 
+# ------------------------------------------------------------------------------------------------ S1b, fp32 accuracy on tcgen05
+def _split(cuda, layers):
+    blob, dims = packed(layers, cuda)
+    img = ops.pack_mlp_params_split(blob, dims)
+    assert img is not None
+    return blob, dims, img
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 255), (2, 256), (2, 257), (3, 2011), (5, 1000), (2, 35000)])
+def test_split_tensor_core_global_max_is_fp32_accurate(cuda, B, N):
+    """The f32 precision on the tensor cores (three fp16 products per fp32 product): 1e-5 of max|ref| against the numpy
+    oracle, and against the FFMA kernel."""
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, img = _split(cuda, layers)
+    pts = syn.lidar_batch(900 + N, B, n_valid=max(N - N // 50 - 1, 1), n_total=N)
+    d = dev_t(pts, cuda)
+    got = ops.pointnet_encode(d, blob, dims, precision=_lib.F32, tc_params=img)
+    assert max_rel(got.cpu().numpy(), orc.pointnet_global(pts, layers)) < FP32_TOL
+    ffma = ops.pointnet_encode(d, blob, dims)
+    assert max_rel(got.cpu().numpy(), ffma.cpu().numpy()) < FP32_TOL
+    assert torch.equal(got, ops.pointnet_encode(d, blob, dims, precision=_lib.F32, tc_params=img))     # deterministic
+
+
+def test_split_tensor_core_vs_reference_golden(cuda, golden):
+    g = golden("lidar_encoder")
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, img = _split(cuda, layers)
+    full = dev_t(syn.lidar_batch(301, 1), cuda)
+    assert max_rel(ops.pointnet_encode(full, blob, dims, precision=_lib.F32, tc_params=img).cpu().numpy(), g["full_global"]) < FP32_TOL
+    small = syn.lidar_batch(201, 2, n_valid=1900, n_total=2011)
+    d = dev_t(small, cuda)
+    assert max_rel(ops.pointnet_encode(d, blob, dims, precision=_lib.F32, tc_params=img).cpu().numpy(), g["small_global"]) < FP32_TOL
+    cell, perm, off = ops.bin_sort(d, 50, 50)
+    np.testing.assert_array_equal(cell.cpu().numpy(), g["small_cell"])
+    glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=2500, precision=_lib.F32, tc_params=img)
+    assert max_rel(glob.cpu().numpy(), g["small_global"]) < FP32_TOL
+    assert max_rel(canvas[:, :, ::16].cpu().numpy(), g["small_canvas_sub"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 3e3])
+def test_split_tensor_core_is_scale_free(cuda, scale):
+    """fp16 operands, fp32 range: a network whose activations sit far from unit scale (1e-8 .. 1e9 across the layers) keeps
+    the 1e-5 bound — the per-channel weight scales and the per-layer activation scales are exact powers of two taken from
+    the data.  ReLU is positively homogeneous, so scaling layer i's weights by f_i (and every bias by the cumulative
+    factor) gives an exactly scaled copy of the unit-scale network."""
+    layers = syn.mlp_weights(131, syn.LIDAR_DIMS, use_bn=False)
+    factors = [scale, 1.0, scale, 1.0 / scale, 1.0 if scale == 1.0 else 7.0]
+    cum = 1.0
+    for lay, f in zip(layers, factors):
+        cum *= f
+        lay["weight"] = (lay["weight"].astype(np.float64) * f).astype(np.float32)
+        lay["bias"] = (lay["bias"].astype(np.float64) * cum).astype(np.float32)
+    blob, dims, img = _split(cuda, layers)
+    pts = syn.lidar_batch(77, 2, n_valid=1500, n_total=1536)
+    got = ops.pointnet_encode(dev_t(pts, cuda), blob, dims, precision=_lib.F32, tc_params=img).cpu().numpy()
+    ref = orc.pointnet_global(pts, layers)
+    assert np.isfinite(got).all() and float(np.abs(ref).max()) > 0 and max_rel(got, ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,N,W", [(2, 2011, 50), (1, 35000, 50), (2, 5000, 100), (3, 300, 7)])
+def test_split_tensor_core_cell_canvas(cuda, B, N, W):
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, img = _split(cuda, layers)
+    pts = syn.lidar_batch(800 + N, B, n_valid=max(N - N // 50 - 1, 1), n_total=N)
+    pts[:, 7::53, 0] = 75.0                                    # out-of-grid points: global max only
+    d = dev_t(pts, cuda)
+    _, perm, off = ops.bin_sort(d, W, W)
+    glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.F32, tc_params=img)
+    g32, c32 = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W)
+    assert float((canvas - c32).abs().max()) < FP32_TOL * float(c32.max())
+    assert float((glob - g32).abs().max()) < FP32_TOL * float(g32.max())
+    empty_cells = (off[:, 1:] - off[:, :-1]) == 0
+    assert not bool(canvas[empty_cells].any())
+    ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, W)
+    for b in range(B):
+        assert max_rel(canvas[b].cpu().numpy(), orc.pointnet_cell_max(pts[b], layers, ref_cell[b], W * W)) < FP32_TOL, b
+    only = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.F32, tc_params=img, want_global=False)
+    assert torch.equal(only, canvas)
+
+
+def test_split_tensor_core_runs_in_passes_when_the_workspace_is_small(cuda):
+    """The C-ABI takes the scratch from the caller: with room for one frame only the batch runs frame by frame, same bits."""
+    import ctypes as C
+
+    layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
+    blob, dims, img = _split(cuda, layers)
+    B, N = 3, 700
+    d = dev_t(syn.lidar_batch(55, B, n_valid=690, n_total=N), cuda)
+    want = ops.pointnet_encode(d, blob, dims, precision=_lib.F32, tc_params=img)
+    lib = _lib.lib()
+    one = lib.b200bev_pointnet_split_workspace_bytes(1, N)
+    assert one < lib.b200bev_pointnet_split_workspace_bytes(B, N)
+    ws = torch.empty(one, dtype=torch.uint8, device=cuda)
+    out = torch.empty((B, 1024), dtype=torch.float32, device=cuda)
+    dd = (C.c_int32 * 6)(*dims)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.b200bev_pointnet_encode_split(C.c_void_p(d.data_ptr()), B, N, 4, dd, 5, None, None, 0, C.c_void_p(img.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), None, C.c_void_p(ws.data_ptr()), one, st)
+    assert rc == 0 and torch.equal(out, want)
+    assert lib.b200bev_pointnet_encode_split(C.c_void_p(d.data_ptr()), B, N, 4, dd, 5, None, None, 0, C.c_void_p(img.data_ptr()),
+                                             C.c_void_p(out.data_ptr()), None, C.c_void_p(ws.data_ptr()), 4096, st) == _lib.ERR_WORKSPACE
+
+
 def _oracle_cells(pts_b, layers, cell_b, cells):
     """Oracle canvas rows of the chosen cells only: the MLP runs on the points that fall into them."""
     keep = np.isin(cell_b, cells)
@@ -509,14 +612,16 @@ def test_cell_canvas_at_the_stress_shape(cuda, precision):
     cell, perm, off = ops.bin_sort(d, W, W)
     ref_cell = orc.cell_index(pts, syn.PC_RANGE, W, W)
     np.testing.assert_array_equal(cell.cpu().numpy(), ref_cell)
-    g32, c32 = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W)
+    g32, c32 = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W)          # FFMA kernel
     if precision == "bf16":
         glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.BF16_TENSOR, tc_params=tc)
         tol = BF16_TOL
-        assert float((canvas - c32).abs().max()) < tol * float(c32.max())
-        assert float((glob - g32).abs().max()) < tol * float(g32.max())
     else:
-        glob, canvas, tol = g32, c32, FP32_TOL
+        img = ops.pack_mlp_params_split(blob, dims)
+        glob, canvas = ops.pointnet_encode(d, blob, dims, perm=perm, offsets=off, n_cells=W * W, precision=_lib.F32, tc_params=img)
+        tol = FP32_TOL
+    assert float((canvas - c32).abs().max()) < tol * float(c32.max())          # ALL cells of all frames against the FFMA kernel
+    assert float((glob - g32).abs().max()) < tol * float(g32.max())
     counts = (off[:, 1:] - off[:, :-1]).cpu().numpy()
     assert int(counts.max()) > 1000 and int(off[:, -1].max()) < N        # a cell far over 255 points; some points out of grid
     rng = np.random.default_rng(77)
