@@ -32,6 +32,13 @@ def main():
     ap.add_argument("--tc", action="store_true", help="include the tcgen05 kernels")
     ap.add_argument("--big", action="store_true", help="add one base.yaml-size frame per kernel")
     args = ap.parse_args()
+    print("SANITIZE-RUN-OK:", "; ".join(run_all(args.tc, args.big)))
+
+
+def run_all(tc: bool = False, big: bool = False):
+    """Every kernel once, on shapes that take its special paths; returns the list of kernel groups that ran."""
+    import types
+    args = types.SimpleNamespace(tc=tc, big=big)
     dev = torch.device("cuda:0")
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     done = []
@@ -155,7 +162,7 @@ def main():
         ops.conv_bn_relu_bf16(nhwc, ops.conv_pack(to(sd["w1"])), None, 70, 1, relu=False)
         done.append("conv3x3_tc_halo / conv_tc_ws")
     torch.cuda.synchronize()
-    print("SANITIZE-RUN-OK:", "; ".join(done))
+    return done
 
 
 if __name__ == "__main__":
