@@ -605,6 +605,9 @@ def run_b200_arm(args):
     affinity = None if args.no_affinity else runtime.bind_to_gpu_numa(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # the fp32 path must BE fp32: torch's default lets cuDNN run fp32 convolutions in TF32 (3.5e-3)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
@@ -687,7 +690,8 @@ def run_b200_arm(args):
             o_res, o_hp = run_workload(args.workload, max(3, min(args.steps, 10)), args.warmup, False, None, args.frames)
             other = {"dtype": state["precision"], "value": o_res["value"], "unit": "frames/s", "ms_per_step": o_res["ms_per_step"],
                      "timed": True, "steps": o_res["steps"], "eager_stage_ms": o_res["eager_stage_ms"],
-                     "note": ("fp32 path: PointNet MLP at fp32 accuracy (parity 1e-5), every convolution the reference's own fp32 cuDNN layer"
+                     "note": ("fp32 path: PointNet MLP at fp32 accuracy on the tensor cores (3 x fp16 products, parity 1e-5), every "
+                              "convolution the reference's own cuDNN layer in true fp32 (TF32 switched off)"
                               if state["precision"] == "f32" else "bf16 path: tcgen05 MLP and convolution kernels (parity 1e-2)")}
             try:
                 ok = kernel_rooflines(o_hp, peaks, fp32_peak, flush)

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "b200bev_nchw_to_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "b200bev_camera_mean_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "b200bev_conv_bn_relu_bf16": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
+    "b200bev_border_expand": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "b200bev_conv_bn_relu_bf16_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p, _p]),
 }
 

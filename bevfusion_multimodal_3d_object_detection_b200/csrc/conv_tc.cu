@@ -705,10 +705,58 @@ __global__ void __launch_bounds__(256) camera_mean_nhwc_bf16_kernel(const float*
   }
 }
 
+// A stack of k 3x3 (padding 1) convolutions applied to a spatially CONSTANT image (the radar branch: a (B,C) vector
+// broadcast to (B,C,H,W), src/fusion.py:277-281) has only (2k+1)^2 distinct output pixels per channel: what a pixel sees
+// depends on how many of the k rows / columns towards each border exist.  The stack therefore runs on a (2k+1) x (2k+1)
+// image and this kernel spreads the result: out[y][x] = small[cls(y)][cls(x)], cls(i) = i for i < k, s-1-(n-1-i) for
+// i >= n-k, k otherwise (s = 2k+1).  Writes NCHW fp32 and/or a channel slice of a channels-last bf16 tensor.
+__device__ __forceinline__ int border_class(int i, int n, int s) {
+  const int k = s >> 1;
+  return i < k ? i : (i >= n - k ? s - (n - i) : k);
+}
+__global__ void __launch_bounds__(256) border_expand_kernel(const float* __restrict__ small, int B, int C, int s, int H, int W,
+                                                            float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_nhwc,
+                                                            int C_total, int c_offset) {
+  const long long HW = (long long)H * W;
+  if (out_nhwc) {
+    const int cg = (C + 7) / 8;
+    const long long n = (long long)B * HW * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const int g = (int)(i % cg);
+      const long long bp = i / cg;
+      const int p = (int)(bp % HW), b = (int)(bp / HW);
+      const int cy = border_class(p / W, H, s), cx = border_class(p % W, W, s);
+      const float* src = small + (((size_t)b * C + g * 8) * s + cy) * s + cx;
+      __nv_bfloat16* dst = out_nhwc + ((size_t)b * HW + p) * C_total + c_offset + g * 8;
+      for (int e = 0; e < 8 && g * 8 + e < C; ++e) dst[e] = __float2bfloat16_rn(__ldg(src + (size_t)e * s * s));
+    }
+  }
+  if (out_nchw) {
+    const long long n = (long long)B * C * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const int p = (int)(i % HW);
+      const long long bc = i / HW;
+      out_nchw[i] = __ldg(small + (bc * s + border_class(p / W, H, s)) * s + border_class(p % W, W, s));
+    }
+  }
+}
+
 }  // namespace
 }  // namespace b200bev
 
 using namespace b200bev;
+
+extern "C" B200BEV_API int b200bev_border_expand(const float* small, int B, int C, int s, int H, int W, float* out_nchw, void* out_nhwc,
+                                     int C_total, int c_offset, void* stream) {
+  if (!small || (!out_nchw && !out_nhwc) || B <= 0 || C <= 0 || s < 1 || !(s & 1) || H < s || W < s) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (out_nhwc && (c_offset < 0 || c_offset + C > C_total)) return B200BEV_ERR_INVALID_ARGUMENT;
+  const long long work = (long long)B * C * H * W / (out_nhwc && !out_nchw ? 8 : 1);
+  long long blocks = (work + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  border_expand_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(small, B, C, s, H, W, out_nchw, (__nv_bfloat16*)out_nhwc, C_total,
+                                                                       c_offset);
+  return launch_status();
+}
 
 extern "C" B200BEV_API size_t b200bev_conv_pack_bytes(int Cout, int Cin, int taps) {
   if (Cout <= 0 || Cin <= 0 || Cin % kKC != 0 || (taps != 1 && taps != 9)) return 0;

@@ -45,10 +45,11 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kStageBytes = 16384;  // 128 rows x 64 bf16
 constexpr int kStagesGlobal = 12;   // ring depth when shared memory holds nothing but weights
-constexpr int kStagesCell = 8;      // cell mode gives 66 KB to the transposing tile below
-constexpr int kStagesCellPair = 4;  // cell mode of a CTA pair: half the ring bytes carry the same number of pairs, the
-                                    // other half holds a SECOND transposing tile (stores of chunk c+1 overlap the walk of c)
-constexpr int kTStride = 132;       // floats per channel row of the tile: 16-B aligned, conflict-free both ways
+constexpr int kStagesCell = 8;      // cell mode gives 72 KB to the per-warp transposing tiles below
+constexpr int kStagesCellPair = 8;  // a CTA pair keeps half of every stage: the same bytes carry twice the ring pairs
+constexpr int kTStride = 36;        // floats per channel row of a warp's private 32 x 32 tile: 16-B aligned rows, and both the
+                                    // lane = point stores and the lane = channel 128-bit loads are free of bank conflicts
+constexpr int kWarpTile = 32 * kTStride;
 constexpr int kEpiThreads = 512;     // 16 epilogue warps: 4 per TMEM lane quadrant
 constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kPairBytes = 2 * kStageBytes;
@@ -267,13 +268,12 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;"
 template <bool CELL, bool TRACE, int CG>
 __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a) {
   constexpr int kStages = CELL ? (CG == 2 ? kStagesCellPair : kStagesCell) : kStagesGlobal;
-  constexpr int kTileBufs = (CELL && CG == 2) ? 2 : 1;   // transposing tiles
   constexpr int kSlotBytes = kPairBytes / CG;                    // bytes of one ring pair in THIS CTA's shared memory
   constexpr int kRingPairs = kStages * kStageBytes / kSlotBytes;  // a pair of CTAs keeps twice as many pairs in flight
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B: 1024-B aligned tiles
-  float* tile_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);   // CELL: [128 channels][kTStride]
-  int* cid_s = reinterpret_cast<int*>(tile_s + (CELL ? kTileBufs * 128 * kTStride : 0));   // CELL: cell id of each tile slot
+  float* tile_s = reinterpret_cast<float*>(ring + (size_t)kStages * kStageBytes);   // CELL: one [32 channels][kTStride] tile per epilogue warp
+  int* cid_s = reinterpret_cast<int*>(tile_s + (CELL ? kEpiWarps * kWarpTile : 0));   // CELL: cell id of each tile slot
   uint32_t* endmask_s = reinterpret_cast<uint32_t*>(cid_s + (CELL ? 128 : 0));      // CELL: run-end flags, one word per warp
   int* scan_s = reinterpret_cast<int*>(endmask_s + (CELL ? 4 : 0));                 // CELL: [0,4) warp maxima, [4,6) "more cells" flags
   float* bias_s = reinterpret_cast<float*>(scan_s + (CELL ? 8 : 0));                // L2 | L3 | L4 | L5
@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     const uint32_t tm = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t full_phase = 0;                   // bit b: parity of the next completion of accumulator b
     // running maximum of the raw layer-5 accumulators of the current frame, one value per 128-channel chunk c:
-    //   global mode: rmax[c] <-> channel c*128 + part*32 + lane (what the butterfly leaves in this lane)
-    //   cell mode  : rmax[c] <-> channel c*128 + row, over the 32 tile slots [part*32, part*32+32) this thread walks
+    //   rmax[c] <-> channel c*128 + part*32 + lane, over the 32 points of this warp's TMEM lane quadrant (global mode: what
+    //   the butterfly leaves in this lane; cell mode: the channel this lane walks after the warp's private transpose)
     float rmax[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       int* o = reinterpret_cast<int*>(a.out_global + (size_t)frame * c_out);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int col = CELL ? i * 128 + row : i * 128 + part * 32 + lane;
+        const int col = i * 128 + part * 32 + lane;
         const float v = fmaxf(rmax[i] + b5[col], 0.0f);   // bias + ReLU commute with the max
         atomicMax(o + col, __float_as_int(v));
         rmax[i] = -INFINITY;
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           const unsigned ends = __ballot_sync(FULL_MASK, cid >= 0 && next != cid);
           if (lane == 0) endmask_s[quad] = ends;
         }
-        // cid_s / endmask_s become visible to the walkers at the barrier after the first tile store of layer 5
+        // cid_s / endmask_s become visible to the walkers at the barrier in front of the layer-5 loop
       }
 
       // ---- layers 2..4: accumulator -> bias, ReLU, bf16 -> next A operand in TMEM ----
@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       // The loop stays ROLLED (the unrolled cell-mode kernel was 164 KB of code and its epilogue warps starved on
       // instruction fetch); the eight running maxima live in registers all the same: rmax[0] is always the
       // current chunk's, and the array is rotated by one after every chunk — back in place after the eighth.
+      if (CELL) epi_bar_sync();     // this tile's cell ids and run-end flags (written by part 0 at the top) are in place
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         const int buf = c & 1;
@@ -807,73 +808,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             rmax[0] = fmaxf(rmax[0], v[0]);  // lane l holds channel c*128 + g*32 + l
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x260 + c);  // layer-5 chunk reduced
           } else {
-            // transpose through shared memory: tile_s[channel][point]; lanes are consecutive points
+            // Transpose this warp's 32 points x 32 channels through its PRIVATE shared-memory tile: tp[channel][point].
+            // Nobody else touches the tile, so the hand-over is a __syncwarp, not a block barrier (the shared 128 x 128
+            // tile of the first version cost one or two 512-thread barriers per chunk: every chunk waited for the
+            // slowest of 16 warps, twice).
+            float* tp = tile_s + (warp - 2) * kWarpTile;
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x270);   // accumulator in registers
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tile_s[(kTileBufs == 2 ? (c & 1) * 128 * kTStride : 0) + (g * 32 + j) * kTStride + row] = v[j];
+            for (int j = 0; j < 32; ++j) tp[j * kTStride + lane] = v[j];
+            __syncwarp();
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x271);   // transposed tile stored
-          }
-        }
-        if (CELL) {
-          epi_bar_sync();
-          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x272);     // everyone's stores visible
-          // Thread (row, part) now owns channel c*128 + row over the 32 tile slots [part*32, part*32+32),
-          // which are in cell order: the maximum of each run of equal cell ids goes to the canvas.  A run
-          // that touches the first or the last slot of this stretch may continue in a neighbouring
-          // stretch or tile -> atomic max; any other run is the cell's only writer -> plain store.  The 32
-          // lanes of a warp see the same run boundaries and write 128 contiguous bytes of a canvas row.
-          const int ch = c * 128 + row;
-          const float bias = b5[ch];
-          float* canvas = a.out_canvas + (size_t)f * a.n_cells * c_out + ch;
-          const float* trow = tile_s + (kTileBufs == 2 ? (c & 1) * 128 * kTStride : 0) + row * kTStride + part * 32;
-          const int* cids = cid_s + part * 32;
-          // the same word in every lane: broadcast through a shuffle so that the compiler knows the branches on its
-          // bits are warp-uniform (a possibly-divergent branch per slot costs a BSSY/BSYNC pair and its resolve latency)
-          const uint32_t ends = __shfl_sync(FULL_MASK, endmask_s[part], 0);
-          float m = -INFINITY, gm = rmax[0];
-          bool first_run = true;
-          // all 32 values first (one shared-memory latency, not eight), then four slots at a time: a group without a
-          // run end — most of them — is four maxima and ONE warp-uniform branch
-          float4 q[8];
+            // This lane now owns channel c*128 + g*32 + lane over the warp's 32 tile slots [quad*32, quad*32+32), which are
+            // in cell order: the maximum of each run of equal cell ids goes to the canvas.  A run that touches the first
+            // or the last slot of the stretch may continue in a neighbouring stretch or tile -> atomic max; any other run
+            // is the cell's only writer -> plain store.  The 32 lanes see the same run boundaries and write 128
+            // contiguous bytes of a canvas row.
+            const int ch = c * 128 + g * 32 + lane;
+            const float bias = b5[ch];
+            float* canvas = a.out_canvas + (size_t)f * a.n_cells * c_out + ch;
+            const float* trow = tp + lane * kTStride;
+            const int* cids = cid_s + quad * 32;
+            // the same word in every lane: broadcast through a shuffle so that the compiler knows the branches on its
+            // bits are warp-uniform (a possibly-divergent branch per slot costs a BSSY/BSYNC pair and its resolve latency)
+            const uint32_t ends = __shfl_sync(FULL_MASK, endmask_s[quad], 0);
+            float m = -INFINITY, gm = rmax[0];
+            bool first_run = true;
+            // all 32 values first (one shared-memory latency, not eight), then four slots at a time: a group without a
+            // run end — most of them — is four maxima and ONE warp-uniform branch
+            float4 q[8];
 #pragma unroll
-          for (int b4 = 0; b4 < 8; ++b4) q[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
+            for (int b4 = 0; b4 < 8; ++b4) q[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
 #pragma unroll
-          for (int b4 = 0; b4 < 8; ++b4) {
-            const float e[4] = {q[b4].x, q[b4].y, q[b4].z, q[b4].w};
-            if (((ends >> (b4 * 4)) & 0xfu) == 0u) {
-              m = fmaxf(fmaxf(m, fmaxf(e[0], e[1])), fmaxf(e[2], e[3]));
-              continue;
-            }
+            for (int b4 = 0; b4 < 8; ++b4) {
+              const float e[4] = {q[b4].x, q[b4].y, q[b4].z, q[b4].w};
+              if (((ends >> (b4 * 4)) & 0xfu) == 0u) {
+                m = fmaxf(fmaxf(m, fmaxf(e[0], e[1])), fmaxf(e[2], e[3]));
+                continue;
+              }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              m = fmaxf(m, e[k]);
-              if (ends & (1u << (b4 * 4 + k))) {
-                const int pt = b4 * 4 + k;
-                const float val = fmaxf(m + bias, 0.0f);
-                if (val > 0.0f) {
-                  float* dst = canvas + (size_t)cids[pt] * c_out;
-                  if (first_run || pt == 31) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
-                  else *dst = val;
+              for (int k = 0; k < 4; ++k) {
+                m = fmaxf(m, e[k]);
+                if (ends & (1u << (b4 * 4 + k))) {
+                  const int pt = b4 * 4 + k;
+                  const float val = fmaxf(m + bias, 0.0f);
+                  if (val > 0.0f) {
+                    float* dst = canvas + (size_t)cids[pt] * c_out;
+                    if (first_run || pt == 31) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
+                    else *dst = val;
+                  }
+                  gm = fmaxf(gm, m);
+                  m = -INFINITY;
+                  first_run = false;
                 }
-                gm = fmaxf(gm, m);
-                m = -INFINITY;
-                first_run = false;
               }
             }
+            // a run still open at the last slot goes on in the next stretch: hand its partial maximum over
+            if (!(ends >> 31) && cids[31] >= 0) {
+              const float val = fmaxf(m + bias, 0.0f);
+              if (val > 0.0f) atomicMax(reinterpret_cast<int*>(canvas + (size_t)cids[31] * c_out), __float_as_int(val));
+            }
+            rmax[0] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
+            __syncwarp();             // the tile is read out: the next chunk may overwrite it
+            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x273);     // runs walked
           }
-          // a run still open at the last slot goes on in the next stretch: hand its partial maximum over
-          if (!(ends >> 31) && cids[31] >= 0) {
-            const float val = fmaxf(m + bias, 0.0f);
-            if (val > 0.0f) atomicMax(reinterpret_cast<int*>(canvas + (size_t)cids[31] * c_out), __float_as_int(val));
-          }
-          rmax[0] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
-          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x273);     // runs walked
-          // One tile: it is free again when everyone has walked it.  Two tiles: the barrier after the NEXT chunk's
-          // stores already proves that (a thread gets there only after this walk), so warps that finish early go
-          // straight on to the next chunk; cid_s / endmask_s are protected once per tile, below.
-          if (kTileBufs == 1 || c == 7) epi_bar_sync();
-          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x274);     // tile free
         }
+        // cid_s / endmask_s belong to this tile until everyone has walked its last chunk
+        if (CELL && c == 7) epi_bar_sync();
         {
           const float r0 = rmax[0];
 #pragma unroll
@@ -974,8 +974,7 @@ int tc_cluster_size() {
 
 size_t tc_smem_bytes(bool cell, int cluster) {
   const int stages = cell ? (cluster == 2 ? kStagesCellPair : kStagesCell) : kStagesGlobal;
-  const int tile_bufs = (cell && cluster == 2) ? 2 : 1;
-  return 1024 + (size_t)stages * kStageBytes + (cell ? (tile_bufs * 128 * kTStride + 128 + 4) * sizeof(float) : 0) +
+  return 1024 + (size_t)stages * kStageBytes + (cell ? (kEpiWarps * kWarpTile + 128 + 4) * sizeof(float) : 0) +
          (cell ? 8 * sizeof(int) : 0) + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
          (3 * stages + 11) * sizeof(uint64_t) + 16;
 }

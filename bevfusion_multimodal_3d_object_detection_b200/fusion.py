@@ -60,6 +60,41 @@ def _stack(module: nn.Module, seq: nn.Sequential, parts) -> torch.Tensor:
     return seq(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
 
 
+def _const_image_size(seq: nn.Sequential, H: int, W: int) -> int:
+    """Side of the small image on which a conv stack over a spatially constant input can run (2k+1 for k 3x3 convolutions),
+    or 0 when the stack is not of that kind or the grid is too small for the shortcut."""
+    k = 0
+    for layer in seq:
+        if isinstance(layer, nn.Conv2d):
+            if layer.kernel_size == (3, 3) and layer.padding == (1, 1) and layer.stride == (1, 1) and layer.dilation == (1, 1) \
+                    and layer.padding_mode == "zeros":
+                k += 1
+            elif layer.kernel_size != (1, 1) or layer.stride != (1, 1):
+                return 0
+        elif not isinstance(layer, (nn.BatchNorm2d, nn.ReLU)):
+            return 0
+    s = 2 * k + 1
+    return s if (k > 0 and H >= s and W >= s) else 0
+
+
+def radar_branch(module: nn.Module, radar_features: torch.Tensor, out_nhwc: Optional[torch.Tensor] = None,
+                 c_offset: int = 0) -> Optional[torch.Tensor]:
+    """src/fusion.py:274-281 in eval mode: radar_proj -> view(B,C,1,1).expand(B,C,H,W) -> radar_refine.  The expanded image
+    is constant over space, so the two 3x3 convolutions run on a 5 x 5 image and `b200bev_border_expand` spreads the 25
+    distinct pixels over the grid (1/100 of the convolution work at 50 x 50, and no 82 MB broadcast copy)."""
+    B, c, H, W = radar_features.shape[0], module.bev_channels, module.bev_h, module.bev_w
+    r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)      # :274
+    s = _const_image_size(module.radar_refine, H, W)
+    if s:
+        small = _stack(module, module.radar_refine, [r.view(B, c, 1, 1).expand(B, c, s, s).contiguous()])
+        return ops.border_expand(small, (H, W), out_nhwc=out_nhwc, c_offset=c_offset, want_nchw=out_nhwc is None)
+    full = r.view(B, c, 1, 1).expand(B, c, H, W)                                                               # :277-278
+    if out_nhwc is not None:
+        conv_blocks.run(module.radar_refine, [full], out_nhwc=out_nhwc, c_offset=c_offset)
+        return None
+    return _stack(module, module.radar_refine, [full])                                                         # :281
+
+
 def lidar_branch(module: nn.Module, lidar_features: torch.Tensor, torch_graph: bool = False) -> torch.Tensor:
     """src/fusion.py:258-262: lidar_init (two dense layers, the second a 164 MB weight) -> (B,128,s,s) ->
     conv+BN+ReLU -> x2 bilinear upsample -> conv+BN+ReLU.  Eval mode on CUDA: the dense layers run on
@@ -123,8 +158,7 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         conv_blocks.run(module.lidar_upsample, [x], out_nhwc=cat, c_offset=off)              # :258-262
         off += c
     if use[2]:
-        r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)
-        conv_blocks.run(module.radar_refine, [r.view(B, c, 1, 1).expand(B, c, H, W)], out_nhwc=cat, c_offset=off)   # :274-281
+        radar_branch(module, radar_features, out_nhwc=cat, c_offset=off)                     # :274-281
     return conv_blocks.run(module.bev_fusion, nhwc=cat)                                      # :292-295
 
 
@@ -158,12 +192,10 @@ def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None,
     if module.use_radar and radar_features is not None:
         B = radar_features.shape[0] if B is None else B
         if torch_graph:
-            r = module.radar_proj(radar_features)
+            r = module.radar_proj(radar_features).view(B, module.bev_channels, 1, 1)
+            parts.append(module.radar_refine(r.expand(B, module.bev_channels, module.bev_h, module.bev_w)))    # :274-281
         else:
-            r = ops.dense_layer(radar_features, module.radar_proj[0].weight, module.radar_proj[0].bias, relu=True)  # :274
-        r = r.view(B, module.bev_channels, 1, 1)
-        r = r.expand(B, module.bev_channels, module.bev_h, module.bev_w)
-        parts.append(module.radar_refine(r) if torch_graph else _stack(module, module.radar_refine, [r]))  # :274-281
+            parts.append(radar_branch(module, radar_features))
     if not parts:
         raise ValueError("No modality features provided")              # :289
     if torch_graph:

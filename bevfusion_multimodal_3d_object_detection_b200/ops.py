@@ -428,6 +428,34 @@ def conv_bn_relu_bf16(x_nhwc: torch.Tensor, image: torch.Tensor, bias: Optional[
     return out if out is not None else out_nhwc
 
 
+def border_class_index(n: int, s: int) -> List[int]:
+    """cls(i) for i in range(n): which row (column) of the s x s image a row (column) of an n-wide image equals when
+    k = s // 2 padded 3x3 convolutions ran over a spatially constant input."""
+    k = s // 2
+    return [i if i < k else (s - (n - i) if i >= n - k else k) for i in range(n)]
+
+
+def border_expand(small: torch.Tensor, size: Tuple[int, int], out_nhwc: Optional[torch.Tensor] = None, c_offset: int = 0,
+                  want_nchw: bool = True) -> Optional[torch.Tensor]:
+    """(B,C,s,s) -> (B,C,H,W): out[y][x] = small[cls(y)][cls(x)] (b200bev_border_expand), optionally (also) into channels
+    [c_offset, c_offset+C) of a channels-last bf16 tensor."""
+    small = _need_cuda(small, "small")
+    B, Cc, s, s2 = small.shape
+    H, W = int(size[0]), int(size[1])
+    if s != s2 or s % 2 == 0 or H < s or W < s:
+        raise ValueError(f"border_expand: small must be (B,C,s,s) with odd s <= H, W; got {tuple(small.shape)} for {(H, W)}")
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=small.device) if want_nchw or out_nhwc is None else None
+    c_total = 0
+    if out_nhwc is not None:
+        if out_nhwc.dtype != torch.bfloat16 or not out_nhwc.is_contiguous() or tuple(out_nhwc.shape[:3]) != (B, H, W):
+            raise ValueError(f"out_nhwc must be a contiguous (B,H,W,C) bf16 tensor matching {(B, H, W)}")
+        c_total = int(out_nhwc.shape[3])
+    with torch.cuda.device(small.device):
+        _lib.check(_lib.lib().b200bev_border_expand(_ptr(small), B, Cc, s, H, W, _ptr(out), _ptr(out_nhwc), c_total, c_offset,
+                                                    _stream(small.device)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # S3
 # ------------------------------------------------------------------------------------------------

@@ -290,6 +290,15 @@ B200BEV_API int b200bev_conv_bn_relu_bf16_nhwc(const void* x_nhwc, int B, int H,
                                    void* out_nhwc, int out_c_total, int out_c_offset,
                                    float* out_nchw, void* stream);
 
+/* The radar branch of FlexibleBEVFusion.forward (src/fusion.py:274-281) feeds `radar_refine` a spatially CONSTANT image:
+ * the (B,C) projection broadcast to (B,C,H,W).  k 3x3 convolutions (padding 1) of a constant image have (2k+1)^2
+ * distinct output pixels per channel, so the stack runs on an s x s image (s = 2k+1) and this entry point spreads it:
+ * out[y][x] = small[cls(y)][cls(x)], cls(i) = i if i < k, s - (n - i) if i >= n - k, else k.  Same values as the full-size
+ * stack (same kernels, same operands per pixel), 1/100 of the work at 50x50.
+ *   small (B,C,s,s) f32; out_nchw (B,C,H,W) f32 or NULL; out_nhwc (B,H,W,C_total) bf16 or NULL, channels from c_offset. */
+B200BEV_API int b200bev_border_expand(const float* small, int B, int C, int s, int H, int W,
+                          float* out_nchw, void* out_nhwc, int C_total, int c_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,24 @@
+"""One eager pass of the bench step (bf16 and f32) for an `ncu --metrics gpu__time_duration.sum` launch list."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+
+dev = torch.device("cuda:0")
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+for precision in ("bf16", "f32"):
+    hp = bench.HotPath("step", frames, precision, dev, 42)
+    for _ in range(2):
+        hp.step(hp.inputs)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push(f"step-{precision}")
+    hp.step(hp.inputs)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+    print("done", precision, flush=True)
+    del hp
+    torch.cuda.empty_cache()

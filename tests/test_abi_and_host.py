@@ -438,3 +438,22 @@ def test_radar_sweeps_are_read_from_the_files_and_calibration_rides_in_the_batch
                 sys.path.remove(str(ref_src))
                 for m in ("train_detect", "fusion", "encoders", "centernet_target", "utils_v2"):
                     sys.modules.pop(m, None)
+
+
+def test_constant_image_conv_stack_has_border_classes_only():
+    """The radar branch's shortcut (fusion.radar_branch): k padded 3x3 convolutions of a spatially constant image give
+    out[y][x] = small[cls(y)][cls(x)] with the stack run on a (2k+1)^2 image — checked here with torch's own convolutions."""
+    torch.manual_seed(3)
+    seq = torch.nn.Sequential(torch.nn.Conv2d(6, 6, 3, padding=1), torch.nn.BatchNorm2d(6), torch.nn.ReLU(),
+                              torch.nn.Conv2d(6, 4, 3, padding=1), torch.nn.BatchNorm2d(4), torch.nn.ReLU()).eval()
+    assert fusion._const_image_size(seq, 11, 9) == 5 and fusion._const_image_size(seq, 4, 9) == 0
+    assert fusion._const_image_size(torch.nn.Sequential(torch.nn.Conv2d(6, 6, 5, padding=2)), 50, 50) == 0
+    r = torch.randn(3, 6)
+    with torch.no_grad():
+        full = seq(r.view(3, 6, 1, 1).expand(3, 6, 11, 9))
+        small = seq(r.view(3, 6, 1, 1).expand(3, 6, 5, 5))
+    iy, ix = ops.border_class_index(11, 5), ops.border_class_index(9, 5)
+    assert iy == [0, 1, 2, 2, 2, 2, 2, 2, 2, 3, 4] and ix == [0, 1, 2, 2, 2, 2, 2, 3, 4]
+    spread = small[:, :, iy][:, :, :, ix]
+    assert torch.allclose(spread, full, rtol=0, atol=1e-6)
+    assert not torch.allclose(full[:, :, 0], full[:, :, 5])            # the borders do differ from the interior

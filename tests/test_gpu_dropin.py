@@ -448,3 +448,41 @@ def test_cache_invalidation_after_data_writes(cuda):
         with torch.no_grad():
             enc.bn5.bias.add_(-0.75)                            # an ordinary in-place op IS seen
         assert torch.allclose(enc(pts), a, atol=1e-5)
+
+
+@pytest.mark.parametrize("H,W,s,C", [(50, 50, 5, 256), (7, 9, 5, 24), (100, 100, 3, 64), (5, 5, 5, 8)])
+def test_border_expand_kernel(cuda, H, W, s, C):
+    """out[y][x] = small[cls(y)][cls(x)] — both output layouts, against torch indexing (bit-exact: it is a copy)."""
+    from bevfusion_multimodal_3d_object_detection_b200 import ops
+
+    small = torch.randn(3, C, s, s, device=cuda)
+    iy = torch.tensor(ops.border_class_index(H, s), device=cuda)
+    ix = torch.tensor(ops.border_class_index(W, s), device=cuda)
+    want = small[:, :, iy][:, :, :, ix]
+    assert torch.equal(ops.border_expand(small, (H, W)), want)
+    if C % 8 == 0:
+        cat = torch.zeros(3, H, W, C + 16, dtype=torch.bfloat16, device=cuda)
+        assert ops.border_expand(small, (H, W), out_nhwc=cat, c_offset=8, want_nchw=False) is None
+        assert torch.equal(cat[..., 8:8 + C], want.permute(0, 2, 3, 1).to(torch.bfloat16))
+        assert not bool(cat[..., :8].any()) and not bool(cat[..., 8 + C:].any())
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_radar_branch_shortcut_equals_the_full_size_stack(cuda, precision, tol):
+    """fusion.radar_branch (5 x 5 image + border classes) against the module's own layers on the broadcast (B,C,H,W) image."""
+    from bevfusion_multimodal_3d_object_detection_b200 import fusion as fus_mod
+
+    fus = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=False, use_radar=True, radar_channels=64, bev_h=50, bev_w=40,
+                                    bev_channels=64)
+    sd = syn.fill_state_dict(61, {k: tuple(v.shape) for k, v in fus.state_dict().items()})
+    fus.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    fus = fus.eval().to(cuda)
+    fus.b200_precision = precision
+    feat = torch.from_numpy(syn.global_features(62, 3, 64)).to(cuda)
+    with torch.no_grad():
+        got = fus_mod.radar_branch(fus, feat)
+        r = fus.radar_proj(feat).view(3, 64, 1, 1).expand(3, 64, 50, 40)
+        want = fus.radar_refine(r)
+        assert max_rel(got.cpu().numpy(), want.cpu().numpy()) < tol
+        whole = fus(radar_features=feat)
+        assert max_rel(whole.cpu().numpy(), fus.bev_fusion(want).cpu().numpy()) < 2 * tol
