@@ -81,6 +81,22 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
+// Split-fp16 tensor-core paths (fp32 accuracy from three fp16 products): 2^k with (tensor maximum) * 2^k in [2^13, 2^14), so
+// that fp16 holds the scaled hi part (< 65504) and the lo part of anything that matters (lo is subnormal only below 2^-17
+// of the maximum).  `max_bits` = the float bits of max|x|, reduced on the device; 1 for an all-zero tensor.
+__host__ __device__ inline float activation_scale(uint32_t max_bits) {
+  const int e = (int)((max_bits >> 23) & 0xff);
+  if (e == 0 || e == 0xff) return 1.f;
+  const uint32_t bits = (uint32_t)(127 + 14 - (e - 126)) << 23;   // max = f * 2^(e-126), f in [0.5, 1)
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(bits);
+#else
+  union { uint32_t u; float f; } c;
+  c.u = bits;
+  return c.f;
+#endif
+}
+
 // Streaming 128-bit load that does not allocate in L1 (data touched once).
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;

@@ -21,6 +21,7 @@
 // mbarriers only), stages released by tcgen05.commit, fp32 accumulation double-buffered in TMEM (2 x 256 columns).  Two
 // kernels: the 3x3 form in which the nine taps share the pixel rows in shared memory, and the per-tap form (1x1, wide images).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -48,7 +49,31 @@ struct ConvArgs {
   int B, H, W, Cin, Cout, taps, relu;
   __nv_bfloat16* out_nhwc;    // (B, H, W, out_ct) bf16 channels-last, channels [out_coff, out_coff + Cout), or null:
   int out_ct, out_coff;       // the input layout of the next convolution, written without a separate layout pass
+  // fp32-accuracy mode (three fp16 products per fp32 product, see pointnet_mlp_split.cu): x is (B,H,W,[hi Cin | lo Cin]) fp16,
+  // scaled by activation_scale(*x_stat); the weight stages come in (hi, hi, lo) triples per 64-channel chunk, scaled per output
+  // channel by a power of two whose inverse is unscale[co]
+  int split;                  // 0: bf16 operands; 1: split fp16 operands
+  int x_pitch;                // elements per pixel of x: Cin, or 2 Cin in split mode
+  const float* unscale;       // (Cout) or null
+  const uint32_t* x_stat;     // float bits of max|x| or null
 };
+
+// k chunks of a (tap): Cin/64, or three times that in split mode — terms (w_hi, x_hi), (w_hi, x_lo), (w_lo, x_hi)
+__device__ __forceinline__ int conv_chunks(const ConvArgs& a) { return (a.Cin / kKC) * (a.split ? 3 : 1); }
+// first input channel (element offset inside a pixel of x) of k chunk j
+__device__ __forceinline__ int conv_chunk_channel(const ConvArgs& a, int j) {
+  const int ncc = a.Cin / kKC;
+  return a.split ? ((j / ncc == 1 ? a.Cin : 0) + (j % ncc) * kKC) : j * kKC;
+}
+__device__ __forceinline__ uint32_t conv_idesc(const ConvArgs& a, int n_cols) {
+  // D f32 (bit 4); A / B formats (bits 7-9 / 10-12): 1 = bf16, 0 = fp16; both K-major; N, M
+  return (1u << 4) | (a.split ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
+}
+// accumulator -> value: acc * (per-channel weight unscale / activation scale) + bias; 1 in bf16 mode (fmaf(acc, 1, b) == acc + b)
+__device__ __forceinline__ float conv_out_scale(const ConvArgs& a, int co) {
+  if (!a.split || co >= a.Cout) return 1.f;
+  return __ldg(a.unscale + co) / activation_scale(__ldg(a.x_stat));
+}
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool real) {
   const int n = real ? 16 : 0;
@@ -149,7 +174,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   const long long n_px = (long long)a.B * HW;
   const int n_px_tiles = (int)((n_px + kTilePx - 1) / kTilePx);
   const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
-  const int ncc = a.Cin / kKC;
+  const int ncc = conv_chunks(a);
   const int n_k = a.taps * ncc;
   const int n_tiles = n_px_tiles * n_co_tiles;
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -184,7 +209,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
               const int p = (int)(n % HW);
               py[j] = p / a.W;
               pxx[j] = p - py[j] * a.W;
-              poff[j] = n * a.Cin + chunk * 8;
+              poff[j] = n * a.x_pitch + chunk * 8;
             } else {
               py[j] = -100000;
               pxx[j] = 0;
@@ -197,7 +222,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         if (it >= kRing) mbarrier_wait(&empty[slot], (((uint32_t)it / kRing) - 1) & 1);
         const int tap = i / ncc, cc = i - tap * ncc;
         const int dy = a.taps == 9 ? tap / 3 - 1 : 0, dx = a.taps == 9 ? tap % 3 - 1 : 0;
-        const long long shift = ((long long)dy * a.W + dx) * a.Cin + cc * kKC;
+        const long long shift = ((long long)dy * a.W + dx) * a.x_pitch + conv_chunk_channel(a, cc);
         const uint32_t bdst = smem_addr(ring + slot * kStage + kStageA) + dst_off;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -218,7 +243,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
     }
   } else if (warp == 12) {
     // ---- MMA issuer ----
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTilePx >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
+    const uint32_t idesc = conv_idesc(a, kTilePx);
     int i = 0, tile_seq = 0;
     for (int c = 0; c < total; ++c) {
       const uint32_t slot = (uint32_t)c % kRing, use = (uint32_t)c / kRing;
@@ -256,6 +281,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
       const int co0 = co_tile * kTileCo + quad * 32;
       const int co = co0 + lane;
       const float bias = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+      const float oscale = conv_out_scale(a, co);
       const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;
       mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
       tc_fence_after_sync();
@@ -268,7 +294,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         const long long n0 = px0 + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]) + bias;
+          float v = fmaf(__uint_as_float(r[j]), oscale, bias);
           if (a.relu) v = fmaxf(v, 0.f);
           r[j] = __float_as_uint(v);
           tp[lane * 33 + j] = v;
@@ -394,7 +420,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
 
   const int W1 = a.W + 1, HW = a.H * a.W;
   const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
-  const int ncc = a.Cin / kKC;
+  const int ncc = conv_chunks(a);
   const int n_tiles = a.B * geo.tiles_per_frame * n_co_tiles;
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // tile -> (co tile, frame, first image row): the co tiles of one pixel tile are neighbours in the grid (shared pixels in L2)
@@ -428,17 +454,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
             const int q = row0 + 32 * j;
             const int ry = q / W1 - 1, x = q - (ry + 1) * W1 - 1;
             const int y = y0 + ry;
-            goff[j] = (q < geo.Q && x >= 0 && y >= 0 && y < a.H) ? (((long long)b * a.H + y) * a.W + x) * a.Cin + chunk * 8 : -1;
+            goff[j] = (q < geo.Q && x >= 0 && y >= 0 && y < a.H) ? (((long long)b * a.H + y) * a.W + x) * a.x_pitch + chunk * 8 : -1;
           }
         }
         const int buf = bi & 1;
         if (bi >= 2) mbarrier_wait(&empty_blk[buf], ((bi >> 1) - 1) & 1);
         const uint32_t bdst = smem_addr(blocks + buf * kHaloBlock) + dst_off;
+        const int c_first = conv_chunk_channel(a, cc);
 #pragma unroll
         for (int j = 0; j < kHaloRowsPerThread; ++j) {
           if (row0 + 32 * j < geo.Q) {
             const bool ok = goff[j] >= 0;
-            cp_async16_zfill(bdst + j * 4096, a.x + (ok ? goff[j] + cc * kKC : 0), ok);
+            cp_async16_zfill(bdst + j * 4096, a.x + (ok ? goff[j] + c_first : 0), ok);
           }
         }
         cp_async_commit_group();
@@ -474,7 +501,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     }
   } else if (warp == 12) {
     // ---- MMA issuer ----
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(geo.N >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
+    const uint32_t idesc = conv_idesc(a, geo.N);
     int g = 0, bi = 0;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       const uint32_t buf = tile_seq & 1;
@@ -517,6 +544,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
       const uint32_t buf = tile_seq & 1;
       const int co0 = co_tile * kTileCo + quad * 32;
       const float bias = (a.bias && co0 + lane < a.Cout) ? __ldg(a.bias + co0 + lane) : 0.f;
+      const float oscale = conv_out_scale(a, co0 + lane);
       const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;   // channels of this warp that exist (may be <= 0)
       float* oplane = a.out + ((size_t)b * a.Cout + co0) * HW;
       mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
@@ -528,7 +556,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]) + bias;
+          float v = fmaf(__uint_as_float(r[j]), oscale, bias);
           if (a.relu) v = fmaxf(v, 0.f);
           r[j] = __float_as_uint(v);
           tp[lane * 33 + j] = v;
@@ -705,6 +733,118 @@ __global__ void __launch_bounds__(256) camera_mean_nhwc_bf16_kernel(const float*
   }
 }
 
+// ---- fp32-accuracy mode: weight image, input layout, max|x| ------------------------------------------------------------------
+// Image: stages [co tile][tap][3 x (Cin/64)] of [128 co][64 ci] fp16 — per 64-channel chunk the triple (w_hi, w_hi, w_lo), in
+// the order the kernels consume them — then unscale[co] (padded to whole co tiles): the inverse of the power of two that
+// brought max |w[co]| into [1, 2).
+__global__ void __launch_bounds__(256) conv_split_scale_kernel(const float* __restrict__ w, int Cout, int per_co, float* __restrict__ unscale,
+                                                               int n_slots) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_slots) return;
+  float m = 0.f;
+  if (warp < Cout)
+    for (int i = lane; i < per_co; i += 32) m = fmaxf(m, fabsf(__ldg(w + (size_t)warp * per_co + i)));
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, d));
+  if (lane == 0) {
+    int ex = 0;
+    float inv = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      frexpf(m, &ex);
+      inv = ldexpf(1.f, ex - 1);
+    }
+    unscale[warp] = inv;
+  }
+}
+__global__ void __launch_bounds__(256) conv_pack_split_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, uint8_t* __restrict__ img,
+                                                              const float* __restrict__ unscale, long long n_chunks) {
+  const int ncc = Cin / kKC, ncc3 = 3 * ncc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 7);
+    const int r = (int)((i >> 3) & 127);
+    const long long stage = i >> 10;
+    const int j = (int)(stage % ncc3);
+    const int tap = (int)((stage / ncc3) % taps);
+    const int ct = (int)(stage / ((long long)ncc3 * taps));
+    const int co = ct * kTileCo + r, term = j / ncc, cc = j % ncc;
+    const float sc = co < Cout ? 1.f / unscale[co] : 0.f;
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ci = cc * kKC + c * 8 + e;
+      const float x = co < Cout ? __ldg(w + ((size_t)co * Cin + ci) * taps + tap) * sc : 0.f;
+      const __half hi = __float2half_rn(x);
+      v[e] = term < 2 ? hi : __float2half_rn(x - __half2float(hi));
+    }
+    *reinterpret_cast<uint4*>(img + stage * kStageA + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// max |x| of a tensor as float bits (non-negative floats order like unsigned integers): atomicMax into *stat
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n, uint32_t* __restrict__ stat) {
+  float m = 0.f;
+  const long long n4 = (((uintptr_t)x & 15) == 0) ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(stat, __float_as_uint(m));
+}
+
+// (B, C, H, W) fp32 -> (B, H, W, [hi C_total | lo C_total]) fp16, channels [c_offset, c_offset + C) of both halves, scaled by
+// activation_scale(*stat).  Thread shape of nchw_to_nhwc_bf16_kernel: four pixels x eight channels, 128-bit loads along the
+// plane, one 16-byte store per pixel and half.
+template <int PX>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __restrict__ in, int B, int C, int HW, __half* __restrict__ out,
+                                                                 int C_total, int c_offset, const uint32_t* __restrict__ stat) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 32 * PX);
+  const long long n_items = (long long)B * n_cg * n_pg;
+  const float S = activation_scale(__ldg(stat));
+  for (long long t = blockIdx.x; t < n_items; t += gridDim.x) {
+    const int pg = (int)(t % n_pg), cg = (int)((t / n_pg) % n_cg), b = (int)(t / ((long long)n_pg * n_cg));
+    const int p = (pg * 32 + lane) * PX, c0 = cg * 64 + warp * 8;
+    if (p >= HW || c0 >= C) continue;
+    const float* src = in + ((size_t)b * C + c0) * HW + p;
+    float v[8][PX];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (PX == 4) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + e < C) q = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)e * HW));
+        v[e][0] = q.x; v[e][PX > 1 ? 1 : 0] = q.y; v[e][PX > 2 ? 2 : 0] = q.z; v[e][PX > 3 ? 3 : 0] = q.w;
+      } else {
+        v[e][0] = (c0 + e < C) ? __ldg(src + (size_t)e * HW) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      if (p + i >= HW) break;
+      __half* dst = out + ((size_t)b * HW + p + i) * (2 * (size_t)C_total) + c_offset + c0;
+      __align__(16) __half hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = v[e][i] * S;
+        hi[e] = __float2half_rn(x);
+        lo[e] = __float2half_rn(x - __half2float(hi[e]));
+      }
+      if (c0 + 8 <= C) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(dst + C_total) = *reinterpret_cast<const uint4*>(lo);
+      } else {
+        for (int e = 0; e < 8 && c0 + e < C; ++e) {
+          dst[e] = hi[e];
+          dst[C_total + e] = lo[e];
+        }
+      }
+    }
+  }
+}
+
 // A stack of k 3x3 (padding 1) convolutions applied to a spatially CONSTANT image (the radar branch: a (B,C) vector
 // broadcast to (B,C,H,W), src/fusion.py:277-281) has only (2k+1)^2 distinct output pixels per channel: what a pixel sees
 // depends on how many of the k rows / columns towards each border exist.  The stack therefore runs on a (2k+1) x (2k+1)
@@ -809,14 +949,20 @@ extern "C" B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int
 
 namespace {
 int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* weight_image, const float* bias, int Cout, int taps,
-                int relu, float* out_nchw, void* out_nhwc, int out_ct, int out_coff, void* stream) {
+                int relu, float* out_nchw, void* out_nhwc, int out_ct, int out_coff, void* stream, const uint32_t* x_stat = nullptr) {
   if (!x_nhwc || !weight_image || (!out_nchw && !out_nhwc) || B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
   if (Cin <= 0 || Cin % kKC != 0 || (taps != 1 && taps != 9)) return B200BEV_ERR_UNSUPPORTED;
   if ((long long)B * H * W * Cin >= (1ll << 40)) return B200BEV_ERR_UNSUPPORTED;
   if (((uintptr_t)x_nhwc | (uintptr_t)weight_image) & 15) return B200BEV_ERR_INVALID_ARGUMENT;
   if (out_nhwc && (out_coff < 0 || out_coff + Cout > out_ct)) return B200BEV_ERR_INVALID_ARGUMENT;
   ConvArgs a{(const __nv_bfloat16*)x_nhwc, (const uint8_t*)weight_image, bias, out_nchw, B, H, W, Cin, Cout, taps, relu,
-             (__nv_bfloat16*)out_nhwc, out_ct, out_coff};
+             (__nv_bfloat16*)out_nhwc, out_ct, out_coff, 0, Cin, nullptr, nullptr};
+  if (x_stat) {   // fp32-accuracy mode: split fp16 operands, the unscale array sits behind the stages
+    a.split = 1;
+    a.x_pitch = 2 * Cin;
+    a.unscale = reinterpret_cast<const float*>((const uint8_t*)weight_image + (size_t)ceil_div(Cout, kTileCo) * taps * 3 * (Cin / kKC) * kStageA);
+    a.x_stat = x_stat;
+  }
   const long long tiles = (((long long)B * H * W + kTilePx - 1) / kTilePx) * ceil_div(Cout, kTileCo);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const char* impl = debug_env("B200BEV_CONV_IMPL");
@@ -846,4 +992,62 @@ extern "C" B200BEV_API int b200bev_conv_bn_relu_bf16_nhwc(const void* x_nhwc, in
                                               int out_c_offset, float* out_nchw, void* stream) {
   if (!out_nhwc) return B200BEV_ERR_INVALID_ARGUMENT;
   return launch_conv(x_nhwc, B, H, W, Cin, weight_image, bias, Cout, taps, relu, out_nchw, out_nhwc, out_c_total, out_c_offset, stream);
+}
+
+// ---- fp32-accuracy convolution blocks (three fp16 products per fp32 product) -------------------------------------------------
+extern "C" B200BEV_API size_t b200bev_conv_pack_split_bytes(int Cout, int Cin, int taps) {
+  if (Cout <= 0 || Cin <= 0 || Cin % kKC != 0 || (taps != 1 && taps != 9)) return 0;
+  const size_t tiles = (size_t)ceil_div(Cout, kTileCo);
+  return tiles * taps * 3 * (Cin / kKC) * kStageA + tiles * kTileCo * sizeof(float);
+}
+
+extern "C" B200BEV_API int b200bev_conv_pack_split(const float* weight, int Cout, int Cin, int taps, void* image, size_t image_bytes,
+                                       void* stream) {
+  const size_t need = b200bev_conv_pack_split_bytes(Cout, Cin, taps);
+  if (!weight || !image) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (need == 0) return B200BEV_ERR_UNSUPPORTED;
+  if (image_bytes < need || ((uintptr_t)image & 15)) return B200BEV_ERR_WORKSPACE;
+  const int n_slots = ceil_div(Cout, kTileCo) * kTileCo;
+  const size_t stage_bytes = need - (size_t)n_slots * sizeof(float);
+  float* unscale = reinterpret_cast<float*>((uint8_t*)image + stage_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_split_scale_kernel<<<(n_slots * 32 + 255) / 256, 256, 0, st>>>(weight, Cout, Cin * taps, unscale, n_slots);
+  B200BEV_CUDA_TRY(cudaGetLastError());
+  const long long n_chunks = (long long)(stage_bytes / 16);
+  long long blocks = (n_chunks + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  conv_pack_split_kernel<<<(int)blocks, 256, 0, st>>>(weight, Cout, Cin, taps, (uint8_t*)image, unscale, n_chunks);
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_absmax(const float* x, int64_t n, void* stat, void* stream) {
+  if (!x || !stat || n <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  long long blocks = (n / 4 + 255) / 256 + 1;
+  if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+  absmax_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, (long long)n, (uint32_t*)stat);
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_nchw_to_nhwc_split(const float* in, int B, int C, int H, int W, void* out_nhwc, int C_total,
+                                          int c_offset, const void* stat, void* stream) {
+  if (!in || !out_nhwc || !stat || B <= 0 || C <= 0 || H <= 0 || W <= 0 || c_offset < 0 || c_offset + C > C_total)
+    return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((C_total & 7) || (c_offset & 7) || ((uintptr_t)out_nhwc & 15)) return B200BEV_ERR_UNSUPPORTED;
+  const bool quad = ((H * W) & 3) == 0 && ((uintptr_t)in & 15) == 0;
+  const long long tiles = (long long)B * ceil_div(C, 64) * ceil_div(H * W, quad ? 128 : 32);
+  long long blocks = tiles < (long long)sm_count() * 16 ? tiles : (long long)sm_count() * 16;
+  if (quad)
+    nchw_to_nhwc_split_kernel<4><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__half*)out_nhwc, C_total, c_offset,
+                                                                              (const uint32_t*)stat);
+  else
+    nchw_to_nhwc_split_kernel<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, B, C, H * W, (__half*)out_nhwc, C_total, c_offset,
+                                                                              (const uint32_t*)stat);
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_conv_bn_relu_split(const void* x_split, const void* x_stat, int B, int H, int W, int Cin,
+                                          const void* weight_image, const float* bias, int Cout, int taps, int relu, float* out_nchw,
+                                          void* stream) {
+  if (!out_nchw || !x_stat) return B200BEV_ERR_INVALID_ARGUMENT;
+  return launch_conv(x_split, B, H, W, Cin, weight_image, bias, Cout, taps, relu, out_nchw, nullptr, 0, 0, stream, (const uint32_t*)x_stat);
 }

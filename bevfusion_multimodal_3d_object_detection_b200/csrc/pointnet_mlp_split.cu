@@ -251,14 +251,6 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t adesc, uint64_t
       : "r"(taddr)                                                                                                         \
       : "memory")
 
-// 2^k with (layer maximum) * 2^k in [2^13, 2^14): fp16 holds the scaled hi part (< 65504) and the lo part of anything that
-// matters (lo is subnormal only below 2^-17 of the layer maximum).  1 for an all-zero layer.
-__device__ __forceinline__ float activation_scale(uint32_t max_bits) {
-  const int e = (int)((max_bits >> 23) & 0xff);
-  if (e == 0 || e == 0xff) return 1.f;
-  return __uint_as_float((uint32_t)(127 + 14 - (e - 126)) << 23);   // max = f * 2^(e-126), f in [0.5, 1)
-}
-
 template <bool FINAL>
 __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
