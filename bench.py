@@ -81,7 +81,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="step", choices=sorted(WORKLOADS), help="the workload of the headline numbers")
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default: the workload's)")
-    ap.add_argument("--precision", default=os.environ.get("B200BEV_PRECISION", "bf16"), choices=["auto", "f32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("B200BEV_PRECISION", "bf16"), choices=["auto", "f32", "f32_cudnn", "bf16"])
     ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline chunk in the e2e leg")
     ap.add_argument("--cpu-frames", type=int, default=None, help="frames per CPU pass (default: as many as fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -613,7 +613,7 @@ def run_b200_arm(args):
     _lib.lib()
     _lib.enable_call_counting()
     peaks = load_peaks()
-    state = {"precision": "bf16" if args.precision in ("auto", "bf16") else "f32"}
+    state = {"precision": "bf16" if args.precision in ("auto", "bf16") else args.precision}
     seed = 42 + 1000 * rank
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
@@ -681,29 +681,33 @@ def run_b200_arm(args):
     del hp
     torch.cuda.empty_cache()
 
-    # ---- the other precision, TIMED in the same contract (graph replays, CUDA events, L2 flush) ----
-    other = None
+    # ---- the other precisions, TIMED in the same contract (graph replays, CUDA events, L2 flush) ----
+    NOTES = {"f32": "fp32 path (the drop-in's default precision, parity 1e-5): PointNet MLP and every convolution block at fp32 accuracy "
+                    "on the tensor cores (three fp16 tcgen05 products per fp32 product), dense layers / radar MLP on fp32 FFMA",
+             "f32_cudnn": "as f32, but the convolution blocks on the reference's own cuDNN layers in true fp32 (TF32 switched off)",
+             "bf16": "bf16 path: tcgen05 MLP and convolution kernels (parity 1e-2)"}
+    others = {}
     if not args.no_alt:
         saved = state["precision"]
-        try:
-            state["precision"] = "f32" if saved == "bf16" else "bf16"
-            o_res, o_hp = run_workload(args.workload, max(3, min(args.steps, 10)), args.warmup, False, None, args.frames)
-            other = {"dtype": state["precision"], "value": o_res["value"], "unit": "frames/s", "ms_per_step": o_res["ms_per_step"],
-                     "timed": True, "steps": o_res["steps"], "eager_stage_ms": o_res["eager_stage_ms"],
-                     "note": ("fp32 path: PointNet MLP at fp32 accuracy on the tensor cores (3 x fp16 products, parity 1e-5), every "
-                              "convolution the reference's own cuDNN layer in true fp32 (TF32 switched off)"
-                              if state["precision"] == "f32" else "bf16 path: tcgen05 MLP and convolution kernels (parity 1e-2)")}
+        for prec in [p for p in ("f32", "f32_cudnn", "bf16") if p != saved]:
             try:
-                ok = kernel_rooflines(o_hp, peaks, fp32_peak, flush)
-                other["pointnet_encode"] = ok.get("pointnet_encode")
-                other["pointnet_encode_global_only"] = ok.get("pointnet_encode_global_only")
+                state["precision"] = prec
+                o_res, o_hp = run_workload(args.workload, max(3, min(args.steps, 10)), args.warmup, False, None, args.frames)
+                other = {"dtype": prec, "value": o_res["value"], "unit": "frames/s", "ms_per_step": o_res["ms_per_step"],
+                         "timed": True, "steps": o_res["steps"], "eager_stage_ms": o_res["eager_stage_ms"], "note": NOTES[prec]}
+                if prec != "f32_cudnn":
+                    try:
+                        ok = kernel_rooflines(o_hp, peaks, fp32_peak, flush)
+                        other["pointnet_encode"] = ok.get("pointnet_encode")
+                        other["pointnet_encode_global_only"] = ok.get("pointnet_encode_global_only")
+                    except Exception as e:
+                        other["kernel_error"] = str(e)[:200]
+                del o_hp
             except Exception as e:
-                other["kernel_error"] = str(e)[:200]
-            del o_hp
-        except Exception as e:
-            other = {"error": str(e)[:300]}
+                other = {"error": str(e)[:300]}
+            others[prec] = other
+            torch.cuda.empty_cache()
         state["precision"] = saved
-        torch.cuda.empty_cache()
 
     # ---- every BASELINE configuration ----
     configs = None
@@ -750,7 +754,7 @@ def run_b200_arm(args):
             "gpu_launches": main["launches_per_step"] * args.steps, "launches_per_step": main["launches_per_step"],
             "clocks": clock_summary, "eager_stage_ms": main["eager_stage_ms"], "eager_ms_per_step": main["eager_ms_per_step"],
             "kernels": kernels, "fp32_fma_peak": fp32_peak,
-            ("fp32_path" if precision == "bf16" else "bf16_path"): other,
+            "fp32_path": others.get("f32"), "fp32_cudnn_path": others.get("f32_cudnn"), "bf16_path": others.get("bf16"),
             "configs": configs, "affinity": affinity,
         }
         print(json.dumps(line), flush=True)

@@ -65,6 +65,11 @@ PROTOTYPES = {
     "b200bev_nchw_to_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "b200bev_camera_mean_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "b200bev_conv_bn_relu_bf16": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
+    "b200bev_absmax": (_i, [_p, C.c_int64, _p, _p]),
+    "b200bev_nchw_to_nhwc_split": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p]),
+    "b200bev_conv_pack_split_bytes": (_z, [_i, _i, _i]),
+    "b200bev_conv_pack_split": (_i, [_p, _i, _i, _i, _p, _z, _p]),
+    "b200bev_conv_bn_relu_split": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
     "b200bev_border_expand": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "b200bev_conv_bn_relu_bf16_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p, _p]),
 }
@@ -112,7 +117,8 @@ def lib() -> C.CDLL:
 KERNELS_PER_CALL = {
     "b200bev_abi_version": 0, "b200bev_error_string": 0, "b200bev_device_info": 0, "b200bev_lidar_prepare_workspace_bytes": 0,
     "b200bev_pointnet_pack_bf16_bytes": 0, "b200bev_centernet_workspace_bytes": 0, "b200bev_conv_pack_bytes": 0,
-    "b200bev_pointnet_pack_split_bytes": 0, "b200bev_pointnet_split_workspace_bytes": 0,
+    "b200bev_pointnet_pack_split_bytes": 0, "b200bev_pointnet_split_workspace_bytes": 0, "b200bev_conv_pack_split_bytes": 0,
+    "b200bev_conv_pack_split": 2,
     "b200bev_radar_encode": 2, "b200bev_lidar_init": 2, "b200bev_lidar_prepare": 1,
     "b200bev_pointnet_encode_split": 5,       # per pass: layer 1 + four GEMM launches (one pass up to ~1M points)
     "b200bev_pointnet_pack_split": 2,

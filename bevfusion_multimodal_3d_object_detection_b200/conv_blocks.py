@@ -1,11 +1,17 @@
 """Host side of SURVEY 8f N1: the Conv2d + BatchNorm2d + ReLU stacks of the reference's fusion module and detection
-head on the tcgen05 convolution kernel (`b200bev_conv_bn_relu_bf16`).
+head on the tcgen05 convolution kernels.
 
-The kernel computes in bf16 with fp32 accumulation (parity 1e-2 of max|ref|, north_star's bf16 bound), so this path is
-opt-in: `module.b200_precision = "bf16"` or `B200BEV_PRECISION=bf16`; the default stays the reference's own fp32
-cuDNN convolutions between the kernels (parity 1e-5).  Eval mode only — BatchNorm is folded with its running
-statistics.  Folded and packed weights are a cache keyed on the parameters' version counters, rebuilt after
-`load_state_dict` or an optimizer step (SURVEY 8b "Ownership / state").
+Three modes, chosen by `module.b200_precision` (else `B200BEV_PRECISION`, else "f32"):
+
+    "f32"        fp32 accuracy on the tensor cores (`b200bev_conv_bn_relu_split`: three fp16 products per fp32 product, exact
+                 power-of-two operand scales; parity 1e-5 of max|ref|) — the default
+    "bf16"       bf16 operands (`b200bev_conv_bn_relu_bf16`, parity 1e-2, north_star's bf16 bound); activations stay
+                 channels-last bf16 between convolutions
+    "f32_cudnn"  the reference's own torch layers (cuDNN; fp32, or TF32 if torch's flags allow it) between the kernels
+
+Eval mode only — BatchNorm is folded with its running statistics.  Folded and packed weights are a cache beside the
+module, rebuilt when the parameters change (weight_cache.py).  Stacks with shapes the kernels do not take (input channels
+not a multiple of 64, other kernel sizes) run on the torch layers.
 """
 from __future__ import annotations
 
@@ -21,8 +27,16 @@ from .weight_cache import mark_dirty, wants_autograd
 HEADS = ("heatmap", "offset", "size", "rot", "vel")       # CenterNetHead's sub-modules, src/fusion.py:822-854
 
 
+def conv_mode(module: nn.Module) -> str:
+    """"bf16" | "split" (fp32 accuracy on tcgen05) | "torch" (the module's own layers)."""
+    name = getattr(module, "b200_precision", None) or default_precision()
+    if name == "bf16":
+        return "bf16"
+    return "torch" if name in ("f32_cudnn", "fp32_cudnn", "torch") else "split"
+
+
 def wants_bf16(module: nn.Module) -> bool:
-    return (getattr(module, "b200_precision", None) or default_precision()) == "bf16"
+    return conv_mode(module) == "bf16"
 
 
 def _conv_ok(conv: nn.Conv2d) -> bool:
@@ -45,11 +59,13 @@ def supported(seq: nn.Sequential) -> bool:
     return True
 
 
-def _plan(seq: nn.Sequential, device: torch.device) -> List[Dict]:
-    key = _state_key(seq, device)
-    cache = seq.__dict__.get("_b200bev_conv_cache")
+def _plan(seq: nn.Sequential, device: torch.device, mode: str = "bf16") -> List[Dict]:
+    key = (_state_key(seq, device), mode)
+    caches = seq.__dict__.setdefault("_b200bev_conv_cache", {})
+    cache = caches.get(mode)
     if cache is not None and cache["key"] == key:
         return cache["steps"]
+    pack = ops.conv_pack if mode == "bf16" else ops.conv_pack_split
     layers = list(seq)
     steps: List[Dict] = []
     i = 0
@@ -60,7 +76,7 @@ def _plan(seq: nn.Sequential, device: torch.device) -> List[Dict]:
             j = i + (2 if bn is not None else 1)
             relu = j < len(layers) and isinstance(layers[j], nn.ReLU)
             w, b = ops.fold_conv_bn(layer, bn)
-            steps.append({"kind": "conv", "image": ops.conv_pack(w.to(device)), "bias": b.to(device),
+            steps.append({"kind": "conv", "image": pack(w.to(device)), "bias": b.to(device),
                           "c_out": layer.out_channels, "taps": layer.kernel_size[0] * layer.kernel_size[1], "relu": relu})
             i = j + (1 if relu else 0)
         elif isinstance(layer, nn.Upsample):
@@ -68,8 +84,26 @@ def _plan(seq: nn.Sequential, device: torch.device) -> List[Dict]:
             i += 1
         else:
             raise RuntimeError(f"conv_blocks: unexpected layer {type(layer).__name__} (check supported() first)")
-    seq.__dict__["_b200bev_conv_cache"] = {"key": key, "steps": steps}
+    caches[mode] = {"key": key, "steps": steps}
     return steps
+
+
+def run_split(seq: nn.Sequential, parts: Sequence[torch.Tensor]) -> torch.Tensor:
+    """`seq(torch.cat(parts, dim=1))` at fp32 accuracy on the tensor cores: per convolution one pass that finds max|x|,
+    one that lays the input out channels-last as scaled fp16 hi / lo halves (the concat happens there), and the split
+    convolution itself, which writes the fp32 NCHW tensor the next layer — or the reference's next module — reads."""
+    parts = list(parts)
+    steps = _plan(seq, parts[0].device, "split")
+    for step in steps:
+        if step["kind"] == "conv":
+            x_split, stat = ops.nchw_to_nhwc_split(parts)
+            parts = [ops.conv_bn_relu_split(x_split, stat, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
+        else:
+            x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+            s = step["scale"]
+            sy, sx = (s, s) if not isinstance(s, (tuple, list)) else s
+            parts = [ops.bilinear_resize(x, (int(x.shape[2] * sy), int(x.shape[3] * sx)))]
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
 
 
 def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc: Optional[torch.Tensor] = None,
@@ -81,7 +115,7 @@ def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc
     stack — and nothing else; returns None."""
     parts = list(parts) if parts is not None else []
     device = nhwc.device if nhwc is not None else parts[0].device
-    steps = _plan(seq, device)
+    steps = _plan(seq, device, "bf16")
     if out_nhwc is not None and steps[-1]["kind"] != "conv":
         raise ValueError("out_nhwc needs a stack that ends in a convolution block")
     for k, step in enumerate(steps):
@@ -121,11 +155,13 @@ def head_supported(head: nn.Module) -> bool:
     return all(len(s) == 3 and _conv_ok(s[0]) and s[2].kernel_size == (1, 1) for s in subs) and hidden % 64 == 0
 
 
-def _head_plan(head: nn.Module, device: torch.device) -> Dict:
-    key = _state_key(head, device)
-    cache = head.__dict__.get("_b200bev_conv_cache")
+def _head_plan(head: nn.Module, device: torch.device, mode: str = "bf16") -> Dict:
+    key = (_state_key(head, device), mode)
+    caches = head.__dict__.setdefault("_b200bev_conv_cache", {})
+    cache = caches.get(mode)
     if cache is not None and cache["key"] == key:
         return cache
+    pack = ops.conv_pack if mode == "bf16" else ops.conv_pack_split
     subs = [getattr(head, f"{n}_head") for n in HEADS]
     w1 = torch.cat([s[0].weight.detach() for s in subs], dim=0).float().to(device).contiguous()   # (5*hc, Cin, 3, 3)
     b1 = torch.cat([s[0].bias.detach() for s in subs], dim=0).float().to(device).contiguous()
@@ -139,8 +175,8 @@ def _head_plan(head: nn.Module, device: torch.device) -> Dict:
         r += n
         c += hc
     b2 = torch.cat([s[2].bias.detach() for s in subs], dim=0).float().to(device).contiguous()
-    cache = {"key": key, "img1": ops.conv_pack(w1), "b1": b1, "hidden": hidden, "img2": ops.conv_pack(w2), "b2": b2, "outs": outs}
-    head.__dict__["_b200bev_conv_cache"] = cache
+    cache = {"key": key, "img1": pack(w1), "b1": b1, "hidden": hidden, "img2": pack(w2), "b2": b2, "outs": outs}
+    caches[mode] = cache
     return cache
 
 
@@ -150,16 +186,23 @@ def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
     `decode_centernet_predictions` feeds to the decode kernel so that the sigmoid is not a separate pass there."""
     if head.training:
         mark_dirty(head)
-    if head.training or not x.is_cuda or not wants_bf16(head) or not head_supported(head) or x.shape[1] % 64 != 0 \
+    mode = conv_mode(head)
+    if head.training or not x.is_cuda or mode == "torch" or not head_supported(head) or x.shape[1] % 64 != 0 \
             or wants_autograd(head, x):
         pred = {n: getattr(head, f"{n}_head")(x) for n in HEADS}
         pred["heatmap"] = torch.sigmoid(pred["heatmap"])
         return pred
-    p = _head_plan(head, x.device)
+    p = _head_plan(head, x.device, mode)
     B, _, H, W = x.shape
-    hid = torch.empty((B, H, W, p["hidden"]), dtype=torch.bfloat16, device=x.device)      # stays channels-last bf16
-    ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), p["img1"], p["b1"], p["hidden"], 9, relu=True, out_nhwc=hid, want_nchw=False)
-    both = ops.conv_bn_relu_bf16(hid, p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
+    if mode == "bf16":
+        hid = torch.empty((B, H, W, p["hidden"]), dtype=torch.bfloat16, device=x.device)      # stays channels-last bf16
+        ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), p["img1"], p["b1"], p["hidden"], 9, relu=True, out_nhwc=hid, want_nchw=False)
+        both = ops.conv_bn_relu_bf16(hid, p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
+    else:       # fp32 accuracy: the same two launches on split fp16 operands, fp32 tensors in between
+        x_split, stat = ops.nchw_to_nhwc_split([x])
+        hid = ops.conv_bn_relu_split(x_split, stat, p["img1"], p["b1"], p["hidden"], 9, relu=True)
+        h_split, h_stat = ops.nchw_to_nhwc_split([hid])
+        both = ops.conv_bn_relu_split(h_split, h_stat, p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
     pred, c = {}, 0
     for n, k in zip(HEADS, p["outs"]):
         pred[n] = both[:, c:c + k].contiguous()

@@ -65,6 +65,9 @@ __device__ __forceinline__ int conv_chunk_channel(const ConvArgs& a, int j) {
   const int ncc = a.Cin / kKC;
   return a.split ? ((j / ncc == 1 ? a.Cin : 0) + (j % ncc) * kKC) : j * kKC;
 }
+// k chunks per accumulator chain of the 3x3 kernel: all of them in bf16 mode; three (3 x 9 taps x 4 = 108 MMAs) in
+// fp32-accuracy mode, where the partial sums are added on the CUDA cores (see the epilogue)
+__device__ __forceinline__ int halo_segment_chunks(const ConvArgs& a, int ncc) { return a.split ? 3 : ncc; }
 __device__ __forceinline__ uint32_t conv_idesc(const ConvArgs& a, int n_cols) {
   // D f32 (bit 4); A / B formats (bits 7-9 / 10-12): 1 = bf16, 0 = fp16; both K-major; N, M
   return (1u << 4) | (a.split ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileCo >> 4) << 24);
@@ -502,12 +505,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
   } else if (warp == 12) {
     // ---- MMA issuer ----
     const uint32_t idesc = conv_idesc(a, geo.N);
-    int g = 0, bi = 0;
+    const int seg = halo_segment_chunks(a, ncc);
+    int g = 0, bi = 0, seg_seq = 0;     // seg_seq counts (tile, K segment) pairs: each gets its own accumulator buffer
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
-      const uint32_t buf = tile_seq & 1;
-      if (tile_seq >= 2) mbarrier_wait(&acc_empty[buf], ((tile_seq >> 1) - 1) & 1);
-      const uint32_t d = tmem + buf * kTilePx;
+      uint32_t buf = 0, d = 0;
       for (int cc = 0; cc < ncc; ++cc, ++bi) {
+        const bool seg_first = cc % seg == 0, seg_last = cc % seg == seg - 1 || cc == ncc - 1;
+        if (seg_first) {
+          buf = seg_seq & 1;
+          if (seg_seq >= 2) mbarrier_wait(&acc_empty[buf], ((seg_seq >> 1) - 1) & 1);
+          d = tmem + buf * kTilePx;
+        }
         mbarrier_wait(&full_blk[bi & 1], (bi >> 1) & 1);
         const uint32_t blk = smem_addr(blocks + (bi & 1) * kHaloBlock);
         for (int tap = 0; tap < 9; ++tap, ++g) {
@@ -520,13 +528,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
 #pragma unroll
             for (int s = 0; s < kKC / 16; ++s)
               umma_ss(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc_at(b_addr + s * 32, base_offset_mode), idesc,
-                      !(cc == 0 && tap == 0 && s == 0));
+                      !(seg_first && tap == 0 && s == 0));
             tc_commit_to(&empty_a[slot]);
             if (tap == 8) tc_commit_to(&empty_blk[bi & 1]);
-            if (tap == 8 && cc == ncc - 1) tc_commit_to(&acc_full[buf]);
+            if (tap == 8 && seg_last) tc_commit_to(&acc_full[buf]);
           }
           __syncwarp();
         }
+        if (seg_last) ++seg_seq;
       }
     }
   } else {
@@ -537,60 +546,80 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     // store instruction writes up to 128 contiguous bytes of one channel plane.
     const int quad = warp & 3;
     float* tp = epi + quad * 32 * 33;
-    int tile = blockIdx.x;
+    const int seg = halo_segment_chunks(a, ncc), n_seg = (ncc + seg - 1) / seg;
+    int tile = blockIdx.x, seg_seq = 0;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
       int co_tile, b, y0;
       tile_coords(tile, co_tile, b, y0);
-      const uint32_t buf = tile_seq & 1;
       const int co0 = co_tile * kTileCo + quad * 32;
       const float bias = (a.bias && co0 + lane < a.Cout) ? __ldg(a.bias + co0 + lane) : 0.f;
       const float oscale = conv_out_scale(a, co0 + lane);
       const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;   // channels of this warp that exist (may be <= 0)
       float* oplane = a.out + ((size_t)b * a.Cout + co0) * HW;
-      mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
-      tc_fence_after_sync();
+      // K segments (fp32-accuracy mode): the tensor core TRUNCATES the fp32 accumulator once per instruction, a bias of
+      // ~2.3e-8 of the sum per MMA in a chain (measured: 1.1e-5 at 432 MMAs, 2.9e-5 at 1,296).  Every `seg` chunks the
+      // partial sum leaves tensor memory and is added — round to nearest, on the CUDA cores — to the output tile this
+      // warp wrote a few microseconds earlier (an L2 hit); bias with the first segment, ReLU with the last.
+      for (int sg = 0; sg < n_seg; ++sg, ++seg_seq) {
+        const uint32_t buf = seg_seq & 1;
+        const bool first = sg == 0, last = sg == n_seg - 1;
+        const float seg_bias = first ? bias : 0.f;
+        mbarrier_wait(&acc_full[buf], (seg_seq >> 1) & 1);
+        tc_fence_after_sync();
 #pragma unroll 1
-      for (int col0 = 0; col0 < geo.N; col0 += 32) {
-        uint32_t r[32];
-        CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = fmaf(__uint_as_float(r[j]), oscale, bias);
-          if (a.relu) v = fmaxf(v, 0.f);
-          r[j] = __float_as_uint(v);
-          tp[lane * 33 + j] = v;
-        }
-        if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
-          int ry = col0 / W1, x = col0 - ry * W1;
+        for (int col0 = 0; col0 < geo.N; col0 += 32) {
+          uint32_t r[32];
+          CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (lane < n_ch && x < a.W && ry < geo.R && y0 + ry < a.H)   // lane = channel: 64 contiguous bytes per pixel
-              a.out_nhwc[(((size_t)b * a.H + y0 + ry) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
-                  __float2bfloat16_rn(__uint_as_float(r[j]));
-            if (++x == W1) {
-              x = 0;
-              ++ry;
+            float v = fmaf(__uint_as_float(r[j]), oscale, seg_bias);
+            if (a.relu && n_seg == 1) v = fmaxf(v, 0.f);
+            r[j] = __float_as_uint(v);
+            tp[lane * 33 + j] = v;
+          }
+          if (a.out_nhwc) {   // bf16 mode only (one segment); kept out of the loop above: the epilogue paces the small blocks
+            int ry = col0 / W1, x = col0 - ry * W1;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (lane < n_ch && x < a.W && ry < geo.R && y0 + ry < a.H)   // lane = channel: 64 contiguous bytes per pixel
+                a.out_nhwc[(((size_t)b * a.H + y0 + ry) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
+                    __float2bfloat16_rn(__uint_as_float(r[j]));
+              if (++x == W1) {
+                x = 0;
+                ++ry;
+              }
             }
           }
-        }
-        __syncwarp();
-        // this lane's pixel: column n = col0 + lane
-        const int n = col0 + lane;
-        const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
-        const bool px_ok = x < a.W && ry < geo.R && y < a.H;
-        float* dst = oplane + (px_ok ? y * a.W + x : 0);
-        if (a.out) {
-          for (int c = 0; c < n_ch; ++c) {
-            const float v = tp[c * 33 + lane];
-            if (px_ok) dst[(size_t)c * HW] = v;
+          __syncwarp();
+          // this lane's pixel: column n = col0 + lane
+          const int n = col0 + lane;
+          const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
+          const bool px_ok = x < a.W && ry < geo.R && y < a.H;
+          float* dst = oplane + (px_ok ? y * a.W + x : 0);
+          if (a.out) {
+            if (n_seg == 1) {
+              for (int c = 0; c < n_ch; ++c) {
+                const float v = tp[c * 33 + lane];
+                if (px_ok) dst[(size_t)c * HW] = v;
+              }
+            } else {
+              for (int c = 0; c < n_ch; ++c) {
+                float v = tp[c * 33 + lane];
+                if (px_ok) {
+                  if (!first) v += dst[(size_t)c * HW];
+                  if (last && a.relu) v = fmaxf(v, 0.f);
+                  dst[(size_t)c * HW] = v;
+                }
+              }
+            }
           }
+          __syncwarp();
         }
+        tc_fence_before_sync();
         __syncwarp();
+        if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
     }
   }
 

@@ -27,7 +27,8 @@ import yaml
 from . import _lib, ops
 from .weight_cache import invalidate_cache, mark_dirty, state_token, wants_autograd  # noqa: F401
 
-PRECISIONS = {"f32": _lib.F32, "fp32": _lib.F32, "bf16": _lib.BF16_TENSOR}
+# MLP precision per name; "f32_cudnn" only differs for the convolution stacks (conv_blocks.conv_mode)
+PRECISIONS = {"f32": _lib.F32, "fp32": _lib.F32, "bf16": _lib.BF16_TENSOR, "f32_cudnn": _lib.F32}
 
 
 def load_config(config_path: str = "configs/base.yaml") -> Dict:

@@ -52,11 +52,12 @@ def camera_branch(module: nn.Module, camera_features: torch.Tensor, torch_graph:
 
 
 def _stack(module: nn.Module, seq: nn.Sequential, parts) -> torch.Tensor:
-    """A conv/BN/ReLU stack of the fusion module in eval mode: the tcgen05 convolution kernel when the bf16 path is
-    enabled on the module (parity 1e-2), else the reference's own fp32 cuDNN layers (parity 1e-5)."""
-    if conv_blocks.wants_bf16(module) and parts[0].is_cuda and conv_blocks.supported(seq) \
-            and sum(int(p.shape[1]) for p in parts) % 64 == 0:
-        return conv_blocks.run(seq, parts)
+    """A conv/BN/ReLU stack of the fusion module in eval mode on the tcgen05 convolution kernels: fp32
+    accuracy by default (split fp16 operands, parity 1e-5), bf16 operands when the bf16 path is enabled (parity 1e-2); the
+    module's own torch layers for "f32_cudnn" or shapes the kernels do not take."""
+    mode = conv_blocks.conv_mode(module)
+    if mode != "torch" and conv_blocks.supported(seq) and sum(int(p.shape[1]) for p in parts) % 64 == 0:
+        return conv_blocks.run(seq, parts) if mode == "bf16" else conv_blocks.run_split(seq, parts)
     return seq(parts[0] if len(parts) == 1 else torch.cat(parts, dim=1))
 
 
@@ -107,8 +108,9 @@ def lidar_branch(module: nn.Module, lidar_features: torch.Tensor, torch_graph: b
     l0, l2 = module.lidar_init[0], module.lidar_init[2]
     x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s, s)
     up = module.lidar_upsample
-    if conv_blocks.wants_bf16(module) and conv_blocks.supported(up) and hidden % 64 == 0:
-        return conv_blocks.run(up, [x])
+    mode = conv_blocks.conv_mode(module)
+    if mode != "torch" and conv_blocks.supported(up) and hidden % 64 == 0:
+        return conv_blocks.run(up, [x]) if mode == "bf16" else conv_blocks.run_split(up, [x])
     for i, layer in enumerate(up):
         if isinstance(layer, nn.Upsample):
             # scale_factor=2, align_corners=False: source coordinate (i+0.5)/2-0.5, what the size-based resize computes

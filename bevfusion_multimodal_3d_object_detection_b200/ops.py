@@ -428,6 +428,62 @@ def conv_bn_relu_bf16(x_nhwc: torch.Tensor, image: torch.Tensor, bias: Optional[
     return out if out is not None else out_nhwc
 
 
+# ---- the same blocks at fp32 accuracy (three fp16 tensor-core products per fp32 product, parity 1e-5) --------------------
+def conv_pack_split(weight: torch.Tensor) -> torch.Tensor:
+    """(Cout,Cin,kh,kw) fp32 on the device -> the split-fp16 stage image of b200bev_conv_bn_relu_split (uint8 tensor)."""
+    weight = _need_cuda(weight, "weight")
+    Cout, Cin, kh, kw = weight.shape
+    taps = kh * kw
+    n = _lib.lib().b200bev_conv_pack_split_bytes(Cout, Cin, taps)
+    if n == 0:
+        raise _lib.B200BevError(_lib.ERR_UNSUPPORTED, f"conv {tuple(weight.shape)}: needs Cin % 64 == 0 and a 3x3 or 1x1 kernel")
+    img = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.lib().b200bev_conv_pack_split(_ptr(weight), Cout, Cin, taps, _ptr(img), n, _stream(weight.device)))
+    return img
+
+
+def nchw_to_nhwc_split(parts: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[(B,C_i,H,W) fp32] -> ((B,H,W,2*sum C_i) fp16 [hi | lo], stat): max|x| over all parts (one read), then layout change,
+    power-of-two scaling, hi/lo split and torch.cat in one pass per part."""
+    parts = [_need_cuda(p, f"parts[{i}]") for i, p in enumerate(parts)]
+    B, _, H, W = parts[0].shape
+    c_sum = sum(int(p.shape[1]) for p in parts)
+    dev = parts[0].device
+    stat = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty((B, H, W, 2 * c_sum), dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        for p in parts:
+            if p.shape[0] != B or tuple(p.shape[2:]) != (H, W):
+                raise RuntimeError("Sizes of tensors must match except in dimension 1")      # what torch.cat says
+            _lib.check(_lib.lib().b200bev_absmax(_ptr(p), p.numel(), _ptr(stat), _stream(dev)))
+        off = 0
+        for p in parts:
+            _lib.check(_lib.lib().b200bev_nchw_to_nhwc_split(_ptr(p), B, int(p.shape[1]), H, W, _ptr(out), c_sum, off, _ptr(stat),
+                                                            _stream(dev)))
+            off += int(p.shape[1])
+    return out, stat
+
+
+def conv_bn_relu_split(x_split: torch.Tensor, stat: torch.Tensor, image: torch.Tensor, bias: Optional[torch.Tensor], c_out: int,
+                       taps: int, relu: bool = True) -> torch.Tensor:
+    """(B,H,W,2*Cin) fp16 [hi | lo] -> (B,Cout,H,W) fp32: 3x3 (padding 1) or 1x1 convolution + folded BatchNorm + ReLU at
+    fp32 accuracy on tcgen05 (b200bev_conv_bn_relu_split)."""
+    x_split = _need_cuda(x_split, "input", torch.float16)
+    image = _need_cuda(image, "weight_image", torch.uint8)
+    stat = _need_cuda(stat, "stat", torch.int32)
+    bias = None if bias is None else _need_cuda(bias, "bias")
+    B, H, W, C2 = x_split.shape
+    Cin = C2 // 2
+    if image.numel() != _lib.lib().b200bev_conv_pack_split_bytes(c_out, Cin, taps):
+        raise ValueError("weight image does not belong to this (Cout, Cin, taps)")
+    out = torch.empty((B, c_out, H, W), dtype=torch.float32, device=x_split.device)
+    with torch.cuda.device(x_split.device):
+        _lib.check(_lib.lib().b200bev_conv_bn_relu_split(_ptr(x_split), _ptr(stat), B, H, W, Cin, _ptr(image), _ptr(bias), c_out, taps,
+                                                         1 if relu else 0, _ptr(out), _stream(x_split.device)))
+    return out
+
+
 def border_class_index(n: int, s: int) -> List[int]:
     """cls(i) for i in range(n): which row (column) of the s x s image a row (column) of an n-wide image equals when
     k = s // 2 padded 3x3 convolutions ran over a spatially constant input."""

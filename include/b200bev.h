@@ -290,6 +290,27 @@ B200BEV_API int b200bev_conv_bn_relu_bf16_nhwc(const void* x_nhwc, int B, int H,
                                    void* out_nhwc, int out_c_total, int out_c_offset,
                                    float* out_nchw, void* stream);
 
+/* The same convolution blocks at FP32 ACCURACY (parity 1e-5 of max|ref|, the default precision of the drop-in): every fp32
+ * product as three fp16 tcgen05 products (w_hi.x_hi + w_hi.x_lo + w_lo.x_hi, fp32 accumulation), operands scaled by exact
+ * powers of two — weights per output channel at pack time, the input tensor by its own maximum, reduced on the device.
+ * Replaces the reference's fp32 cuDNN layers (src/fusion.py:126-133,151-166,176-183,199-207,822-854) without TF32.
+ *   b200bev_absmax               atomicMax of max|x| (as float bits) into *stat (4 bytes, zeroed by the caller); call it
+ *                                once per input part before the layout kernel
+ *   b200bev_nchw_to_nhwc_split   (B,C,H,W) f32 -> channels [c_offset, c_offset+C) of BOTH halves of a
+ *                                (B,H,W,[hi C_total | lo C_total]) fp16 tensor, scaled by 2^k(*stat)
+ *   b200bev_conv_pack_split      (Cout,Cin,kh,kw) f32 -> image (stage triples hi,hi,lo per 64-channel chunk + per-channel
+ *                                unscale); _bytes gives its size (0: unsupported)
+ *   b200bev_conv_bn_relu_split   x_split + x_stat + image + bias -> (B,Cout,H,W) f32 */
+B200BEV_API int b200bev_absmax(const float* x, int64_t n, void* stat, void* stream);
+B200BEV_API int b200bev_nchw_to_nhwc_split(const float* in, int B, int C, int H, int W, void* out_nhwc,
+                               int C_total, int c_offset, const void* stat, void* stream);
+B200BEV_API size_t b200bev_conv_pack_split_bytes(int Cout, int Cin, int taps);
+B200BEV_API int b200bev_conv_pack_split(const float* weight, int Cout, int Cin, int taps,
+                            void* image, size_t image_bytes, void* stream);
+B200BEV_API int b200bev_conv_bn_relu_split(const void* x_split, const void* x_stat, int B, int H, int W, int Cin,
+                               const void* weight_image, const float* bias, int Cout, int taps, int relu,
+                               float* out_nchw, void* stream);
+
 /* The radar branch of FlexibleBEVFusion.forward (src/fusion.py:274-281) feeds `radar_refine` a spatially CONSTANT image:
  * the (B,C) projection broadcast to (B,C,H,W).  k 3x3 convolutions (padding 1) of a constant image have (2k+1)^2
  * distinct output pixels per channel, so the stack runs on an s x s image (s = 2k+1) and this entry point spreads it:

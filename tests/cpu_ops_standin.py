@@ -45,6 +45,10 @@ def pointnet_encode(points, params, dims, perm=None, offsets=None, n_cells=0, pr
     return _mlp(points, params, dims).max(dim=1)[0]
 
 
+def pack_mlp_params_split(params, dims):
+    return None          # "layer widths not taken by the tensor-core path": the caller then runs pointnet_encode without an image
+
+
 def radar_encode(radar_list, params, dims, fusion, fc_weight, fc_bias):
     per = torch.stack([_mlp(r, params, dims).max(dim=1)[0] for r in radar_list], dim=1)
     if fusion == "concat":
@@ -71,6 +75,26 @@ def lidar_init(feats, w1, b1, w2, b2, return_hidden=False):
     hid = torch.relu(F.linear(feats, w1, b1))
     out = F.linear(hid, w2, b2)
     return (out, hid) if return_hidden else out
+
+
+def conv_pack_split(weight):
+    return weight                                   # the "image" of the stand-in is the folded fp32 weight itself
+
+
+def nchw_to_nhwc_split(parts):
+    return (parts[0] if len(parts) == 1 else torch.cat(list(parts), dim=1)), None      # concat only; no layout, no scale
+
+
+def conv_bn_relu_split(x, stat, image, bias, c_out, taps, relu=True):
+    y = F.conv2d(x, image, bias, padding=image.shape[-1] // 2)
+    return torch.relu(y) if relu else y
+
+
+def border_expand(small, size, out_nhwc=None, c_offset=0, want_nchw=True):
+    s = small.shape[-1]
+    k = s // 2
+    cls = lambda n: [i if i < k else (s - (n - i) if i >= n - k else k) for i in range(n)]
+    return small[:, :, cls(size[0])][:, :, :, cls(size[1])]
 
 
 def centernet_nms(heat):
@@ -100,8 +124,8 @@ def centernet_decode(heatmap, offset, size, rot, vel, K, voxel, origin=(-51.2, -
     return o
 
 
-STAND_INS = ("pointnet_encode", "radar_encode", "camera_mean", "bilinear_resize", "dense_layer", "lidar_init",
-             "centernet_nms", "centernet_topk", "centernet_decode")
+STAND_INS = ("pointnet_encode", "pack_mlp_params_split", "radar_encode", "camera_mean", "bilinear_resize", "dense_layer", "lidar_init",
+             "conv_pack_split", "nchw_to_nhwc_split", "conv_bn_relu_split", "border_expand", "centernet_nms", "centernet_topk", "centernet_decode")
 
 
 CALLS = {name: 0 for name in STAND_INS}

@@ -791,6 +791,46 @@ def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
     assert max_rel(got.cpu().numpy(), ref32.cpu().numpy()) < BF16_TOL
 
 
+CONV_SHAPES = [
+    (2, 12, 20, 64, 64, 3, True), (3, 50, 50, 128, 320, 3, True), (2, 25, 25, 512, 256, 1, True), (1, 7, 9, 64, 19, 1, False),
+    (4, 50, 50, 256, 256, 3, False), (2, 57, 100, 64, 64, 3, True), (1, 3, 300, 64, 32, 3, True), (5, 5, 6, 64, 130, 3, True),
+    (3, 1, 1, 64, 1, 3, False), (1, 1, 7, 128, 5, 1, True), (2, 50, 50, 768, 512, 3, True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,relu", CONV_SHAPES)
+@pytest.mark.parametrize("scale", [1.0, 3e-4, 2e3])
+def test_conv_bn_relu_fp32_accuracy_on_tcgen05(cuda, B, H, W, Cin, Cout, k, relu, scale):
+    """The split-fp16 mode of both convolution kernels (three fp16 products per fp32 product): 1e-5 of max|ref| against the
+    float64 convolution, for inputs and weights far from unit scale too (the operand scales are exact powers of two taken
+    from the data)."""
+    if scale != 1.0 and (B, H, W) not in ((2, 12, 20), (2, 25, 25), (5, 5, 6)):
+        pytest.skip("scale sweep on three shapes")
+    g = np.random.default_rng(Cin * 7 + Cout)
+    x = (g.standard_normal((B, Cin, H, W)) * scale).astype(np.float32)
+    w = (g.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k) / scale * 3.0).astype(np.float32)
+    w[Cout // 2] *= np.float32(1e-3)                     # an output channel with tiny weights: the scales are per channel
+    b = g.standard_normal(Cout).astype(np.float32)
+    xd, wd, bd = dev_t(x, cuda), dev_t(w, cuda), dev_t(b, cuda)
+    half = Cin // 2 // 8 * 8 or Cin
+    parts = [xd[:, :half].contiguous(), xd[:, half:].contiguous()] if half < Cin else [xd]
+    x_split, stat = ops.nchw_to_nhwc_split(parts)
+    assert tuple(x_split.shape) == (B, H, W, 2 * Cin) and x_split.dtype == torch.float16
+    assert float(stat.view(torch.float32)) == float(np.abs(x).max())
+    S = 2.0 ** (14 - np.frexp(np.abs(x).max())[1])
+    back = (x_split[..., :Cin].double() + x_split[..., Cin:].double()) / S          # hi + lo reproduces x to ~2^-22
+    assert max_rel(back.cpu().numpy(), xd.permute(0, 2, 3, 1).cpu().numpy()) < 2e-6
+    got = ops.conv_bn_relu_split(x_split, stat, ops.conv_pack_split(wd), bd, Cout, k * k, relu=relu)
+    ref = torch.nn.functional.conv2d(xd.double(), wd.double(), bd.double(), padding=k // 2)
+    ref = torch.relu(ref) if relu else ref
+    assert tuple(got.shape) == (B, Cout, H, W) and max_rel(got.cpu().numpy(), ref.cpu().numpy()) < FP32_TOL
+    # per-channel check: the tiny-weight channel is as accurate relative to ITS OWN maximum (its scale is its own)
+    c = Cout // 2
+    own = float(ref[:, c].abs().max())
+    if own > 0:
+        assert float((got[:, c].double() - ref[:, c]).abs().max()) < 3 * FP32_TOL * max(own, float(bd[c].abs()))
+
+
 def test_camera_mean_channels_last_bf16_is_the_rounded_mean(cuda):
     """The fused mean + layout kernel gives exactly bf16(camera_mean): same summation order, IEEE divide."""
     for B, C, h, w, n_cam in ((2, 64, 8, 14, 6), (1, 72, 6, 10, 6), (3, 512, 8, 8, 6), (2, 64, 4, 6, 3)):

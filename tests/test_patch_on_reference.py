@@ -75,12 +75,18 @@ for modality in ('lidar+radar', 'all', 'camera_only'):
         for d, w in zip(got_dets[name], ref_dets[name]):
             assert set(d) == set(w) and d['labels'].dtype == torch.int64
             assert d['scores'].shape == w['scores'].shape, (modality, name)
-            assert torch.allclose(d['boxes'], w['boxes'], atol=1e-4) and torch.allclose(d['scores'], w['scores'], atol=1e-6)
+            assert torch.allclose(d['scores'], w['scores'], atol=1e-5), (modality, name, float((d['scores'] - w['scores']).abs().max()))
+            # same winners in the same order wherever neighbouring scores are further apart than the fp32 noise of the folded BatchNorm
+            gap = (w['scores'][:-1] - w['scores'][1:]).abs() > 1e-4
+            stable = torch.cat([torch.tensor([True]), gap]) & torch.cat([gap, torch.tensor([True])])
+            assert torch.allclose(d['boxes'][stable], w['boxes'][stable], atol=1e-3), (modality, name)
     results[modality] = sorted(ref)
 # the patched forwards really went through the kernel front end (not the reference's own layers)
 c = cpu_ops_standin.CALLS
 assert c['pointnet_encode'] == 2 and c['radar_encode'] == 2 and c['camera_mean'] == 2 and c['lidar_init'] == 2, c
 assert c['bilinear_resize'] >= 4 and c['dense_layer'] == 2 and c['centernet_decode'] == 6, c
+# ... and through the convolution-stack plumbing (BatchNorm folding, plan cache, the radar branch's 5 x 5 shortcut)
+assert c['conv_bn_relu_split'] == 18 and c['border_expand'] == 2 and c['conv_pack_split'] == 18, c
 print('PATCHED-REFERENCE-OK', results)
 """
 

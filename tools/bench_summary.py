@@ -12,7 +12,7 @@ for key in ("e2e", "e2e_features_on_device"):
     e = d.get(key)
     if e:
         print(key, {k: (round(v, 2) if isinstance(v, float) else v) for k, v in e.items() if k != "api"})
-for key in ("fp32_path", "bf16_path"):
+for key in ("fp32_path", "fp32_cudnn_path", "bf16_path"):
     o = d.get(key)
     if o:
         print(key, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in o.items() if k not in ("note", "pointnet_encode", "pointnet_encode_global_only")})
