@@ -122,6 +122,16 @@ __device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bde
       : "r"(taddr)                                                                                                         \
       : "memory")
 
+#define CONV_TC_ST32(taddr, r)                                                                                             \
+  asm volatile(                                                                                                            \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"  \
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),                                                    \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),     \
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),     \
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),     \
+      "r"(r[31])                                                                                                           \
+      : "memory")
+
 // ---- per-tap form: 1x1 convolutions, and 3x3 when an image row does not fit a tile ----------------------------------------
 // 256 flat pixels per tile, one 48 KB stage (weight stage + the tap's pixel rows) per (tap, 64-channel chunk) in a ring of
 // four.  (The first version ran producers, MMA issue and epilogue in ONE instruction stream: every stage paid the chain
@@ -361,13 +371,16 @@ struct HaloGeom {
   int tiles_per_frame;
 };
 
-__host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g) {
-  const int R = kTilePx / (W + 1);
+// max_cols: 256 (the two accumulator halves of tensor memory), or kSplitCols in fp32-accuracy mode, where tensor memory holds two
+// partial accumulators AND the running total (3 x 160 columns)
+constexpr int kSplitCols = 160;
+__host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g, int max_cols = kTilePx) {
+  const int R = max_cols / (W + 1);
   if (R < 1) return false;
   const int rows = R < H ? R : H;
   const int N = (rows * (W + 1) + 15) & ~15;
   const int Q = N + 2 * (W + 1) + 2;
-  if (N > kTilePx || Q > kHaloMaxRows) return false;
+  if (N > max_cols || Q > kHaloMaxRows) return false;
   g->R = rows;
   g->N = N;
   g->Q = Q;
@@ -506,6 +519,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     // ---- MMA issuer ----
     const uint32_t idesc = conv_idesc(a, geo.N);
     const int seg = halo_segment_chunks(a, ncc);
+    const uint32_t acc_stride = a.split ? kSplitCols : kTilePx;
     int g = 0, bi = 0, seg_seq = 0;     // seg_seq counts (tile, K segment) pairs: each gets its own accumulator buffer
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       uint32_t buf = 0, d = 0;
@@ -514,7 +528,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         if (seg_first) {
           buf = seg_seq & 1;
           if (seg_seq >= 2) mbarrier_wait(&acc_empty[buf], ((seg_seq >> 1) - 1) & 1);
-          d = tmem + buf * kTilePx;
+          d = tmem + buf * acc_stride;
         }
         mbarrier_wait(&full_blk[bi & 1], (bi >> 1) & 1);
         const uint32_t blk = smem_addr(blocks + (bi & 1) * kHaloBlock);
@@ -558,27 +572,43 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
       float* oplane = a.out + ((size_t)b * a.Cout + co0) * HW;
       // K segments (fp32-accuracy mode): the tensor core TRUNCATES the fp32 accumulator once per instruction, a bias of
       // ~2.3e-8 of the sum per MMA in a chain (measured: 1.1e-5 at 432 MMAs, 2.9e-5 at 1,296).  Every `seg` chunks the
-      // partial sum leaves tensor memory and is added — round to nearest, on the CUDA cores — to the output tile this
-      // warp wrote a few microseconds earlier (an L2 hit); bias with the first segment, ReLU with the last.
+      // partial sum is therefore added — round to nearest, on the CUDA cores — to a running total that lives in a third
+      // region of tensor memory (columns [2 x 160, 3 x 160); only this warp's lanes of it, so no synchronisation): one
+      // tcgen05.ld of the partial, one of the total, 32 adds, one tcgen05.st per 32 columns, hidden behind the next
+      // segment's 108 MMAs.  Scale, bias and ReLU are applied once, to the total.  (A first version added the partial sums
+      // into the output tile in global memory: 24.9 ms for the fusion module against 5.8 ms unsegmented.)
+      const uint32_t acc_stride = a.split ? kSplitCols : kTilePx;
+      const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
       for (int sg = 0; sg < n_seg; ++sg, ++seg_seq) {
         const uint32_t buf = seg_seq & 1;
         const bool first = sg == 0, last = sg == n_seg - 1;
-        const float seg_bias = first ? bias : 0.f;
         mbarrier_wait(&acc_full[buf], (seg_seq >> 1) & 1);
         tc_fence_after_sync();
 #pragma unroll 1
         for (int col0 = 0; col0 < geo.N; col0 += 32) {
           uint32_t r[32];
-          CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          CONV_TC_LD32(r, lane_base + buf * acc_stride + (uint32_t)col0);
+          if (!first) {
+            uint32_t t[32];
+            CONV_TC_LD32(t, lane_base + 2 * kSplitCols + (uint32_t)col0);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+          } else {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+          if (!last) {
+            CONV_TC_ST32(lane_base + 2 * kSplitCols + (uint32_t)col0, r);
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float v = fmaf(__uint_as_float(r[j]), oscale, seg_bias);
-            if (a.relu && n_seg == 1) v = fmaxf(v, 0.f);
+            float v = fmaf(__uint_as_float(r[j]), oscale, bias);
+            if (a.relu) v = fmaxf(v, 0.f);
             r[j] = __float_as_uint(v);
             tp[lane * 33 + j] = v;
           }
-          if (a.out_nhwc) {   // bf16 mode only (one segment); kept out of the loop above: the epilogue paces the small blocks
+          if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
             int ry = col0 / W1, x = col0 - ry * W1;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -595,27 +625,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
           // this lane's pixel: column n = col0 + lane
           const int n = col0 + lane;
           const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
-          const bool px_ok = x < a.W && ry < geo.R && y < a.H;
+          const bool px_ok = n < geo.N && x < a.W && ry < geo.R && y < a.H;
           float* dst = oplane + (px_ok ? y * a.W + x : 0);
           if (a.out) {
-            if (n_seg == 1) {
-              for (int c = 0; c < n_ch; ++c) {
-                const float v = tp[c * 33 + lane];
-                if (px_ok) dst[(size_t)c * HW] = v;
-              }
-            } else {
-              for (int c = 0; c < n_ch; ++c) {
-                float v = tp[c * 33 + lane];
-                if (px_ok) {
-                  if (!first) v += dst[(size_t)c * HW];
-                  if (last && a.relu) v = fmaxf(v, 0.f);
-                  dst[(size_t)c * HW] = v;
-                }
-              }
+            for (int c = 0; c < n_ch; ++c) {
+              const float v = tp[c * 33 + lane];
+              if (px_ok) dst[(size_t)c * HW] = v;
             }
           }
           __syncwarp();
         }
+        if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the total is re-read by this thread next segment
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
@@ -997,7 +1017,7 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
   const char* impl = debug_env("B200BEV_CONV_IMPL");
   HaloGeom geo;
   const bool want_halo = !(impl && impl[0] == 'p');   // "per-tap": the per-tap kernel for 3x3 too (A/B timing)
-  if (taps == 9 && want_halo && halo_geometry(H, W, &geo)) {
+  if (taps == 9 && want_halo && halo_geometry(H, W, &geo, a.split ? kSplitCols : kTilePx)) {
     B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
     const long long htiles = (long long)B * geo.tiles_per_frame * ceil_div(Cout, kTileCo);
     const int hgrid = (int)(htiles < sm_count() ? htiles : sm_count());

@@ -264,9 +264,13 @@ def test_all_three_branches_on_the_tcgen05_convs(cuda):
     lidar = torch.rand(2, 128, device=cuda)
     radar = torch.rand(2, 64, device=cuda)
     with torch.no_grad():
-        ref = fus(camera_features=cam, lidar_features=lidar, radar_features=radar)      # fp32 convolutions
+        fus.b200_precision = "f32_cudnn"
+        ref = fus(camera_features=cam, lidar_features=lidar, radar_features=radar)      # the module's own fp32 cuDNN convolutions
+        fus.b200_precision = None
+        acc = fus(camera_features=cam, lidar_features=lidar, radar_features=radar)      # default: fp32 accuracy on tcgen05
         fus.b200_precision = "bf16"
         got = fus(camera_features=cam, lidar_features=lidar, radar_features=radar)
+    assert max_rel(acc.cpu().numpy(), ref.cpu().numpy()) < 4 * FP32_TOL                 # four convolution layers deep
     assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < BF16_TOL
 
 
@@ -289,10 +293,15 @@ def test_centernet_head_mirror_vs_reference_golden_and_fused_path(cuda, golden):
     big = big.eval().to(cuda)
     xb = torch.from_numpy(syn._rng(714).standard_normal((3, 64, 50, 50)).astype(np.float32)).to(cuda)
     with torch.no_grad():
+        big.b200_precision = "f32_cudnn"            # the module's own torch layers: the reference on this device
         ref = big(xb)
+        big.b200_precision = None                   # the default: fp32 accuracy on the tensor cores
+        acc = big(xb)
         big.b200_precision = "bf16"
         got = big(xb)
     from bevfusion_multimodal_3d_object_detection_b200 import conv_blocks
+    for k in ("heatmap", "offset", "size", "rot", "vel"):
+        assert max_rel(acc[k].cpu().numpy(), ref[k].cpu().numpy()) < 2 * FP32_TOL, k       # two layers deep
     assert set(got) == set(ref) == {"heatmap", "offset", "size", "rot", "vel"}          # the reference's five keys, nothing else
     assert conv_blocks.logits_of(got["heatmap"]) is not None and conv_blocks.logits_of(ref["heatmap"]) is None
     for k in ("heatmap", "offset", "size", "rot", "vel"):
