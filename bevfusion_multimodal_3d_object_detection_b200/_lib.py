@@ -39,6 +39,7 @@ PROTOTYPES = {
     "b200bev_lidar_prepare_workspace_bytes": (_z, [_i, C.c_int64, _i]),
     "b200bev_lidar_prepare": (_i, [_p, _p, _i, _i, C.c_int64, C.POINTER(C.c_float), _i, _p, _p, _p, _p, _z, _p]),
     "b200bev_bin_sort": (_i, [_p, _i, _i, _i, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p]),
+    "b200bev_lidar_prepare_bin_sort": (_i, [_p, _p, _i, _i, C.c_int64, C.POINTER(C.c_float), _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
     "b200bev_pointnet_encode": (_i, [_p, _i, _i, _i, _p, C.POINTER(C.c_int32), _i, _p, _p, _i, _i, _p, _p, _p, _p]),
     "b200bev_pointnet_pack_bf16_bytes": (_z, [C.POINTER(C.c_int32), _i]),
     "b200bev_pointnet_pack_bf16": (_i, [_p, C.POINTER(C.c_int32), _i, _p, _z, _p]),

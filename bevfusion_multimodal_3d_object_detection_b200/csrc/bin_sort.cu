@@ -31,13 +31,13 @@
 #include <cstdlib>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
+#include "lidar_prepare.cuh"
 
 namespace b200bev {
 namespace {
 
 constexpr int kBinThreads = 256;
+static_assert(kBinThreads == kPrepThreads, "the fused kernel runs lidar_prepare_frame with bin_sort's block shape");
 constexpr int kMaxCluster = 8;
 
 struct BinArgs {
@@ -218,12 +218,24 @@ __device__ __forceinline__ uint32_t row_prefix(const uint16_t* row, int NW, int 
   return s;
 }
 
-__global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs ra) {
+// FUSED (b200bev_lidar_prepare_bin_sort, SURVEY 8f N3 "filter + compact fused into bin-and-sort"): the frame's cluster first
+// runs the range filter + stable compaction + zero padding of the raw sweep (lidar_prepare_frame writes a.pts), then — after a
+// fence and a cluster barrier — bins and sorts what it wrote.  The rows were written by this launch, so phase 1 reads them
+// through L2 (ld.global.cg), not through the non-coherent path.
+template <bool FUSED>
+__global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs ra, PrepArgs pa) {
   const BinArgs& a = ra.a;
   int dbg_n = 0;
   auto stamp = [&]() { if (ra.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ra.dbg[dbg_n++] = clock64(); };
   stamp();
   cg::cluster_group cluster = cg::this_cluster();
+  if constexpr (FUSED) {
+    __shared__ uint32_t prep_warp_cnt[kPrepThreads / 32];
+    __shared__ uint32_t prep_cta_tot[kPrepMaxCluster];
+    lidar_prepare_frame(pa, cluster, prep_warp_cnt, prep_cta_tot);
+    __threadfence();
+    cluster.sync();
+  }
   const int CL = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -270,12 +282,13 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
         y[u] = 0.0f;
         if (i < s1) {
           if (vec2) {
-            const float2 xy = __ldg(reinterpret_cast<const float2*>(pts + (size_t)i * a.C));
+            const float2* q = reinterpret_cast<const float2*>(pts + (size_t)i * a.C);
+            const float2 xy = FUSED ? __ldcg(q) : __ldg(q);
             x[u] = xy.x;
             y[u] = xy.y;
           } else {
-            x[u] = __ldg(pts + (size_t)i * a.C);
-            y[u] = __ldg(pts + (size_t)i * a.C + 1);
+            x[u] = FUSED ? __ldcg(pts + (size_t)i * a.C) : __ldg(pts + (size_t)i * a.C);
+            y[u] = FUSED ? __ldcg(pts + (size_t)i * a.C + 1) : __ldg(pts + (size_t)i * a.C + 1);
           }
         }
       }
@@ -410,13 +423,12 @@ __global__ void __launch_bounds__(kBinThreads) bin_sort_ranked_kernel(RankedArgs
 
 using namespace b200bev;
 
-extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, int C, float x_min, float y_min, float voxel_x,
-                                float voxel_y, int W, int H, int32_t* cell, int32_t* perm, int32_t* offsets,
-                                void* stream) {
-  if (!points || !cell || !perm || !offsets || B <= 0 || N <= 0 || C < 2 || W <= 0 || H <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
-  if (!(voxel_x > 0.0f) || !(voxel_y > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
-  if ((long long)W * H > 48000 || B > 65535) return B200BEV_ERR_UNSUPPORTED;
-
+namespace {
+// prep == nullptr: bin-and-sort of `points`.  prep != nullptr: the raw sweeps are filtered / compacted / padded into `points`
+// first — in the same launch when the ranked kernel takes the shape, as a launch of its own in front of the fallback kernel.
+int launch_bin_sort(const float* points, int B, int N, int C, float x_min, float y_min, float voxel_x, float voxel_y, int W, int H,
+                    int32_t* cell, int32_t* perm, int32_t* offsets, const PrepArgs* prep, int64_t max_frame_rows, const float* pc_range,
+                    void* stream) {
   BinArgs a{};
   a.pts = points; a.B = B; a.N = N; a.C = C;
   a.x_min = x_min; a.y_min = y_min; a.vx = voxel_x; a.vy = voxel_y; a.W = W; a.H = H;
@@ -459,10 +471,10 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
       else if ((long long)W * H >= 0xffff) break;   // cell ids would not fit the packed form: legacy kernel
       RankedArgs ra{a, NW, sub, nullptr};
       if (debug_env("B200BEV_BINSORT_TRACE")) B200BEV_CUDA_TRY(cudaMalloc(&ra.dbg, 16 * sizeof(unsigned long long)));
-      if (smem > 48 * 1024)
-        B200BEV_CUDA_TRY(cudaFuncSetAttribute(bin_sort_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      auto kern = prep ? bin_sort_ranked_kernel<true> : bin_sort_ranked_kernel<false>;
+      if (smem > 48 * 1024) B200BEV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cfg.dynamicSmemBytes = smem;
-      B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, bin_sort_ranked_kernel, ra));
+      B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ra, prep ? *prep : PrepArgs{}));
       if (ra.dbg) {   // debug: phase boundaries of CTA (0,0) in SM clocks since its start
         unsigned long long h[16];
         B200BEV_CUDA_TRY(cudaStreamSynchronize(cfg.stream));
@@ -475,6 +487,11 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
     }
   }
 
+  if (prep) {   // shapes the ranked kernel does not take: the two steps as two launches
+    const int rc = b200bev_lidar_prepare(prep->raw, prep->frame_off, B, C, max_frame_rows, pc_range, N, nullptr, prep->out, prep->count,
+                                         nullptr, 0, stream);
+    if (rc != B200BEV_OK) return rc;
+  }
   const size_t fixed = (nb + kMaxCluster + kBinThreads / 32) * sizeof(uint32_t);
   size_t smem = fixed + (size_t)a.slice * sizeof(int32_t);
   a.cache_cells = 1;
@@ -487,4 +504,34 @@ extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, i
   cfg.dynamicSmemBytes = smem;
   B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, bin_sort_kernel, a));
   return launch_status();
+}
+}  // namespace
+
+extern "C" B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, int C, float x_min, float y_min, float voxel_x,
+                                float voxel_y, int W, int H, int32_t* cell, int32_t* perm, int32_t* offsets,
+                                void* stream) {
+  if (!points || !cell || !perm || !offsets || B <= 0 || N <= 0 || C < 2 || W <= 0 || H <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (!(voxel_x > 0.0f) || !(voxel_y > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((long long)W * H > 48000 || B > 65535) return B200BEV_ERR_UNSUPPORTED;
+  return launch_bin_sort(points, B, N, C, x_min, y_min, voxel_x, voxel_y, W, H, cell, perm, offsets, nullptr, 0, nullptr, stream);
+}
+
+extern "C" B200BEV_API int b200bev_lidar_prepare_bin_sort(const float* raw, const int64_t* frame_offsets, int B, int C,
+                                              int64_t max_frame_rows, const float* pc_range, int max_points, float voxel_x,
+                                              float voxel_y, int W, int H, float* points, int32_t* count, int32_t* cell,
+                                              int32_t* perm, int32_t* offsets, void* stream) {
+  if (!raw || !frame_offsets || !pc_range || !points || !count || !cell || !perm || !offsets || B <= 0 || C < 3 || max_points <= 0 ||
+      max_frame_rows < 0 || W <= 0 || H <= 0)
+    return B200BEV_ERR_INVALID_ARGUMENT;
+  if (!(voxel_x > 0.0f) || !(voxel_y > 0.0f)) return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((long long)W * H > 48000 || B > 65535 || max_frame_rows > 0x7fffffffLL) return B200BEV_ERR_UNSUPPORTED;
+  PrepArgs pa{};
+  pa.raw = raw; pa.frame_off = frame_offsets; pa.B = B; pa.C = C; pa.max_points = max_points;
+  for (int i = 0; i < 3; ++i) {
+    pa.lo[i] = pc_range[i];
+    pa.hi[i] = pc_range[3 + i];
+  }
+  pa.select = nullptr; pa.out = points; pa.count = count; pa.kept_index = nullptr; pa.cap = max_frame_rows;
+  return launch_bin_sort(points, B, max_points, C, pc_range[0], pc_range[1], voxel_x, voxel_y, W, H, cell, perm, offsets, &pa,
+                         max_frame_rows, pc_range, stream);
 }

@@ -101,6 +101,33 @@ def bin_sort(points: torch.Tensor, W: int, H: int,
     return cell, perm, offsets
 
 
+def lidar_prepare_bin_sort(raw: torch.Tensor, frame_offsets: torch.Tensor, max_points: int, W: int, H: int,
+                           pc_range: Sequence[float] = DEFAULT_PC_RANGE, max_frame_rows: Optional[int] = None):
+    """lidar_prepare (without `select`) + bin_sort in ONE launch: raw sweeps -> (points (B,max_points,C), count (B) i32,
+    cell (B,max_points) i32, perm (B,max_points) i32, offsets (B,H*W+1) i32), bit-identical to the two calls."""
+    raw = _need_cuda(raw, "raw")
+    frame_offsets = _need_cuda(frame_offsets, "frame_offsets", torch.int64)
+    if raw.dim() != 2 or raw.shape[1] < 3:
+        raise ValueError("raw must be (total_rows, C) with C >= 3")
+    if frame_offsets.dim() != 1 or frame_offsets.numel() < 2:
+        raise ValueError("frame_offsets must be (B + 1,)")
+    B, Cc, dev = frame_offsets.numel() - 1, int(raw.shape[1]), raw.device
+    if max_frame_rows is None:
+        max_frame_rows = int(raw.shape[0])
+    points = torch.empty((B, max_points, Cc), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    cell = torch.empty((B, max_points), dtype=torch.int32, device=dev)
+    perm = torch.empty((B, max_points), dtype=torch.int32, device=dev)
+    offsets = torch.empty((B, H * W + 1), dtype=torch.int32, device=dev)
+    vx, vy = voxel_size(pc_range, W, H)
+    rng = (C.c_float * 6)(*[float(v) for v in pc_range])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200bev_lidar_prepare_bin_sort(_ptr(raw), _ptr(frame_offsets), B, Cc, max_frame_rows, rng, max_points, vx, vy,
+                                                             W, H, _ptr(points), _ptr(count), _ptr(cell), _ptr(perm), _ptr(offsets),
+                                                             _stream(dev)))
+    return points, count, cell, perm, offsets
+
+
 # ------------------------------------------------------------------------------------------------
 # S1b / S1c
 # ------------------------------------------------------------------------------------------------

@@ -96,6 +96,18 @@ B200BEV_API int b200bev_bin_sort(const float* points, int B, int N, int C,
                      float x_min, float y_min, float voxel_x, float voxel_y, int W, int H,
                      int32_t* cell, int32_t* perm, int32_t* offsets, void* stream);
 
+/* N3 + S1a in ONE launch ("filter + compact fused into bin-and-sort", src/train_detect.py:147-189 in front of
+ * the binning): per frame one thread-block cluster filters the raw sweep by range (strict, NaN fails), compacts it in file
+ * order, zero-pads to max_points — exactly b200bev_lidar_prepare without `select` (a frame with more in-range points than
+ * max_points keeps the first max_points) — and then bins and sorts the rows it has just written, exactly b200bev_bin_sort
+ * on them with x_min/y_min = pc_range[0..1].  Outputs of both: points (B,max_points,C), count (B), cell / perm (B,max_points),
+ * offsets (B,H*W+1).  Shapes the fused kernel does not take run as two launches behind the same call. */
+B200BEV_API int b200bev_lidar_prepare_bin_sort(const float* raw, const int64_t* frame_offsets, int B, int C,
+                                   int64_t max_frame_rows, const float* pc_range, int max_points,
+                                   float voxel_x, float voxel_y, int W, int H,
+                                   float* points, int32_t* count, int32_t* cell, int32_t* perm, int32_t* offsets,
+                                   void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * S1b  fused PointNet shared-MLP + max.
  * Replaces: PointNetLiDAREncoder.forward, src/encoders.py:271-306 (eval mode, BN folded);

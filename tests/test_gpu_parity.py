@@ -78,6 +78,30 @@ def test_lidar_prepare_ragged_batches(cuda, rows, C, max_points):
             np.testing.assert_array_equal(got[b].cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("rows,C,max_points,W", [([35211, 0, 1, 40000, 777], 4, 35000, 50), ([3000, 2999, 10], 5, 1024, 7),
+                                                  ([300000, 280000], 4, 300000, 100), ([5000], 4, 2048, 50)])
+def test_lidar_prepare_bin_sort_in_one_launch(cuda, rows, C, max_points, W):
+    """SURVEY 8f N3 as worded: range filter + compaction + padding fused into the bin-and-sort launch — bit-identical to
+    lidar_prepare followed by bin_sort, and to the oracle."""
+    sweeps = [syn.raw_sweep(900 + i, r, channels=C) for i, r in enumerate(rows)]
+    raw = dev_t(np.concatenate(sweeps, axis=0) if sum(rows) else np.zeros((0, C), np.float32), cuda)
+    off = torch.tensor([0] + list(np.cumsum(rows)), dtype=torch.int64, device=cuda)
+    pts, count, cell, perm, offs = ops.lidar_prepare_bin_sort(raw, off, max_points, W, W, syn.PC_RANGE, max_frame_rows=max(rows))
+    want_pts, want_count = ops.lidar_prepare(raw, off, max_points, syn.PC_RANGE, max_frame_rows=max(rows))
+    want_cell, want_perm, want_offs = ops.bin_sort(want_pts, W, W, syn.PC_RANGE)
+    for got, want in ((pts, want_pts), (count, want_count), (cell, want_cell), (perm, want_perm), (offs, want_offs)):
+        assert torch.equal(got, want)
+    for b, sw in enumerate(sweeps[:2]):
+        ref, n = orc.lidar_prepare(sw, max_points, syn.PC_RANGE)
+        assert int(count[b]) == n
+        np.testing.assert_array_equal(pts[b].cpu().numpy(), ref)
+        rc = orc.cell_index(ref[None], syn.PC_RANGE, W, W)[0]
+        np.testing.assert_array_equal(cell[b].cpu().numpy(), rc)
+        rp, ro = orc.bin_sort(rc, W * W)
+        np.testing.assert_array_equal(perm[b].cpu().numpy(), rp)
+        np.testing.assert_array_equal(offs[b].cpu().numpy(), ro)
+
+
 def test_prepare_lidar_batch_feeds_the_encoder_path(cuda, tmp_path):
     """dataset.prepare_lidar_batch: .bin files -> filtered/padded batch -> bin_sort accepts every kept point."""
     from bevfusion_multimodal_3d_object_detection_b200 import dataset
