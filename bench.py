@@ -479,6 +479,19 @@ def kernel_rooflines(hp: HotPath, peaks, fp32_peak, flush):
                         "tensor pipe executes 3x the algorithmic flops; `achieved` counts the ALGORITHMIC flops")
                 put("pointnet_encode", ms_cell, "tensor", flops, "cell canvas + global max; " + note)
                 put("pointnet_encode_global_only", ms_glob, "tensor", flops, note)
+            if N <= 40000:
+                # N3, the step in front of the path (not part of the timed step): raw sweeps -> filtered / padded points, alone and
+                # fused into the bin-and-sort launch
+                import numpy as np
+                from bevfusion_multimodal_3d_object_detection_b200 import synthetic as syn
+                rows = N + 8000
+                raw = torch.from_numpy(np.concatenate([syn.raw_sweep(9000 + i, rows) for i in range(F)], axis=0)).to(dev)
+                offs = torch.tensor([rows * i for i in range(F + 1)], dtype=torch.int64, device=dev)
+                put("lidar_prepare", med_ms(lambda: ops.lidar_prepare(raw, offs, N, syn.PC_RANGE, max_frame_rows=rows)), "hbm",
+                    F * 16.0 * (rows + N), f"{F} x {rows} raw rows -> {N}; the stage in front of the step")
+                put("lidar_prepare_bin_sort", med_ms(lambda: ops.lidar_prepare_bin_sort(raw, offs, N, G, G, syn.PC_RANGE, max_frame_rows=rows)),
+                    "hbm", F * (16.0 * (rows + N) + 24.0 * N + 4.0 * (HW + 1)), "range filter + compaction + padding + bin-and-sort, one launch")
+                del raw
         if wl["radar"]:
             radars = [hp.inputs[f"radar{i}"] for i in range(5)]
             put("radar_encode", med_ms(lambda: hp.chain.radar_encoder(radars)), "fp32_fma",

@@ -67,13 +67,19 @@ def weight_producer(n_tiles, ncc, ring, bars, st):
         yield ("step",)
 
 
-def issuer(n_tiles, ncc, ring, bars, st):
-    g = bi = 0
+def issuer(n_tiles, ncc, ring, bars, st, seg=None):
+    """seg: k chunks per accumulator chain (fp32-accuracy mode: every `seg` chunks the partial sum gets its own accumulator
+    buffer and is added to the running total by the epilogue); None = the whole tile in one chain (bf16 mode)."""
+    seg = seg or ncc
+    g = bi = seq = 0
+    buf = 0
     for t in range(n_tiles):
-        buf = t & 1
-        if t >= 2:
-            yield ("wait", bars["acc_empty"][buf], ((t >> 1) - 1) & 1)
         for cc in range(ncc):
+            seg_first, seg_last = cc % seg == 0, (cc % seg == seg - 1 or cc == ncc - 1)
+            if seg_first:
+                buf = seq & 1
+                if seq >= 2:
+                    yield ("wait", bars["acc_empty"][buf], ((seq >> 1) - 1) & 1)
             yield ("wait", bars["full_blk"][bi & 1], (bi >> 1) & 1)
             if st["blk_data"][bi & 1] != bi:
                 st["hazard"] = f"MMAs of block {bi} issued on pixel data of block {st['blk_data'][bi & 1]}"
@@ -85,18 +91,21 @@ def issuer(n_tiles, ncc, ring, bars, st):
                 commits = [("empty_a", slot)]
                 if tap == TAPS - 1:
                     commits.append(("empty_blk", bi & 1))
-                    if cc == ncc - 1:
+                    if seg_last:
                         commits.append(("acc_full", buf))
                 st["a_reading"][slot] += 1
                 st["blk_reading"][bi & 1] += 1
-                st["pipe"].append({"slot": slot, "blk": bi & 1, "commits": commits, "tile": t, "buf": buf,
-                                   "first": cc == 0 and tap == 0})
+                st["pipe"].append({"slot": slot, "blk": bi & 1, "commits": commits, "tile": seq, "buf": buf,
+                                   "first": seg_first and tap == 0})
                 g += 1
                 yield ("step",)
             bi += 1
+            if seg_last:
+                seq += 1
 
 
 def epilogue(q, n_tiles, bars, st):
+    """n_tiles here = (tile, K segment) pairs: the epilogue's loop is over accumulator hand-overs."""
     for t in range(n_tiles):
         buf = t & 1
         yield ("wait", bars["acc_full"][buf], (t >> 1) & 1)
@@ -108,16 +117,19 @@ def epilogue(q, n_tiles, bars, st):
         yield ("step",)
 
 
-def run(n_tiles: int, ncc: int, seed: int, ring: int = 4, bars=None, max_steps: int = 400_000, slow=(), slow_factor: int = 40) -> str:
-    """slow: agent kinds ('epilogue', 'producer', 'weights', 'issuer', 'copy', 'retire') scheduled `slow_factor` times less often."""
+def run(n_tiles: int, ncc: int, seed: int, ring: int = 4, bars=None, max_steps: int = 400_000, slow=(), slow_factor: int = 40,
+        seg=None) -> str:
+    """slow: agent kinds ('epilogue', 'producer', 'weights', 'issuer', 'copy', 'retire') scheduled `slow_factor` times less often.
+    seg: k chunks per accumulator chain (the kernel's halo_segment_chunks: 3 in fp32-accuracy mode)."""
+    n_seg = -(-ncc // (seg or ncc))
     rng = random.Random(seed)
     bars = bars or make_bars(ring)
     st = {"inflight": [], "pipe": deque(), "hazard": None, "a_reading": [0] * ring, "blk_reading": [0, 0],
           "a_data": [None] * ring, "blk_data": [None, None], "blk_landed": {}, "acc_tile": [None, None], "acc_unread": [0, 0],
           "landed": set()}
     agents = [pixel_producer(w, n_tiles, ncc, bars, st) for w in range(N_PRODUCERS)]
-    agents += [weight_producer(n_tiles, ncc, ring, bars, st), issuer(n_tiles, ncc, ring, bars, st)]
-    agents += [epilogue(q, n_tiles, bars, st) for q in range(N_EPILOGUE)]
+    agents += [weight_producer(n_tiles, ncc, ring, bars, st), issuer(n_tiles, ncc, ring, bars, st, seg)]
+    agents += [epilogue(q, n_tiles * n_seg, bars, st) for q in range(N_EPILOGUE)]
     kinds = ["producer"] * N_PRODUCERS + ["weights", "issuer"] + ["epilogue"] * N_EPILOGUE
     pending = [None] * len(agents)
     alive = set(range(len(agents)))

@@ -15,6 +15,16 @@ def test_conv_protocol_has_no_deadlock_or_hazard(n_tiles, ncc):
         assert model.run(n_tiles, ncc, 100 + seed, slow=(slow,)) == "ok", f"slow {slow}"
 
 
+@pytest.mark.parametrize("n_tiles,ncc,seg", [(1, 3, 3), (2, 6, 3), (3, 7, 3), (2, 36, 3), (4, 2, 3)])
+def test_conv_protocol_with_k_segments(n_tiles, ncc, seg):
+    """fp32-accuracy mode: every `seg` chunks the accumulator is handed to the epilogue (which adds it to the running total),
+    so accumulator hand-overs outnumber tiles — same barriers, counted per (tile, segment)."""
+    for seed in range(6):
+        assert model.run(n_tiles, ncc, seed, seg=seg) == "ok", f"seed {seed}"
+    for seed, slow in enumerate(("epilogue", "producer", "weights", "issuer", "copy", "retire")):
+        assert model.run(n_tiles, ncc, 200 + seed, slow=(slow,), seg=seg) == "ok", f"slow {slow}"
+
+
 def test_model_catches_a_missing_accumulator_handshake():
     """Without the acc_empty wait the third tile's first MMA overwrites a half the epilogue has not read."""
     outcomes = set()
