@@ -409,6 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
       const uint32_t buf = tile_seq & 1;
       const int co = co_tile * kCo + quad * 32 + lane;
       const float unscale = __ldg(a.tail + co) * inv_S, bias = __ldg(a.tail + a.Cout + co);
+      int c_cur = -1;
+      if (FINAL && a.out_canvas != nullptr) c_cur = __ldg(a.cid + row_base + lane);
       mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
       tcs_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + buf * kPx;
@@ -436,39 +438,49 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
         for (int col0 = 0; col0 < kPx; col0 += 32) {
           uint32_t r[32];
           SPLIT_LD32(r, tbase + (uint32_t)col0);
+          // the cell ids of the NEXT 32 slots travel while this group is walked (the first group's were fetched before the
+          // wait for the accumulator): a dependent global load per group was a third of the cell-mode epilogue
+          int c_nxt = INT_MIN;
+          if (canvas != nullptr && col0 + 32 < kPx) c_nxt = __ldg(a.cid + row_base + col0 + 32 + lane);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (col0 >= n_valid) continue;                             // warp-uniform
-          if (canvas == nullptr) {
+          if (col0 < n_valid) {                                       // warp-uniform
+            if (col0 + 32 > n_valid) {                                // the frame's last, ragged group: padding never counts
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < n_valid) gmax = fmaxf(gmax, __uint_as_float(r[j]));
-            continue;
-          }
-          const int c_l = __ldg(a.cid + row_base + col0 + lane);
-          int c_n = __shfl_down_sync(FULL_MASK, c_l, 1);
-          if (lane == 31) c_n = col0 + 32 < kPx ? __ldg(a.cid + row_base + col0 + 32) : INT_MIN;   // the tile's last slot ends a run
-          const unsigned ends = __ballot_sync(FULL_MASK, c_l != c_n);
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j >= n_valid) r[j] = 0xff800000u;          // -inf
+            }
+            if (canvas == nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = col0 + j < n_valid ? __uint_as_float(r[j]) : -INFINITY;
-            gmax = fmaxf(gmax, v);
-            m = fmaxf(m, v);
-            if (ends & (1u << j)) {                                   // the same word in every lane
-              const int cj = __shfl_sync(FULL_MASK, c_l, j);
-              if (cj >= 0) {
-                const float val = fmaxf(fmaf(m, unscale, bias), 0.f);
-                if (val > 0.f) {
-                  float* dst = canvas + (size_t)cj * a.Cout;          // 32 lanes: 128 contiguous bytes of the cell's row
-                  // a run touching the tile's first or last slot may go on in a neighbouring tile: atomic; else the only writer
-                  if (first_run || col0 + j == kPx - 1) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
-                  else *dst = val;
+              for (int j = 0; j < 32; ++j) gmax = fmaxf(gmax, __uint_as_float(r[j]));
+            } else {
+              int c_n = __shfl_down_sync(FULL_MASK, c_cur, 1);
+              const int c_first_next = __shfl_sync(FULL_MASK, c_nxt, 0);
+              if (lane == 31) c_n = col0 + 32 < kPx ? c_first_next : INT_MIN;   // the tile's last slot ends a run
+              const unsigned ends = __ballot_sync(FULL_MASK, c_cur != c_n);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                m = fmaxf(m, __uint_as_float(r[j]));
+                if (ends & (1u << j)) {                               // the same word in every lane
+                  const int cj = __shfl_sync(FULL_MASK, c_cur, j);
+                  if (cj >= 0) {
+                    const float val = fmaxf(fmaf(m, unscale, bias), 0.f);
+                    if (val > 0.f) {
+                      float* dst = canvas + (size_t)cj * a.Cout;      // 32 lanes: 128 contiguous bytes of the cell's row
+                      // a run touching the tile's first or last slot may go on in a neighbouring tile: atomic; else the only writer
+                      if (first_run || col0 + j == kPx - 1) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
+                      else *dst = val;
+                    }
+                  }
+                  gmax = fmaxf(gmax, m);                              // the global maximum is the maximum of the runs' maxima
+                  m = -INFINITY;
+                  first_run = false;
                 }
               }
-              m = -INFINITY;
-              first_run = false;
             }
           }
+          c_cur = c_nxt;
         }
+        gmax = fmaxf(gmax, m);
         if (a.out_global) {
           const float val = fmaxf(fmaf(gmax, unscale, bias), 0.f);    // bias + ReLU commute with the max (unscale > 0)
           if (val > 0.f) atomicMax(reinterpret_cast<int*>(a.out_global + (size_t)fl * a.Cout + co), __float_as_int(val));
