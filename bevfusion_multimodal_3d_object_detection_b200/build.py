@@ -71,7 +71,9 @@ def build(force: bool = False, verbose: bool = False, debug_env: bool = False) -
     procs = []
     for src in sources():
         obj = OUT_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *(["-DB200BEV_DEBUG_ENV"] if debug_env else []), "-c", str(src), "-o", str(obj)]
+        # B200BEV_NVCC_EXTRA: extra flags for experiment builds on the GPU box (-D switches of a kernel under study)
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DB200BEV_DEBUG_ENV"] if debug_env else []), *os.environ.get("B200BEV_NVCC_EXTRA", "").split(),
+               "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -35,6 +35,9 @@
 
 #include "common.cuh"
 
+#ifndef B200BEV_CELL_MMA_UNROLL
+#define B200BEV_CELL_MMA_UNROLL 0   // 1: the MMA issuer's chunk loop unrolled in cell mode too (experiments)
+#endif
 #ifndef B200BEV_TC_TRIP
 #define B200BEV_TC_TRIP 0   // 0: per-mode default; 1 or 2 forces the ring pairs per MMA trip (experiments)
 #endif
@@ -135,6 +138,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive2(uint64_t* bar) {   // two arrivals at once
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 2;" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -166,6 +172,14 @@ __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive2_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra], 2;\n\t}" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
 }
@@ -286,7 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   uint64_t* acc_empty = acc_full + 3;       // [3]        accumulator drained by the epilogue (one arrival per warp)
   uint64_t* act_ready = acc_empty + 3;      // [4]        K-pair kp (128 channels) of the next A operand is in TMEM (one arrival per warp)
   uint64_t* accx = act_ready + 4;           // [1]        this CTA's warps have drained accX (layer 4, chunk 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accx + 1);
+  uint64_t* l5_done = accx + 1;             // [1]        every MMA of the tile has completed (cell mode: the warps that do not drain chunk 7)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l5_done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -305,6 +320,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     }
     for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps * CG);
     mbar_init(accx, kEpiWarps);
+    mbar_init(l5_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -463,7 +479,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             if (elect_one()) {
               issue_pair(d_addr, a_addr, pair, kp == 0, layer == 0);
               if (two) issue_pair(d_addr, a_addr + 64, pr1, false, false);
-              if (kp + kTrip >= kpairs) commit_acc(buf);
+              if (kp + kTrip >= kpairs) {
+                commit_acc(buf);
+                if (CELL && layer == 3 && c == nchunks - 1) {   // the tile's last MMAs: tell the warps that do not drain this chunk
+                  if constexpr (CG == 1) tc_commit(l5_done);
+                  else tc_commit_pair(l5_done);
+                }
+              }
             }
             __syncwarp();
             if (two) { pair = pr1; phase = ph1; }
@@ -474,7 +496,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         // Global mode unrolls the chunks too (accumulator choice and the c == 0 tests fold away: 1.10 -> 1.05 ms).
         // Cell mode keeps them rolled: its epilogue is the bottleneck and lives on instruction fetch — with
         // the chunks unrolled here the issuer got faster and the epilogue 40 % slower.
-        if constexpr (CELL) {
+        if constexpr (CELL && !(B200BEV_CELL_MMA_UNROLL)) {
 #pragma unroll 1
           for (int c = 0; c < nchunks; ++c) issue_chunk(c);
         } else {
@@ -500,9 +522,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     const int row = quad * 32 + lane;          // point within the tile = TMEM lane
     const uint32_t tm = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t full_phase = 0;                   // bit b: parity of the next completion of accumulator b
-    // running maximum of the raw layer-5 accumulators of the current frame, one value per 128-channel chunk c:
-    //   rmax[c] <-> channel c*128 + part*32 + lane, over the 32 points of this warp's TMEM lane quadrant (global mode: what
-    //   the butterfly leaves in this lane; cell mode: the channel this lane walks after the warp's private transpose)
+    // global mode: running maximum of the raw layer-5 accumulators of the current frame, one value per 128-channel chunk c:
+    //   rmax[c] <-> channel c*128 + part*32 + lane, over the 32 points of this warp's TMEM lane quadrant (what the
+    //   butterfly leaves in this lane)
     float rmax[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
@@ -531,7 +553,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         else mbar_arrive_remote_relaxed(bar, 0);
       }
     };
-    uint32_t accx_parity = 0;
+    // the same, counting for two warps (cell mode, layer 5: half of the warps drain a chunk, the barrier expects all of them)
+    auto warp_arrive2 = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1 || cta_rank == 0) mbar_arrive2(bar);
+        else mbar_arrive2_remote_relaxed(bar, 0);
+      }
+    };
+    uint32_t accx_parity = 0, l5_parity = 0;
     auto acc_wait = [&](int buf) {
       mbar_wait(&acc_full[buf], (full_phase >> buf) & 1);
       full_phase ^= 1u << buf;
@@ -539,7 +570,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     };
 
     auto flush = [&](int frame) {
-      if (a.out_global == nullptr) return;
+      if (CELL || a.out_global == nullptr) return;   // cell mode sends its maxima chunk by chunk
       int* o = reinterpret_cast<int*>(a.out_global + (size_t)frame * c_out);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -756,50 +787,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       }
 
       // ---- layer 5: max over the tile's points, channel chunk by channel chunk ----
-      // The loop stays ROLLED (the unrolled cell-mode kernel was 164 KB of code and its epilogue warps starved on
-      // instruction fetch); the eight running maxima live in registers all the same: rmax[0] is always the
-      // current chunk's, and the array is rotated by one after every chunk — back in place after the eighth.
-      if (CELL) epi_bar_sync();     // this tile's cell ids and run-end flags (written by part 0 at the top) are in place
+      // layer 1 of the NEXT tile (computed while the tensor pipe works on this tile's last chunk)
+      auto next_layer1 = [&](uint32_t* packed1) {
+        float x[kMaxCin];
+        if (have_pre) {
+          x[0] = xpre.x; x[1] = xpre.y; x[2] = xpre.z; x[3] = xpre.w;
+#pragma unroll
+          for (int k = 4; k < kMaxCin; ++k) x[k] = 0.0f;
+        } else {
+          load_point(fn, slotn, x);
+        }
+        layer1(x, packed1);
+      };
+      if constexpr (!CELL) {
+        // The loop stays ROLLED; the eight running maxima live in registers all the same: rmax[0] is always the
+        // current chunk's, and the array is rotated by one after every chunk — back in place after the eighth.
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const int buf = c & 1;
-        uint32_t packed1[8];
-        if (c == 7 && more) {
-          // layer 1 of the NEXT tile, computed while the tensor pipe works on this tile's last chunk
-          float x[kMaxCin];
-          if (have_pre) {
-            x[0] = xpre.x; x[1] = xpre.y; x[2] = xpre.z; x[3] = xpre.w;
-#pragma unroll
-            for (int k = 4; k < kMaxCin; ++k) x[k] = 0.0f;
-          } else {
-            load_point(fn, slotn, x);
+        for (int c = 0; c < 8; ++c) {
+          const int buf = c & 1;
+          uint32_t packed1[8];
+          if (c == 7 && more) next_layer1(packed1);
+          acc_wait(buf);
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
+          // every MMA of this tile has completed (the pipe retires in order): act4 is dead, act1 may be replaced
+          if (c == 7 && more) publish_act1(packed1);
+          const uint32_t acc_col = buf ? kColAcc1 : kColAcc0;
+          if (a.debug & 2) {   // debug bit 1: no layer-5 epilogue at all (results are garbage; timing experiment)
+            warp_arrive(&acc_empty[buf]);
+            continue;
           }
-          layer1(x, packed1);
-        }
-        acc_wait(buf);
-        if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
-        // every MMA of this tile has completed (the pipe retires in order): act4 is dead, act1 may be replaced
-        if (c == 7 && more) publish_act1(packed1);
-        const uint32_t acc_col = buf ? kColAcc1 : kColAcc0;
-        if (a.debug & 2) {   // debug bit 1: no layer-5 epilogue at all (results are garbage; timing experiment)
-          warp_arrive(&acc_empty[buf]);
-          continue;
-        }
-        {
-          const int g = part;   // this warp's 32 of the chunk's 128 channels
-          uint32_t r[32];
-          TC_LD32(r, tm + acc_col + g * 32);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          // this warp's share of the chunk is in registers: hand the accumulator back to the MMA warp
-          warp_arrive(&acc_empty[buf]);
-          float v[32];
+          {
+            const int g = part;   // this warp's 32 of the chunk's 128 channels
+            uint32_t r[32];
+            TC_LD32(r, tm + acc_col + g * 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // this warp's share of the chunk is in registers: hand the accumulator back to the MMA warp
+            warp_arrive(&acc_empty[buf]);
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (partial && !valid) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (partial && !valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
-          }
-          if (!CELL) {
+              for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
+            }
             butterfly_level<16>(v, lane);
             butterfly_level<8>(v, lane);
             butterfly_level<4>(v, lane);
@@ -807,79 +837,170 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             butterfly_level<1>(v, lane);
             rmax[0] = fmaxf(rmax[0], v[0]);  // lane l holds channel c*128 + g*32 + l
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x260 + c);  // layer-5 chunk reduced
+          }
+          {
+            const float r0 = rmax[0];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) rmax[i] = rmax[i + 1];
+            rmax[7] = r0;
+          }
+        }
+      } else {
+        // Cell mode.  A warp drains every SECOND chunk (the chunks whose accumulator buffer is part >> 1) and takes 64 of its
+        // 128 channels, as two 32 x 32 blocks A and B that go through the SAME run walk: the run boundaries belong to the
+        // warp's 32 slots, not to the channels, so the control flow of the walk (one warp-uniform test per four slots, one
+        // branch per run end, the cell id, the canvas address) is paid once per 64 channels, and the two maximum chains
+        // are independent instructions that hide each other's latency.  (One block per warp and chunk, the first form:
+        // ~230 dependent instructions per chunk and warp at four warps per scheduler took 2,500 clk against 1,750 clk of
+        // MMAs — the run walk alone was 0.32 ms of the 1.40 ms kernel.)  A warp never looks at the accumulator barriers of
+        // the other buffer during layer 5 (four phases each per tile: its parity bookkeeping stays right), the draining warps
+        // arrive for two on acc_empty, and the one thing the other warps need from chunk 7 — that every MMA of the tile has
+        // completed, so that act1 may be replaced — comes from a barrier of its own, l5_done, one phase per tile.
+        // The per-frame global maximum goes to out_global chunk by chunk (two 128-byte atomics per warp and chunk, L2-resident)
+        // instead of living in eight rotating registers: at 96 registers per thread those were spilled.
+        epi_bar_sync();     // this tile's cell ids and run-end flags (written by part 0 at the top) are in place
+        const int own = part >> 1;                 // accumulator buffer / chunk parity this warp drains
+        const int half = part & 1;                 // which 64 channels of the chunk
+        float* tp = tile_s + (warp - 2) * kWarpTile;
+        const float* trow = tp + lane * kTStride;
+        const int* cids = cid_s + quad * 32;
+        // the same word in every lane: broadcast through a shuffle so that the compiler knows the branches on its
+        // bits are warp-uniform (a possibly-divergent branch per slot costs a BSSY/BSYNC pair and its resolve latency)
+        const uint32_t ends = __shfl_sync(FULL_MASK, endmask_s[quad], 0);
+        const int first_end = __ffs(ends) - 1;     // the run that ends here may have begun in the stretch before
+        float* canvas_f = a.out_canvas + (size_t)(f < 0 ? 0 : f) * a.n_cells * c_out;
+        uint32_t packed1[8];
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const bool last = cc == 3;
+          const int c = 2 * cc + own;
+          if (own == 1 && last && more) next_layer1(packed1);
+          acc_wait(own);
+          if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
+          // chunk 7 complete: every MMA of this tile has completed (the pipe retires in order), act4 is dead, act1 may be replaced
+          if (own == 1 && last && more) publish_act1(packed1);
+          const uint32_t acc_col = (own ? kColAcc1 : kColAcc0) + half * 64;
+          if (a.debug & 2) {   // debug bit 1: no layer-5 epilogue at all (results are garbage; timing experiment)
+            warp_arrive2(&acc_empty[own]);
           } else {
-            // Transpose this warp's 32 points x 32 channels through its PRIVATE shared-memory tile: tp[channel][point].
-            // Nobody else touches the tile, so the hand-over is a __syncwarp, not a block barrier (the shared 128 x 128
-            // tile of the first version cost one or two 512-thread barriers per chunk: every chunk waited for the
-            // slowest of 16 warps, twice).
-            float* tp = tile_s + (warp - 2) * kWarpTile;
-            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x270);   // accumulator in registers
+            // Transpose the two 32 points x 32 channels blocks through the warp's PRIVATE shared-memory tile, one after the
+            // other: tp[channel][point].  Nobody else touches the tile, so the hand-over is a __syncwarp, not a block barrier.
+            float4 qa[8], qb[8];
+            {
+              uint32_t ra[32], rb[32];
+              TC_LD32(ra, tm + acc_col);
+              TC_LD32(rb, tm + acc_col + 32);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              // both blocks are in registers: hand the accumulator back to the MMA warp
+              warp_arrive2(&acc_empty[own]);
+              if (partial && !valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tp[j * kTStride + lane] = v[j];
-            __syncwarp();
-            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x271);   // transposed tile stored
-            // This lane now owns channel c*128 + g*32 + lane over the warp's 32 tile slots [quad*32, quad*32+32), which are
-            // in cell order: the maximum of each run of equal cell ids goes to the canvas.  A run that touches the first
-            // or the last slot of the stretch may continue in a neighbouring stretch or tile -> atomic max; any other run
-            // is the cell's only writer -> plain store.  The 32 lanes see the same run boundaries and write 128
-            // contiguous bytes of a canvas row.
-            const int ch = c * 128 + g * 32 + lane;
-            const float bias = b5[ch];
-            float* canvas = a.out_canvas + (size_t)f * a.n_cells * c_out + ch;
-            const float* trow = tp + lane * kTStride;
-            const int* cids = cid_s + quad * 32;
-            // the same word in every lane: broadcast through a shuffle so that the compiler knows the branches on its
-            // bits are warp-uniform (a possibly-divergent branch per slot costs a BSSY/BSYNC pair and its resolve latency)
-            const uint32_t ends = __shfl_sync(FULL_MASK, endmask_s[quad], 0);
-            float m = -INFINITY, gm = rmax[0];
-            bool first_run = true;
-            // all 32 values first (one shared-memory latency, not eight), then four slots at a time: a group without a
-            // run end — most of them — is four maxima and ONE warp-uniform branch
-            float4 q[8];
+                for (int j = 0; j < 32; ++j) ra[j] = rb[j] = 0xff800000u;   // -inf
+              }
 #pragma unroll
-            for (int b4 = 0; b4 < 8; ++b4) q[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
+              for (int j = 0; j < 32; ++j) tp[j * kTStride + lane] = __uint_as_float(ra[j]);
+              __syncwarp();
 #pragma unroll
-            for (int b4 = 0; b4 < 8; ++b4) {
-              const float e[4] = {q[b4].x, q[b4].y, q[b4].z, q[b4].w};
-              if (((ends >> (b4 * 4)) & 0xfu) == 0u) {
-                m = fmaxf(fmaxf(m, fmaxf(e[0], e[1])), fmaxf(e[2], e[3]));
-                continue;
+              for (int b4 = 0; b4 < 8; ++b4) qa[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
+              __syncwarp();             // block A is read out
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tp[j * kTStride + lane] = __uint_as_float(rb[j]);
+              __syncwarp();
+              // block B: the first sixteen slots now, the rest half way through the walk (96 registers per thread do not
+              // hold 2 x 32 values next to the walk's state)
+#pragma unroll
+              for (int b4 = 0; b4 < 4; ++b4) qb[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
+            }
+            if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x271);   // both blocks transposed
+            // This lane now owns channels ch and ch + 32 over the warp's 32 tile slots [quad*32, quad*32+32), which are in
+            // cell order: the maximum of each run of equal cell ids goes to the canvas.  A run that touches the first or
+            // the last slot of the stretch may continue in a neighbouring stretch or tile -> atomic max; any other run is
+            // the cell's only writer -> plain store.  The 32 lanes see the same run boundaries and write two 128-byte
+            // pieces of a canvas row.  Zeros are stored like any other value (the canvas starts at zero, and a store that
+            // depends on the value would be a divergent branch per run end).
+            const int ch = c * 128 + half * 64 + lane;
+            const float bias_a = b5[ch], bias_b = b5[ch + 32];
+            float* canvas = canvas_f + ch;
+            float ma = -INFINITY, mb = -INFINITY, ga = -INFINITY, gb = -INFINITY;
+            auto walk_group = [&](int b4) {
+              const float ea[4] = {qa[b4].x, qa[b4].y, qa[b4].z, qa[b4].w};
+              const float eb[4] = {qb[b4].x, qb[b4].y, qb[b4].z, qb[b4].w};
+              if (((ends >> (b4 * 4)) & 0xfu) == 0u) {   // no run ends in these four slots: most groups
+                ma = fmaxf(fmaxf(ma, fmaxf(ea[0], ea[1])), fmaxf(ea[2], ea[3]));
+                mb = fmaxf(fmaxf(mb, fmaxf(eb[0], eb[1])), fmaxf(eb[2], eb[3]));
+                return;
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                m = fmaxf(m, e[k]);
-                if (ends & (1u << (b4 * 4 + k))) {
-                  const int pt = b4 * 4 + k;
-                  const float val = fmaxf(m + bias, 0.0f);
-                  if (val > 0.0f) {
-                    float* dst = canvas + (size_t)cids[pt] * c_out;
-                    if (first_run || pt == 31) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
-                    else *dst = val;
+                const int pt = b4 * 4 + k;
+                ma = fmaxf(ma, ea[k]);
+                mb = fmaxf(mb, eb[k]);
+                if (ends & (1u << pt)) {
+                  const float va = fmaxf(ma + bias_a, 0.0f), vb = fmaxf(mb + bias_b, 0.0f);
+                  float* dst = canvas + (size_t)cids[pt] * c_out;
+#ifdef B200BEV_DEBUG_ENV
+                  if (a.debug & 16) {          // debug bit 4: no canvas stores at all (garbage results; timing experiment)
+                    ga = fmaxf(ga, va);
+                    gb = fmaxf(gb, vb);
+                  } else if (a.debug & 8) {    // debug bit 3: plain stores in place of the atomics
+                    dst[0] = va;
+                    dst[32] = vb;
+                  } else
+#endif
+                  if (pt == first_end || pt == 31) {
+                    atomicMax(reinterpret_cast<int*>(dst), __float_as_int(va));
+                    atomicMax(reinterpret_cast<int*>(dst + 32), __float_as_int(vb));
+                  } else {
+                    dst[0] = va;
+                    dst[32] = vb;
                   }
-                  gm = fmaxf(gm, m);
-                  m = -INFINITY;
-                  first_run = false;
+                  ga = fmaxf(ga, ma);
+                  gb = fmaxf(gb, mb);
+                  ma = -INFINITY;
+                  mb = -INFINITY;
                 }
               }
-            }
+            };
+#pragma unroll
+            for (int b4 = 0; b4 < 4; ++b4) walk_group(b4);
+#pragma unroll
+            for (int b4 = 4; b4 < 8; ++b4) qb[b4] = *reinterpret_cast<const float4*>(trow + b4 * 4);
+            __syncwarp();             // the tile is read out: the next chunk may overwrite it
+#pragma unroll
+            for (int b4 = 4; b4 < 8; ++b4) walk_group(b4);
             // a run still open at the last slot goes on in the next stretch: hand its partial maximum over
             if (!(ends >> 31) && cids[31] >= 0) {
-              const float val = fmaxf(m + bias, 0.0f);
-              if (val > 0.0f) atomicMax(reinterpret_cast<int*>(canvas + (size_t)cids[31] * c_out), __float_as_int(val));
+              float* dst = canvas + (size_t)cids[31] * c_out;
+#ifdef B200BEV_DEBUG_ENV
+              if (a.debug & 16) {
+              } else if (a.debug & 8) {
+                dst[0] = fmaxf(ma + bias_a, 0.0f);
+                dst[32] = fmaxf(mb + bias_b, 0.0f);
+              } else
+#endif
+              {
+                atomicMax(reinterpret_cast<int*>(dst), __float_as_int(fmaxf(ma + bias_a, 0.0f)));
+                atomicMax(reinterpret_cast<int*>(dst + 32), __float_as_int(fmaxf(mb + bias_b, 0.0f)));
+              }
             }
-            rmax[0] = fmaxf(gm, m);   // whatever is left (open run, out-of-grid tail) still counts globally
-            __syncwarp();             // the tile is read out: the next chunk may overwrite it
+            // whatever is left (open run, out-of-grid tail) still counts globally; bias + ReLU commute with the max
+            if (a.out_global != nullptr && f >= 0) {
+              int* o = reinterpret_cast<int*>(a.out_global + (size_t)f * c_out + ch);
+              atomicMax(o, __float_as_int(fmaxf(fmaxf(ga, ma) + bias_a, 0.0f)));
+              atomicMax(o + 32, __float_as_int(fmaxf(fmaxf(gb, mb) + bias_b, 0.0f)));
+            }
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x273);     // runs walked
           }
+          if (own == 0 && last && more) {   // chunk 7 belongs to the other warps: wait for the end of the tile's MMAs
+            next_layer1(packed1);
+            mbar_wait(l5_done, l5_parity);
+            tc_fence_after();
+            publish_act1(packed1);
+          }
         }
+        l5_parity ^= 1;
         // cid_s / endmask_s belong to this tile until everyone has walked its last chunk
-        if (CELL && c == 7) epi_bar_sync();
-        {
-          const float r0 = rmax[0];
-#pragma unroll
-          for (int i = 0; i < 7; ++i) rmax[i] = rmax[i + 1];
-          rmax[7] = r0;
-        }
+        epi_bar_sync();
       }
       tf = tf_next;
       tt = tt_next;
@@ -976,7 +1097,7 @@ size_t tc_smem_bytes(bool cell, int cluster) {
   const int stages = cell ? (cluster == 2 ? kStagesCellPair : kStagesCell) : kStagesGlobal;
   return 1024 + (size_t)stages * kStageBytes + (cell ? (kEpiWarps * kWarpTile + 128 + 4) * sizeof(float) : 0) +
          (cell ? 8 * sizeof(int) : 0) + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
-         (3 * stages + 11) * sizeof(uint64_t) + 16;
+         (3 * stages + 12) * sizeof(uint64_t) + 16;
 }
 
 }  // namespace
