@@ -258,6 +258,28 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                    \
                : "memory")
 
+// relu, round to bf16 and pack in one instruction (F2FP.RELU); element with the even k index in the low half
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// two fp32 additions / fused multiply-adds per instruction (FADD2 / FFMA2 of sm_100): the same IEEE results as the scalar forms
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   // element with the even k index in the low half (verified on hardware by tests/cuda/umma_probe.cu)
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -300,8 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
   uint64_t* acc_empty = acc_full + 3;       // [3]        accumulator drained by the epilogue (one arrival per warp)
   uint64_t* act_ready = acc_empty + 3;      // [4]        K-pair kp (128 channels) of the next A operand is in TMEM (one arrival per warp)
   uint64_t* accx = act_ready + 4;           // [1]        this CTA's warps have drained accX (layer 4, chunk 1)
-  uint64_t* l5_done = accx + 1;             // [1]        every MMA of the tile has completed (cell mode: the warps that do not drain chunk 7)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l5_done + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accx + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -320,7 +341,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
     }
     for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps * CG);
     mbar_init(accx, kEpiWarps);
-    mbar_init(l5_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -479,13 +499,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             if (elect_one()) {
               issue_pair(d_addr, a_addr, pair, kp == 0, layer == 0);
               if (two) issue_pair(d_addr, a_addr + 64, pr1, false, false);
-              if (kp + kTrip >= kpairs) {
-                commit_acc(buf);
-                if (CELL && layer == 3 && c == nchunks - 1) {   // the tile's last MMAs: tell the warps that do not drain this chunk
-                  if constexpr (CG == 1) tc_commit(l5_done);
-                  else tc_commit_pair(l5_done);
-                }
-              }
+              if (kp + kTrip >= kpairs) commit_acc(buf);
             }
             __syncwarp();
             if (two) { pair = pr1; phase = ph1; }
@@ -562,7 +576,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         else mbar_arrive2_remote_relaxed(bar, 0);
       }
     };
-    uint32_t accx_parity = 0, l5_parity = 0;
+    uint32_t accx_parity = 0;
     auto acc_wait = [&](int buf) {
       mbar_wait(&acc_full[buf], (full_phase >> buf) & 1);
       full_phase ^= 1u << buf;
@@ -597,12 +611,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         for (int k = 0; k < kMaxCin; ++k) x[k] = (k < a.C && ok) ? __ldg(src + k) : 0.0f;
       }
     };
-    // layer 1 on CUDA cores (K = C_in is 4): this part's 16 of the 64 channels of relu(W1 x + b1), as bf16 pairs.
+    // layer 1 on CUDA cores (K = C_in is 4): part p's 16 of the 64 channels of relu(W1 x + b1), as bf16 pairs.
     // Weights and bias of a part are contiguous: 128-bit broadcast loads.
-    auto layer1 = [&](const float* x, uint32_t* packed) {
+    auto layer1 = [&](const float* x, uint32_t* packed, int p) {
       float acc[16];
       {
-        const float4* bp = reinterpret_cast<const float4*>(w1_s + a.C * 64 + part * 16);
+        const float4* bp = reinterpret_cast<const float4*>(w1_s + a.C * 64 + p * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 b4 = bp[q];
@@ -610,14 +624,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         }
       }
       auto add_k = [&](int k, float xk) {
-        const float4* wp = reinterpret_cast<const float4*>(w1_s + k * 64 + part * 16);
+        const float4* wp = reinterpret_cast<const float4*>(w1_s + k * 64 + p * 16);
+        const float2 x2 = make_float2(xk, xk);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 w4 = wp[q];
-          acc[4 * q] = fmaf(w4.x, xk, acc[4 * q]);
-          acc[4 * q + 1] = fmaf(w4.y, xk, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(w4.z, xk, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(w4.w, xk, acc[4 * q + 3]);
+          const float2 a0 = fma_f32x2(make_float2(w4.x, w4.y), x2, make_float2(acc[4 * q], acc[4 * q + 1]));
+          const float2 a1 = fma_f32x2(make_float2(w4.z, w4.w), x2, make_float2(acc[4 * q + 2], acc[4 * q + 3]));
+          acc[4 * q] = a0.x; acc[4 * q + 1] = a0.y; acc[4 * q + 2] = a1.x; acc[4 * q + 3] = a1.y;
         }
       };
       if (a.C == 4) {
@@ -628,10 +642,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           if (k < a.C) add_k(k, x[k]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) packed[j] = pack_bf16x2(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
+      for (int j = 0; j < 8; ++j) packed[j] = relu_pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
     };
     // act1 -> TMEM [0,32) and tell the MMA warp.  Legal only while no MMA reads act4 (which aliases act1):
     // before the first tile, or after the last layer-5 accumulator of the previous tile has completed.
+    // cell mode, from the second tile on: the warps that drain chunk 7 (parts 2 and 3) see the end of the tile's MMAs first,
+    // so they compute and store layer 1 for parts 0 and 1 as well (same TMEM lane quadrant, same points) and arrive for two;
+    // parts 0 and 1 walk chunk 6 meanwhile and are off the path to the next tile's first MMA
+    auto publish_act1_pair = [&](const uint32_t* packed) {
+      TC_ST8(tm + kColAct1 + part * 8, packed);
+      TC_ST8(tm + kColAct1 + (part - 2) * 8, (packed + 8));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      warp_arrive2(&act_ready[0]);
+    };
     auto publish_act1 = [&](const uint32_t* packed) {
       TC_ST8(tm + kColAct1 + part * 8, packed);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -648,7 +671,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       float x[kMaxCin];
       load_point(dummy0 ? 0 : tf, dummy0 ? a.N : tt * kTileM + row, x);
       uint32_t packed[8];
-      layer1(x, packed);
+      layer1(x, packed, part);
       publish_act1(packed);
     }
     for (long long t = t_begin; t < t_end; ++t) {
@@ -750,12 +773,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             warp_arrive(&acc_empty[buf]);   // the values are in registers: the next chunk may overwrite the accumulator
             if (layer == 2 && c == 1 && lane == 0) mbar_arrive(accx);   // ... and, locally: this warp is done with accX
             uint32_t packed[16];
-            const float* bq = bl + c * 128 + q * 32;
+            const float4* bq = reinterpret_cast<const float4*>(bl + c * 128 + q * 32);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bq[2 * j], 0.0f);
-              const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bq[2 * j + 1], 0.0f);
-              packed[j] = pack_bf16x2(v0, v1);
+            for (int j = 0; j < 8; ++j) {     // bias by FADD2, ReLU + bf16 + pack by F2FP.RELU: two instructions per two values
+              const float4 b4 = bq[j];
+              const float2 s0 = add_f32x2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
+              const float2 s1 = add_f32x2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
+              packed[2 * j] = relu_pack_bf16x2(s0.x, s0.y);
+              packed[2 * j + 1] = relu_pack_bf16x2(s1.x, s1.y);
             }
             // chunks 2 and 3 of layer 4 land on accX: every warp of this CTA must have drained it (layer 4, chunk 1) first
             if (layer == 2 && c == 2) {
@@ -777,7 +802,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       const int fn = dn ? 0 : tf_next;
       const int slotn = dn ? a.N : tt_next * kTileM + row;
       have_pre = false;
-      if (vec4_points && more) {
+      if (vec4_points && more && (!CELL || part >= 2)) {
         xpre = make_float4(0.f, 0.f, 0.f, 0.f);
         if (slotn < a.N) {
           const int pn = CELL ? __ldg(a.perm + (size_t)fn * a.N + slotn) : slotn;
@@ -797,7 +822,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         } else {
           load_point(fn, slotn, x);
         }
-        layer1(x, packed1);
+        layer1(x, packed1, part);
+        if constexpr (CELL) layer1(x, packed1 + 8, part - 2);   // cell mode: also the share of the warp that does not drain chunk 7
       };
       if constexpr (!CELL) {
         // The loop stays ROLLED; the eight running maxima live in registers all the same: rmax[0] is always the
@@ -854,8 +880,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         // ~230 dependent instructions per chunk and warp at four warps per scheduler took 2,500 clk against 1,750 clk of
         // MMAs — the run walk alone was 0.32 ms of the 1.40 ms kernel.)  A warp never looks at the accumulator barriers of
         // the other buffer during layer 5 (four phases each per tile: its parity bookkeeping stays right), the draining warps
-        // arrive for two on acc_empty, and the one thing the other warps need from chunk 7 — that every MMA of the tile has
-        // completed, so that act1 may be replaced — comes from a barrier of its own, l5_done, one phase per tile.
+        // arrive for two on acc_empty, and the one thing that hangs on chunk 7 — act1 of the next tile may be stored once every
+        // MMA of this tile has completed — is done by the warps that drain chunk 7, for all four parts (publish_act1_pair).
         // The per-frame global maximum goes to out_global chunk by chunk (two 128-byte atomics per warp and chunk, L2-resident)
         // instead of living in eight rotating registers: at 96 registers per thread those were spilled.
         epi_bar_sync();     // this tile's cell ids and run-end flags (written by part 0 at the top) are in place
@@ -869,7 +895,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
         const uint32_t ends = __shfl_sync(FULL_MASK, endmask_s[quad], 0);
         const int first_end = __ffs(ends) - 1;     // the run that ends here may have begun in the stretch before
         float* canvas_f = a.out_canvas + (size_t)(f < 0 ? 0 : f) * a.n_cells * c_out;
-        uint32_t packed1[8];
+        uint32_t packed1[16];
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const bool last = cc == 3;
@@ -878,7 +904,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
           acc_wait(own);
           if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x250 + c);    // layer-5 accumulator seen
           // chunk 7 complete: every MMA of this tile has completed (the pipe retires in order), act4 is dead, act1 may be replaced
-          if (own == 1 && last && more) publish_act1(packed1);
+          if (own == 1 && last && more) publish_act1_pair(packed1);
           const uint32_t acc_col = (own ? kColAcc1 : kColAcc0) + half * 64;
           if (a.debug & 2) {   // debug bit 1: no layer-5 epilogue at all (results are garbage; timing experiment)
             warp_arrive2(&acc_empty[own]);
@@ -991,14 +1017,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
             }
             if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x273);     // runs walked
           }
-          if (own == 0 && last && more) {   // chunk 7 belongs to the other warps: wait for the end of the tile's MMAs
-            next_layer1(packed1);
-            mbar_wait(l5_done, l5_parity);
-            tc_fence_after();
-            publish_act1(packed1);
-          }
         }
-        l5_parity ^= 1;
         // cid_s / endmask_s belong to this tile until everyone has walked its last chunk
         epi_bar_sync();
       }
@@ -1097,7 +1116,7 @@ size_t tc_smem_bytes(bool cell, int cluster) {
   const int stages = cell ? (cluster == 2 ? kStagesCellPair : kStagesCell) : kStagesGlobal;
   return 1024 + (size_t)stages * kStageBytes + (cell ? (kEpiWarps * kWarpTile + 128 + 4) * sizeof(float) : 0) +
          (cell ? 8 * sizeof(int) : 0) + (kBiasFloats + kMaxCin * 64 + 64) * sizeof(float) +
-         (3 * stages + 12) * sizeof(uint64_t) + 16;
+         (3 * stages + 11) * sizeof(uint64_t) + 16;
 }
 
 }  // namespace
