@@ -11,6 +11,13 @@ the loops of the kernel one to one: change both together.
 cg = 1: one CTA.  cg = 2: a CTA pair — two producers (each fills its own half of every ring pair), the relay
 (follower: full -> leader's peer_full), ONE issuer (the leader's) whose commits reach the barriers of both CTAs,
 two epilogues whose acc_empty / act_ready arrivals all go to the leader's barriers (count 2 here: one per CTA).
+
+cell = True: the per-cell mode.  The 16 epilogue warps of a CTA are two agents ("sets" of 8 warps): both take part in
+layers 2-4; in layer 5 set s drains only the chunks of accumulator buffer s and arrives for two on acc_empty, and set 1
+— which drains chunk 7 — stores the next tile's layer 1 for both.  A set does not look at the other buffer's acc_full
+during layer 5 (four phases: its parity bookkeeping stays right), which is only safe because of the block-wide barrier
+at the end of the tile: without it set 0 reaches its next wait on acc_full[1] (layer 2 of the next tile) while chunk 7
+is still in flight, and the parity wait takes chunk 5's phase for layer 2's (found on the GPU as a launch failure).
 """
 from __future__ import annotations
 
@@ -42,8 +49,9 @@ class Bar:
     def done(self, parity: int) -> bool:      # mbarrier.try_wait.parity
         return self.bit != parity
 
-    def arrive(self):
-        self.pending += 1
+    def arrive(self, n: int = 1):
+        self.pending += n
+        assert self.pending <= self.count, "more arrivals than the barrier expects in one phase"
         if self.pending == self.count:
             self.pending = 0
             self.bit ^= 1
@@ -163,7 +171,59 @@ def epilogue(n_tiles, bars, state, r):
             yield ("step",)
 
 
-def make_bars(ring_pairs: int, cg: int):
+def epilogue_cell(n_tiles, bars, state, r, s, tile_barrier=True):
+    """Cell mode: warp set s (0 or 1) of CTA r, see the module docstring."""
+    full_phase = [0, 0, 0]
+    accx_parity = tile_parity = 0
+    acc_full, accx, tile_bar = bars["acc_full"][r], bars["accx"][r], bars["tile_bar"][r]
+    bars["act_ready"][0].arrive()              # layer 1 of the first tile: every warp stores its own share
+    yield ("step",)
+    for t in range(n_tiles):
+        more = t + 1 < n_tiles
+        for layer in range(3):
+            for c in range(N_CHUNKS[layer]):
+                buf = acc_buffer(layer, c)
+                yield ("wait", acc_full[buf], full_phase[buf])
+                full_phase[buf] ^= 1
+                assert state["acc_done"][r][buf] == (t, layer, c), "epilogue drains an accumulator that holds another chunk"
+                bars["acc_empty"][buf].arrive()
+                if s == 1:
+                    state["acc_owner"][r][buf] = None   # (both sets have read their columns once the barrier completes)
+                if layer == 2 and c == 1:
+                    accx.arrive()
+                yield ("step",)
+                if layer == 2 and c == 2:
+                    yield ("wait", accx, accx_parity)
+                    accx_parity ^= 1
+                bars["act_ready"][c].arrive()
+                yield ("step",)
+        for cc in range(4):
+            c = 2 * cc + s                       # the chunks of accumulator buffer s
+            yield ("wait", acc_full[s], full_phase[s])
+            full_phase[s] ^= 1
+            assert state["acc_done"][r][s] == (t, 3, c), "epilogue drains an accumulator that holds another chunk"
+            if c == 7 and more:
+                bars["act_ready"][0].arrive(2)   # layer 1 of the next tile, for both sets
+                yield ("step",)
+            state["acc_owner"][r][s] = None
+            bars["acc_empty"][s].arrive(2)       # the draining set arrives for two
+            yield ("step",)                      # ... and walks the runs
+        if tile_barrier:                         # bar.sync over the 16 epilogue warps
+            tile_bar.arrive()
+            yield ("wait", tile_bar, tile_parity)
+            tile_parity ^= 1
+
+
+def make_bars(ring_pairs: int, cg: int, cell: bool = False):
+    if cell:
+        return {"full": [[Bar() for _ in range(ring_pairs)] for _ in range(cg)],
+                "empty": [[Bar() for _ in range(ring_pairs)] for _ in range(cg)],
+                "peer_full": [Bar() for _ in range(ring_pairs)],
+                "acc_full": [[Bar() for _ in range(3)] for _ in range(cg)],
+                "accx": [Bar(2) for _ in range(cg)],
+                "tile_bar": [Bar(2) for _ in range(cg)],
+                "acc_empty": [Bar(2 * cg) for _ in range(3)],
+                "act_ready": [Bar(2 * cg) for _ in range(4)]}
     return {"full": [[Bar() for _ in range(ring_pairs)] for _ in range(cg)],
             "empty": [[Bar() for _ in range(ring_pairs)] for _ in range(cg)],
             "peer_full": [Bar() for _ in range(ring_pairs)],
@@ -173,17 +233,22 @@ def make_bars(ring_pairs: int, cg: int):
             "act_ready": [Bar(cg) for _ in range(4)]}
 
 
-def run(n_tiles: int, ring_pairs: int, seed: int, max_steps: int = 4_000_000, trip: int = 1, cg: int = 1, bars=None):
+def run(n_tiles: int, ring_pairs: int, seed: int, max_steps: int = 4_000_000, trip: int = 1, cg: int = 1, bars=None,
+        cell: bool = False, tile_barrier: bool = True):
     """Returns 'ok' or a description of the failure.  n_tiles = tile slots per cluster."""
     rnd = random.Random(seed)
-    bars = bars if bars is not None else make_bars(ring_pairs, cg)
+    bars = bars if bars is not None else make_bars(ring_pairs, cg, cell)
     inflight, pipe = [], deque()
     state = {"ring": [[None] * ring_pairs for _ in range(cg)], "acc_owner": [[None] * 3 for _ in range(cg)],
              "acc_done": [[None] * 3 for _ in range(cg)]}
     agents = {"issuer": issuer(n_tiles, ring_pairs, bars, pipe, state, trip, cg)}
     for r in range(cg):
         agents[f"producer{r}"] = producer(n_tiles, ring_pairs, bars["full"][r], bars["empty"][r], inflight, r)
-        agents[f"epilogue{r}"] = epilogue(n_tiles, bars, state, r)
+        if cell:
+            for st in range(2):
+                agents[f"epilogue{r}.{st}"] = epilogue_cell(n_tiles, bars, state, r, st, tile_barrier)
+        else:
+            agents[f"epilogue{r}"] = epilogue(n_tiles, bars, state, r)
     if cg == 2:
         agents["relay"] = relay(n_tiles, ring_pairs, bars["full"][1], bars["peer_full"])
     pending = {name: next(g) for name, g in agents.items()}

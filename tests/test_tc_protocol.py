@@ -34,3 +34,18 @@ def test_model_catches_a_pair_without_the_relay():
             b.done = lambda parity: True           # the leader never waits
         outcomes.add(model.run(2, 12, seed, cg=2, bars=bars))
     assert any(o.startswith("hazard") for o in outcomes), outcomes
+
+
+@pytest.mark.parametrize("ring_pairs,cg", [(4, 1), (8, 2)])
+@pytest.mark.parametrize("n_tiles", [1, 2, 3])
+def test_cell_mode_protocol_has_no_deadlock_or_hazard(ring_pairs, cg, n_tiles):
+    """Cell mode: two warp sets per CTA, each draining one layer-5 accumulator buffer and arriving for two."""
+    for seed in range(25):
+        assert model.run(n_tiles, ring_pairs, seed, cg=cg, cell=True) == "ok", f"seed {seed}"
+
+
+def test_model_catches_cell_mode_without_the_tile_barrier():
+    """The launch failure of round 2: without the block barrier at the end of a tile, the warps that do not drain chunk 7
+    reach layer 2 of the next tile while chunk 7 is in flight, and their parity wait on acc_full[1] passes four phases early."""
+    outcomes = {model.run(3, 8, seed, cg=2, cell=True, tile_barrier=False) for seed in range(40)}
+    assert any(o.startswith("hazard") or o.startswith("deadlock") for o in outcomes), outcomes
