@@ -371,9 +371,8 @@ struct HaloGeom {
   int tiles_per_frame;
 };
 
-// max_cols: 256 (the two accumulator halves of tensor memory), or kSplitCols in fp32-accuracy mode, where tensor memory holds two
-// partial accumulators AND the running total (3 x 160 columns)
-constexpr int kSplitCols = 160;
+// max_cols: 256, the two accumulator halves of tensor memory (in fp32-accuracy mode one half carries a tile's running total and
+// the other its partial sums, see the epilogue)
 __host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g, int max_cols = kTilePx) {
   const int R = max_cols / (W + 1);
   if (R < 1) return false;
@@ -519,16 +518,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     // ---- MMA issuer ----
     const uint32_t idesc = conv_idesc(a, geo.N);
     const int seg = halo_segment_chunks(a, ncc);
-    const uint32_t acc_stride = a.split ? kSplitCols : kTilePx;
-    int g = 0, bi = 0, seg_seq = 0;     // seg_seq counts (tile, K segment) pairs: each gets its own accumulator buffer
+    // Accumulator halves: tile t keeps its TOTAL in half t & 1 — the first K segment accumulates straight into it — and every
+    // later segment (fp32-accuracy mode) goes to the other half, from where the epilogue adds it to the total (see there).
+    // A half is reused when the epilogue has released it: uses0 / uses1 count how often each half has been handed to the MMAs.
+    int g = 0, bi = 0, uses0 = 0, uses1 = 0;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       uint32_t buf = 0, d = 0;
       for (int cc = 0; cc < ncc; ++cc, ++bi) {
         const bool seg_first = cc % seg == 0, seg_last = cc % seg == seg - 1 || cc == ncc - 1;
         if (seg_first) {
-          buf = seg_seq & 1;
-          if (seg_seq >= 2) mbarrier_wait(&acc_empty[buf], ((seg_seq >> 1) - 1) & 1);
-          d = tmem + buf * acc_stride;
+          buf = (uint32_t)((tile_seq & 1) ^ (cc == 0 ? 0 : 1));
+          const int k = buf ? uses1++ : uses0++;
+          if (k >= 1) mbarrier_wait(&acc_empty[buf], (k - 1) & 1);
+          d = tmem + buf * kTilePx;
         }
         mbarrier_wait(&full_blk[bi & 1], (bi >> 1) & 1);
         const uint32_t blk = smem_addr(blocks + (bi & 1) * kHaloBlock);
@@ -549,7 +551,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
           }
           __syncwarp();
         }
-        if (seg_last) ++seg_seq;
       }
     }
   } else {
@@ -561,7 +562,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     const int quad = warp & 3;
     float* tp = epi + quad * 32 * 33;
     const int seg = halo_segment_chunks(a, ncc), n_seg = (ncc + seg - 1) / seg;
-    int tile = blockIdx.x, seg_seq = 0;
+    int tile = blockIdx.x, uses0 = 0, uses1 = 0;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
       int co_tile, b, y0;
       tile_coords(tile, co_tile, b, y0);
@@ -571,75 +573,82 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
       const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;   // channels of this warp that exist (may be <= 0)
       float* oplane = a.out + ((size_t)b * a.Cout + co0) * HW;
       // K segments (fp32-accuracy mode): the tensor core TRUNCATES the fp32 accumulator once per instruction, a bias of
-      // ~2.3e-8 of the sum per MMA in a chain (measured: 1.1e-5 at 432 MMAs, 2.9e-5 at 1,296).  Every `seg` chunks the
-      // partial sum is therefore added — round to nearest, on the CUDA cores — to a running total that lives in a third
-      // region of tensor memory (columns [2 x 160, 3 x 160); only this warp's lanes of it, so no synchronisation): one
-      // tcgen05.ld of the partial, one of the total, 32 adds, one tcgen05.st per 32 columns, hidden behind the next
-      // segment's 108 MMAs.  Scale, bias and ReLU are applied once, to the total.  (A first version added the partial sums
-      // into the output tile in global memory: 24.9 ms for the fusion module against 5.8 ms unsegmented.)
-      const uint32_t acc_stride = a.split ? kSplitCols : kTilePx;
-      const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
-      for (int sg = 0; sg < n_seg; ++sg, ++seg_seq) {
-        const uint32_t buf = seg_seq & 1;
-        const bool first = sg == 0, last = sg == n_seg - 1;
-        mbarrier_wait(&acc_full[buf], (seg_seq >> 1) & 1);
+      // ~2.3e-8 of the sum per MMA in a chain (measured: 1.1e-5 at 432 MMAs, 2.9e-5 at 1,296).  So a chain is `seg` chunks
+      // (108 MMAs) long, and the partial sums are added — round to nearest, on the CUDA cores — to the tile's total.
+      // Tensor memory is two halves of 256 columns: the tile's first segment accumulates straight into half T = tile & 1 (the
+      // total), every later one into the other half P, and this warp adds P to T (one tcgen05.ld of each, 32 adds, one
+      // tcgen05.st per 32 columns; only its own lanes, so no synchronisation) and hands P back.  After the last segment the
+      // total is read once more, scaled, biased and stored, and T goes back too — by then the next tile's first segment is
+      // accumulating in what was P.  (First version: two partial halves AND a total, 3 x 160 columns: tiles of at most 160
+      // pixels, 112 for a 100-pixel-wide map, and the A operand re-read from shared memory every 56 clk; a version before
+      // that added the partial sums into the output tile in global memory: 24.9 ms for the fusion module against 5.8.)
+      const uint32_t T = (uint32_t)(tile_seq & 1), P = T ^ 1u;
+      {
+        const int k = T ? uses1++ : uses0++;
+        mbarrier_wait(&acc_full[T], k & 1);
+        tc_fence_after_sync();
+      }
+      for (int sg = 1; sg < n_seg; ++sg) {
+        const int k = P ? uses1++ : uses0++;
+        mbarrier_wait(&acc_full[P], k & 1);
         tc_fence_after_sync();
 #pragma unroll 1
         for (int col0 = 0; col0 < geo.N; col0 += 32) {
-          uint32_t r[32];
-          CONV_TC_LD32(r, lane_base + buf * acc_stride + (uint32_t)col0);
-          if (!first) {
-            uint32_t t[32];
-            CONV_TC_LD32(t, lane_base + 2 * kSplitCols + (uint32_t)col0);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t r[32], t[32];
+          CONV_TC_LD32(r, lane_base + P * kTilePx + (uint32_t)col0);
+          CONV_TC_LD32(t, lane_base + T * kTilePx + (uint32_t)col0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
-          } else {
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          }
-          if (!last) {
-            CONV_TC_ST32(lane_base + 2 * kSplitCols + (uint32_t)col0, r);
-            continue;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = fmaf(__uint_as_float(r[j]), oscale, bias);
-            if (a.relu) v = fmaxf(v, 0.f);
-            r[j] = __float_as_uint(v);
-            tp[lane * 33 + j] = v;
-          }
-          if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
-            int ry = col0 / W1, x = col0 - ry * W1;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (lane < n_ch && x < a.W && ry < geo.R && y0 + ry < a.H)   // lane = channel: 64 contiguous bytes per pixel
-                a.out_nhwc[(((size_t)b * a.H + y0 + ry) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
-                    __float2bfloat16_rn(__uint_as_float(r[j]));
-              if (++x == W1) {
-                x = 0;
-                ++ry;
-              }
-            }
-          }
-          __syncwarp();
-          // this lane's pixel: column n = col0 + lane
-          const int n = col0 + lane;
-          const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
-          const bool px_ok = n < geo.N && x < a.W && ry < geo.R && y < a.H;
-          float* dst = oplane + (px_ok ? y * a.W + x : 0);
-          if (a.out) {
-            for (int c = 0; c < n_ch; ++c) {
-              const float v = tp[c * 33 + lane];
-              if (px_ok) dst[(size_t)c * HW] = v;
-            }
-          }
-          __syncwarp();
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+          CONV_TC_ST32(lane_base + T * kTilePx + (uint32_t)col0, r);
         }
-        if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the total is re-read by this thread next segment
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the total is re-read by this thread
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
+        if (lane == 0) mbarrier_arrive(&acc_empty[P]);
       }
+#pragma unroll 1
+      for (int col0 = 0; col0 < geo.N; col0 += 32) {
+        uint32_t r[32];
+        CONV_TC_LD32(r, lane_base + T * kTilePx + (uint32_t)col0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = fmaf(__uint_as_float(r[j]), oscale, bias);
+          if (a.relu) v = fmaxf(v, 0.f);
+          r[j] = __float_as_uint(v);
+          tp[lane * 33 + j] = v;
+        }
+        if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
+          int ry = col0 / W1, x = col0 - ry * W1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (lane < n_ch && x < a.W && ry < geo.R && y0 + ry < a.H)   // lane = channel: 64 contiguous bytes per pixel
+              a.out_nhwc[(((size_t)b * a.H + y0 + ry) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
+                  __float2bfloat16_rn(__uint_as_float(r[j]));
+            if (++x == W1) {
+              x = 0;
+              ++ry;
+            }
+          }
+        }
+        __syncwarp();
+        // this lane's pixel: column n = col0 + lane
+        const int n = col0 + lane;
+        const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
+        const bool px_ok = n < geo.N && x < a.W && ry < geo.R && y < a.H;
+        float* dst = oplane + (px_ok ? y * a.W + x : 0);
+        if (a.out) {
+          for (int c = 0; c < n_ch; ++c) {
+            const float v = tp[c * 33 + lane];
+            if (px_ok) dst[(size_t)c * HW] = v;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&acc_empty[T]);
     }
   }
 
@@ -1017,7 +1026,7 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
   const char* impl = debug_env("B200BEV_CONV_IMPL");
   HaloGeom geo;
   const bool want_halo = !(impl && impl[0] == 'p');   // "per-tap": the per-tap kernel for 3x3 too (A/B timing)
-  if (taps == 9 && want_halo && halo_geometry(H, W, &geo, a.split ? kSplitCols : kTilePx)) {
+  if (taps == 9 && want_halo && halo_geometry(H, W, &geo, kTilePx)) {
     B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
     const long long htiles = (long long)B * geo.tiles_per_frame * ceil_div(Cout, kTileCo);
     const int hgrid = (int)(htiles < sm_count() ? htiles : sm_count());

@@ -68,18 +68,24 @@ def weight_producer(n_tiles, ncc, ring, bars, st):
 
 
 def issuer(n_tiles, ncc, ring, bars, st, seg=None):
-    """seg: k chunks per accumulator chain (fp32-accuracy mode: every `seg` chunks the partial sum gets its own accumulator
-    buffer and is added to the running total by the epilogue); None = the whole tile in one chain (bf16 mode)."""
+    """seg: k chunks per accumulator chain; None = the whole tile in one chain (bf16 mode).  fp32-accuracy mode: tile t keeps
+    its total in accumulator half t & 1 — the first chain accumulates straight into it — and every later chain goes to the
+    other half, from where the epilogue adds it to the total; a half is reused when the epilogue has released it."""
     seg = seg or ncc
-    g = bi = seq = 0
+    g = bi = 0
     buf = 0
+    uses = [0, 0]
+    seq = (0, 0)
     for t in range(n_tiles):
         for cc in range(ncc):
             seg_first, seg_last = cc % seg == 0, (cc % seg == seg - 1 or cc == ncc - 1)
             if seg_first:
-                buf = seq & 1
-                if seq >= 2:
-                    yield ("wait", bars["acc_empty"][buf], ((seq >> 1) - 1) & 1)
+                buf = (t & 1) ^ (0 if cc == 0 else 1)
+                seq = (t, cc // seg)
+                k = uses[buf]
+                uses[buf] += 1
+                if k >= 1:
+                    yield ("wait", bars["acc_empty"][buf], (k - 1) & 1)
             yield ("wait", bars["full_blk"][bi & 1], (bi >> 1) & 1)
             if st["blk_data"][bi & 1] != bi:
                 st["hazard"] = f"MMAs of block {bi} issued on pixel data of block {st['blk_data'][bi & 1]}"
@@ -100,20 +106,35 @@ def issuer(n_tiles, ncc, ring, bars, st, seg=None):
                 g += 1
                 yield ("step",)
             bi += 1
-            if seg_last:
-                seq += 1
 
 
-def epilogue(q, n_tiles, bars, st):
-    """n_tiles here = (tile, K segment) pairs: the epilogue's loop is over accumulator hand-overs."""
+def epilogue(q, n_tiles, n_seg, bars, st):
+    """Per tile: the total's half T = t & 1 completes with the first chain; every later chain lands in the other half P and is
+    added to T (P is released after each addition); after the last one the total is stored and T is released."""
+    uses = [0, 0]
+
+    def wait_full(buf, what):
+        k = uses[buf]
+        uses[buf] += 1
+        return ("wait", bars["acc_full"][buf], k & 1), what
+
     for t in range(n_tiles):
-        buf = t & 1
-        yield ("wait", bars["acc_full"][buf], (t >> 1) & 1)
-        if st["acc_tile"][buf] != t:
-            st["hazard"] = f"epilogue warp {q} read accumulator {buf} for tile {t} but it holds {st['acc_tile'][buf]}"
-        yield ("step",)                                                # tcgen05.ld + stores
-        st["acc_unread"][buf] -= 1
-        bars["acc_empty"][buf].arrive()
+        T, P = t & 1, (t & 1) ^ 1
+        req, what = wait_full(T, (t, 0))
+        yield req
+        if st["acc_tile"][T] != what:
+            st["hazard"] = f"epilogue warp {q} took accumulator {T} for {what} but it holds {st['acc_tile'][T]}"
+        for sg in range(1, n_seg):
+            req, what = wait_full(P, (t, sg))
+            yield req
+            if st["acc_tile"][P] != what:
+                st["hazard"] = f"epilogue warp {q} took accumulator {P} for {what} but it holds {st['acc_tile'][P]}"
+            yield ("step",)                                            # tcgen05.ld of both halves, add, tcgen05.st of the total
+            st["acc_unread"][P] -= 1
+            bars["acc_empty"][P].arrive()
+        yield ("step",)                                                # tcgen05.ld of the total + stores
+        st["acc_unread"][T] -= 1
+        bars["acc_empty"][T].arrive()
         yield ("step",)
 
 
@@ -129,7 +150,7 @@ def run(n_tiles: int, ncc: int, seed: int, ring: int = 4, bars=None, max_steps: 
           "landed": set()}
     agents = [pixel_producer(w, n_tiles, ncc, bars, st) for w in range(N_PRODUCERS)]
     agents += [weight_producer(n_tiles, ncc, ring, bars, st), issuer(n_tiles, ncc, ring, bars, st, seg)]
-    agents += [epilogue(q, n_tiles * n_seg, bars, st) for q in range(N_EPILOGUE)]
+    agents += [epilogue(q, n_tiles, n_seg, bars, st) for q in range(N_EPILOGUE)]
     kinds = ["producer"] * N_PRODUCERS + ["weights", "issuer"] + ["epilogue"] * N_EPILOGUE
     pending = [None] * len(agents)
     alive = set(range(len(agents)))

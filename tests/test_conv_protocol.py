@@ -18,7 +18,8 @@ def test_conv_protocol_has_no_deadlock_or_hazard(n_tiles, ncc):
 @pytest.mark.parametrize("n_tiles,ncc,seg", [(1, 3, 3), (2, 6, 3), (3, 7, 3), (2, 36, 3), (4, 2, 3)])
 def test_conv_protocol_with_k_segments(n_tiles, ncc, seg):
     """fp32-accuracy mode: every `seg` chunks the accumulator is handed to the epilogue (which adds it to the running total),
-    so accumulator hand-overs outnumber tiles — same barriers, counted per (tile, segment)."""
+    so accumulator hand-overs outnumber tiles: the first chain of a tile lands in the half that keeps its total, the later
+    ones in the other half — same barriers, each half counting its own uses."""
     for seed in range(6):
         assert model.run(n_tiles, ncc, seed, seg=seg) == "ok", f"seed {seed}"
     for seed, slow in enumerate(("epilogue", "producer", "weights", "issuer", "copy", "retire")):
