@@ -86,12 +86,22 @@ __global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __res
                                                               long long planes, int h, int w, int H, int W) {
   const float sy = __fdiv_rn((float)h, (float)H), sx = __fdiv_rn((float)w, (float)W);
   const long long total = planes * H * W;
+  const bool small = total < (1ll << 31);     // 32-bit index arithmetic: two 64-bit divisions per output were most of this kernel
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const long long t = i / W;
-    const int y = (int)(t % H);
-    const long long p = t / H;
+    int x, y;
+    long long p;
+    if (small) {
+      const unsigned iu = (unsigned)i, tu = iu / (unsigned)W, pu = tu / (unsigned)H;
+      x = (int)(iu - tu * (unsigned)W);
+      y = (int)(tu - pu * (unsigned)H);
+      p = pu;
+    } else {
+      x = (int)(i % W);
+      const long long t = i / W;
+      y = (int)(t % H);
+      p = t / H;
+    }
     int y0, y1, x0, x1;
     float ly0, ly1, lx0, lx1;
     resize_coord(y, sy, h, y0, y1, ly0, ly1);

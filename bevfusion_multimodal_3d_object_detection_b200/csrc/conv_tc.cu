@@ -919,6 +919,7 @@ __global__ void __launch_bounds__(256) border_expand_kernel(const float* __restr
   if (out_nhwc) {
     const int cg = (C + 7) / 8;
     const long long n = (long long)B * HW * cg;
+    const bool vec_ok = (C_total & 7) == 0 && (c_offset & 7) == 0 && (reinterpret_cast<uintptr_t>(out_nhwc) & 15) == 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
       const int g = (int)(i % cg);
       const long long bp = i / cg;
@@ -926,7 +927,14 @@ __global__ void __launch_bounds__(256) border_expand_kernel(const float* __restr
       const int cy = border_class(p / W, H, s), cx = border_class(p % W, W, s);
       const float* src = small + (((size_t)b * C + g * 8) * s + cy) * s + cx;
       __nv_bfloat16* dst = out_nhwc + ((size_t)b * HW + p) * C_total + c_offset + g * 8;
-      for (int e = 0; e < 8 && g * 8 + e < C; ++e) dst[e] = __float2bfloat16_rn(__ldg(src + (size_t)e * s * s));
+      if (vec_ok && g * 8 + 8 <= C) {     // eight channels of a pixel: one 16-byte store
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(__ldg(src + (size_t)e * s * s));
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+      } else {
+        for (int e = 0; e < 8 && g * 8 + e < C; ++e) dst[e] = __float2bfloat16_rn(__ldg(src + (size_t)e * s * s));
+      }
     }
   }
   if (out_nchw) {
