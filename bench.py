@@ -323,6 +323,7 @@ class HotPath:
         self.chain.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         del sd
         self.chain = self.chain.eval().to(dev)
+        self.chain.fusion.b200_parallel_branches = PARALLEL_BRANCHES
         self.inputs = {}
         if wl["lidar"]:
             self.inputs["lidar"] = to(syn.lidar_batch(seed, frames, n_valid=wl["valid"], n_total=wl["points"]))
@@ -351,7 +352,19 @@ class HotPath:
         mark = (lambda n: marks.append((n, _event(torch)))) if marks is not None else (lambda n: None)
         out = {}
         lidar_feat = radar_feat = None
+        # Graph capture (no stage marks): the radar encoder and the calibrated projection do not depend on the LiDAR encoder and
+        # go to side streams — parallel branches of the captured graph.  The eager, stage-by-stage timing pass stays serial.
+        import contextlib
+        from bevfusion_multimodal_3d_object_detection_b200 import runtime
+        fork = runtime.BranchStreams(self.dev) if (marks is None and PARALLEL_BRANCHES and inp["lidar" if wl["lidar"] else "feats"].is_cuda) else None
+        side = (lambda i: fork.fork(i)) if fork else (lambda i: contextlib.nullcontext())
         with torch.no_grad():
+            if fork and wl["radar"]:
+                with side(1):
+                    radar_feat = self.chain.radar_encoder([inp[f"radar{i}"] for i in range(5)])
+            if fork and wl["cam"]:
+                with side(0):
+                    out["proj"] = ops.camera_project(inp["feats"], self.K, self.E, (IMG_W, IMG_H), (G, G))
             if wl["lidar"]:
                 prec, blob, dims, tc = self.lidar_params()
                 mark("bin_sort")
@@ -359,12 +372,14 @@ class HotPath:
                 mark("pointnet_encode")
                 lidar_feat, out["canvas"] = ops.pointnet_encode(inp["lidar"], blob, dims, perm=perm, offsets=off, n_cells=G * G,
                                                                 precision=prec, tc_params=tc)
-            if wl["radar"]:
+            if wl["radar"] and not fork:
                 mark("radar_encode")
                 radar_feat = self.chain.radar_encoder([inp[f"radar{i}"] for i in range(5)])
-            if wl["cam"]:
+            if wl["cam"] and not fork:
                 mark("camera_project")
                 out["proj"] = ops.camera_project(inp["feats"], self.K, self.E, (IMG_W, IMG_H), (G, G))
+            if fork:
+                fork.join()
             mark("fusion")
             bev = self.chain.fusion(camera_features=inp.get("feats"), lidar_features=lidar_feat, radar_features=radar_feat)
             mark("head")
@@ -385,6 +400,9 @@ class HotPath:
         wl = self.wl
         return (["bin_sort", "pointnet_encode"] if wl["lidar"] else []) + (["radar_encode"] if wl["radar"] else []) + \
                (["camera_project"] if wl["cam"] else []) + ["fusion", "head", "centernet_decode"]
+
+
+PARALLEL_BRANCHES = os.environ.get("B200BEV_BENCH_SERIAL", "0") != "1"   # B200BEV_BENCH_SERIAL=1: one stream (A/B timing)
 
 
 def timed_steps(hp: HotPath, steps: int, warmup: int, flush, barrier, clocks=None):

@@ -15,6 +15,7 @@ describes: calibrated projection of the BEV cell centres and a one-pass gather o
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -22,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import conv_blocks, ops
+from . import conv_blocks, ops, runtime
 from .encoders import load_config
 from .weight_cache import mark_dirty, wants_autograd
 
@@ -142,7 +143,22 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         return None
     B, H, W = first.shape[0], module.bev_h, module.bev_w
     cat = torch.empty((B, H, W, c * sum(use)), dtype=torch.bfloat16, device=first.device)
-    off = 0
+    off_cam, off_lidar, off_radar = 0, c * use[0], c * (use[0] + use[1])
+    # The branches are independent and write disjoint channel slices of `cat`: the lidar and radar branches — a dozen small,
+    # latency-bound kernels — go to side streams next to the camera branch (parallel branches of the CUDA graph when the step
+    # is captured); bev_fusion waits for all of them.
+    fork = runtime.BranchStreams(first.device) if (_parallel_branches(module) and sum(use) > 1) else None
+    if use[1]:
+        with (fork.fork(0) if fork and use[0] else contextlib.nullcontext()):
+            s0 = lidar_start_size(module)
+            hidden = module.lidar_init[2].out_features // (s0 * s0)
+            l0, l2 = module.lidar_init[0], module.lidar_init[2]
+            x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s0, s0)
+            conv_blocks.run(module.lidar_upsample, [x], out_nhwc=cat, c_offset=off_lidar)    # :258-262
+            del x
+    if use[2]:
+        with (fork.fork(1) if fork and (use[0] or use[1]) else contextlib.nullcontext()):
+            radar_branch(module, radar_features, out_nhwc=cat, c_offset=off_radar)           # :274-281
     if use[0]:
         hw = camera_features.shape[-2] * camera_features.shape[-1]
         if camera_features.dim() == 5 and hw % 4 == 0:
@@ -150,18 +166,15 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         else:
             cam = ops.camera_mean(camera_features) if camera_features.dim() == 5 else camera_features
             x = conv_blocks.run(module.camera_proj, [cam])
-        ops.nchw_to_nhwc_bf16([ops.bilinear_resize(x, (H, W))], out=cat, c_offset=off)      # src/fusion.py:242-247
-        off += c
-    if use[1]:
-        s0 = lidar_start_size(module)
-        hidden = module.lidar_init[2].out_features // (s0 * s0)
-        l0, l2 = module.lidar_init[0], module.lidar_init[2]
-        x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s0, s0)
-        conv_blocks.run(module.lidar_upsample, [x], out_nhwc=cat, c_offset=off)              # :258-262
-        off += c
-    if use[2]:
-        radar_branch(module, radar_features, out_nhwc=cat, c_offset=off)                     # :274-281
+        ops.nchw_to_nhwc_bf16([ops.bilinear_resize(x, (H, W))], out=cat, c_offset=off_cam)  # src/fusion.py:242-247
+    if fork:
+        fork.join()
     return conv_blocks.run(module.bev_fusion, nhwc=cat)                                      # :292-295
+
+
+def _parallel_branches(module: nn.Module) -> bool:
+    """Side streams for the independent branches of the fused path: on unless `module.b200_parallel_branches = False`."""
+    return bool(getattr(module, "b200_parallel_branches", True))
 
 
 def _torch_graph_wanted(module: nn.Module, *feats) -> bool:

@@ -254,3 +254,36 @@ class GraphedStep:
         """Enqueues the whole step on the current stream; returns the (static) output tensors."""
         self.graph.replay()
         return self.outputs
+
+
+class BranchStreams:
+    """Side streams for work that is independent of what the caller's stream is doing (the modality branches of the fusion
+    module, the radar encoder next to the LiDAR encoder): `fork(i)` returns a context in which kernels are enqueued on side
+    stream i, ordered after everything enqueued on the caller's stream so far; `join()` makes the caller's stream wait for
+    every side stream used since the last join.  Works eagerly and inside a CUDA-graph capture (the capture then records
+    parallel branches).  Tensors allocated inside a fork belong to the side stream's pool: keep their use inside the fork,
+    or on the caller's stream AFTER the join (what the fused fusion path does: the branches write slices of a tensor the
+    caller allocated).  The streams are created once per device and reused.
+    """
+
+    _pool: dict = {}
+
+    def __init__(self, device: torch.device, n: int = 2):
+        key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+        if key not in BranchStreams._pool:
+            BranchStreams._pool[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        self.streams = BranchStreams._pool[key]
+        self.device = device
+        self.used: list = []
+
+    def fork(self, i: int):
+        side = self.streams[i]
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        self.used.append(side)
+        return torch.cuda.stream(side)
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for side in self.used:
+            cur.wait_stream(side)
+        self.used = []
