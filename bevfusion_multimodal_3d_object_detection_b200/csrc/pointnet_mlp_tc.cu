@@ -675,7 +675,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) pointnet_mlp_tc_kernel(TcArgs a
       publish_act1(packed);
     }
     for (long long t = t_begin; t < t_end; ++t) {
-      const bool tracer = (tid == 64);
+#ifndef B200BEV_TC_TRACER_TID
+#define B200BEV_TC_TRACER_TID 64   // the epilogue thread whose clock stamps the debug timeline records (64: warp 2, part 0; 320: warp 10, part 2)
+#endif
+      const bool tracer = (tid == B200BEV_TC_TRACER_TID);
       if (tracer) trace_ev<TRACE>(a, tr, kTraceEpi, 0x200);          // tile start
       const long long tile = t * CG + cta_rank;
       const bool dummy = tile >= a.total_tiles;
