@@ -339,15 +339,15 @@ def test_parallel_branches_of_the_fused_path_change_nothing(cuda):
     fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=True, camera_channels=64, lidar_channels=128,
                                     radar_channels=64, bev_h=50, bev_w=50, bev_channels=64).eval().to(cuda)
     fus.b200_precision = "bf16"
-    outs = {}
     with torch.no_grad():
         for rep in range(6):
             cam = torch.from_numpy(syn.camera_features(900 + rep, 2, n_cam=6, channels=64, h=28, w=50)).to(cuda)
             lidar, radar = torch.rand(2, 128, device=cuda), torch.rand(2, 64, device=cuda)
-            for parallel in (True, False, True):
+            outs = []
+            for parallel in (True, False, True, True):
                 fus.b200_parallel_branches = parallel
-                outs[parallel] = fus(camera_features=cam, lidar_features=lidar, radar_features=radar).clone()
-                assert torch.equal(outs[parallel], outs.get(not parallel, outs[parallel])), (rep, parallel)
+                outs.append(fus(camera_features=cam, lidar_features=lidar, radar_features=radar).clone())
+            assert all(torch.equal(o, outs[1]) for o in outs), rep
 
 
 def test_graphed_step_replays_the_chain_bit_for_bit(cuda):
