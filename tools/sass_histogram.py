@@ -14,7 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 NATIVE = ROOT / "bevfusion_multimodal_3d_object_detection_b200" / "_native"
 WATCH = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "ELECT",
-         "HMMA", "HGMMA", "LDGSTS", "RED", "ATOMG", "ATOM", "MATCH", "SHFL", "FFMA", "HFMA2", "FMNMX", "BAR", "UCGABAR_ARV", "UCGABAR_WAIT"]
+         "HMMA", "HGMMA", "FADD2", "FFMA2", "F2FP", "LDGSTS", "RED", "ATOMG", "ATOM", "MATCH", "SHFL", "FFMA", "HFMA2", "FMNMX", "BAR", "UCGABAR_ARV", "UCGABAR_WAIT"]
 
 
 def histogram(obj: Path):
