@@ -346,10 +346,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
 // ---- 3x3 form with the pixel rows shared by the nine taps (default for 3x3 when an image row fits) ---------------------
 // In the kernels above every tap re-reads its 256 pixel rows from L2: 48 KB per 512 clk of tensor work, 96 B/clk per SM,
 // and with ~2,000 clk from "slot free" to "MMA issued" the four-slot ring cannot keep that in flight (ncu: tensor pipe
-// active 49 % on the 768->512 block).  A 3x3 tap is the SAME pixels displaced by (dy, dx).  Here a tile is R whole image
-// rows of one frame, laid out in shared memory with ONE zero pixel between consecutive image rows and a halo row above
-// and below:   padded index L(y, x) = (y - y0 + 1) (W + 1) + x + 1,   x = -1 is the shared pad pixel.
-// Output column n = ry (W + 1) + x  (x = W is a dummy column) then needs, for tap (dy, dx), padded row
+// active 49 % on the 768->512 block).  A 3x3 tap is the SAME pixels displaced by (dy, dx).  Here a frame is walked in its
+// padded row-major order — flat index F = y (W + 1) + x with ONE zero pixel (x = W) between consecutive image rows — and a
+// tile is N consecutive flat indices starting at n0 (any n0: tiles need not begin at an image row), laid out in shared
+// memory from flat index n0 - (W + 1) - 1 on: one image row and one pixel of halo in front, the same behind.
+// Output column n (flat index n0 + n; x = W is a dummy column) then needs, for tap (dy, dx), block row
 // n + (1 + dy)(W + 1) + (1 + dx): one block of N + 2 (W + 1) + 2 rows per 64 input channels serves all nine taps, each tap
 // being the same shared-memory block entered `off` rows later (the 128-byte swizzle is a function of the shared-memory
 // address, so a row-displaced descriptor reads every row with the phase it was written with).  Zero padding of the
@@ -358,32 +359,33 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
 //   warps 0-7 pixel blocks (cp.async, two buffers) | warp 13 weight stages (bulk copies, ring of 4) | warp 12 MMA issue
 //   | warps 8-11 epilogue (accumulator double-buffered in tensor memory), all meeting at mbarriers only.
 constexpr int kHaloThreads = 448;
-constexpr int kHaloMaxRows = 448;                       // 56 KB per pixel block
+constexpr int kHaloMaxRows = 480;                       // 60 KB per pixel block
 constexpr int kHaloBlock = kHaloMaxRows * 128;
 constexpr int kHaloEpi = 4 * 32 * 33 * 4;                // per epilogue warp: a 32 x 32 transposing tile
 constexpr int kHaloSmem = 2 * kHaloBlock + kRing * kStageA + kHaloEpi + 1024 + 256;
-constexpr int kHaloRowsPerThread = kHaloMaxRows / 32;   // 14
+constexpr int kHaloRowsPerThread = kHaloMaxRows / 32;   // 15
 
+// A frame is walked in its PADDED row-major order: flat index F = y (W + 1) + x, x = W being the zero pixel between image rows.
+// A tile is N consecutive flat indices, wherever they start — not whole image rows: a 100-pixel-wide map gets tiles of 256
+// columns (2.5 rows) instead of 208 (two rows), 23 tiles per frame instead of 29.
 struct HaloGeom {
-  int R;       // image rows per tile
-  int N;       // MMA columns: R (W + 1) rounded up to 16
-  int Q;       // rows of a pixel block
+  int N;       // MMA columns = flat indices per tile (a multiple of 16)
+  int Q;       // rows of a pixel block: N + 2 (W + 1) + 2
   int tiles_per_frame;
 };
 
 // max_cols: 256, the two accumulator halves of tensor memory (in fp32-accuracy mode one half carries a tile's running total and
 // the other its partial sums, see the epilogue)
 __host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g, int max_cols = kTilePx) {
-  const int R = max_cols / (W + 1);
-  if (R < 1) return false;
-  const int rows = R < H ? R : H;
-  const int N = (rows * (W + 1) + 15) & ~15;
-  const int Q = N + 2 * (W + 1) + 2;
-  if (N > max_cols || Q > kHaloMaxRows) return false;
-  g->R = rows;
+  const int W1 = W + 1, total = H * W1;
+  int n_max = (kHaloMaxRows - 2 * W1 - 2) & ~15;          // the block of N + 2 (W + 1) + 2 rows has to fit
+  if (n_max > max_cols) n_max = max_cols;
+  if (n_max < 16 || total < 1) return false;
+  const int need = (total + 15) & ~15;
+  const int N = need < n_max ? need : n_max;
   g->N = N;
-  g->Q = Q;
-  g->tiles_per_frame = (H + rows - 1) / rows;
+  g->Q = N + 2 * W1 + 2;
+  g->tiles_per_frame = (total + N - 1) / N;
   return true;
 }
 
@@ -438,12 +440,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
   const int ncc = conv_chunks(a);
   const int n_tiles = a.B * geo.tiles_per_frame * n_co_tiles;
   const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  // tile -> (co tile, frame, first image row): the co tiles of one pixel tile are neighbours in the grid (shared pixels in L2)
-  auto tile_coords = [&](int tile, int& co_tile, int& b, int& y0) {
+  // tile -> (co tile, frame, first flat index): the co tiles of one pixel tile are neighbours in the grid (shared pixels in L2)
+  auto tile_coords = [&](int tile, int& co_tile, int& b, int& n0) {
     co_tile = tile % n_co_tiles;
     const int pt = tile / n_co_tiles;
     b = pt / geo.tiles_per_frame;
-    y0 = (pt - b * geo.tiles_per_frame) * geo.R;
+    n0 = (pt - b * geo.tiles_per_frame) * geo.N;
   };
 
   if (warp < 8) {
@@ -462,14 +464,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
       }
       if (bi < n_blocks) {
         if (cc == 0) {
-          int co_tile, b, y0;
-          tile_coords(tile, co_tile, b, y0);
+          int co_tile, b, n0;
+          tile_coords(tile, co_tile, b, n0);
 #pragma unroll
           for (int j = 0; j < kHaloRowsPerThread; ++j) {
+            // block row q holds the pixel of flat index n0 + q - (W + 1) - 1 (one image row and one pixel before the tile's
+            // first output); the slot x = W of every row, and everything outside the frame, is zero
             const int q = row0 + 32 * j;
-            const int ry = q / W1 - 1, x = q - (ry + 1) * W1 - 1;
-            const int y = y0 + ry;
-            goff[j] = (q < geo.Q && x >= 0 && y >= 0 && y < a.H) ? (((long long)b * a.H + y) * a.W + x) * a.x_pitch + chunk * 8 : -1;
+            const int gflat = n0 + q - W1 - 1;
+            const int y = gflat >= 0 ? gflat / W1 : -1, x = gflat - y * W1;
+            goff[j] = (q < geo.Q && gflat >= 0 && y < a.H && x < a.W) ? (((long long)b * a.H + y) * a.W + x) * a.x_pitch + chunk * 8 : -1;
           }
         }
         const int buf = bi & 1;
@@ -565,8 +569,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     int tile = blockIdx.x, uses0 = 0, uses1 = 0;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
-      int co_tile, b, y0;
-      tile_coords(tile, co_tile, b, y0);
+      int co_tile, b, n0;
+      tile_coords(tile, co_tile, b, n0);
       const int co0 = co_tile * kTileCo + quad * 32;
       const float bias = (a.bias && co0 + lane < a.Cout) ? __ldg(a.bias + co0 + lane) : 0.f;
       const float oscale = conv_out_scale(a, co0 + lane);
@@ -620,23 +624,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
           tp[lane * 33 + j] = v;
         }
         if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
-          int ry = col0 / W1, x = col0 - ry * W1;
+          int y = (n0 + col0) / W1, x = n0 + col0 - y * W1;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (lane < n_ch && x < a.W && ry < geo.R && y0 + ry < a.H)   // lane = channel: 64 contiguous bytes per pixel
-              a.out_nhwc[(((size_t)b * a.H + y0 + ry) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
+            if (lane < n_ch && x < a.W && y < a.H && col0 + j < geo.N)   // lane = channel: 64 contiguous bytes per pixel
+              a.out_nhwc[(((size_t)b * a.H + y) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
                   __float2bfloat16_rn(__uint_as_float(r[j]));
             if (++x == W1) {
               x = 0;
-              ++ry;
+              ++y;
             }
           }
         }
         __syncwarp();
-        // this lane's pixel: column n = col0 + lane
+        // this lane's pixel: column n = col0 + lane, flat index n0 + n
         const int n = col0 + lane;
-        const int ry = n / W1, x = n - ry * W1, y = y0 + ry;
-        const bool px_ok = n < geo.N && x < a.W && ry < geo.R && y < a.H;
+        const int y = (n0 + n) / W1, x = n0 + n - y * W1;
+        const bool px_ok = n < geo.N && x < a.W && y < a.H;
         float* dst = oplane + (px_ok ? y * a.W + x : 0);
         if (a.out) {
           for (int c = 0; c < n_ch; ++c) {
