@@ -382,6 +382,7 @@ __host__ __device__ inline bool halo_geometry(int H, int W, HaloGeom* g, int max
   if (n_max > max_cols) n_max = max_cols;
   if (n_max < 16 || total < 1) return false;
   const int need = (total + 15) & ~15;
+  if (need > n_max && n_max < 128) return false;          // very wide maps: tiles that narrow lose to the per-tap kernel
   const int N = need < n_max ? need : n_max;
   g->N = N;
   g->Q = N + 2 * W1 + 2;

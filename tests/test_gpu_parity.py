@@ -776,7 +776,8 @@ def test_decode_from_logits_vs_reference_head_golden(cuda, golden):
     (2, 25, 25, 512, 256, 1, True),      # 1x1 (camera_proj's second block): HW = 625 is not a multiple of 4 -> scalar stores
     (1, 7, 9, 64, 19, 1, False),         # tiny: one ragged tile, no ReLU (the head's second layer)
     (4, 50, 50, 256, 256, 3, False),     # more tiles than one wave of the ring phases
-    (2, 57, 100, 64, 64, 3, True),       # camera_proj's image: two image rows per tile (N = 208), last tile one row
+    (2, 57, 100, 64, 64, 3, True),       # camera_proj's image: tiles of 256 flat indices = 2.5 image rows, starting mid-row
+    (1, 9, 150, 64, 32, 3, True),        # a wide map: the pixel block only leaves room for tiles of 176 flat indices
     (1, 3, 300, 64, 32, 3, True),        # an image row wider than a tile: the per-tap kernel takes the 3x3 too
     (5, 5, 6, 64, 130, 3, True),         # whole frames smaller than a tile; a 2-channel last channel tile
     (3, 1, 1, 64, 1, 3, False),          # one pixel, one output channel: every tap but the centre is padding
@@ -817,7 +818,7 @@ def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
 
 CONV_SHAPES = [
     (2, 12, 20, 64, 64, 3, True), (3, 50, 50, 128, 320, 3, True), (2, 25, 25, 512, 256, 1, True), (1, 7, 9, 64, 19, 1, False),
-    (4, 50, 50, 256, 256, 3, False), (2, 57, 100, 64, 64, 3, True), (1, 3, 300, 64, 32, 3, True), (5, 5, 6, 64, 130, 3, True),
+    (4, 50, 50, 256, 256, 3, False), (2, 57, 100, 64, 64, 3, True), (1, 9, 150, 64, 32, 3, True), (1, 3, 300, 64, 32, 3, True), (5, 5, 6, 64, 130, 3, True),
     (3, 1, 1, 64, 1, 3, False), (1, 1, 7, 128, 5, 1, True), (2, 50, 50, 768, 512, 3, True),
 ]
 
