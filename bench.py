@@ -323,7 +323,8 @@ class HotPath:
         self.chain.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         del sd
         self.chain = self.chain.eval().to(dev)
-        self.chain.fusion.b200_parallel_branches = PARALLEL_BRANCHES
+        if not PARALLEL_BRANCHES:
+            self.chain.fusion.b200_parallel_branches = False
         self.inputs = {}
         if wl["lidar"]:
             self.inputs["lidar"] = to(syn.lidar_batch(seed, frames, n_valid=wl["valid"], n_total=wl["points"]))
@@ -356,7 +357,9 @@ class HotPath:
         # go to side streams — parallel branches of the captured graph.  The eager, stage-by-stage timing pass stays serial.
         import contextlib
         from bevfusion_multimodal_3d_object_detection_b200 import runtime
-        fork = runtime.BranchStreams(self.dev) if (marks is None and PARALLEL_BRANCHES and inp["lidar" if wl["lidar"] else "feats"].is_cuda) else None
+        small = self.F * G * G <= 32 * 50 * 50      # measured: the side streams gain 2.5 % up to here and lose 1-2 % beyond
+        fork = runtime.BranchStreams(self.dev) if (marks is None and PARALLEL_BRANCHES and small and
+                                                   inp["lidar" if wl["lidar"] else "feats"].is_cuda) else None
         side = (lambda i: fork.fork(i)) if fork else (lambda i: contextlib.nullcontext())
         with torch.no_grad():
             if fork and wl["radar"]:
