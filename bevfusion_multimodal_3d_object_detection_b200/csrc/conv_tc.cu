@@ -686,43 +686,74 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
 }
 
 // (B, C, H, W) fp32 -> channels [c_offset, c_offset + C) of (B, H, W, C_total) bf16.  A thread owns one pixel (or four
-// consecutive ones) and 8 consecutive channels: eight loads, each 128 (512) contiguous bytes per warp (a lane is a pixel of one channel plane), one
-// 16-byte store; the eight warps of a block cover the 64 channels of the same 32 pixels, so every 128-byte line of the
-// output is completed by one block within a few hundred cycles.  No shared memory, 8 independent loads per thread.
+// consecutive ones) and 8 consecutive channels: eight loads, each 128 (512) contiguous bytes per warp (a lane is a pixel of one
+// channel plane).  PX = 4 with 16-byte-aligned output: the block's 128 pixels x 64 channels are turned through shared memory
+// (chunks XOR-swizzled, no bank conflicts either way) and a warp's store instruction writes four whole 128-byte lines; else
+// every thread stores its own 16 bytes (or scalars).
 template <int PX>   // pixels per thread: 4 (128-bit loads along the plane; needs HW % 4 == 0) or 1
 __global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int B, int C, int HW,
                                                                 __nv_bfloat16* __restrict__ out, int C_total, int c_offset) {
+  __shared__ __align__(16) uint4 stage[PX == 4 ? 128 * 8 : 1];   // [pixel][chunk of eight channels]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_cg = ceil_div(C, 64), n_pg = ceil_div(HW, 32 * PX);
   const long long n_items = (long long)B * n_cg * n_pg;   // block items: 64 channels x 32*PX pixels
   const bool vec_out = (C_total & 7) == 0 && (c_offset & 7) == 0 && ((uintptr_t)out & 15) == 0;
+  const bool staged = PX == 4 && vec_out;
   for (long long t = blockIdx.x; t < n_items; t += gridDim.x) {
     const int pg = (int)(t % n_pg), cg = (int)((t / n_pg) % n_cg), b = (int)(t / ((long long)n_pg * n_cg));
     const int p = (pg * 32 + lane) * PX, c0 = cg * 64 + warp * 8;
-    if (p >= HW || c0 >= C) continue;
-    const float* src = in + ((size_t)b * C + c0) * HW + p;
+    const bool live = p < HW && c0 < C;
+    if (!staged && !live) continue;
     float v[8][PX];
+    if (live) {
+      const float* src = in + ((size_t)b * C + c0) * HW + p;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (PX == 4) {
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + e < C) q = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)e * HW));
-        v[e][0] = q.x; v[e][PX > 1 ? 1 : 0] = q.y; v[e][PX > 2 ? 2 : 0] = q.z; v[e][PX > 3 ? 3 : 0] = q.w;
-      } else {
-        v[e][0] = (c0 + e < C) ? __ldg(src + (size_t)e * HW) : 0.f;
+      for (int e = 0; e < 8; ++e) {
+        if (PX == 4) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + e < C) q = ld_stream_f4(reinterpret_cast<const float4*>(src + (size_t)e * HW));
+          v[e][0] = q.x; v[e][PX > 1 ? 1 : 0] = q.y; v[e][PX > 2 ? 2 : 0] = q.z; v[e][PX > 3 ? 3 : 0] = q.w;
+        } else {
+          v[e][0] = (c0 + e < C) ? __ldg(src + (size_t)e * HW) : 0.f;
+        }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < PX; ++i) {
-      __nv_bfloat16* dst = out + ((size_t)b * HW + p + i) * C_total + c_offset + c0;
-      if (vec_out && c0 + 8 <= C) {
+      for (int i = 0; i < PX; ++i) {
+        if (p + i >= HW) break;
         __align__(16) __nv_bfloat162 w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) w[e] = __floats2bfloat162_rn(v[2 * e][i], v[2 * e + 1][i]);
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
-      } else {
-        for (int e = 0; e < 8 && c0 + e < C; ++e) dst[e] = __float2bfloat16_rn(v[e][i]);
+        if (staged) {
+          stage[(lane * 4 + i) * 8 + (warp ^ (lane & 7))] = *reinterpret_cast<const uint4*>(w);
+        } else {
+          __nv_bfloat16* dst = out + ((size_t)b * HW + p + i) * C_total + c_offset + c0;
+          if (vec_out && c0 + 8 <= C) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
+          } else {
+            for (int e = 0; e < 8 && c0 + e < C; ++e) dst[e] = __float2bfloat16_rn(v[e][i]);
+          }
+        }
       }
+    }
+    if (staged) {
+      __syncthreads();
+      // 128 pixels x 8 chunks = 1024 pieces of 16 bytes: four per thread, the chunk index fastest
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = k * 256 + (int)threadIdx.x;
+        const int r = idx >> 3, ch = idx & 7;
+        const int pix = pg * 128 + r, c = cg * 64 + ch * 8;
+        if (pix >= HW || c >= C) continue;
+        const uint4 val = stage[r * 8 + (ch ^ ((r >> 2) & 7))];
+        __nv_bfloat16* dst = out + ((size_t)b * HW + pix) * C_total + c_offset + c;
+        if (c + 8 <= C) {
+          *reinterpret_cast<uint4*>(dst) = val;
+        } else {
+          const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&val);
+          for (int e = 0; e < 8 && c + e < C; ++e) dst[e] = hv[e];
+        }
+      }
+      __syncthreads();   // the stage is reused by the next item
     }
   }
 }
