@@ -64,6 +64,7 @@ PROTOTYPES = {
     "b200bev_conv_pack_bytes": (_z, [_i, _i, _i]),
     "b200bev_conv_pack_bf16": (_i, [_p, _i, _i, _i, _p, _z, _p]),
     "b200bev_nchw_to_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "b200bev_bilinear_resize_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     "b200bev_camera_mean_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "b200bev_conv_bn_relu_bf16": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
     "b200bev_absmax": (_i, [_p, C.c_int64, _p, _p]),

@@ -123,7 +123,8 @@ def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc
             if nhwc is None:
                 nhwc = ops.nchw_to_nhwc_bf16(parts)      # layout + cast + concat in one pass per part
             last = k + 1 == len(steps)
-            chained = not last and steps[k + 1]["kind"] == "conv"
+            # the next consumer reads channels-last bf16: a convolution, or an upsample that a convolution follows
+            chained = not last and (steps[k + 1]["kind"] == "conv" or (k + 2 < len(steps) and steps[k + 2]["kind"] == "conv"))
             if chained or (last and out_nhwc is not None):
                 B, H, W, _ = nhwc.shape
                 nxt, off = (out_nhwc, c_offset) if last else (torch.empty((B, H, W, step["c_out"]), dtype=torch.bfloat16, device=device), 0)
@@ -134,9 +135,12 @@ def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc
                 parts = [ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
                 nhwc = None
         else:
-            x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
             s = step["scale"]
             sy, sx = (s, s) if not isinstance(s, (tuple, list)) else s
+            if nhwc is not None and k + 1 < len(steps):      # between two convolutions: stay channels-last bf16
+                nhwc = ops.bilinear_resize_nhwc_bf16(nhwc, (int(nhwc.shape[1] * sy), int(nhwc.shape[2] * sx)))
+                continue
+            x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
             parts = [ops.bilinear_resize(x, (int(x.shape[2] * sy), int(x.shape[3] * sx)))]
     if out_nhwc is not None:
         return None

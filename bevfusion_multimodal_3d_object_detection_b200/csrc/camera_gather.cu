@@ -6,6 +6,8 @@
 //
 // All three are HBM-bound streaming/gather kernels: 16-byte accesses where the layout allows,
 // every output written exactly once, no intermediate tensors.
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 #include "async_copy.cuh"
@@ -112,6 +114,47 @@ __global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __res
     const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
     const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
     out[i] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+  }
+}
+
+// The same arithmetic on channels-last bf16 (the tensors between the tcgen05 convolution kernels): in (B,h,w,C) bf16 ->
+// channels [c_offset, c_offset + C) of (B,H,W,C_total) bf16.  A thread owns one output pixel and eight channels: four 16-byte
+// loads (the taps), fp32 interpolation in the op order above, one 16-byte store; the channel groups of a pixel are
+// neighbouring threads, so every access of a warp is contiguous.
+__global__ void __launch_bounds__(256) bilinear_resize_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ in, int B, int h, int w, int C,
+                                                                        __nv_bfloat16* __restrict__ out, int H, int W, int C_total, int c_offset) {
+  const float sy = __fdiv_rn((float)h, (float)H), sx = __fdiv_rn((float)w, (float)W);
+  const unsigned cg = (unsigned)C / 8;
+  const long long total = (long long)B * H * W * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned g = (unsigned)(i % cg);
+    const long long pix = i / cg;
+    const int x = (int)(pix % W);
+    const long long t = pix / W;
+    const int y = (int)(t % H), b = (int)(t / H);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    resize_coord(y, sy, h, y0, y1, ly0, ly1);
+    resize_coord(x, sx, w, x0, x1, lx0, lx1);
+    const __nv_bfloat16* src = in + (size_t)b * h * w * C + g * 8;
+    const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y0 * w + x0) * C));
+    const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y0 * w + x1) * C));
+    const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y1 * w + x0) * C));
+    const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y1 * w + x1) * C));
+    const __nv_bfloat162* a00 = reinterpret_cast<const __nv_bfloat162*>(&q00);
+    const __nv_bfloat162* a01 = reinterpret_cast<const __nv_bfloat162*>(&q01);
+    const __nv_bfloat162* a10 = reinterpret_cast<const __nv_bfloat162*>(&q10);
+    const __nv_bfloat162* a11 = reinterpret_cast<const __nv_bfloat162*>(&q11);
+    __align__(16) __nv_bfloat162 r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 v00 = __bfloat1622float2(a00[e]), v01 = __bfloat1622float2(a01[e]);
+      const float2 v10 = __bfloat1622float2(a10[e]), v11 = __bfloat1622float2(a11[e]);
+      const float tx = __fadd_rn(__fmul_rn(lx0, v00.x), __fmul_rn(lx1, v01.x)), bx = __fadd_rn(__fmul_rn(lx0, v10.x), __fmul_rn(lx1, v11.x));
+      const float ty = __fadd_rn(__fmul_rn(lx0, v00.y), __fmul_rn(lx1, v01.y)), by = __fadd_rn(__fmul_rn(lx0, v10.y), __fmul_rn(lx1, v11.y));
+      r[e] = __floats2bfloat162_rn(__fadd_rn(__fmul_rn(ly0, tx), __fmul_rn(ly1, bx)), __fadd_rn(__fmul_rn(ly0, ty), __fmul_rn(ly1, by)));
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)pix * C_total + c_offset + g * 8) = *reinterpret_cast<const uint4*>(r);
   }
 }
 
@@ -238,5 +281,17 @@ extern "C" B200BEV_API int b200bev_bilinear_resize(const float* in, int B, int C
   } else {
     bilinear_resize_kernel<<<grid_for(planes * H * W, 256), 256, 0, st>>>(in, out, planes, h, w, H, W);
   }
+  return launch_status();
+}
+
+extern "C" B200BEV_API int b200bev_bilinear_resize_nhwc_bf16(const void* in_nhwc, int B, int h, int w, int C, void* out_nhwc, int H, int W,
+                                                             int C_total, int c_offset, void* stream) {
+  if (!in_nhwc || !out_nhwc || B <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return B200BEV_ERR_INVALID_ARGUMENT;
+  if (c_offset < 0 || c_offset + C > C_total) return B200BEV_ERR_INVALID_ARGUMENT;
+  if ((C & 7) || (C_total & 7) || (c_offset & 7) || ((reinterpret_cast<uintptr_t>(in_nhwc) | reinterpret_cast<uintptr_t>(out_nhwc)) & 15))
+    return B200BEV_ERR_UNSUPPORTED;
+  const long long total = (long long)B * H * W * (C / 8);
+  bilinear_resize_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in_nhwc), B, h, w, C, reinterpret_cast<__nv_bfloat16*>(out_nhwc), H, W, C_total, c_offset);
   return launch_status();
 }

@@ -161,12 +161,14 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
             radar_branch(module, radar_features, out_nhwc=cat, c_offset=off_radar)           # :274-281
     if use[0]:
         hw = camera_features.shape[-2] * camera_features.shape[-1]
+        fh, fw = int(camera_features.shape[-2]), int(camera_features.shape[-1])
+        proj = torch.empty((B, fh, fw, c), dtype=torch.bfloat16, device=first.device)       # camera_proj's output, channels-last
         if camera_features.dim() == 5 and hw % 4 == 0:
-            x = conv_blocks.run(module.camera_proj, nhwc=ops.camera_mean_nhwc_bf16(camera_features))
+            conv_blocks.run(module.camera_proj, nhwc=ops.camera_mean_nhwc_bf16(camera_features), out_nhwc=proj)
         else:
             cam = ops.camera_mean(camera_features) if camera_features.dim() == 5 else camera_features
-            x = conv_blocks.run(module.camera_proj, [cam])
-        ops.nchw_to_nhwc_bf16([ops.bilinear_resize(x, (H, W))], out=cat, c_offset=off_cam)  # src/fusion.py:242-247
+            conv_blocks.run(module.camera_proj, [cam], out_nhwc=proj)
+        ops.bilinear_resize_nhwc_bf16(proj, (H, W), out=cat, c_offset=off_cam)               # src/fusion.py:242-247
     if fork:
         fork.join()
     return conv_blocks.run(module.bev_fusion, nhwc=cat)                                      # :292-295

@@ -416,6 +416,25 @@ def nchw_to_nhwc_bf16(parts: Sequence[torch.Tensor], out: Optional[torch.Tensor]
     return out
 
 
+def bilinear_resize_nhwc_bf16(x: torch.Tensor, size: Tuple[int, int], out: Optional[torch.Tensor] = None, c_offset: int = 0) -> torch.Tensor:
+    """(B,h,w,C) bf16 channels-last -> (B,H,W,C) bf16, or channels [c_offset, c_offset + C) of `out` (B,H,W,C_total) bf16:
+    F.interpolate(mode='bilinear', align_corners=False) (src/fusion.py:242-247) between two convolutions of the bf16 path."""
+    x = _need_cuda(x, "x", torch.bfloat16)
+    if x.dim() != 4:
+        raise ValueError("x must be (B, h, w, C) channels-last")
+    B, h, w, Cc = (int(v) for v in x.shape)
+    H, W = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+        c_offset = 0
+    elif out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape[:3]) != (B, H, W) or c_offset + Cc > out.shape[3]:
+        raise ValueError(f"out must be a contiguous (B,H,W,C) bf16 tensor with room for {Cc} channels at offset {c_offset}")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().b200bev_bilinear_resize_nhwc_bf16(_ptr(x), B, h, w, Cc, _ptr(out), H, W, int(out.shape[3]), c_offset,
+                                                                _stream(x.device)))
+    return out
+
+
 def camera_mean_nhwc_bf16(feats: torch.Tensor) -> torch.Tensor:
     """(B,n_cam,C,h,w) fp32 -> (B,h,w,C) bf16: camera_features.mean(dim=1) (src/fusion.py:234) delivered as the
     channels-last input of camera_proj's first convolution."""

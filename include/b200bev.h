@@ -279,6 +279,9 @@ B200BEV_API int b200bev_lidar_init(const float* lidar_features, int B, int K, co
  *   b200bev_conv_pack_bytes gives the image size (0: unsupported shape).
  * b200bev_nchw_to_nhwc_bf16: (B,C,H,W) f32 -> channels [c_offset, c_offset+C) of a (B,H,W,C_total) bf16 tensor; writing
  *   the parts of a concatenated input into their slices replaces torch.cat of src/fusion.py:292.
+ * b200bev_bilinear_resize_nhwc_bf16: F.interpolate(size=(H,W), mode='bilinear', align_corners=False) of src/fusion.py:242-247
+ *   between two convolutions of the bf16 path: in (B,h,w,C) bf16 channels-last -> channels [c_offset, c_offset+C) of
+ *   (B,H,W,C_total) bf16; fp32 interpolation in b200bev_bilinear_resize's op order, rounded to bf16.  C, C_total, c_offset % 8 == 0.
  * b200bev_camera_mean_nhwc_bf16: camera_features.mean(dim=1) (src/fusion.py:233-234) fused with that layout step:
  *   feats (B,n_cam,C,H,W) f32 -> channels [c_offset, c_offset+C) of (B,H,W,C_total) bf16 = the bf16 rounding of
  *   b200bev_camera_mean's result (same summation order, IEEE divide).  Needs H*W % 4 == 0 and C_total, c_offset % 8 == 0.
@@ -290,6 +293,8 @@ B200BEV_API int b200bev_conv_pack_bf16(const float* weight, int Cout, int Cin, i
                            void* image, size_t image_bytes, void* stream);
 B200BEV_API int b200bev_nchw_to_nhwc_bf16(const float* in, int B, int C, int H, int W,
                               void* out_nhwc, int C_total, int c_offset, void* stream);
+B200BEV_API int b200bev_bilinear_resize_nhwc_bf16(const void* in_nhwc, int B, int h, int w, int C,
+                                      void* out_nhwc, int H, int W, int C_total, int c_offset, void* stream);
 B200BEV_API int b200bev_conv_bn_relu_bf16(const void* x_nhwc, int B, int H, int W, int Cin,
                               const void* weight_image, const float* bias, int Cout, int taps, int relu,
                               float* out_nchw, void* stream);

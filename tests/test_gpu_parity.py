@@ -268,6 +268,28 @@ def test_camera_mean_and_resize(cuda, golden, name, shape):
     assert max_rel(out, g[f"{name}_resize_out"]) < FP32_TOL
 
 
+@pytest.mark.parametrize("B,h,w,C,H,W,C_total,c_off", [(2, 57, 100, 64, 50, 50, 192, 64),     # camera_proj's map into a slice of bev_fusion's input
+                                                         (3, 25, 25, 128, 50, 50, 128, 0),      # the lidar branch's x2 upsample
+                                                         (1, 7, 5, 8, 3, 11, 24, 16)])          # down in y, up in x, one channel group
+def test_bilinear_resize_channels_last_bf16(cuda, B, h, w, C, H, W, C_total, c_off):
+    """b200bev_bilinear_resize_nhwc_bf16: the resize of src/fusion.py:242-247 on channels-last bf16, between two convolutions of
+    the bf16 path.  Bit-exact against the fp32 kernel applied to the same bf16 values and rounded to bf16 (same op order);
+    the channels of `out` outside the slice stay untouched."""
+    rng = np.random.default_rng(B * 100 + C)
+    x = torch.from_numpy(rng.standard_normal((B, C, h, w)).astype(np.float32)).to(cuda).to(torch.bfloat16)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((B, H, W, C_total), 7.0, dtype=torch.bfloat16, device=cuda)
+    ops.bilinear_resize_nhwc_bf16(x_nhwc, (H, W), out=out, c_offset=c_off)
+    ref = ops.bilinear_resize(x.float().contiguous(), (H, W)).to(torch.bfloat16).permute(0, 2, 3, 1)
+    assert torch.equal(out[..., c_off:c_off + C], ref)
+    assert bool((out[..., :c_off] == 7.0).all()) and bool((out[..., c_off + C:] == 7.0).all())
+    # and against torch's own interpolate, at the bf16 bound
+    tref = torch.nn.functional.interpolate(x.float(), size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert max_rel(out[..., c_off:c_off + C].float().cpu().numpy(), tref.cpu().numpy()) < BF16_TOL
+    alone = ops.bilinear_resize_nhwc_bf16(x_nhwc, (H, W))
+    assert torch.equal(alone, ref.contiguous())
+
+
 def test_camera_mean_odd_sizes(cuda):
     rng = np.random.default_rng(3)
     x = rng.standard_normal((2, 5, 3, 7, 11)).astype(np.float32)          # inner not a multiple of 4, 5 cameras
