@@ -357,7 +357,8 @@ class HotPath:
         # go to side streams — parallel branches of the captured graph.  The eager, stage-by-stage timing pass stays serial.
         import contextlib
         from bevfusion_multimodal_3d_object_detection_b200 import runtime
-        small = self.F * G * G <= 32 * 50 * 50      # measured: the side streams gain 2.5 % up to here and lose 1-2 % beyond
+        n_frames = int(inp["lidar" if wl["lidar"] else "feats"].shape[0])      # a pipeline chunk is smaller than the workload
+        small = n_frames * G * G <= 32 * 50 * 50    # measured: the side streams gain 2.5 % up to here and lose 1-2 % beyond
         fork = runtime.BranchStreams(self.dev) if (marks is None and PARALLEL_BRANCHES and small and
                                                    inp["lidar" if wl["lidar"] else "feats"].is_cuda) else None
         side = (lambda i: fork.fork(i)) if fork else (lambda i: contextlib.nullcontext())
