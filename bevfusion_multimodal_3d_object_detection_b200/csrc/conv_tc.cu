@@ -149,6 +149,24 @@ __device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bde
 constexpr int kWsThreads = 416;
 constexpr int kLag = 3;   // a producer hands stage c over (waits for its own copies of it) three stages after issuing them
 
+// Channels-last bf16 output of one pixel from a warp's transposing tile (tp[channel][33], lane = pixel): the lane gathers its
+// pixel's 32 channels (conflict-free: bank = channel + lane), rounds to bf16 and writes 64 contiguous bytes as four 16-byte
+// stores.  (With lane = channel, as the accumulator comes out of tensor memory, a store instruction wrote 2 bytes per lane: 32
+// such instructions per 32 pixels paced the epilogue of every block that feeds another convolution.)
+__device__ __forceinline__ void store_pixel_nhwc_bf16(const float* tp, int lane, __nv_bfloat16* dst, int n_ch, bool vec_ok) {
+  if (vec_ok && n_ch == 32) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      __align__(16) __nv_bfloat162 w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = __floats2bfloat162_rn(tp[(g * 8 + 2 * e) * 33 + lane], tp[(g * 8 + 2 * e + 1) * 33 + lane]);
+      *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<const uint4*>(w);
+    }
+  } else {
+    for (int c = 0; c < n_ch; ++c) dst[c] = __float2bfloat16_rn(tp[c * 33 + lane]);
+  }
+}
+
 __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -284,6 +302,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
     // ---- epilogue: warp 8+q owns TMEM lanes [32q, 32q+32) = 32 output channels; each 32 x 32 piece is turned through a
     // private shared-memory tile so that a store instruction writes contiguous pixels of ONE channel plane (see the 3x3
     // kernel below) ----
+    const bool nhwc_vec = (a.out_ct & 7) == 0 && (a.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out_nhwc) & 15) == 0;
     const int quad = warp & 3;
     float* tp = epi + quad * 32 * 33;
     int tile = blockIdx.x;
@@ -312,13 +331,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
           r[j] = __float_as_uint(v);
           tp[lane * 33 + j] = v;
         }
-        if (a.out_nhwc && co < a.Cout) {
-          // a lane is a channel: for one pixel the warp writes 32 consecutive bf16 channels (64 contiguous bytes)
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < n_px) a.out_nhwc[(size_t)(n0 + j) * a.out_ct + a.out_coff + co] = __float2bfloat16_rn(__uint_as_float(r[j]));
-        }
         __syncwarp();
+        if (a.out_nhwc && n0 + lane < n_px && n_ch > 0)
+          store_pixel_nhwc_bf16(tp, lane, a.out_nhwc + (size_t)(n0 + lane) * a.out_ct + a.out_coff + co0, n_ch, nhwc_vec);
         if (a.out) {
           const long long n = n0 + lane;   // this lane's pixel
           const bool px_ok = n < n_px;
@@ -569,6 +584,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     const int seg = halo_segment_chunks(a, ncc), n_seg = (ncc + seg - 1) / seg;
     int tile = blockIdx.x, uses0 = 0, uses1 = 0;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const bool nhwc_vec = (a.out_ct & 7) == 0 && (a.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out_nhwc) & 15) == 0;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
       int co_tile, b, n0;
       tile_coords(tile, co_tile, b, n0);
@@ -624,24 +640,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
           r[j] = __float_as_uint(v);
           tp[lane * 33 + j] = v;
         }
-        if (a.out_nhwc) {   // kept out of the loop above: the epilogue paces the blocks with few input channels
-          int y = (n0 + col0) / W1, x = n0 + col0 - y * W1;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (lane < n_ch && x < a.W && y < a.H && col0 + j < geo.N)   // lane = channel: 64 contiguous bytes per pixel
-              a.out_nhwc[(((size_t)b * a.H + y) * a.W + x) * a.out_ct + a.out_coff + co0 + lane] =
-                  __float2bfloat16_rn(__uint_as_float(r[j]));
-            if (++x == W1) {
-              x = 0;
-              ++y;
-            }
-          }
-        }
         __syncwarp();
         // this lane's pixel: column n = col0 + lane, flat index n0 + n
         const int n = col0 + lane;
         const int y = (n0 + n) / W1, x = n0 + n - y * W1;
         const bool px_ok = n < geo.N && x < a.W && y < a.H;
+        if (a.out_nhwc && px_ok && n_ch > 0)
+          store_pixel_nhwc_bf16(tp, lane, a.out_nhwc + (((size_t)b * a.H + y) * a.W + x) * a.out_ct + a.out_coff + co0, n_ch, nhwc_vec);
         float* dst = oplane + (px_ok ? y * a.W + x : 0);
         if (a.out) {
           for (int c = 0; c < n_ch; ++c) {
