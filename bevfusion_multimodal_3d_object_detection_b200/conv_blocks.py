@@ -107,12 +107,14 @@ def run_split(seq: nn.Sequential, parts: Sequence[torch.Tensor]) -> torch.Tensor
 
 
 def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc: Optional[torch.Tensor] = None,
-        out_nhwc: Optional[torch.Tensor] = None, c_offset: int = 0) -> Optional[torch.Tensor]:
+        out_nhwc: Optional[torch.Tensor] = None, c_offset: int = 0, note_nhwc: bool = False) -> Optional[torch.Tensor]:
     """`seq(torch.cat(parts, dim=1))` for a conv/BN/ReLU(/Upsample) stack: (B,C_i,H,W) fp32 parts -> (B,C_out,H',W') fp32.
     Between two convolutions the activations stay channels-last bf16 (written by the first launch's epilogue).
     nhwc: the input already as a (B,H,W,C) bf16 tensor (instead of `parts`).  out_nhwc / c_offset: the stack's last
     convolution writes channels [c_offset, ...) of this channels-last bf16 tensor — the concatenated input of the next
-    stack — and nothing else; returns None."""
+    stack — and nothing else; returns None.  note_nhwc: the last convolution writes the fp32 NCHW result AND its
+    channels-last bf16 form in the same launch, and the returned tensor remembers the latter (`nhwc_of`): a following
+    `CenterNetHead` on the bf16 path starts from it instead of running a layout pass."""
     parts = list(parts) if parts is not None else []
     device = nhwc.device if nhwc is not None else parts[0].device
     steps = _plan(seq, device, "bf16")
@@ -131,6 +133,11 @@ def run(seq: nn.Sequential, parts: Optional[Sequence[torch.Tensor]] = None, nhwc
                 ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"],
                                       out_nhwc=nxt, c_offset=off, want_nchw=False)
                 nhwc, parts = nxt, []
+            elif last and note_nhwc:
+                B, H, W, _ = nhwc.shape
+                twin = torch.empty((B, H, W, step["c_out"]), dtype=torch.bfloat16, device=device)
+                res = ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"], out_nhwc=twin)
+                parts, nhwc = [attach_nhwc(res, twin)], None
             else:
                 parts = [ops.conv_bn_relu_bf16(nhwc, step["image"], step["bias"], step["c_out"], step["taps"], step["relu"])]
                 nhwc = None
@@ -200,7 +207,10 @@ def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
     B, _, H, W = x.shape
     if mode == "bf16":
         hid = torch.empty((B, H, W, p["hidden"]), dtype=torch.bfloat16, device=x.device)      # stays channels-last bf16
-        ops.conv_bn_relu_bf16(ops.nchw_to_nhwc_bf16([x]), p["img1"], p["b1"], p["hidden"], 9, relu=True, out_nhwc=hid, want_nchw=False)
+        x_nhwc = nhwc_of(x)      # left by the fusion module's last convolution, if `x` is still its output
+        if x_nhwc is None:
+            x_nhwc = ops.nchw_to_nhwc_bf16([x])
+        ops.conv_bn_relu_bf16(x_nhwc, p["img1"], p["b1"], p["hidden"], 9, relu=True, out_nhwc=hid, want_nchw=False)
         both = ops.conv_bn_relu_bf16(hid, p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
     else:       # fp32 accuracy: the same two launches on split fp16 operands, fp32 tensors in between
         x_split, stat = ops.nchw_to_nhwc_split([x])
@@ -217,6 +227,31 @@ def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
 
 
 _LOGITS_ATTR = "_b200bev_logits"
+_NHWC_ATTR = "_b200bev_nhwc"
+
+
+def attach_nhwc(x: torch.Tensor, twin: torch.Tensor) -> torch.Tensor:
+    """Remembers, ON an fp32 NCHW activation, its channels-last bf16 form written by the same convolution launch (the same
+    note mechanism as `attach_logits`: an edited or replaced tensor carries no valid note)."""
+    try:
+        setattr(x, _NHWC_ATTR, (twin, x._version))
+    except RuntimeError:
+        pass
+    return x
+
+
+def nhwc_of(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """The channels-last bf16 form of `x` if `x` is still, bit for bit, the tensor the convolution wrote; else None."""
+    note = getattr(x, _NHWC_ATTR, None)
+    if note is None:
+        return None
+    twin, version = note
+    try:
+        same = x._version == version
+    except RuntimeError:
+        same = False
+    B, Cc, H, W = x.shape
+    return twin if same and tuple(twin.shape) == (B, H, W, Cc) and twin.device == x.device else None
 
 
 def attach_logits(heatmap: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:

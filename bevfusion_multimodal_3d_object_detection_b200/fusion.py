@@ -171,7 +171,7 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         ops.bilinear_resize_nhwc_bf16(proj, (H, W), out=cat, c_offset=off_cam)               # src/fusion.py:242-247
     if fork:
         fork.join()
-    return conv_blocks.run(module.bev_fusion, nhwc=cat)                                      # :292-295
+    return conv_blocks.run(module.bev_fusion, nhwc=cat, note_nhwc=True)                      # :292-295
 
 
 PARALLEL_MAX_PIXELS = 32 * 50 * 50

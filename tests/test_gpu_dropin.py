@@ -350,6 +350,31 @@ def test_parallel_branches_of_the_fused_path_change_nothing(cuda):
             assert all(torch.equal(o, outs[1]) for o in outs), rep
 
 
+def test_head_starts_from_the_channels_last_twin_of_the_fusion_output(cuda):
+    """bf16 path: bev_fusion's last convolution also writes its result channels-last bf16 and the returned tensor remembers it;
+    the head then skips its layout pass.  Same outputs as from a copy of the tensor (no note), and an edited tensor loses the note."""
+    from bevfusion_multimodal_3d_object_detection_b200 import conv_blocks
+
+    torch.manual_seed(11)
+    fus = b200bev.FlexibleBEVFusion(use_camera=True, use_lidar=True, use_radar=False, camera_channels=64, lidar_channels=128,
+                                    bev_h=50, bev_w=50, bev_channels=64).eval().to(cuda)
+    head = b200bev.CenterNetHead(in_channels=64, num_classes=10, head_conv=64)
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in syn.head_weights(717, 64, 64, 10, out_scale=0.3).items()})
+    head = head.eval().to(cuda)
+    fus.b200_precision = head.b200_precision = "bf16"
+    cam = torch.from_numpy(syn.camera_features(735, 2, n_cam=6, channels=64, h=28, w=50)).to(cuda)
+    with torch.no_grad():
+        bev = fus(camera_features=cam, lidar_features=torch.rand(2, 128, device=cuda))
+        twin = conv_blocks.nhwc_of(bev)
+        assert twin is not None and torch.equal(twin, bev.permute(0, 2, 3, 1).to(torch.bfloat16))
+        with_note = head(bev)
+        without = head(bev.clone())
+        for k in with_note:
+            assert torch.equal(with_note[k], without[k]), k
+        bev.mul_(2.0)                                    # edited in place: the note no longer describes the tensor
+        assert conv_blocks.nhwc_of(bev) is None
+
+
 def test_graphed_step_replays_the_chain_bit_for_bit(cuda):
     """runtime.GraphedStep: fusion -> head -> fixed-size decode captured in one CUDA graph; new inputs are copied into
     the captured tensors, a replay gives what the eager calls give."""
