@@ -205,23 +205,34 @@ def fusion_forward(module: nn.Module, camera_features=None, lidar_features=None,
         out = _fused_bf16_path(module, camera_features, lidar_features, radar_features)
         if out is not None:
             return out
-    parts = []
-    B = None
-    if module.use_camera and camera_features is not None:
-        B = camera_features.shape[0]
-        parts.append(camera_branch(module, camera_features, torch_graph))
-    if module.use_lidar and lidar_features is not None:
-        B = lidar_features.shape[0] if B is None else B
-        parts.append(lidar_branch(module, lidar_features, torch_graph))
-    if module.use_radar and radar_features is not None:
-        B = radar_features.shape[0] if B is None else B
-        if torch_graph:
-            r = module.radar_proj(radar_features).view(B, module.bev_channels, 1, 1)
-            parts.append(module.radar_refine(r.expand(B, module.bev_channels, module.bev_h, module.bev_w)))    # :274-281
-        else:
-            parts.append(radar_branch(module, radar_features))
-    if not parts:
+    use = [module.use_camera and camera_features is not None, module.use_lidar and lidar_features is not None,
+           module.use_radar and radar_features is not None]
+    if not any(use):
         raise ValueError("No modality features provided")              # :289
+    first = next(t for t, u in zip((camera_features, lidar_features, radar_features), use) if u)
+    B = first.shape[0]
+    # kernel path on CUDA: the lidar and radar branches next to the camera branch (side streams, see _fused_bf16_path); their
+    # results are read on the caller's stream after the join
+    fork = None
+    if not torch_graph and first.is_cuda and sum(use) > 1 and _parallel_branches(module, B * module.bev_h * module.bev_w):
+        fork = runtime.BranchStreams(first.device)
+    side = (lambda i: fork.fork(i)) if fork else (lambda i: contextlib.nullcontext())
+    cam = lidar = radar = None
+    if use[1]:
+        with (side(0) if use[0] else contextlib.nullcontext()):
+            lidar = lidar_branch(module, lidar_features, torch_graph)
+    if use[2]:
+        with (side(1) if (use[0] or use[1]) else contextlib.nullcontext()):
+            if torch_graph:
+                r = module.radar_proj(radar_features).view(B, module.bev_channels, 1, 1)
+                radar = module.radar_refine(r.expand(B, module.bev_channels, module.bev_h, module.bev_w))       # :274-281
+            else:
+                radar = radar_branch(module, radar_features)
+    if use[0]:
+        cam = camera_branch(module, camera_features, torch_graph)
+    if fork:
+        fork.join()
+    parts = [p for p in (cam, lidar, radar) if p is not None]          # the reference's order: camera, lidar, radar
     if torch_graph:
         return module.bev_fusion(torch.cat(parts, dim=1))              # :292-295
     return _stack(module, module.bev_fusion, parts)                    # the concat happens inside the layout kernel
