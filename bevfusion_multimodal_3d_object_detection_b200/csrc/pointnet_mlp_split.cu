@@ -456,24 +456,33 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
               int c_n = __shfl_down_sync(FULL_MASK, c_cur, 1);
               const int c_first_next = __shfl_sync(FULL_MASK, c_nxt, 0);
               if (lane == 31) c_n = col0 + 32 < kPx ? c_first_next : INT_MIN;   // the tile's last slot ends a run
-              const unsigned ends = __ballot_sync(FULL_MASK, c_cur != c_n);
+              // the same word in every lane: broadcast through a shuffle so that the branches on its bits are provably warp-uniform
+              const unsigned ends = __shfl_sync(FULL_MASK, __ballot_sync(FULL_MASK, c_cur != c_n), 0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                m = fmaxf(m, __uint_as_float(r[j]));
-                if (ends & (1u << j)) {                               // the same word in every lane
-                  const int cj = __shfl_sync(FULL_MASK, c_cur, j);
-                  if (cj >= 0) {
-                    const float val = fmaxf(fmaf(m, unscale, bias), 0.f);
-                    if (val > 0.f) {
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                if (((ends >> j4) & 0xfu) == 0u) {                    // no run ends in these four slots: most groups
+                  m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]))),
+                            fmaxf(__uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3])));
+                  continue;
+                }
+#pragma unroll
+                for (int j = j4; j < j4 + 4; ++j) {
+                  m = fmaxf(m, __uint_as_float(r[j]));
+                  if (ends & (1u << j)) {
+                    const int cj = __shfl_sync(FULL_MASK, c_cur, j);
+                    if (cj >= 0) {
+                      // zeros are stored like any value (the canvas starts at zero): a store that depends on the value would be a
+                      // divergent branch per run end
+                      const float val = fmaxf(fmaf(m, unscale, bias), 0.f);
                       float* dst = canvas + (size_t)cj * a.Cout;      // 32 lanes: 128 contiguous bytes of the cell's row
                       // a run touching the tile's first or last slot may go on in a neighbouring tile: atomic; else the only writer
                       if (first_run || col0 + j == kPx - 1) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(val));
                       else *dst = val;
                     }
+                    gmax = fmaxf(gmax, m);                            // the global maximum is the maximum of the runs' maxima
+                    m = -INFINITY;
+                    first_run = false;
                   }
-                  gmax = fmaxf(gmax, m);                              // the global maximum is the maximum of the runs' maxima
-                  m = -INFINITY;
-                  first_run = false;
                 }
               }
             }
