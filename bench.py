@@ -514,6 +514,20 @@ def kernel_rooflines(hp: HotPath, peaks, fp32_peak, flush):
                 put("lidar_prepare_bin_sort", med_ms(lambda: ops.lidar_prepare_bin_sort(raw, offs, N, G, G, syn.PC_RANGE, max_frame_rows=rows)),
                     "hbm", F * (16.0 * (rows + N) + 24.0 * N + 4.0 * (HW + 1)), "range filter + compaction + padding + bin-and-sort, one launch")
                 del raw
+            try:
+                # N2: the dense layers behind the encoder (FlexibleBEVFusion.lidar_init; the second layer's weight is the largest
+                # single read of the step) as the step runs them: tensor cores at fp32 accuracy from the split-fp16 image
+                from bevfusion_multimodal_3d_object_detection_b200.fusion import lidar_init_dense
+                fus = hp.chain.fusion
+                l0, l2 = fus.lidar_init[0], fus.lidar_init[2]
+                gf = torch.rand((F, l0.in_features), device=dev)
+                put("lidar_init", med_ms(lambda: lidar_init_dense(fus, gf)), "hbm",
+                    4.0 * (l0.weight.numel() + l2.weight.numel() + l0.out_features + 2 * l2.out_features
+                           + F * (l0.in_features + 2 * l0.out_features + l2.out_features)),
+                    f"Linear({l0.in_features},{l0.out_features}) + ReLU + Linear({l2.in_features},{l2.out_features}), two launches")
+                del gf
+            except Exception as e:          # a chain without a lidar branch
+                out["lidar_init"] = {"error": str(e)[:120]}
         if wl["radar"]:
             radars = [hp.inputs[f"radar{i}"] for i in range(5)]
             put("radar_encode", med_ms(lambda: hp.chain.radar_encoder(radars)), "fp32_fma",

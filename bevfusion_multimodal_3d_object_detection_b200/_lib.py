@@ -61,6 +61,10 @@ PROTOTYPES = {
                                              _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "b200bev_dense_layer": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p]),
     "b200bev_lidar_init": (_i, [_p, _i, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "b200bev_dense_pack_split_bytes": (_z, [_i, _i]),
+    "b200bev_dense_pack_split": (_i, [_p, _p, _i, _i, _p, _z, _p]),
+    "b200bev_dense_layer_split": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
+    "b200bev_lidar_init_split": (_i, [_p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p]),
     "b200bev_conv_pack_bytes": (_z, [_i, _i, _i]),
     "b200bev_conv_pack_bf16": (_i, [_p, _i, _i, _i, _p, _z, _p]),
     "b200bev_nchw_to_nhwc_bf16": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
@@ -120,7 +124,7 @@ KERNELS_PER_CALL = {
     "b200bev_abi_version": 0, "b200bev_error_string": 0, "b200bev_device_info": 0, "b200bev_lidar_prepare_workspace_bytes": 0,
     "b200bev_pointnet_pack_bf16_bytes": 0, "b200bev_centernet_workspace_bytes": 0, "b200bev_conv_pack_bytes": 0,
     "b200bev_pointnet_pack_split_bytes": 0, "b200bev_pointnet_split_workspace_bytes": 0, "b200bev_conv_pack_split_bytes": 0,
-    "b200bev_conv_pack_split": 2,
+    "b200bev_conv_pack_split": 2, "b200bev_dense_pack_split_bytes": 0, "b200bev_lidar_init_split": 2,
     "b200bev_radar_encode": 2, "b200bev_lidar_init": 2, "b200bev_lidar_prepare": 1,
     "b200bev_pointnet_encode_split": 5,       # per pass: layer 1 + four GEMM launches (one pass up to ~1M points)
     "b200bev_pointnet_pack_split": 2,

@@ -40,6 +40,19 @@ __device__ __forceinline__ void bulk_copy_global_to_shared(void* dst, const void
                "l"(src), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
+// the same copy with an L2 eviction policy for the lines it reads (`l2_evict_first_policy()`: data that is read exactly once)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_copy_global_to_shared_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                                uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+               : "memory");
+}
 // One lane of a fully converged warp.  Issue bulk copies from inside `if (elect_one())` with the WHOLE warp running
 // the surrounding loop: the copy's operands then live in uniform registers.  Issued from a lane that diverged long
 // before (`if (lane == 0) { loop }`), every UBLKCP sits in an ELECT + R2UR.BROADCAST waterfall and costs ~380 clk

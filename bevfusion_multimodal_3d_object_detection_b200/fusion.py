@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import conv_blocks, ops, runtime
 from .encoders import load_config
-from .weight_cache import mark_dirty, wants_autograd
+from .weight_cache import mark_dirty, state_token, wants_autograd
 
 
 def _conv_bn_relu(c_in: int, c_out: int, k: int) -> List[nn.Module]:
@@ -97,6 +97,31 @@ def radar_branch(module: nn.Module, radar_features: torch.Tensor, out_nhwc: Opti
     return _stack(module, module.radar_refine, [full])                                                         # :281
 
 
+DENSE_TC_MIN_BATCH = 1      # measured on B200 (512 -> 80000): 33 us at batch 1, 39 at 32 against 41 and 98 for the FFMA kernels
+
+
+def lidar_init_dense(module: nn.Module, lidar_features: torch.Tensor) -> torch.Tensor:
+    """`module.lidar_init(lidar_features)` (src/fusion.py:144-148, :258) on the dense kernels.  The 164 MB second layer runs
+    on the tensor cores at fp32 accuracy (`b200bev_lidar_init_split`) from a split-fp16 image of the weight — as large as the
+    weight itself, cached beside the module like the convolutions' stage images (weight_cache: rebuilt when a parameter
+    changes).  Shapes without a tensor-core form and `module.b200_dense_tc = False` (no second copy of the weight on the
+    device) take the FFMA kernels, which read torch's own weight."""
+    l0, l2 = module.lidar_init[0], module.lidar_init[2]
+    B = int(lidar_features.shape[0])
+    if B >= DENSE_TC_MIN_BATCH and getattr(module, "b200_dense_tc", True) and lidar_features.is_cuda:
+        seq = module.lidar_init
+        key = state_token(seq, lidar_features.device)
+        caches = seq.__dict__.setdefault("_b200bev_conv_cache", {})
+        cache = caches.get("dense")
+        if cache is None or cache["key"] != key:
+            cache = {"key": key, "image": ops.dense_pack_split(l2.weight.to(lidar_features.device),
+                                                                None if l2.bias is None else l2.bias.to(lidar_features.device))}
+            caches["dense"] = cache
+        if cache["image"] is not None:
+            return ops.lidar_init_split(lidar_features, l0.weight, l0.bias, cache["image"], l2.out_features)
+    return ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias)
+
+
 def lidar_branch(module: nn.Module, lidar_features: torch.Tensor, torch_graph: bool = False) -> torch.Tensor:
     """src/fusion.py:258-262: lidar_init (two dense layers, the second a 164 MB weight) -> (B,128,s,s) ->
     conv+BN+ReLU -> x2 bilinear upsample -> conv+BN+ReLU.  Eval mode on CUDA: the dense layers run on
@@ -106,8 +131,7 @@ def lidar_branch(module: nn.Module, lidar_features: torch.Tensor, torch_graph: b
     hidden = module.lidar_init[2].out_features // (s * s)
     if torch_graph:
         return module.lidar_upsample(module.lidar_init(lidar_features).view(B, hidden, s, s))
-    l0, l2 = module.lidar_init[0], module.lidar_init[2]
-    x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s, s)
+    x = lidar_init_dense(module, lidar_features).view(B, hidden, s, s)
     up = module.lidar_upsample
     mode = conv_blocks.conv_mode(module)
     if mode != "torch" and conv_blocks.supported(up) and hidden % 64 == 0:
@@ -152,8 +176,7 @@ def _fused_bf16_path(module: nn.Module, camera_features, lidar_features, radar_f
         with (fork.fork(0) if fork and use[0] else contextlib.nullcontext()):
             s0 = lidar_start_size(module)
             hidden = module.lidar_init[2].out_features // (s0 * s0)
-            l0, l2 = module.lidar_init[0], module.lidar_init[2]
-            x = ops.lidar_init(lidar_features, l0.weight, l0.bias, l2.weight, l2.bias).view(B, hidden, s0, s0)
+            x = lidar_init_dense(module, lidar_features).view(B, hidden, s0, s0)
             conv_blocks.run(module.lidar_upsample, [x], out_nhwc=cat, c_offset=off_lidar)    # :258-262
             del x
     if use[2]:

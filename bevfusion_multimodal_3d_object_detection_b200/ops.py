@@ -370,6 +370,50 @@ def lidar_init(feats: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torc
     return (out, hid) if return_hidden else out
 
 
+def dense_pack_split(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """(O,K) fp32 nn.Linear weight (+ bias) on the device -> the split-fp16 stage image of b200bev_dense_layer_split
+    (uint8 tensor of the weight's own size), or None when the shape has no tensor-core form (O % 128, K % 64)."""
+    weight = _need_cuda(weight.detach(), "weight")
+    O, K = (int(v) for v in weight.shape)
+    n = _lib.lib().b200bev_dense_pack_split_bytes(O, K)
+    if n == 0:
+        return None
+    if bias is not None:
+        bias = _need_cuda(bias.detach(), "bias")
+    img = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.lib().b200bev_dense_pack_split(_ptr(weight), _ptr(bias) if bias is not None else None, O, K,
+                                                       _ptr(img), n, _stream(weight.device)))
+    return img
+
+
+def dense_layer_split(x: torch.Tensor, image: torch.Tensor, out_features: int, relu: bool = False) -> torch.Tensor:
+    """act(x W^T + b) from a `dense_pack_split` image: fp32 accuracy (1e-5) on the tensor cores."""
+    x = _need_cuda(x, "x")
+    B, K = (int(v) for v in x.shape)
+    out = torch.empty((B, out_features), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().b200bev_dense_layer_split(_ptr(x), B, K, _ptr(image), int(out_features), int(bool(relu)),
+                                                        _ptr(out), _stream(x.device)))
+    return out
+
+
+def lidar_init_split(feats: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, image2: torch.Tensor, out_features: int) -> torch.Tensor:
+    """`lidar_init` with the second layer read from its `dense_pack_split` image (b200bev_lidar_init_split)."""
+    feats = _need_cuda(feats, "lidar_features")
+    w1, b1 = _need_cuda(w1.detach(), "w1"), _need_cuda(b1.detach(), "b1")
+    B, K = (int(v) for v in feats.shape)
+    hidden = int(w1.shape[0])
+    if w1.shape[1] != K:
+        raise RuntimeError(f"lidar_init: shapes do not chain: x {tuple(feats.shape)}, w1 {tuple(w1.shape)}")
+    hid = torch.empty((B, hidden), dtype=torch.float32, device=feats.device)
+    out = torch.empty((B, int(out_features)), dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().b200bev_lidar_init_split(_ptr(feats), B, K, _ptr(w1), _ptr(b1), hidden, _ptr(image2),
+                                                       int(out_features), _ptr(hid), _ptr(out), _stream(feats.device)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # N1: convolution blocks on tcgen05 (bf16, parity 1e-2)
 # ------------------------------------------------------------------------------------------------

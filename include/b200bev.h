@@ -266,6 +266,23 @@ B200BEV_API int b200bev_lidar_init(const float* lidar_features, int B, int K, co
                        int hidden, const float* w2, const float* b2, int O,
                        float* hidden_ws, float* out, void* stream);
 
+/* The same dense layer at fp32 accuracy ON THE TENSOR CORES (parity 1e-5): every fp32 product as three fp16 tcgen05
+ * products with fp32 accumulation, from a weight image of the fp32 weight's size — for the 164 MB lidar_init.2 at batch
+ * 9..64, where the FFMA form is paced by the FMA pipe instead of by the one read of the weight.
+ * b200bev_dense_pack_split: weight (O,K) f32 (torch's nn.Linear layout), bias (O) or NULL -> image (once per weight
+ *   update); O % 128 == 0 and K % 64 == 0, else b200bev_dense_pack_split_bytes is 0 and the calls return UNSUPPORTED.
+ * b200bev_dense_layer_split: out (B,O) = act(x W^T + bias) from the image; any B (64 rows of x per launch).
+ * b200bev_lidar_init_split: b200bev_lidar_init with the second layer (src/fusion.py:147) read from its image.
+ */
+B200BEV_API size_t b200bev_dense_pack_split_bytes(int O, int K);
+B200BEV_API int b200bev_dense_pack_split(const float* weight, const float* bias, int O, int K,
+                             void* image, size_t image_bytes, void* stream);
+B200BEV_API int b200bev_dense_layer_split(const float* x, int B, int K, const void* image, int O,
+                              int relu, float* out, void* stream);
+B200BEV_API int b200bev_lidar_init_split(const float* lidar_features, int B, int K, const float* w1, const float* b1,
+                             int hidden, const void* image2, int O,
+                             float* hidden_ws, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * N1  the convolution blocks between the hot-path kernels, bf16 on tcgen05 tensor cores (parity 1e-2).
  * b200bev_conv_bn_relu_bf16: Conv2d(k=3, padding=1 | k=1) [+ BatchNorm2d eval, folded by the caller] [+ ReLU] as one

@@ -123,6 +123,13 @@ def main():
             print(f"lidar_init batch {Bd:3d} (both layers) median {med * 1e3:8.1f} us  best {best * 1e3:8.1f} us | 512->80000 alone "
                   f"median {med2 * 1e3:8.1f} us  best {best2 * 1e3:8.1f} us  {by / med2 / 1e6:8.1f} GB/s  "
                   f"{2.0 * Bd * 512 * 80000 / med2 / 1e9:6.2f} TFLOP/s", flush=True)
+        img = ops.dense_pack_split(w2, b2)
+        for Bd in sorted({1, 8, 16, F, 64}):
+            hid = torch.rand((Bd, 512), device=dev, generator=g)
+            med2, best2 = timeit(lambda: ops.dense_layer_split(hid, img, 80000), reps=20)
+            by = 4.0 * (80000 * 512 + 2 * 80000 + Bd * (512 + 80000))
+            print(f"dense_layer_split batch {Bd:3d} 512->80000 (tensor cores, fp32 accuracy) median {med2 * 1e3:8.1f} us  best "
+                  f"{best2 * 1e3:8.1f} us  {by / med2 / 1e6:8.1f} GB/s", flush=True)
         ref = x @ w1.t()
         torch.backends.cuda.matmul.allow_tf32 = False
         med3, _ = timeit(lambda: torch.addmm(b2, torch.relu(torch.addmm(b1, x, w1.t())), w2.t()), reps=20)

@@ -161,6 +161,12 @@ def run_all(tc: bool = False, big: bool = False):
         assert rel(cv16.cpu().numpy(), orc.conv_bn_relu(xin, sd["w"], sd["b"])) < 1e-2
         ops.conv_bn_relu_bf16(nhwc, ops.conv_pack(to(sd["w1"])), None, 70, 1, relu=False)
         done.append("conv3x3_tc_halo / conv_tc_ws")
+        for (B, K_, O) in [(5, 128, 384), (33, 64, 128)]:
+            w, b = syn.linear_weights(51 + B, K_, O)
+            x = syn.global_features(53, B, K_)
+            y = ops.dense_layer_split(to(x), ops.dense_pack_split(to(w), to(b)), O, relu=True)
+            assert rel(y.cpu().numpy(), orc.dense_layer(x, w, b, relu=True)) < 1e-5
+        done.append("dense_split_tc (fp32 accuracy on tcgen05)")
     torch.cuda.synchronize()
     return done
 

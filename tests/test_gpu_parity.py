@@ -767,6 +767,60 @@ def test_lidar_init_vs_reference_golden(cuda, golden):
     assert max_rel(rp.cpu().numpy(), g["radar_proj"]) < FP32_TOL
 
 
+@pytest.mark.parametrize("B,K,O,relu,bias", [
+    (32, 512, 80000, False, True),      # lidar_init.2 at the bench batch
+    (9, 512, 80000, False, True),       # the smallest batch the module sends here: 16-row operand, 7 padding rows
+    (64, 512, 12800, True, True),       # 64-row operand, ring of 3
+    (70, 64, 128, True, False),         # two launches (64 + 6 rows), one tile, one k block, no bias
+    (17, 1024, 640, False, True),       # K = 1024 (lidar_init.0's shape class), 5 tiles
+    (1, 256, 256, True, True),          # one row
+    (32, 512, 128 * 50 * 50, False, True),   # the stress configuration's lidar_init.2 (lidar_start_size = 50): 655 MB image
+])
+def test_dense_layer_split_vs_oracle(cuda, B, K, O, relu, bias):
+    """The tensor-core dense layer (three fp16 products per fp32 product) against the float64 oracle at the fp32 bound."""
+    g = np.random.default_rng(B * 1000 + O)
+    x = g.standard_normal((B, K)).astype(np.float32)            # both signs: the scale comes from max|x|
+    x[0, :3] = (0.0, 1e-30, -1e-30)
+    w, b = syn.linear_weights(B + K + O, K, O)
+    w[5] = 0.0                                                  # an all-zero row keeps scale 1
+    w[7] *= 1e4                                                 # rows of very different magnitude: the scale is per row
+    img = ops.dense_pack_split(dev_t(w, cuda), dev_t(b, cuda) if bias else None)
+    assert img is not None and img.numel() == O * K * 4 + 8 * O
+    got = ops.dense_layer_split(dev_t(x, cuda), img, O, relu=relu).cpu().numpy()
+    assert got.shape == (B, O)
+    ref = orc.dense_layer(x, w, b if bias else None, relu=relu)
+    keep = np.ones(O, bool)
+    keep[7] = False                                             # the big row has its own maximum
+    assert max_rel(got[:, keep], ref[:, keep]) < FP32_TOL
+    assert max_rel(got[:, 7], ref[:, 7]) < FP32_TOL
+    again = ops.dense_layer_split(dev_t(x, cuda), img, O, relu=relu).cpu().numpy()
+    np.testing.assert_array_equal(got, again)                   # no atomics, no split-K: the same bits every run
+
+
+def test_dense_split_shapes_without_a_tensor_core_form(cuda):
+    w, b = syn.linear_weights(1, 100, 33)
+    assert ops.dense_pack_split(dev_t(w, cuda), dev_t(b, cuda)) is None
+    w, b = syn.linear_weights(2, 64, 100)
+    assert ops.dense_pack_split(dev_t(w, cuda), dev_t(b, cuda)) is None
+
+
+def test_lidar_init_split_vs_reference_golden(cuda, golden):
+    """lidar_init with its second layer on the tensor cores against what the reference's FlexibleBEVFusion.lidar_init
+    produced (3 frames), and against the FFMA kernels on a 32-frame batch."""
+    g = golden("bev_glue")
+    w1, b1 = syn.linear_weights(701, 1024, 512)
+    w2, b2 = syn.linear_weights(702, 512, 128 * 25 * 25)
+    feats = syn.global_features(704, 3, 1024)
+    d = [dev_t(t, cuda) for t in (w1, b1, w2, b2)]
+    img = ops.dense_pack_split(d[2], d[3])
+    out = ops.lidar_init_split(dev_t(feats, cuda), d[0], d[1], img, 128 * 25 * 25)
+    assert np.abs(out.cpu().numpy()[:, ::16] - g["lidar_init_sub"]).max() < FP32_TOL * float(g["lidar_init_absmax"])
+    feats32 = dev_t(syn.global_features(706, 32, 1024), cuda)
+    a = ops.lidar_init_split(feats32, d[0], d[1], img, 128 * 25 * 25)
+    ref = ops.lidar_init(feats32, *d)
+    assert float((a - ref).abs().max()) < FP32_TOL * float(ref.abs().max())
+
+
 # ------------------------------------------------------------------------------------------------ N1: sigmoid fused into the decode
 def test_decode_from_logits_vs_reference_head_golden(cuda, golden):
     g = golden("bev_glue")
