@@ -486,6 +486,39 @@ def test_eval_mode_under_autograd_stays_differentiable(cuda):
     assert not frozen["heatmap"].requires_grad and torch.equal(frozen["heatmap"], fast["heatmap"])
 
 
+def test_lidar_init_on_the_tensor_cores_follows_the_module(cuda):
+    """`lidar_init` of the fusion module: the second layer runs from its split-fp16 image on the tensor cores (every batch
+    size), equals the module's own torch layers at the fp32 bound, follows weight updates, and `b200_dense_tc = False` keeps
+    the FFMA kernels on torch's own weight."""
+    from bevfusion_multimodal_3d_object_detection_b200 import _lib
+    from bevfusion_multimodal_3d_object_detection_b200.fusion import lidar_init_dense
+    torch.manual_seed(5)
+    fus = b200bev.FlexibleBEVFusion(use_camera=False, use_lidar=True, use_radar=False, lidar_channels=1024, bev_h=50, bev_w=50,
+                                    bev_channels=256).eval().to(cuda)
+    _lib.enable_call_counting()
+    with torch.no_grad():
+        for B in (1, 8, 32, 70):
+            x = torch.rand(B, 1024, device=cuda)
+            ref = fus.lidar_init(x)
+            _lib.reset_call_counts()
+            got = lidar_init_dense(fus, x)
+            assert _lib._call_counts.get("b200bev_lidar_init_split", 0) == 1 and "b200bev_lidar_init" not in _lib._call_counts
+            assert float((got - ref).abs().max()) < FP32_TOL * float(ref.abs().max())
+        x = torch.rand(32, 1024, device=cuda)
+        before = lidar_init_dense(fus, x)
+        fus.lidar_init[2].weight.mul_(2.0)                      # an in-place update: the image is rebuilt
+        fus.lidar_init[2].bias.zero_()
+        after = lidar_init_dense(fus, x)
+        ref = fus.lidar_init(x)
+        assert float((after - ref).abs().max()) < FP32_TOL * float(ref.abs().max())
+        assert float((after - before).abs().max()) > 0.1 * float(ref.abs().max())
+        fus.b200_dense_tc = False
+        _lib.reset_call_counts()
+        ffma = lidar_init_dense(fus, x)
+        assert _lib._call_counts.get("b200bev_lidar_init", 0) == 1 and "b200bev_lidar_init_split" not in _lib._call_counts
+        assert float((ffma - ref).abs().max()) < FP32_TOL * float(ref.abs().max())
+
+
 def test_cache_invalidation_after_data_writes(cuda):
     """`.data` writes do not bump a tensor's version counter: `invalidate_cache` is the documented call after them."""
     layers = syn.mlp_weights(101, syn.LIDAR_DIMS)
