@@ -149,6 +149,9 @@ def main():
             img = ops.conv_pack(w)
             med, best = timeit(lambda: ops.conv_bn_relu_bf16(nhwc, img, b, cout, k * k), reps=10)
             medl, _ = timeit(lambda: ops.nchw_to_nhwc_bf16([x]), reps=10)
+            nxt = torch.empty((F, H, W, cout), dtype=torch.bfloat16, device=dev)     # channels-last bf16 only: what the step runs
+            medn, _ = timeit(lambda: ops.conv_bn_relu_bf16(nhwc, img, b, cout, k * k, out_nhwc=nxt, want_nchw=False), reps=10)
+            print(f"conv {name:36s} channels-last bf16 output only {medn * 1e3:8.1f} us ({2.0 * F * H * W * cout * cin * k * k / medn / 1e9:7.1f} TFLOP/s)", flush=True)
             xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             wb = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             bb = b.to(torch.bfloat16)

@@ -858,6 +858,9 @@ def test_decode_from_logits_vs_reference_head_golden(cuda, golden):
     (5, 5, 6, 64, 130, 3, True),         # whole frames smaller than a tile; a 2-channel last channel tile
     (3, 1, 1, 64, 1, 3, False),          # one pixel, one output channel: every tap but the centre is padding
     (1, 1, 7, 128, 5, 1, True),          # a single image row through the 1x1 form
+    (8, 57, 100, 512, 256, 1, True),     # camera_proj's 1x1 at its own size: several pixel tiles per CTA, both co tiles
+    (4, 50, 50, 256, 192, 1, False),     # 1x1 with a half-empty second co tile
+    (6, 40, 40, 192, 128, 1, True),      # 1x1, three k chunks, one co tile
 ])
 def test_conv_bn_relu_tcgen05(cuda, B, H, W, Cin, Cout, k, relu):
     g = np.random.default_rng(Cin * 7 + Cout)
