@@ -414,6 +414,68 @@ __device__ __forceinline__ uint64_t kmajor_sw128_desc_at(uint32_t saddr, int bas
   return d;
 }
 
+// ---- CTA-pair (cta_group::2) helpers, as in pointnet_mlp_tc.cu ----
+__device__ __forceinline__ uint32_t cluster_ctarank_conv() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_conv() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (release: what this thread wrote before is
+// visible to whoever the barrier lets through)
+__device__ __forceinline__ void mbarrier_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+// the same without release semantics: the relay forwards the completion of a bulk copy and has written nothing itself
+__device__ __forceinline__ void mbarrier_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    tc_commit_to(bar);
+  } else {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_addr(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+// CG = 2: one instruction of the leader drives both CTAs: M = 256, each CTA its own 128 rows of A and of D and half of B's rows
+template <int CG>
+__device__ __forceinline__ void umma_ss_cg(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    umma_ss(d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// CG = 2: a CTA PAIR (thread-block cluster of two) computes 256 output channels x N pixels per tile with tcgen05.mma.cta_group::2.
+// Each CTA keeps its own co tile's weight ring (the A operand, 128 rows) and HALF of the pixel block (the B operand: the rows of
+// N/2 output columns plus the halo), so the tensor core reads 8 KB of shared memory per 128 clk and SM instead of 12, and a CTA
+// copies 0.7 of the pixel rows it copied alone — shared-memory bandwidth was what held the single-CTA kernel at 0.78 of the bf16
+// peak.  The leader (cluster rank 0) issues every MMA; the follower's producers report their half block to the
+// leader's `peer_blk`, its otherwise idle MMA warp relays the completion of its weight stages to `peer_a` (a bulk copy can
+// only signal a barrier of the CTA it writes to), tcgen05.commit arrives on the barriers of BOTH CTAs, and both CTAs' epilogue
+// warps hand the accumulator halves back to the leader.
+template <int CG>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvArgs a, HaloGeom geo, int base_offset_mode /* 0: see kmajor_sw128_desc_at */) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* blocks = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // [2][kHaloBlock]
@@ -425,63 +487,83 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
   uint64_t* full_blk = bars + 2 * kRing;       // [2]
   uint64_t* empty_blk = bars + 2 * kRing + 2;  // [2]
   uint64_t* acc_full = bars + 2 * kRing + 4;   // [2]
-  uint64_t* acc_empty = bars + 2 * kRing + 6;  // [2]
+  uint64_t* acc_empty = bars + 2 * kRing + 6;  // [2] one arrival per epilogue warp of the pair, at the leader
+  uint64_t* peer_a = bars + 2 * kRing + 8;     // [kRing] CG = 2, leader: the follower's weight stage has landed (relayed)
+  uint64_t* peer_blk = bars + 3 * kRing + 8;   // [2]     CG = 2, leader: the follower's half block has landed (its producer warps)
   __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = CG == 2 ? cluster_ctarank_conv() : 0u;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (warp == 12) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   if (tid == 0) {
     for (int s = 0; s < kRing; ++s) {
       mbarrier_init(&full_a[s], 1);
       mbarrier_init(&empty_a[s], 1);
+      mbarrier_init(&peer_a[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbarrier_init(&full_blk[s], 8);
       mbarrier_init(&empty_blk[s], 1);
       mbarrier_init(&acc_full[s], 1);
-      mbarrier_init(&acc_empty[s], 4);
+      mbarrier_init(&acc_empty[s], 4 * CG);
+      mbarrier_init(&peer_blk[s], 8);
     }
     mbarrier_init_fence();
   }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_conv();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
   const int W1 = a.W + 1, HW = a.H * a.W;
   const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
   const int ncc = conv_chunks(a);
-  const int n_tiles = a.B * geo.tiles_per_frame * n_co_tiles;
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  // tile -> (co tile, frame, first flat index): the co tiles of one pixel tile are neighbours in the grid (shared pixels in L2)
+  // a tile is CG co tiles x N pixels, walked by a cluster of CG CTAs in lock step (host: n_co_tiles % CG == 0)
+  const int n_co_groups = n_co_tiles / CG;
+  const int n_tiles = a.B * geo.tiles_per_frame * n_co_groups;
+  const int first_tile = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
+  const int my_tiles = (n_tiles - first_tile + tile_step - 1) / tile_step;
+  // tile -> (this CTA's co tile, frame, first flat index): the co groups of one pixel tile are neighbours in the grid (shared pixels in L2)
   auto tile_coords = [&](int tile, int& co_tile, int& b, int& n0) {
-    co_tile = tile % n_co_tiles;
-    const int pt = tile / n_co_tiles;
+    co_tile = (tile % n_co_groups) * CG + (int)rank;
+    const int pt = tile / n_co_groups;
     b = pt / geo.tiles_per_frame;
     n0 = (pt - b * geo.tiles_per_frame) * geo.N;
   };
+  const int n_half = geo.N / CG;                       // output columns whose pixel rows this CTA holds
+  const int q_rows = n_half + 2 * W1 + 2;              // rows of this CTA's pixel block
 
   if (warp < 8) {
     // ---- pixel blocks: one per (tile, 64-channel chunk) ----
     const int row0 = tid >> 3, chunk = tid & 7;
     const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
     const int n_blocks = my_tiles * ncc;
-    int tile = blockIdx.x, cc = 0;
+    int tile = first_tile, cc = 0;
     long long goff[kHaloRowsPerThread];   // element offset of this thread's piece of padded row q = row0 + 32 j, or -1: zeros
     for (int bi = 0; bi <= n_blocks; ++bi) {
       if (bi >= 1) {
         cp_async_wait_group<0>();      // block bi-1 has landed (this thread's part)
         fence_proxy_async_shared();
         __syncwarp();
-        if (lane == 0) mbarrier_arrive(&full_blk[(bi - 1) & 1]);
+        if (lane == 0) {
+          if (CG == 1 || rank == 0) mbarrier_arrive(&full_blk[(bi - 1) & 1]);
+          else mbarrier_arrive_cluster(&peer_blk[(bi - 1) & 1], 0);      // the leader issues the MMAs that read this half block
+        }
       }
       if (bi < n_blocks) {
         if (cc == 0) {
           int co_tile, b, n0;
           tile_coords(tile, co_tile, b, n0);
+          n0 += (int)rank * n_half;                    // this CTA's columns start here
 #pragma unroll
           for (int j = 0; j < kHaloRowsPerThread; ++j) {
             // block row q holds the pixel of flat index n0 + q - (W + 1) - 1 (one image row and one pixel before the tile's
@@ -489,7 +571,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
             const int q = row0 + 32 * j;
             const int gflat = n0 + q - W1 - 1;
             const int y = gflat >= 0 ? gflat / W1 : -1, x = gflat - y * W1;
-            goff[j] = (q < geo.Q && gflat >= 0 && y < a.H && x < a.W) ? (((long long)b * a.H + y) * a.W + x) * a.x_pitch + chunk * 8 : -1;
+            goff[j] = (q < q_rows && gflat >= 0 && y < a.H && x < a.W) ? (((long long)b * a.H + y) * a.W + x) * a.x_pitch + chunk * 8 : -1;
           }
         }
         const int buf = bi & 1;
@@ -498,7 +580,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         const int c_first = conv_chunk_channel(a, cc);
 #pragma unroll
         for (int j = 0; j < kHaloRowsPerThread; ++j) {
-          if (row0 + 32 * j < geo.Q) {
+          if (row0 + 32 * j < q_rows) {
             const bool ok = goff[j] >= 0;
             cp_async16_zfill(bdst + j * 4096, a.x + (ok ? goff[j] + c_first : 0), ok);
           }
@@ -506,14 +588,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         cp_async_commit_group();
         if (++cc == ncc) {
           cc = 0;
-          tile += gridDim.x;
+          tile += tile_step;
         }
       }
     }
   } else if (warp == 13) {
     // ---- weight stages: (tile, chunk, tap) in the order the MMAs use them ----
     const int total = my_tiles * ncc * 9;
-    int tile = blockIdx.x, cc = 0, tap = 0;
+    int tile = first_tile, cc = 0, tap = 0;
     int co_tile, b, y0;
     tile_coords(tile, co_tile, b, y0);
     for (int g = 0; g < total; ++g) {
@@ -529,14 +611,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         tap = 0;
         if (++cc == ncc) {
           cc = 0;
-          tile += gridDim.x;
+          tile += tile_step;
           tile_coords(tile, co_tile, b, y0);
         }
       }
     }
+  } else if (warp == 12 && CG == 2 && rank != 0) {
+    // ---- follower of a pair: forward the completion of every weight stage to the leader ----
+    const int total = my_tiles * ncc * 9;
+    for (int g = 0; g < total; ++g) {
+      const uint32_t slot = (uint32_t)g % kRing;
+      mbarrier_wait(&full_a[slot], ((uint32_t)g / kRing) & 1);
+      if (lane == 0) mbarrier_arrive_cluster_relaxed(&peer_a[slot], 0);
+      __syncwarp();
+    }
   } else if (warp == 12) {
     // ---- MMA issuer ----
-    const uint32_t idesc = conv_idesc(a, geo.N);
+    const uint32_t idesc = conv_idesc(a, geo.N) + (CG == 2 ? ((uint32_t)(kTileCo >> 4) << 24) : 0u);   // M = 128 CG
     const int seg = halo_segment_chunks(a, ncc);
     // Accumulator halves: tile t keeps its TOTAL in half t & 1 — the first K segment accumulates straight into it — and every
     // later segment (fp32-accuracy mode) goes to the other half, from where the epilogue adds it to the total (see there).
@@ -553,21 +644,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
           d = tmem + buf * kTilePx;
         }
         mbarrier_wait(&full_blk[bi & 1], (bi >> 1) & 1);
+        if constexpr (CG == 2) mbarrier_wait(&peer_blk[bi & 1], (bi >> 1) & 1);
         const uint32_t blk = smem_addr(blocks + (bi & 1) * kHaloBlock);
         for (int tap = 0; tap < 9; ++tap, ++g) {
           const uint32_t slot = (uint32_t)g % kRing;
           mbarrier_wait(&full_a[slot], ((uint32_t)g / kRing) & 1);
+          if constexpr (CG == 2) mbarrier_wait(&peer_a[slot], ((uint32_t)g / kRing) & 1);
           tc_fence_after_sync();
           if (elect_one()) {
             const uint32_t a_addr = smem_addr(wring + slot * kStageA);
             const uint32_t b_addr = blk + (uint32_t)((tap / 3) * W1 + tap % 3) * 128;   // (1+dy)(W+1) + (1+dx) rows in
 #pragma unroll
             for (int s = 0; s < kKC / 16; ++s)
-              umma_ss(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc_at(b_addr + s * 32, base_offset_mode), idesc,
-                      !(seg_first && tap == 0 && s == 0));
-            tc_commit_to(&empty_a[slot]);
-            if (tap == 8) tc_commit_to(&empty_blk[bi & 1]);
-            if (tap == 8 && seg_last) tc_commit_to(&acc_full[buf]);
+              umma_ss_cg<CG>(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc_at(b_addr + s * 32, base_offset_mode), idesc,
+                             !(seg_first && tap == 0 && s == 0));
+            tc_commit_cg<CG>(&empty_a[slot]);
+            if (tap == 8) tc_commit_cg<CG>(&empty_blk[bi & 1]);
+            if (tap == 8 && seg_last) tc_commit_cg<CG>(&acc_full[buf]);
           }
           __syncwarp();
         }
@@ -582,10 +675,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
     const int quad = warp & 3;
     float* tp = epi + quad * 32 * 33;
     const int seg = halo_segment_chunks(a, ncc), n_seg = (ncc + seg - 1) / seg;
-    int tile = blockIdx.x, uses0 = 0, uses1 = 0;
+    int tile = first_tile, uses0 = 0, uses1 = 0;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    auto release = [&](uint32_t half) {     // hand an accumulator half back to the MMA issuer (the leader's barrier)
+      if (CG == 1 || rank == 0) mbarrier_arrive(&acc_empty[half]);
+      else mbarrier_arrive_cluster(&acc_empty[half], 0);
+    };
     const bool nhwc_vec = (a.out_ct & 7) == 0 && (a.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out_nhwc) & 15) == 0;
-    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += tile_step) {
       int co_tile, b, n0;
       tile_coords(tile, co_tile, b, n0);
       const int co0 = co_tile * kTileCo + quad * 32;
@@ -626,7 +723,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the total is re-read by this thread
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbarrier_arrive(&acc_empty[P]);
+        if (lane == 0) release(P);
       }
 #pragma unroll 1
       for (int col0 = 0; col0 < geo.N; col0 += 32) {
@@ -658,14 +755,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_tc_halo_kernel(ConvAr
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbarrier_arrive(&acc_empty[T]);
+      if (lane == 0) release(T);
     }
   }
 
   cp_async_wait_group<0>();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  if constexpr (CG == 2) cluster_sync_conv();   // no CTA leaves (or frees tensor memory) while its peer may still signal or compute
+  if (warp == 12) {
+    tc_fence_after_sync();
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  }
 }
 
 // (Cout, Cin, taps) fp32 -> stages [co tile][tap][ci chunk] of [128 co][64 ci] bf16, 16-byte chunk c of row r at c ^ (r & 7)
@@ -1108,10 +1210,33 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
   HaloGeom geo;
   const bool want_halo = !(impl && impl[0] == 'p');   // "per-tap": the per-tap kernel for 3x3 too (A/B timing)
   if (taps == 9 && want_halo && halo_geometry(H, W, &geo, kTilePx)) {
-    B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
-    const long long htiles = (long long)B * geo.tiles_per_frame * ceil_div(Cout, kTileCo);
+    const int n_co = ceil_div(Cout, kTileCo);
+    const long long htiles = (long long)B * geo.tiles_per_frame * n_co;
+    // CTA pairs (cta_group::2) when the output channels come in pairs of co tiles and a block has enough k chunks to pay for
+    // the pair's hand-overs (measured, 32 frames: 768->512 358 -> 338 us, 512->512 at 57 x 100 545 -> 514 us — both then AT the
+    // measured bf16 burst peak —, 512->256 141 -> 137, 256->256 80 -> 80, 128->256 51 -> 55)
+    const bool pair_ok = n_co % 2 == 0 && geo.N % 32 == 0 && Cin >= 256 && !(impl && impl[0] == '1');
+    if (pair_ok) {
+      B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
+      cudaLaunchConfig_t cfg{};
+      const long long pair_tiles = htiles / 2;
+      cfg.gridDim = dim3((unsigned)(2 * (pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2)));
+      cfg.blockDim = dim3(kHaloThreads);
+      cfg.dynamicSmemBytes = kHaloSmem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_tc_halo_kernel<2>, a, geo, 0));
+      return launch_status();
+    }
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
     const int hgrid = (int)(htiles < sm_count() ? htiles : sm_count());
-    conv3x3_tc_halo_kernel<<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, 0);
+    conv3x3_tc_halo_kernel<1><<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, 0);
     return launch_status();
   }
   B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
