@@ -146,6 +146,59 @@ __device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bde
 //               halves of tensor memory
 //   warps 8-11  epilogue: one TMEM lane quadrant each; tile t is read out, biased, clamped and stored while the MMAs
 //               of tile t+1 run into the other half (`acc_full` / `acc_empty`)
+// ---- CTA-pair (cta_group::2) helpers, as in pointnet_mlp_tc.cu ----
+__device__ __forceinline__ uint32_t cluster_ctarank_conv() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_conv() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (release: what this thread wrote before is
+// visible to whoever the barrier lets through)
+__device__ __forceinline__ void mbarrier_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+// the same without release semantics: the relay forwards the completion of a bulk copy and has written nothing itself
+__device__ __forceinline__ void mbarrier_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    tc_commit_to(bar);
+  } else {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_addr(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+// CG = 2: one instruction of the leader drives both CTAs: M = 256, each CTA its own 128 rows of A and of D and half of B's rows
+template <int CG>
+__device__ __forceinline__ void umma_ss_cg(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    umma_ss(d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 constexpr int kWsThreads = 416;
 constexpr int kLag = 3;   // a producer hands stage c over (waits for its own copies of it) three stages after issuing them
 
@@ -167,6 +220,11 @@ __device__ __forceinline__ void store_pixel_nhwc_bf16(const float* tp, int lane,
   }
 }
 
+// CG = 2: a CTA pair per tile of 256 output channels x 256 pixels (tcgen05.mma.cta_group::2), as in the 3x3 kernel below: each
+// CTA streams its own co tile's weight stage and HALF of the tap's pixel rows (128 of 256: every pixel then crosses L2 -> SM once
+// for both co tiles), the leader issues, the follower's producers report to the leader's `peer_b`, its idle MMA warp relays the
+// weight stages' completions to `peer_a`, commits arrive in both CTAs.
+template <int CG>
 __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -176,28 +234,39 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   uint64_t* full_b = bars + kRing;
   uint64_t* empty = bars + 2 * kRing;
   uint64_t* acc_full = bars + 3 * kRing;       // [2]
-  uint64_t* acc_empty = bars + 3 * kRing + 2;  // [2]
+  uint64_t* acc_empty = bars + 3 * kRing + 2;  // [2] one arrival per epilogue warp of the pair, at the leader
+  uint64_t* peer_a = bars + 3 * kRing + 4;     // [kRing] CG = 2, leader: the follower's weight stage has landed (relayed)
+  uint64_t* peer_b = bars + 4 * kRing + 4;     // [kRing] CG = 2, leader: the follower's pixel rows have landed
   __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = CG == 2 ? cluster_ctarank_conv() : 0u;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (warp == 12) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   if (tid == 0) {
     for (int s = 0; s < kRing; ++s) {
       mbarrier_init(&full_a[s], 1);
       mbarrier_init(&full_b[s], 8);
       mbarrier_init(&empty[s], 1);
+      mbarrier_init(&peer_a[s], 1);
+      mbarrier_init(&peer_b[s], 8);
     }
     for (int s = 0; s < 2; ++s) {
       mbarrier_init(&acc_full[s], 1);
-      mbarrier_init(&acc_empty[s], 4);
+      mbarrier_init(&acc_empty[s], 4 * CG);
     }
     mbarrier_init_fence();
   }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_conv();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
@@ -207,9 +276,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
   const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
   const int ncc = conv_chunks(a);
   const int n_k = a.taps * ncc;
-  const int n_tiles = n_px_tiles * n_co_tiles;
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // a tile is CG co tiles x 256 pixels, walked by a cluster of CG CTAs in lock step (host: n_co_tiles % CG == 0)
+  const int n_co_groups = n_co_tiles / CG;
+  const int n_tiles = n_px_tiles * n_co_groups;
+  const int first_tile = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
+  const int my_tiles = (n_tiles - first_tile + tile_step - 1) / tile_step;
   const int total = my_tiles * n_k;   // stages this CTA streams
+  constexpr int kRowsJ = 8 / CG;      // this CTA's pixel rows of a stage: 256 / CG, 32 per step of j
 
   if (warp < 8) {
     // ---- producers ----
@@ -217,7 +290,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
     const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
     int py[8], pxx[8];
     long long poff[8];
-    int tile = blockIdx.x, i = 0;   // the stage being produced: k-stage i of `tile`
+    int tile = first_tile, i = 0;   // the stage being produced: k-stage i of `tile`
     const uint8_t* wtile = nullptr;
     for (int it = 0; it < total + kLag; ++it) {
       // first hand over the oldest stage in flight (nothing below may delay the MMAs: the ring wait of the new stage is
@@ -227,14 +300,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         cp_async_wait_group<kLag - 1>();   // this thread's rows of stage c have landed (groups it-kLag+1 .. it-1 may be pending)
         fence_proxy_async_shared();        // ... and are ordered before the tensor core's asynchronous-proxy reads
         __syncwarp();
-        if (lane == 0) mbarrier_arrive(&full_b[(uint32_t)c % kRing]);
+        if (lane == 0) {
+          if (CG == 1 || rank == 0) mbarrier_arrive(&full_b[(uint32_t)c % kRing]);
+          else mbarrier_arrive_cluster(&peer_b[(uint32_t)c % kRing], 0);   // the leader issues the MMAs that read these rows
+        }
       }
       if (it < total) {
         if (i == 0) {
-          const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
-          const long long px0 = (long long)px_tile * kTilePx;
+          const int co_tile = (tile % n_co_groups) * CG + (int)rank, px_tile = tile / n_co_groups;
+          const long long px0 = (long long)px_tile * kTilePx + (long long)rank * (kTilePx / CG);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kRowsJ; ++j) {
             const long long n = px0 + row0 + 32 * j;
             if (n < n_px) {
               const int p = (int)(n % HW);
@@ -256,7 +332,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         const long long shift = ((long long)dy * a.W + dx) * a.x_pitch + conv_chunk_channel(a, cc);
         const uint32_t bdst = smem_addr(ring + slot * kStage + kStageA) + dst_off;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kRowsJ; ++j) {
           const int yy = py[j] + dy, xx = pxx[j] + dx;
           const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
           cp_async16_zfill(bdst + j * 4096, a.x + (ok ? poff[j] + shift : 0), ok);
@@ -267,14 +343,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
         }
         if (++i == n_k) {
           i = 0;
-          tile += gridDim.x;
+          tile += tile_step;
         }
       }
       cp_async_commit_group();
     }
+  } else if (warp == 12 && CG == 2 && rank != 0) {
+    // ---- follower of a pair: forward the completion of every weight stage to the leader ----
+    for (int c = 0; c < total; ++c) {
+      const uint32_t slot = (uint32_t)c % kRing;
+      mbarrier_wait(&full_a[slot], ((uint32_t)c / kRing) & 1);
+      if (lane == 0) mbarrier_arrive_cluster_relaxed(&peer_a[slot], 0);
+      __syncwarp();
+    }
   } else if (warp == 12) {
     // ---- MMA issuer ----
-    const uint32_t idesc = conv_idesc(a, kTilePx);
+    const uint32_t idesc = conv_idesc(a, kTilePx) + (CG == 2 ? ((uint32_t)(kTileCo >> 4) << 24) : 0u);   // M = 128 CG
     int i = 0, tile_seq = 0;
     for (int c = 0; c < total; ++c) {
       const uint32_t slot = (uint32_t)c % kRing, use = (uint32_t)c / kRing;
@@ -282,15 +366,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
       if (i == 0 && tile_seq >= 2) mbarrier_wait(&acc_empty[buf], ((tile_seq >> 1) - 1) & 1);
       mbarrier_wait(&full_b[slot], use & 1);
       mbarrier_wait(&full_a[slot], use & 1);
+      if constexpr (CG == 2) {
+        mbarrier_wait(&peer_b[slot], use & 1);
+        mbarrier_wait(&peer_a[slot], use & 1);
+      }
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t a_addr = smem_addr(ring + slot * kStage), b_addr = a_addr + kStageA;
         const uint32_t d = tmem + buf * kTilePx;
 #pragma unroll
         for (int s = 0; s < kKC / 16; ++s)
-          umma_ss(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc(b_addr + s * 32), idesc, !(i == 0 && s == 0));
-        tc_commit_to(&empty[slot]);
-        if (i == n_k - 1) tc_commit_to(&acc_full[buf]);
+          umma_ss_cg<CG>(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc(b_addr + s * 32), idesc, !(i == 0 && s == 0));
+        tc_commit_cg<CG>(&empty[slot]);
+        if (i == n_k - 1) tc_commit_cg<CG>(&acc_full[buf]);
       }
       __syncwarp();
       if (++i == n_k) {
@@ -305,9 +393,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
     const bool nhwc_vec = (a.out_ct & 7) == 0 && (a.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out_nhwc) & 15) == 0;
     const int quad = warp & 3;
     float* tp = epi + quad * 32 * 33;
-    int tile = blockIdx.x;
-    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
-      const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
+    int tile = first_tile;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += tile_step) {
+      const int co_tile = (tile % n_co_groups) * CG + (int)rank, px_tile = tile / n_co_groups;
       const long long px0 = (long long)px_tile * kTilePx;
       const uint32_t buf = tile_seq & 1;
       const int co0 = co_tile * kTileCo + quad * 32;
@@ -348,14 +436,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
       }
       tc_fence_before_sync();   // the tensor-memory loads above are complete (wait::ld) before the half is handed back
       __syncwarp();
-      if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (CG == 1 || rank == 0) mbarrier_arrive(&acc_empty[buf]);
+        else mbarrier_arrive_cluster(&acc_empty[buf], 0);
+      }
     }
   }
 
   cp_async_wait_group<0>();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  if constexpr (CG == 2) cluster_sync_conv();   // no CTA leaves (or frees tensor memory) while its peer may still signal or compute
+  if (warp == 12) {
+    tc_fence_after_sync();
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  }
 }
 
 // ---- 3x3 form with the pixel rows shared by the nine taps (default for 3x3 when an image row fits) ---------------------
@@ -414,58 +510,6 @@ __device__ __forceinline__ uint64_t kmajor_sw128_desc_at(uint32_t saddr, int bas
   return d;
 }
 
-// ---- CTA-pair (cta_group::2) helpers, as in pointnet_mlp_tc.cu ----
-__device__ __forceinline__ uint32_t cluster_ctarank_conv() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_conv() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (release: what this thread wrote before is
-// visible to whoever the barrier lets through)
-__device__ __forceinline__ void mbarrier_arrive_cluster(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
-      "r"(rank)
-      : "memory");
-}
-// the same without release semantics: the relay forwards the completion of a bulk copy and has written nothing itself
-__device__ __forceinline__ void mbarrier_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
-      "r"(rank)
-      : "memory");
-}
-template <int CG>
-__device__ __forceinline__ void tc_commit_cg(uint64_t* bar) {
-  if constexpr (CG == 1) {
-    tc_commit_to(bar);
-  } else {   // arrives on the barrier at this offset in BOTH CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_addr(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-  }
-}
-// CG = 2: one instruction of the leader drives both CTAs: M = 256, each CTA its own 128 rows of A and of D and half of B's rows
-template <int CG>
-__device__ __forceinline__ void umma_ss_cg(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (CG == 1) {
-    umma_ss(d, adesc, bdesc, idesc, accumulate);
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
 
 // CG = 2: a CTA PAIR (thread-block cluster of two) computes 256 output channels x N pixels per tile with tcgen05.mma.cta_group::2.
 // Each CTA keeps its own co tile's weight ring (the A operand, 128 rows) and HALF of the pixel block (the B operand: the rows of
@@ -1239,8 +1283,30 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
     conv3x3_tc_halo_kernel<1><<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, 0);
     return launch_status();
   }
-  B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
-  conv_tc_ws_kernel<<<grid, kWsThreads, kConvSmem, (cudaStream_t)stream>>>(a);
+  // per-tap kernel (1x1, and 3x3 on maps too wide for the shared pixel block), optionally as CTA pairs.
+  // Measured: correct (parity green) and SLOWER — camera_proj.3 (1x1, 512 -> 256, 32 x 57 x 100) 94 -> 152 us: this kernel is
+  // paced by the turn-around of its four ring slots, not by shared-memory bandwidth, and a pair adds a hop to every stage.  The
+  // pair instantiation stays in the source behind the debug switch B200BEV_CONV_IMPL=2.
+  if (ceil_div(Cout, kTileCo) % 2 == 0 && Cin >= 256 && impl && impl[0] == '2') {
+    B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+    const long long pair_tiles = tiles / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * (pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2)));
+    cfg.blockDim = dim3(kWsThreads);
+    cfg.dynamicSmemBytes = kConvSmem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_ws_kernel<2>, a));
+    return launch_status();
+  }
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv_tc_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  conv_tc_ws_kernel<1><<<grid, kWsThreads, kConvSmem, (cudaStream_t)stream>>>(a);
   return launch_status();
 }
 }  // namespace
