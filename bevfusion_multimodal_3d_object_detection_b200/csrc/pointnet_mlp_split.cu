@@ -43,7 +43,7 @@ constexpr int kProducerWarps = 16;
 // warps kProducerWarps .. +3 are the epilogue: warp % 4 == the TMEM lane quadrant a warp may read
 constexpr int kMmaWarp = kProducerWarps + 4, kWeightWarp = kProducerWarps + 5;
 constexpr int kThreads = (kProducerWarps + 6) * 32;
-constexpr int kSmem = kXRing * kXStage + kWRing * kWStage + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kSmem = kXRing * kXStage + kWRing * kWStage + 1024 /*alignment*/ + 256 /*barriers: 19 + the tensor-memory slot*/;
 constexpr int kMaxCin = 16;
 __host__ __device__ constexpr int cin_of(int l) { return 64 << l; }      // layers 2..5 = l 0..3
 __host__ __device__ constexpr int cout_of(int l) { return 128 << l; }
@@ -240,6 +240,55 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t adesc, uint64_t
       : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) helpers, as in pointnet_mlp_tc.cu / conv_tc.cu ----
+__device__ __forceinline__ uint32_t split_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void split_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void split_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void split_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tcs_commit_cg(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    tcs_commit(bar);
+  } else {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_addr(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_ss_cg(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    umma_f16_ss(d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 #define SPLIT_LD32(r, taddr)                                                                                               \
   asm volatile(                                                                                                            \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"      \
@@ -251,7 +300,14 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t adesc, uint64_t
       : "r"(taddr)                                                                                                         \
       : "memory")
 
-template <bool FINAL>
+// CG = 2: a CTA pair (thread-block cluster of two, tcgen05.mma.cta_group::2) per tile of 256 output channels x 256 points.  Each
+// CTA streams its own co tile's weight stages and converts HALF of the points (128 rows of x_hi / x_lo): the fp32 activations
+// cross L2 -> SM and the producers' split once for two co tiles, and the tensor core reads 8 KB of shared memory per MMA and SM
+// instead of 12 (shared-memory bandwidth held the single-CTA kernel at 0.6-0.7 of the fp16 peak).  The leader
+// (cluster rank 0) issues every MMA; the follower's producer warps arrive on the leader's `peer_x`, its otherwise idle MMA warp
+// relays its weight stages' completions to `peer_w`; tcgen05.commit arrives in both CTAs; both CTAs' epilogue warps release the
+// accumulator halves at the leader.
+template <bool FINAL, int CG>
 __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* xring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -262,61 +318,77 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
   uint64_t* full_w = bars + 2 * kXRing;            // [3] bulk-copy bytes
   uint64_t* empty_w = full_w + kWRing;             // [3] tcgen05.commit
   uint64_t* acc_full = empty_w + kWRing;           // [2]
-  uint64_t* acc_empty = acc_full + 2;              // [2] one arrival per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 2;              // [2] one arrival per epilogue warp of the pair, at the leader
+  uint64_t* peer_x = acc_empty + 2;                // [2] CG = 2, leader: the follower's half of the x stage is in place
+  uint64_t* peer_w = peer_x + kXRing;              // [3] CG = 2, leader: the follower's weight stage has landed (relayed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_w + kWRing);
+  const uint32_t rank = CG == 2 ? split_cluster_ctarank() : 0u;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   if (tid == 0) {
     for (int s = 0; s < kXRing; ++s) {
       mbarrier_init(&full_x[s], kProducerWarps);
       mbarrier_init(&empty_x[s], 1);
+      mbarrier_init(&peer_x[s], kProducerWarps);
     }
     for (int s = 0; s < kWRing; ++s) {
       mbarrier_init(&full_w[s], 1);
       mbarrier_init(&empty_w[s], 1);
+      mbarrier_init(&peer_w[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbarrier_init(&acc_full[s], 1);
-      mbarrier_init(&acc_empty[s], 4);
+      mbarrier_init(&acc_empty[s], 4 * CG);
     }
     mbarrier_init_fence();
   }
   tcs_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) split_cluster_sync();   // the peer's barriers are initialised before anyone signals them
   tcs_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   const int n_co = a.Cout / kCo, nkb = a.Cin / kKB;
   const int tiles_per_frame = a.Npad / kPx;
-  const int n_tiles = a.nB * tiles_per_frame * n_co;     // co tiles of one point tile are neighbours in the grid (shared x in L2)
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // a tile is CG co tiles x 256 points, walked by a cluster of CG CTAs in lock step (host: n_co % CG == 0); the co groups of one
+  // point tile are neighbours in the grid (shared x in L2)
+  const int n_cg = n_co / CG;
+  const int n_tiles = a.nB * tiles_per_frame * n_cg;
+  const int first_tile = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
+  const int my_tiles = (n_tiles - first_tile + tile_step - 1) / tile_step;
   const int total = my_tiles * nkb;
+  constexpr int kRowsJ = 4 / CG;             // this CTA's rows of an x stage: 256 / CG points, 64 per step of j
 
   if (warp < kProducerWarps) {
     // ---- producers: fp32 rows -> scale by the layer's power of two -> fp16 hi / lo -> swizzled shared memory ----
     const float S = activation_scale(__ldg(a.stat_in));
     const int row0 = tid >> 3, chunk = tid & 7;                 // rows row0 + 64 j, j = 0..3; 8 floats of the 64-wide k block
     const uint32_t dst_off = (uint32_t)(row0 * 128 + ((chunk ^ (row0 & 7)) << 4));
-    float4 raw[8];
-    int tile = blockIdx.x, kb = 0;
+    float4 raw[2 * kRowsJ];
+    int tile = first_tile, kb = 0;
     auto load = [&](int t, int k) {
-      const long long px0 = (long long)(t / n_co) * kPx;
+      const long long px0 = (long long)(t / n_cg) * kPx + (long long)rank * (kPx / CG);
       const float* src = a.x + (px0 + row0) * a.Cin + k * kKB + chunk * 8;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kRowsJ; ++j) {
         raw[2 * j] = __ldg(reinterpret_cast<const float4*>(src + (size_t)j * 64 * a.Cin));
         raw[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src + (size_t)j * 64 * a.Cin + 4));
       }
     };
     if (total > 0) load(tile, 0);
     for (int it = 0; it < total; ++it) {
-      uint4 hi[4], lo[4];
+      uint4 hi[kRowsJ], lo[kRowsJ];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kRowsJ; ++j) {
         const float v[8] = {raw[2 * j].x * S,     raw[2 * j].y * S,     raw[2 * j].z * S,     raw[2 * j].w * S,
                             raw[2 * j + 1].x * S, raw[2 * j + 1].y * S, raw[2 * j + 1].z * S, raw[2 * j + 1].w * S};
         uint32_t h[4], l[4];
@@ -334,61 +406,77 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
       // the next stage's rows are in flight while this one waits for its slot and is stored
       if (++kb == nkb) {
         kb = 0;
-        tile += gridDim.x;
+        tile += tile_step;
       }
       if (it + 1 < total) load(tile, kb);
       const uint32_t slot = (uint32_t)it % kXRing;
       if (it >= kXRing) mbarrier_wait(&empty_x[slot], (((uint32_t)it / kXRing) - 1) & 1);
       uint8_t* dst = xring + slot * kXStage + dst_off;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kRowsJ; ++j) {
         *reinterpret_cast<uint4*>(dst + j * 64 * 128) = hi[j];
         *reinterpret_cast<uint4*>(dst + j * 64 * 128 + kXHalf) = lo[j];
       }
       fence_proxy_async_shared();        // generic-proxy stores ordered before the tensor core's asynchronous-proxy reads
       __syncwarp();
-      if (lane == 0) mbarrier_arrive(&full_x[slot]);
+      if (lane == 0) {
+        if (CG == 1 || rank == 0) mbarrier_arrive(&full_x[slot]);
+        else split_arrive_cluster(&peer_x[slot], 0);       // the leader issues the MMAs that read these rows
+      }
     }
   } else if (warp == kWeightWarp) {
     // ---- weight stages, (tile, k block) in the order the MMAs use them: one 32 KB bulk copy each ----
-    int tile = blockIdx.x, kb = 0;
+    int tile = first_tile, kb = 0;
     for (int g = 0; g < total; ++g) {
       const uint32_t slot = (uint32_t)g % kWRing;
       if (g >= kWRing) mbarrier_wait(&empty_w[slot], (((uint32_t)g / kWRing) - 1) & 1);
       if (elect_one()) {
         mbarrier_expect_tx(&full_w[slot], kWStage);
-        bulk_copy_global_to_shared(wring + slot * kWStage, a.stages + ((size_t)(tile % n_co) * nkb + kb) * kWStage, kWStage, &full_w[slot]);
+        bulk_copy_global_to_shared(wring + slot * kWStage, a.stages + ((size_t)((tile % n_cg) * CG + (int)rank) * nkb + kb) * kWStage, kWStage,
+                                   &full_w[slot]);
       }
       __syncwarp();
       if (++kb == nkb) {
         kb = 0;
-        tile += gridDim.x;
+        tile += tile_step;
       }
+    }
+  } else if (warp == kMmaWarp && CG == 2 && rank != 0) {
+    // ---- follower of a pair: forward the completion of every weight stage to the leader ----
+    for (int c = 0; c < total; ++c) {
+      const uint32_t ws = (uint32_t)c % kWRing;
+      mbarrier_wait(&full_w[ws], ((uint32_t)c / kWRing) & 1);
+      if (lane == 0) split_arrive_cluster_relaxed(&peer_w[ws], 0);
+      __syncwarp();
     }
   } else if (warp == kMmaWarp) {
     // ---- MMA issuer: 12 x (128 x 256 x 16) per k block: hi.hi, w_hi.x_lo, w_lo.x_hi ----
     // instruction descriptor: D f32 (bit 4), A and B fp16 (format 0), both K-major, N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(kPx >> 3) << 17) | ((uint32_t)(kCo >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(kPx >> 3) << 17) | ((uint32_t)((kCo * CG) >> 4) << 24);
     int kb = 0, tile_seq = 0;
     for (int c = 0; c < total; ++c) {
       const uint32_t xs = (uint32_t)c % kXRing, ws = (uint32_t)c % kWRing, buf = tile_seq & 1;
       if (kb == 0 && tile_seq >= 2) mbarrier_wait(&acc_empty[buf], ((tile_seq >> 1) - 1) & 1);
       mbarrier_wait(&full_x[xs], ((uint32_t)c / kXRing) & 1);
       mbarrier_wait(&full_w[ws], ((uint32_t)c / kWRing) & 1);
+      if constexpr (CG == 2) {
+        mbarrier_wait(&peer_x[xs], ((uint32_t)c / kXRing) & 1);
+        mbarrier_wait(&peer_w[ws], ((uint32_t)c / kWRing) & 1);
+      }
       tcs_fence_after();
       if (elect_one()) {
         const uint32_t x_hi = smem_addr(xring + xs * kXStage), x_lo = x_hi + kXHalf;
         const uint32_t w_hi = smem_addr(wring + ws * kWStage), w_lo = w_hi + kWHalf;
         const uint32_t d = tmem + buf * kPx;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) umma_f16_ss(d, sw128_desc(w_hi + s * 32), sw128_desc(x_hi + s * 32), idesc, !(kb == 0 && s == 0));
+        for (int s = 0; s < 4; ++s) umma_f16_ss_cg<CG>(d, sw128_desc(w_hi + s * 32), sw128_desc(x_hi + s * 32), idesc, !(kb == 0 && s == 0));
 #pragma unroll
-        for (int s = 0; s < 4; ++s) umma_f16_ss(d, sw128_desc(w_hi + s * 32), sw128_desc(x_lo + s * 32), idesc, 1u);
+        for (int s = 0; s < 4; ++s) umma_f16_ss_cg<CG>(d, sw128_desc(w_hi + s * 32), sw128_desc(x_lo + s * 32), idesc, 1u);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) umma_f16_ss(d, sw128_desc(w_lo + s * 32), sw128_desc(x_hi + s * 32), idesc, 1u);
-        tcs_commit(&empty_x[xs]);
-        tcs_commit(&empty_w[ws]);
-        if (kb == nkb - 1) tcs_commit(&acc_full[buf]);
+        for (int s = 0; s < 4; ++s) umma_f16_ss_cg<CG>(d, sw128_desc(w_lo + s * 32), sw128_desc(x_hi + s * 32), idesc, 1u);
+        tcs_commit_cg<CG>(&empty_x[xs]);
+        tcs_commit_cg<CG>(&empty_w[ws]);
+        if (kb == nkb - 1) tcs_commit_cg<CG>(&acc_full[buf]);
       }
       __syncwarp();
       if (++kb == nkb) {
@@ -401,9 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
     const int quad = warp & 3;
     const float inv_S = 1.f / activation_scale(__ldg(a.stat_in));   // exact: a power of two
     float layer_max = 0.f;
-    int tile = blockIdx.x;
-    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
-      const int co_tile = tile % n_co, px_tile = tile / n_co;
+    int tile = first_tile;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += tile_step) {
+      const int co_tile = (tile % n_cg) * CG + (int)rank, px_tile = tile / n_cg;
       const int fl = px_tile / tiles_per_frame, s0 = (px_tile - fl * tiles_per_frame) * kPx;
       const long long row_base = (long long)px_tile * kPx;          // = fl * Npad + s0
       const uint32_t buf = tile_seq & 1;
@@ -497,7 +585,10 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
       }
       tcs_fence_before();    // the tensor-memory loads above are complete (wait::ld) before the half is handed back
       __syncwarp();
-      if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (CG == 1 || rank == 0) mbarrier_arrive(&acc_empty[buf]);
+        else split_arrive_cluster(&acc_empty[buf], 0);
+      }
     }
     if (!FINAL) {
 #pragma unroll
@@ -508,9 +599,11 @@ __global__ void __launch_bounds__(kThreads, 1) split_gemm_kernel(GemmArgs a) {
 
   tcs_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) split_cluster_sync();   // no CTA leaves (or frees tensor memory) while its peer may still signal or compute
   if (warp == kMmaWarp) {
     tcs_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -549,8 +642,37 @@ int pointnet_encode_split(const float* points, int B, int N, int C, const int32_
   const SplitLayout L = split_layout(C);
   if (out_global) B200BEV_CUDA_TRY(cudaMemsetAsync(out_global, 0, (size_t)B * 1024 * sizeof(float), st));
   if (out_canvas) B200BEV_CUDA_TRY(cudaMemsetAsync(out_canvas, 0, (size_t)B * n_cells * 1024 * sizeof(float), st));
-  B200BEV_CUDA_TRY(cudaFuncSetAttribute(split_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  B200BEV_CUDA_TRY(cudaFuncSetAttribute(split_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(split_gemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(split_gemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(split_gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  B200BEV_CUDA_TRY(cudaFuncSetAttribute(split_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  // layers with at least two co tiles run as CTA pairs (cta_group::2)
+  auto launch_gemm = [&](const GemmArgs& g, bool final_layer) -> int {
+    const long long tiles = (long long)g.nB * (g.Npad / kPx) * (g.Cout / kCo);
+    const bool pair = (g.Cout / kCo) % 2 == 0 && !debug_env("B200BEV_SPLIT_SINGLE");
+    if (!pair) {
+      const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+      if (final_layer) split_gemm_kernel<true, 1><<<grid, kThreads, kSmem, st>>>(g);
+      else split_gemm_kernel<false, 1><<<grid, kThreads, kSmem, st>>>(g);
+      return launch_status();
+    }
+    const long long pair_tiles = tiles / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * (pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (final_layer) B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, split_gemm_kernel<true, 2>, g));
+    else B200BEV_CUDA_TRY(cudaLaunchKernelEx(&cfg, split_gemm_kernel<false, 2>, g));
+    return launch_status();
+  };
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   for (int b0 = 0; b0 < B; b0 += per_pass) {
     const int nB = B - b0 < per_pass ? B - b0 : per_pass;
@@ -573,18 +695,14 @@ int pointnet_encode_split(const float* points, int B, int N, int C, const int32_
       g.tail = reinterpret_cast<const float*>(img + L.tail[l]);
       g.stat_in = stat + l; g.stat_out = l < 3 ? stat + l + 1 : nullptr;
       g.Cin = cin_of(l); g.Cout = cout_of(l); g.nB = nB; g.N = N; g.Npad = Npad;
-      const long long tiles = (long long)nB * (Npad / kPx) * (g.Cout / kCo);
-      const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-      if (l < 3) {
-        split_gemm_kernel<false><<<grid, kThreads, kSmem, st>>>(g);
-      } else {
+      if (l == 3) {
         g.out_global = out_global ? out_global + (size_t)b0 * 1024 : nullptr;
         g.out_canvas = out_canvas ? out_canvas + (size_t)b0 * n_cells * 1024 : nullptr;
         g.cid = cell ? cid : nullptr;
         g.n_cells = n_cells;
-        split_gemm_kernel<true><<<grid, kThreads, kSmem, st>>>(g);
       }
-      B200BEV_CUDA_TRY(cudaGetLastError());
+      const int rc = launch_gemm(g, l == 3);
+      if (rc) return rc;
       x = y;
     }
   }
