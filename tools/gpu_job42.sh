@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU job 42: evidence set on the committed code after the tensor-core dense layer: GPU suite, smoke, default bench (both arms),
+# GPU job 42: evidence set on the committed code (tensor-core dense layer, CTA-pair convolution and fp32-accuracy MLP): GPU suite, smoke, default bench (both arms),
 # kernel timings (bench / stress shapes), ncu launch list of the step
 mkdir -p gpurun_out
 : > gpurun_out/rc.txt
@@ -9,7 +9,7 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 ( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?" >> gpurun_out/rc.txt
 timeout 300 python tests/perf_kernels.py all > gpurun_out/perf_all.log 2>&1
 timeout 300 python tests/perf_kernels.py all --frames 8 --grid 100 --points 300000 > gpurun_out/perf_stress.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_l.csv python tests/probes/launch_list.py 32 > gpurun_out/launch_ncu.log 2>&1; echo "ncu list rc=$?" >> gpurun_out/rc.txt
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_m.csv python tests/probes/launch_list.py 32 > gpurun_out/launch_ncu.log 2>&1; echo "ncu list rc=$?" >> gpurun_out/rc.txt
 cat gpurun_out/rc.txt
 grep -E "passed|failed" gpurun_out/gpu_tests.log | tail -2
 tail -2 gpurun_out/smoke.log
