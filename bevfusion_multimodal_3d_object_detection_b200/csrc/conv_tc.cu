@@ -25,6 +25,8 @@
 
 #include <cstdlib>
 
+#include <cuda.h>   // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no link to libcuda)
+
 #include "async_copy.cuh"
 #include "common.cuh"
 
@@ -452,6 +454,195 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(ConvArgs a) {
     if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem));
   }
+}
+
+// ---- 1x1 form fed by TMA tensor loads ------------------------------------------------------------------------------------------
+// The per-tap kernel above moves a stage's 256 pixel rows with 2,048 sixteen-byte cp.async per CTA, and a 1x1 convolution has
+// only four MMAs (512 clk) per stage to hide them behind: measured, the kernel is paced by its ring turn-around (2,400 clk per
+// stage on camera_proj.3, 0.29 of the bf16 peak; neither resident weights, nor CTA pairs, nor an L2 prefetch hint changed that —
+// the copies' own latency did: ~8,000 clk from issue to hand-over with ~6,000 sixteen-byte requests in flight per SM).  Here the
+// input is described ONCE as a 2-D tensor (rows = pixels, columns = channels, host: cuTensorMapEncodeTiled) and a stage's pixel
+// rows are ONE instruction: cp.async.bulk.tensor.2d with a 64-channel x 256-pixel box, 128-byte swizzle — the layout the MMA
+// descriptor reads — and zero fill past the last pixel.  No producer warps: one elected lane issues the tensor load and the
+// weight stage's bulk copy onto the same barrier.  192 threads: warp 0 copies, warp 1 MMA issue, warps 2-5 epilogue.
+constexpr int kTmaThreads = 192;
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_addr(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1) conv1x1_tma_kernel(ConvArgs a, const __grid_constant__ CUtensorMap xmap) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+  float* epi = reinterpret_cast<float*>(ring + kRing * kStage);   // [4][32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRing * kStage + kEpiTile);
+  uint64_t* full = bars;                       // [kRing] transaction bytes: weight stage + pixel box
+  uint64_t* empty = bars + kRing;              // [kRing] tcgen05.commit
+  uint64_t* acc_full = bars + 2 * kRing;       // [2]
+  uint64_t* acc_empty = bars + 2 * kRing + 2;  // [2] one arrival per epilogue warp
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbarrier_init(&full[s], 1);
+      mbarrier_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbarrier_init(&acc_full[s], 1);
+      mbarrier_init(&acc_empty[s], 4);
+    }
+    mbarrier_init_fence();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  const int HW = a.H * a.W;
+  const long long n_px = (long long)a.B * HW;
+  const int n_px_tiles = (int)((n_px + kTilePx - 1) / kTilePx);
+  const int n_co_tiles = (a.Cout + kTileCo - 1) / kTileCo;
+  const int ncc = conv_chunks(a);              // taps == 1: one stage per k chunk
+  const int n_tiles = n_px_tiles * n_co_tiles;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * ncc;
+
+  if (warp == 0) {
+    // ---- copies: per stage one tensor load (the tap's 256 pixel rows x 64 channels) and one bulk copy (the weight stage) ----
+    int tile = blockIdx.x, i = 0;
+    for (int c = 0; c < total; ++c) {
+      const uint32_t slot = (uint32_t)c % kRing;
+      if (c >= kRing) mbarrier_wait(&empty[slot], (((uint32_t)c / kRing) - 1) & 1);
+      if (elect_one()) {
+        const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
+        mbarrier_expect_tx(&full[slot], kStage);
+        bulk_copy_global_to_shared(ring + slot * kStage, a.wimg + ((size_t)co_tile * ncc + i) * kStageA, kStageA, &full[slot]);
+        tma_load_2d(ring + slot * kStage + kStageA, &xmap, conv_chunk_channel(a, i), px_tile * kTilePx, &full[slot]);
+      }
+      __syncwarp();
+      if (++i == ncc) {
+        i = 0;
+        tile += gridDim.x;
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    const uint32_t idesc = conv_idesc(a, kTilePx);
+    int i = 0, tile_seq = 0;
+    for (int c = 0; c < total; ++c) {
+      const uint32_t slot = (uint32_t)c % kRing, use = (uint32_t)c / kRing;
+      const uint32_t buf = tile_seq & 1;
+      if (i == 0 && tile_seq >= 2) mbarrier_wait(&acc_empty[buf], ((tile_seq >> 1) - 1) & 1);
+      mbarrier_wait(&full[slot], use & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_addr(ring + slot * kStage), b_addr = a_addr + kStageA;
+        const uint32_t d = tmem + buf * kTilePx;
+#pragma unroll
+        for (int s = 0; s < kKC / 16; ++s)
+          umma_ss(d, kmajor_sw128_desc(a_addr + s * 32), kmajor_sw128_desc(b_addr + s * 32), idesc, !(i == 0 && s == 0));
+        tc_commit_to(&empty[slot]);
+        if (i == ncc - 1) tc_commit_to(&acc_full[buf]);
+      }
+      __syncwarp();
+      if (++i == ncc) {
+        i = 0;
+        ++tile_seq;
+      }
+    }
+  } else {
+    // ---- epilogue (as in conv_tc_ws_kernel): warp w owns TMEM lanes [32 (w % 4), +32) ----
+    const bool nhwc_vec = (a.out_ct & 7) == 0 && (a.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out_nhwc) & 15) == 0;
+    const int quad = warp & 3;
+    float* tp = epi + quad * 32 * 33;
+    int tile = blockIdx.x;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq, tile += gridDim.x) {
+      const int co_tile = tile % n_co_tiles, px_tile = tile / n_co_tiles;
+      const long long px0 = (long long)px_tile * kTilePx;
+      const uint32_t buf = tile_seq & 1;
+      const int co0 = co_tile * kTileCo + quad * 32;
+      const int co = co0 + lane;
+      const float bias = (a.bias && co < a.Cout) ? __ldg(a.bias + co) : 0.f;
+      const float oscale = conv_out_scale(a, co);
+      const int n_ch = a.Cout - co0 < 32 ? a.Cout - co0 : 32;
+      mbarrier_wait(&acc_full[buf], (tile_seq >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int q = 0; q < kTilePx / 32; ++q) {
+        uint32_t r[32];
+        const int col0 = q * 32;
+        CONV_TC_LD32(r, tmem + ((uint32_t)(quad * 32) << 16) + buf * kTilePx + (uint32_t)col0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const long long n0 = px0 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = fmaf(__uint_as_float(r[j]), oscale, bias);
+          if (a.relu) v = fmaxf(v, 0.f);
+          tp[lane * 33 + j] = v;
+        }
+        __syncwarp();
+        if (a.out_nhwc && n0 + lane < n_px && n_ch > 0)
+          store_pixel_nhwc_bf16(tp, lane, a.out_nhwc + (size_t)(n0 + lane) * a.out_ct + a.out_coff + co0, n_ch, nhwc_vec);
+        if (a.out) {
+          const long long n = n0 + lane;   // this lane's pixel
+          const bool px_ok = n < n_px;
+          const int b = px_ok ? (int)(n / HW) : 0, p = px_ok ? (int)(n - (long long)b * HW) : 0;
+          float* dst = a.out + ((size_t)b * a.Cout + co0) * HW + p;
+          for (int c = 0; c < n_ch; ++c) {
+            const float v = tp[c * 33 + lane];
+            if (px_ok) dst[(size_t)c * HW] = v;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before_sync();   // the tensor-memory loads above are complete (wait::ld) before the half is handed back
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: libb200bev.so keeps loading where there is no driver
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// (n_px, x_pitch) elements of 2 bytes, rows x_pitch apart, as boxes of 256 rows x 64 columns, 128-byte swizzle, zeros out of bounds
+inline bool make_pixel_map(CUtensorMap* map, const void* x, long long n_px, int x_pitch, bool fp16) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)x_pitch, (cuuint64_t)n_px};
+  const cuuint64_t strides[1] = {(cuuint64_t)x_pitch * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)kTilePx};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---- 3x3 form with the pixel rows shared by the nine taps (default for 3x3 when an image row fits) ---------------------
@@ -1282,6 +1473,15 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
     const int hgrid = (int)(htiles < sm_count() ? htiles : sm_count());
     conv3x3_tc_halo_kernel<1><<<hgrid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(a, geo, 0);
     return launch_status();
+  }
+  // 1x1: the TMA-fed kernel (one tensor load per stage instead of 2,048 cp.async)
+  if (taps == 1 && (long long)B * H * W < (1ll << 31) && !(impl && impl[0] == 'c')) {   // "c": the cp.async kernel (A/B timing)
+    CUtensorMap xmap;
+    if (make_pixel_map(&xmap, x_nhwc, (long long)B * H * W, a.x_pitch, a.split != 0)) {
+      B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+      conv1x1_tma_kernel<<<grid, kTmaThreads, kConvSmem, (cudaStream_t)stream>>>(a, xmap);
+      return launch_status();
+    }
   }
   // per-tap kernel (1x1, and 3x3 on maps too wide for the shared pixel block), optionally as CTA pairs.
   // Measured: correct (parity green) and SLOWER — camera_proj.3 (1x1, 512 -> 256, 32 x 57 x 100) 94 -> 152 us: this kernel is
