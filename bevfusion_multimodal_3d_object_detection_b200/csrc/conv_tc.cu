@@ -1450,7 +1450,8 @@ int launch_conv(const void* x_nhwc, int B, int H, int W, int Cin, const void* we
     // CTA pairs (cta_group::2) when the output channels come in pairs of co tiles and a block has enough k chunks to pay for
     // the pair's hand-overs (measured, 32 frames: 768->512 358 -> 338 us, 512->512 at 57 x 100 545 -> 514 us — both then AT the
     // measured bf16 burst peak —, 512->256 141 -> 137, 256->256 80 -> 80, 128->256 51 -> 55)
-    const bool pair_ok = n_co % 2 == 0 && geo.N % 32 == 0 && Cin >= 256 && !(impl && impl[0] == '1');
+    // (full 256-column tiles only: the narrower tiles of small maps stay on the single-CTA form, the one they were tested on)
+    const bool pair_ok = n_co % 2 == 0 && geo.N == kTilePx && Cin >= 256 && !(impl && impl[0] == '1');
     if (pair_ok) {
       B200BEV_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
       cudaLaunchConfig_t cfg{};
