@@ -217,10 +217,9 @@ def head_forward(head: nn.Module, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         hid = ops.conv_bn_relu_split(x_split, stat, p["img1"], p["b1"], p["hidden"], 9, relu=True)
         h_split, h_stat = ops.nchw_to_nhwc_split([hid])
         both = ops.conv_bn_relu_split(h_split, h_stat, p["img2"], p["b2"], sum(p["outs"]), 1, relu=False)
-    pred, c = {}, 0
-    for n, k in zip(HEADS, p["outs"]):
-        pred[n] = both[:, c:c + k].contiguous()
-        c += k
+    # the five heads as contiguous tensors: one fused copy launch (split_with_sizes_copy) instead of five
+    parts = torch.split_with_sizes_copy(both, list(p["outs"]), dim=1)
+    pred = dict(zip(HEADS, parts))
     logits = pred["heatmap"]
     pred["heatmap"] = attach_logits(torch.sigmoid(logits), logits)
     return pred
